@@ -1,0 +1,125 @@
+"""Shared helpers: run a seeded update case through a backend and compare the
+result with the golden fixtures produced from the real reference
+(oracle/make_golden.py)."""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from oracle import cases as C
+from oracle import recnn_oracle as O
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+SNAP_AFTER = (1, 2, 11, 12)
+
+
+def load_golden(name):
+    return dict(np.load(os.path.join(GOLDEN_DIR, name)))
+
+
+def oracle_optimizers(kind, algo):
+    mk = (lambda: O.make_optimizer("adam", lr=1e-5)) if kind == "adam" else \
+         (lambda: O.make_optimizer("sgd", lr=1e-3))
+    names = ("policy_optimizer", "value_optimizer") if algo == "ddpg" else \
+            ("policy_optimizer", "value_optimizer1", "value_optimizer2")
+    return {n: mk() for n in names}
+
+
+def run_oracle_case(case, algo, opt_kind, golden=None):
+    """Same bookkeeping as oracle/make_golden.py:run_update_case, numpy oracle."""
+    spec = C.CASES[case]
+    inp = C.make_inputs(spec, algo)
+    out = {"input_checksums": C.input_checksums(inp)}
+    nets = {k: O.copy_net(v) for k, v in inp["nets"].items()}
+    opts = oracle_optimizers(opt_kind, algo)
+    batch = O.frame_gather(inp["table"], inp["items"], inp["ratings"], inp["sizes"], spec["frame"])
+    params = dict(C.DDPG_PARAMS if algo == "ddpg" else C.TD3_PARAMS)
+    loss_keys = ("value", "policy") if algo == "ddpg" else ("value1", "value2", "policy")
+    losses = {k: [] for k in loss_keys}
+    for step in range(spec["steps"]):
+        masks = inp["masks"][step]
+        if algo == "ddpg":
+            loss, dbg = O.ddpg_update(batch, params, nets, opts, masks, step, learn=True)
+        else:
+            noise = golden["noise.%d" % step] if golden is not None else inp["noise"][step]
+            loss, dbg = O.td3_update(batch, params, nets, opts, masks, noise, step, learn=True)
+        for k in loss_keys:
+            losses[k].append(loss[k])
+        done_steps = step + 1
+        if done_steps in SNAP_AFTER:
+            for name, p in nets.items():
+                for k, v in C.net_digest(p).items():
+                    out["after%d.%s.%s" % (done_steps, name, k)] = v
+        if step == 0 and algo == "ddpg":
+            for k, v in C.net_digest(dbg["policy_grads"]).items():
+                out["grad_step0.policy_net.%s" % k] = v
+        if step == 1 and algo == "ddpg":
+            for k, v in C.net_digest(dbg["value_grads"]).items():
+                out["grad_step1.value_net.%s" % k] = v
+    for k in loss_keys:
+        out["loss." + k] = np.asarray(losses[k], dtype=np.float64)
+    for name, p in nets.items():
+        for k, v in p.items():
+            out["final.%s.%s" % (name, k)] = v
+    return out
+
+
+def rel_err(got, want, floor):
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    return float(np.max(np.abs(got - want) / (np.abs(want) + floor))) if got.size else 0.0
+
+
+def compare_with_golden(got: dict, gold: dict, rtol=1e-5, floor_frac=1e-2, delta_rtol=2e-3,
+                        grad_rtol=1e-4, check_grads=True, loss_floor=0.1):
+    """The north-star bar: losses and every updated weight within 1e-5 relative.
+
+    Weights: |got-want| <= rtol*(|want| + floor_frac*max|tensor|).  The reference
+    defines no floor for near-zero weights; floor_frac=1e-2 makes
+    the absolute part 1e-7*max|tensor| ~ one fp32 ulp of the tensor's largest
+    weight, which is what two fp32 BLAS builds already differ by.
+    Losses: |got-want| <= rtol*(|want| + loss_floor).  The policy loss is a
+    signed mean of Q-values of magnitude O(1..10) that nearly cancels, so a pure
+    relative bound is below one fp32 ulp of the summands (torch/MKL and
+    numpy/OpenBLAS differ by 3e-5 relative there); loss_floor=0.1 makes the
+    absolute part 1e-6 ~ 1 ulp at |Q| ~ 10 = max_value.
+    Deltas: with lr=1e-5 the 1e-5 bar alone would be met by not training at
+    all, so the *change* of each tensor since init must also agree to
+    ``delta_rtol`` of its largest change (differences below 2 ulp of the
+    tensor's largest weight are rounding, not signal, and are accepted).
+    Grads: within ``grad_rtol`` of the largest gradient entry of the tensor."""
+    np.testing.assert_allclose(got["input_checksums"], gold["input_checksums"], rtol=1e-12,
+                               err_msg="regenerated inputs differ from the golden run's inputs")
+    report = {}
+    for key in sorted(k for k in gold if k.startswith("loss.")):
+        e = rel_err(got[key], gold[key], loss_floor)
+        report[key] = e
+        assert e <= rtol, "%s: rel err %.3g > %.3g\n got  %s\n want %s" % (key, e, rtol, got[key], gold[key])
+    for key in sorted(gold):
+        if not key.startswith("after") or not key.endswith(".sample"):
+            continue
+        wmax = float(np.max(np.abs(gold[key])))
+        e = rel_err(got[key], gold[key], floor_frac * wmax)
+        report[key] = e
+        assert e <= rtol, "%s: rel err %.3g > %.3g" % (key, e, rtol)
+        _, name, tensor, _ = key.split(".")
+        init = gold["init.%s.%s.sample" % (name, tensor)].astype(np.float64)
+        d_got = got[key].astype(np.float64) - init
+        d_want = gold[key].astype(np.float64) - init
+        scale = np.max(np.abs(d_want))
+        err = float(np.max(np.abs(d_got - d_want)))
+        ulp2 = 2.0 * 1.1920929e-07 * wmax
+        de = err / scale if scale > 0 else (0.0 if err == 0 else np.inf)
+        report[key + ".delta"] = de
+        assert de <= delta_rtol or err <= ulp2, \
+            "%s: delta err %.3g > %.3g (scale %.3g, abs %.3g)" % (key, de, delta_rtol, scale, err)
+    if check_grads:
+        for key in sorted(k for k in gold if k.startswith("grad_") and k.endswith(".sample")):
+            if key not in got:
+                continue
+            scale = np.max(np.abs(gold[key])) + 1e-30
+            e = float(np.max(np.abs(got[key].astype(np.float64) - gold[key])) / scale)
+            report[key] = e
+            assert e <= grad_rtol, "%s: grad err %.3g > %.3g of max |g|" % (key, e, grad_rtol)
+    return report
