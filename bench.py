@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""Benchmark of the DDPG update hot path (BASELINE.json metric:
+"DDPG update-steps/sec @ batch 4096 ...; embed-gather HBM GB/s").
+
+  python bench.py --gpus N --steps K --warmup W            # this framework (CUDA path)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores
+                                                           # (numpy port in oracle/; /root/reference is Python
+                                                           # and does not exist on the GPU box)
+
+One "step" = one DDPG update (ddpg_update) over one synthetic ML-20M-shaped minibatch:
+26,744 items x 128-d table, frame_size 10, 4096 sample rows per GPU, policy step every 10th
+step, Adam(lr=1e-5), dropout active (perf mode: on-device Philox).  Prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_ITEMS, DIM, FRAME, HIDDEN = 26744, 128, 10, 256
+S_DIM = DIM * FRAME + FRAME
+ROWS_PER_GPU = 4096
+POLICY_STEP = 10
+# algorithmic work per sample row
+GATHER_BYTES_PER_ROW = 16604
+DDPG_FLOP_NONPOLICY, DDPG_FLOP_POLICY = 5276160, 6526976
+L1_FWD_FLOP_PER_ROW = 2 * S_DIM * HIDDEN           # the dominant kernel: layer-1 forward GEMM
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            p = json.load(fh)
+        return dict(hbm=float(p["hbm_gbs"]), bf16=float(p["bf16_tflops"]),
+                    bf16_sustained=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), source="measured")
+    except Exception:
+        return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(prefix="clocks_", suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()          # exact PID, never by pattern
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        try:
+            rows = [r.strip().split(",") for r in open(self.path) if r.strip()]
+            os.unlink(self.path)
+            sm = [float(r[0]) for r in rows]
+            out["samples"] = len(sm)
+            if sm:
+                busy = [x for x in sm if x > 0.5 * max(sm)] or sm
+                out["sm_mhz"] = float(np.median(busy))
+                out["sm_max_mhz"] = float(rows[0][1])
+                out["power_w_max"] = max(float(r[2]) for r in rows)
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                for i, nm in enumerate(names):
+                    if any(r[3 + i].strip().lower().startswith("active") for r in rows):
+                        out["reasons"].append(nm)
+        except Exception:
+            pass
+        return out
+
+
+def synth_step_inputs(seed, n_rows, n_steps):
+    """Per-step minibatches: items ~ U{0..n_items-1}, ratings ~ U{-4..5}, one pseudo-user."""
+    rng = np.random.default_rng(seed)
+    items = rng.integers(0, N_ITEMS, size=(n_steps, n_rows, FRAME + 1), dtype=np.int64)
+    ratings = rng.integers(-4, 6, size=(n_steps, n_rows, FRAME + 1)).astype(np.float32)
+    done = np.zeros((n_rows,), dtype=np.float32)
+    done[-1] = 1.0
+    return items, ratings, done
+
+
+# =============================================================================== reference arm
+def run_reference(args):
+    """The reference algorithm (gather + ddpg_update) on the host CPU: numpy port in oracle/."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import recnn_oracle as O
+    from oracle import cases as C
+    rng = np.random.default_rng(0)
+    table = rng.standard_normal((N_ITEMS, DIM), dtype=np.float32)
+    n_rows = ROWS_PER_GPU * args.gpus
+    total = args.steps + args.warmup
+    items, ratings, done = synth_step_inputs(1, n_rows, total)
+    nets = {"policy_net": O.make_actor(rng, S_DIM, DIM, HIDDEN, 6e-1),
+            "value_net": O.make_critic(rng, S_DIM, DIM, HIDDEN, 54e-2)}
+    nets["target_policy_net"] = O.copy_net(nets["policy_net"])
+    nets["target_value_net"] = O.copy_net(nets["value_net"])
+    opts = {"policy_optimizer": O.make_optimizer("adam", lr=1e-5),
+            "value_optimizer": O.make_optimizer("adam", lr=1e-5)}
+    params = dict(C.DDPG_PARAMS)
+    sizes = np.asarray([n_rows + FRAME], dtype=np.int64)
+    t_total = 0.0
+    for step in range(total):
+        masks = O.synth_masks(rng, 6, n_rows, HIDDEN)          # dropout draw (not timed: RNG differs per impl)
+        t0 = time.perf_counter()
+        batch = O.frame_gather(table, items[step], ratings[step], sizes, FRAME)
+        O.ddpg_update(batch, params, nets, opts, masks, step, learn=True)
+        dt = time.perf_counter() - t0
+        if step >= args.warmup:
+            t_total += dt
+    value = args.steps / t_total
+    cores = os.cpu_count() or 1
+    line = {
+        "impl": "reference", "metric": "ddpg_update_steps_per_sec", "value": value, "unit": "steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "DDPG batch %d rows, 128-d embeddings, 26744 items, frame 10" % n_rows,
+                   "rows_per_step": n_rows, "optimizer": "adam lr=1e-5", "policy_step": POLICY_STEP},
+        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port",
+                         "sample": "%d full steps (gather + ddpg_update, numpy/OpenBLAS fp32, all host threads)" % args.steps},
+        "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def cpu_baseline_sample(seconds_budget=20.0):
+    """Oracle port on the host cores, bounded: N=4096 DDPG steps until ~budget is used."""
+    from oracle import recnn_oracle as O
+    from oracle import cases as C
+    rng = np.random.default_rng(0)
+    table = rng.standard_normal((N_ITEMS, DIM), dtype=np.float32)
+    n_rows = ROWS_PER_GPU
+    nets = {"policy_net": O.make_actor(rng, S_DIM, DIM, HIDDEN, 6e-1),
+            "value_net": O.make_critic(rng, S_DIM, DIM, HIDDEN, 54e-2)}
+    nets["target_policy_net"] = O.copy_net(nets["policy_net"])
+    nets["target_value_net"] = O.copy_net(nets["value_net"])
+    opts = {"policy_optimizer": O.make_optimizer("adam", lr=1e-5),
+            "value_optimizer": O.make_optimizer("adam", lr=1e-5)}
+    sizes = np.asarray([n_rows + FRAME], dtype=np.int64)
+    items, ratings, _ = synth_step_inputs(2, n_rows, 4)
+    timed, t_total, step = 0, 0.0, 0
+    t_start = time.perf_counter()
+    while True:
+        masks = O.synth_masks(rng, 6, n_rows, HIDDEN)
+        t0 = time.perf_counter()
+        batch = O.frame_gather(table, items[step % 4], ratings[step % 4], sizes, FRAME)
+        O.ddpg_update(batch, dict(C.DDPG_PARAMS), nets, opts, masks, step, learn=True)
+        dt = time.perf_counter() - t0
+        if step >= 2:
+            timed += 1
+            t_total += dt
+        step += 1
+        if (timed >= 10 and time.perf_counter() - t_start > seconds_budget) or timed >= 60:
+            break
+    return {"value": timed / t_total, "unit": "steps/s", "cores": os.cpu_count() or 1, "kind": "port",
+            "sample": "%d DDPG steps at 4096 rows (gather + update, numpy/OpenBLAS fp32, all host threads)" % timed}
+
+
+# =============================================================================== native arm
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    import recnn_b200
+    from recnn_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    assert world == args.gpus, "launch with torchrun --nproc-per-node %d" % args.gpus
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+
+    torch.manual_seed(1234)                       # same weights on every rank
+    rng = np.random.default_rng(0)
+    table = torch.from_numpy(rng.standard_normal((N_ITEMS, DIM), dtype=np.float32)).to(dev)
+    actor = recnn_b200.nn.Actor(S_DIM, DIM, HIDDEN, 6e-1)
+    critic = recnn_b200.nn.Critic(S_DIM, DIM, HIDDEN, 54e-2)
+    agent = recnn_b200.nn.DDPG(actor, critic).to(dev)
+    for k, net in (("policy_optimizer", "policy_net"), ("value_optimizer", "value_net")):
+        agent.optimizers[k] = recnn_b200.optim.Adam(agent.nets[net].parameters(), lr=1e-5)
+    if world > 1:
+        recnn_b200.dist.enable_data_parallel(agent)
+
+    n_rows = ROWS_PER_GPU
+    total = args.steps + args.warmup
+    n_distinct = min(total, 16)
+    items_np, ratings_np, done_np = synth_step_inputs(100 + rank, n_rows, n_distinct)
+    items_h = [torch.from_numpy(items_np[i]).pin_memory() for i in range(n_distinct)]
+    ratings_h = [torch.from_numpy(ratings_np[i]).pin_memory() for i in range(n_distinct)]
+    done_h = torch.from_numpy(done_np).pin_memory()
+    items_d = [t.to(dev) for t in items_h]
+    ratings_d = [t.to(dev) for t in ratings_h]
+    done_d = done_h.to(dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)    # 256 MB > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def run_loop(host_inputs, steps, warmup, flush_l2=True):
+        agent._step = 0
+        eng_kernels0 = None
+        times = []
+        ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        for it in range(warmup + steps):
+            i = it % n_distinct
+            if it == warmup:
+                barrier()
+                from recnn_b200.nn.update._engine import get_engine
+                eng = get_engine(_lib.ALGO_DDPG, agent.nets, dev)
+                eng_kernels0 = eng.kernels
+                t_wall0 = time.perf_counter()
+            if flush_l2:
+                flush.zero_()
+            batch = {"items": items_h[i] if host_inputs else items_d[i],
+                     "ratings": ratings_h[i] if host_inputs else ratings_d[i],
+                     "done": done_h if host_inputs else done_d, "table": table}
+            if it >= warmup:
+                ev0[it - warmup].record()
+            loss = agent.update(batch, learn=True)          # H2D (if host) + fused step + D2H of the losses
+            agent.step()
+            if it >= warmup:
+                ev1[it - warmup].record()
+        barrier()
+        wall = time.perf_counter() - t_wall0
+        dev_ms = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
+        t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        eng = get_engine(_lib.ALGO_DDPG, agent.nets, dev)
+        return float(t.item()), wall, eng.kernels - eng_kernels0, loss
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    dev_ms, wall_s, kernels, last_loss = run_loop(False, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else {}
+    e2e_ms, e2e_wall, _, _ = run_loop(True, args.steps, max(3, args.warmup // 2))
+    warm_ms, _, _, _ = run_loop(False, args.steps, 3, flush_l2=False)
+
+    rows_global = n_rows * world
+    value = args.steps / (dev_ms / 1e3)
+    e2e_value = args.steps / (e2e_ms / 1e3)
+    line = None
+    if rank == 0:
+        L = _lib.lib()
+        st = torch.cuda.current_stream(dev).cuda_stream
+
+        def time_kernel(fn, iters=20):
+            for _ in range(3):
+                fn()
+            ts = []
+            for _ in range(iters):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                b.record()
+                torch.cuda.synchronize(dev)
+                ts.append(a.elapsed_time(b))
+            return float(np.mean(ts))
+
+        # (1) the materialising gather kernel  (HBM bound)
+        g_state = torch.empty(n_rows, S_DIM, device=dev)
+        g_next = torch.empty(n_rows, S_DIM, device=dev)
+        g_act = torch.empty(n_rows, DIM, device=dev)
+        g_rew = torch.empty(n_rows, device=dev)
+        gather_ms = time_kernel(lambda: _lib.check(L.recnn_frame_gather(
+            table.data_ptr(), N_ITEMS, DIM, items_d[0].data_ptr(), ratings_d[0].data_ptr(), n_rows, FRAME,
+            g_state.data_ptr(), g_next.data_ptr(), g_act.data_ptr(), g_rew.data_ptr(), None, st)))
+        gather_gbs = n_rows * GATHER_BYTES_PER_ROW / (gather_ms * 1e-3) / 1e9
+        # (2) the dominant kernel of the step: layer-1 forward GEMM [4096,1290] x [1290,256]
+        w1 = agent.nets["policy_net"].linear1
+        h1 = torch.empty(n_rows, HIDDEN, device=dev)
+        l1_ms = time_kernel(lambda: _lib.check(L.recnn_linear_forward(
+            g_state.data_ptr(), n_rows, S_DIM, w1.weight.data_ptr(), w1.bias.data_ptr(), HIDDEN, 1,
+            h1.data_ptr(), st)))
+        l1_tflops = n_rows * L1_FWD_FLOP_PER_ROW / (l1_ms * 1e-3) / 1e12
+        tf32_peak = peaks["bf16"] / 2.0           # dense TF32 = half the dense bf16 rate
+        flop_step = rows_global * (DDPG_FLOP_POLICY + (POLICY_STEP - 1) * DDPG_FLOP_NONPOLICY) / POLICY_STEP
+        cpu = cpu_baseline_sample() if world == 1 else None
+        line = {
+            "metric": "ddpg_update_steps_per_sec", "value": value, "unit": "steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "DDPG batch 4096 rows/GPU, 128-d embeddings, 26744 items, frame 10 (BASELINE configs[1])",
+                       "rows_per_gpu": n_rows, "global_rows": rows_global, "parallelism": "dp%d" % world,
+                       "optimizer": "adam lr=1e-5 (fused)", "policy_step": POLICY_STEP,
+                       "dropout": "on (device Philox)", "l2": "flushed between timed steps (256 MB write)",
+                       "inputs": "items/ratings/done resident in HBM; frames gathered on device inside the step",
+                       "matmul": "fp32 CUDA-core FMA (exact fp32)"},
+            "rows_per_sec": value * rows_global,
+            "update_tflops": flop_step * value / 1e12,
+            "value_warm_l2": args.steps / (warm_ms / 1e3),
+            "wall_s": wall_s,
+            "e2e": {"value": e2e_value, "unit": "steps/s",
+                    "h2d_bytes_per_step": int(n_rows * ((FRAME + 1) * 12 + 4)), "d2h_bytes_per_step": 16,
+                    "what": "ddpg_update(batch of pinned host items/ratings/done) -> dict of python floats"},
+            "gpu_launches": int(kernels),
+            "roofline": {"bound": "tensor", "kernel": "layer-1 forward GEMM [4096x1290]x[1290x256] (gemm_simt_kernel)",
+                         "achieved": l1_tflops, "peak": tf32_peak, "unit": "TFLOP/s", "frac": l1_tflops / tf32_peak,
+                         "traffic": None, "peak_source": "%s bf16 %.0f TF/s / 2 (TF32 kind)" % (peaks["source"], peaks["bf16"]),
+                         "ms": l1_ms},
+            "roofline_gather": {"bound": "hbm", "kernel": "frame_gather_kernel", "achieved": gather_gbs,
+                                "peak": peaks["hbm"], "unit": "GB/s", "frac": gather_gbs / peaks["hbm"],
+                                "traffic": None, "peak_source": peaks["source"], "ms": gather_ms,
+                                "bytes_per_launch": n_rows * GATHER_BYTES_PER_ROW},
+            "clocks": clocks,
+            "last_loss": last_loss,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps > 40:          # bounded: the CPU port does ~3-10 steps/s
+            args.steps = 40
+        args.warmup = min(args.warmup, 3)
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,219 @@
+/*
+ * recnn_b200 -- C ABI of the B200-native RecNN DDPG/TD3 update hot path.
+ *
+ * The reference (awarebayes/RecNN) is pure Python on PyTorch and has NO FFI:
+ * its seams for this path are Python call sites.  Each entry
+ * point below names the reference function (file:line under /root/reference)
+ * whose work it replaces; the Python host layer in recnn_b200/ binds them with
+ * ctypes and keeps the reference's own signatures on top.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer unless it says host;
+ *   - every call takes the CUDA stream to launch on (cudaStream_t as void*);
+ *     nothing synchronises, nothing allocates: scratch comes from the caller
+ *     (recnn_step_workspace_bytes);
+ *   - return 0 on success, a negative RECNN_E_* code otherwise;
+ *     recnn_b200_last_error() returns a thread-local message;
+ *   - all floating point data is fp32, item indices are int64 (as the
+ *     reference's LongTensor), dropout masks are uint8 {0,1}.
+ *   - a "net" is one 3-layer MLP stored as ONE flat fp32 arena in
+ *     nn.Module.parameters() order: linear1.weight [H,in], linear1.bias [H],
+ *     linear2.weight [H,H], linear2.bias [H], linear3.weight [out,H],
+ *     linear3.bias [out]  (nn.Linear layout, y = x W^T + b;
+ *     recnn/nn/models.py:41-57 Actor, :187-203 Critic).
+ */
+#ifndef RECNN_B200_H
+#define RECNN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RECNN_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define RECNN_API __attribute__((visibility("default")))
+#else
+#define RECNN_API
+#endif
+
+enum {
+  RECNN_OK = 0,
+  RECNN_E_INVALID = -1,   /* bad argument (null pointer, non-positive size ...) */
+  RECNN_E_CUDA = -2,      /* a CUDA runtime call / launch failed */
+  RECNN_E_WORKSPACE = -3, /* workspace too small */
+  RECNN_E_UNSUPPORTED = -4
+};
+
+RECNN_API int recnn_b200_abi_version(void);
+RECNN_API const char* recnn_b200_last_error(void);
+/* number of kernels this library has launched in this process (bench accounting) */
+RECNN_API int64_t recnn_b200_launch_count(void);
+/* struct-layout probes so a foreign binding can verify its mirror of recnn_step_args */
+RECNN_API int64_t recnn_sizeof_step_args(void);
+RECNN_API int64_t recnn_offsetof_step_args(int field);
+
+/* ------------------------------------------------------------------ data path */
+
+/* recnn/data/utils.py:51-68 batch_tensor_embeddings: gather table rows for the
+ * F+1 items of every sample and assemble state / next_state / action / reward.
+ *   table  fp32[n_items, dim] row-major      items   int64[n_rows, frame+1]
+ *   ratings fp32[n_rows, frame+1]
+ *   state, next_state fp32[n_rows, frame*dim+frame]; action fp32[n_rows, dim];
+ *   reward fp32[n_rows].  Any output pointer may be NULL (skipped).
+ * Bit-exact copy semantics.  Indices are checked on device; an out-of-range
+ * index sets *oob_flag (device int32, may be NULL) and the row reads item 0. */
+RECNN_API int recnn_frame_gather(const float* table, int64_t n_items, int dim,
+                       const int64_t* items, const float* ratings,
+                       int64_t n_rows, int frame,
+                       float* state, float* next_state, float* action, float* reward,
+                       int* oob_flag, void* stream);
+
+/* recnn/data/utils.py:70-71: done = zeros(n_rows); done[cumsum(sizes-frame)-1] = 1.
+ * sizes int64[n_users] (device). */
+RECNN_API int recnn_done_from_sizes(const int64_t* sizes, int64_t n_users, int frame,
+                          float* done, int64_t n_rows, void* stream);
+
+/* ------------------------------------------------------------------ networks */
+
+typedef struct recnn_dims {
+  int32_t state_dim;   /* S = frame*dim + frame (1290) */
+  int32_t action_dim;  /* A (128) */
+  int32_t hidden;      /* H (256) */
+  int32_t reserved;
+} recnn_dims;
+
+/* number of fp32 in an Actor / Critic arena for these dims */
+RECNN_API int64_t recnn_actor_param_count(const recnn_dims* d);
+RECNN_API int64_t recnn_critic_param_count(const recnn_dims* d);
+
+/* recnn/nn/models.py:59-73 Actor.forward.  masks: two uint8[n_rows,H] arrays
+ * (train mode: h = relu(z) * mask * 2) or NULL,NULL for eval().  apply_tanh as
+ * the reference's `tanh` argument.  scratch: fp32[2*n_rows*H]. */
+RECNN_API int recnn_actor_forward(const recnn_dims* d, const float* params, const float* state,
+                        int64_t n_rows, const uint8_t* mask1, const uint8_t* mask2,
+                        int apply_tanh, float* action_out, float* scratch, void* stream);
+
+/* recnn/nn/models.py:205-213 Critic.forward (concat is virtual).  value_out fp32[n_rows]. */
+RECNN_API int recnn_critic_forward(const recnn_dims* d, const float* params, const float* state,
+                         const float* action, int64_t n_rows,
+                         const uint8_t* mask1, const uint8_t* mask2,
+                         float* value_out, float* scratch, void* stream);
+
+/* One nn.Linear (+ optional ReLU) on its own: out[n_rows,out_dim] = act(x W^T + b)
+ * (recnn/nn/models.py:52-54 layers; exposed so a single layer can be timed / reused). */
+RECNN_API int recnn_linear_forward(const float* x, int64_t n_rows, int in_dim, const float* weight,
+                         const float* bias, int out_dim, int relu, float* out, void* stream);
+
+/* recnn/utils/misc.py:1-5 soft_update over one flat arena:
+ * target = target*(1-tau) + net*tau   (tau==1 is an exact copy, as in the reference) */
+RECNN_API int recnn_polyak_update(float* target, const float* net, int64_t count, double tau, void* stream);
+
+/* ------------------------------------------------------------------ update step */
+
+typedef struct recnn_net {
+  float* params;      /* arena */
+  float* grads;       /* arena, same layout; NULL for target nets */
+  float* opt_m;       /* Adam exp_avg / SGD momentum buffer (built-in optimizers), else NULL */
+  float* opt_v;       /* Adam exp_avg_sq, else NULL */
+  int32_t* opt_t;     /* device int32: number of optimizer steps taken so far */
+} recnn_net;
+
+enum { RECNN_OPT_EXTERNAL = 0, RECNN_OPT_SGD = 1, RECNN_OPT_ADAM = 2 };
+
+typedef struct recnn_optim {   /* torch.optim.SGD / torch.optim.Adam semantics */
+  int32_t kind;
+  int32_t reserved;
+  /* doubles: torch keeps these as python floats and rounds to fp32 only where the
+   * tensor op consumes them (e.g. step_size = lr / (1 - beta1**t) is formed in double) */
+  double lr, beta1, beta2, eps, weight_decay, momentum;
+} recnn_optim;
+
+/* what one call executes; OR them.  A drop-in single-GPU step passes RECNN_PH_ALL.
+ * Multi-GPU data parallel and external torch optimizers split the step at the
+ * two points where gradients are complete. */
+enum {
+  RECNN_PH_VALUE_GRAD = 1,   /* targets, TD target, value loss, critic backward        */
+  RECNN_PH_VALUE_OPT = 2,    /* built-in critic optimizer step(s)                      */
+  RECNN_PH_POLICY_LOSS = 4,  /* pi(s), Q(s,pi(s)) with the *updated* critic, loss      */
+  RECNN_PH_POLICY_GRAD = 8,  /* actor backward through the critic (policy steps only)  */
+  RECNN_PH_POLICY_OPT = 16,  /* L1 "clip" quirk (+ built-in actor optimizer step)      */
+  RECNN_PH_SOFT_UPDATE = 32, /* Polyak target updates (policy steps only)              */
+  RECNN_PH_GATHER = 64,      /* frame form: materialise state/next_state/action into the
+                              * workspace (split-phase callers pass it once per step)  */
+  RECNN_PH_ALL = 127
+};
+
+enum { RECNN_ALGO_DDPG = 0, RECNN_ALGO_TD3 = 1 };
+
+typedef struct recnn_step_args {
+  int32_t algo;            /* RECNN_ALGO_* */
+  int32_t phases;          /* RECNN_PH_* mask */
+  int32_t learn;           /* reference `learn` flag */
+  int32_t do_policy_step;  /* learn && step % policy_step == 0 (ddpg.py:89 / td3.py:130) */
+  recnn_dims dims;
+
+  /* batch: EITHER dense (state,next_state,action) OR frames (table,items,ratings).
+   * reward/done fp32[n_rows] may be NULL in frame form for reward (= ratings[:,F]). */
+  int64_t n_rows;          /* rows in this call (this rank's shard)          */
+  int64_t n_rows_global;   /* denominator of the batch means (all ranks)     */
+  const float* state;
+  const float* next_state;
+  const float* action;
+  const float* table;
+  int64_t n_items;
+  int32_t frame;
+  int32_t emb_dim;
+  const int64_t* items;
+  const float* ratings;
+  const float* reward;
+  const float* done;
+
+  /* nets.  DDPG: value[0], target_value[0].  TD3: [0] and [1]. */
+  recnn_net policy, target_policy;
+  recnn_net value[2], target_value[2];
+  recnn_optim policy_optim, value_optim;
+
+  /* hyper-parameters (recnn/nn/algo.py:103-109, :164-174) */
+  float gamma, min_value, max_value, noise_std, noise_clip;
+  int32_t dropout;         /* 1: online nets are in train() mode (Dropout p=.5 active) */
+  double soft_tau;
+
+  /* randomness.  Parity mode: explicit masks (uint8[n_rows,H]) in the reference's
+   * drop_layer call order -- DDPG: value(2) policy(2) value(2); TD3: value1(2)
+   * value2(2) policy(2) value1(2) -- and the raw N(0,noise_std) draw fp32[n_rows,A].
+   * Perf mode: all NULL; Philox4x32-10 keyed by (seed, *rng_step) on device. */
+  const uint8_t* masks[8];
+  const float* noise;
+  uint64_t seed;
+  const int64_t* rng_step;   /* device int64 counter, read (not written) by the step */
+
+  /* outputs */
+  float* losses;           /* device fp32[4]: value(1), value2, policy, ||actor grad||_1 */
+  float* next_action_out;  /* optional fp32[n_rows,A] (debug["next_action"]) */
+  float* gen_action_out;   /* optional fp32[n_rows,A] (debug["gen_action"])  */
+
+  void* workspace;
+  int64_t workspace_bytes;
+} recnn_step_args;
+
+/* bytes of scratch a step with these shapes needs (frame form included). */
+RECNN_API int64_t recnn_step_workspace_bytes(const recnn_dims* d, int64_t n_rows, int32_t algo);
+
+/* recnn/nn/update/ddpg.py:8-104 (with misc.py:10-55 value_update inlined). */
+RECNN_API int recnn_ddpg_step(const recnn_step_args* args, void* stream);
+/* recnn/nn/update/td3.py:8-150. */
+RECNN_API int recnn_td3_step(const recnn_step_args* args, void* stream);
+
+/* built-in optimizer step on one arena, exposed for recnn_b200.optim
+ * (torch.optim.Adam/SGD semantics; increments *net->opt_t).
+ * grad_scale: optional device scalar the gradient is multiplied by first. */
+RECNN_API int recnn_optimizer_step(const recnn_optim* o, const recnn_net* net, int64_t count,
+                         const float* grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RECNN_B200_H */

@@ -1,0 +1,290 @@
+// Non-GEMM kernels of the update step: critic head (256 -> 1) forward with the TD
+// target / losses fused in, its backward, split-K partial reduction, the L1
+// "clip" quirk, the fused optimizers and the Polyak update.  All of them touch
+// a few MB that sit in L2; they exist to keep the launch count and the number
+// of passes low, and to make every reduction order-deterministic.
+#include "pointwise.cuh"
+
+namespace recnn {
+
+// Every block calls this after writing its partial result; returns true in the
+// block that arrives last.  The ticket wraps to 0 so it never needs a reset.
+__device__ __forceinline__ bool last_block_done(unsigned* ticket) {
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicInc(ticket, gridDim.x - 1);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  return is_last;
+}
+
+// ---------------------------------------------------------------- critic head
+__global__ void __launch_bounds__(256) critic_head_kernel(HeadArgs a) {
+  __shared__ float red[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const float b3 = a.b3[0];
+  const float inv_n = 1.0f / (float)a.n_rows_global;
+  float warp_acc = 0.f;
+  for (long long n = (long long)blockIdx.x * wpb + warp; n < a.n_rows; n += (long long)gridDim.x * wpb) {
+    const float* row = a.h2 + n * a.hidden;
+    float s = 0.f;
+    for (int c = lane; c < a.hidden; c += 32) s = fmaf(row[c], __ldg(a.w3 + c), s);
+    s = warp_sum(s);
+    const float q = s + b3;
+    if (lane == 0) {
+      if (a.out) a.out[n] = q;
+      switch (a.mode) {
+        case HEAD_TARGET_DDPG: {
+          // reward + (1.0 - done) * gamma * target, then clamp   (misc.py:6-7, :33-35)
+          const float t = __fadd_rn(a.reward[n], __fmul_rn(__fmul_rn(__fsub_rn(1.0f, a.done[n]), a.gamma), q));
+          a.y[n] = fminf(fmaxf(t, a.min_value), a.max_value);
+        } break;
+        case HEAD_TARGET_TD3_A: a.tmp[n] = q; break;
+        case HEAD_TARGET_TD3_B: {
+          const float qm = fminf(a.tmp[n], q);
+          a.y[n] = __fadd_rn(a.reward[n], __fmul_rn(__fmul_rn(__fsub_rn(1.0f, a.done[n]), a.gamma), qm));
+        } break;
+        case HEAD_VALUE: {
+          const float diff = __fsub_rn(q, a.y[n]);
+          a.dq[n] = __fmul_rn(__fmul_rn(2.0f, diff), inv_n);
+          warp_acc = __fadd_rn(warp_acc, __fmul_rn(diff, diff));
+        } break;
+        case HEAD_POLICY: warp_acc = __fsub_rn(warp_acc, q); break;
+        default: break;
+      }
+    }
+  }
+  if (a.mode != HEAD_VALUE && a.mode != HEAD_POLICY) return;
+  // deterministic two-level sum: warps in order, then blocks in order
+  if (lane == 0) red[warp] = warp_acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < wpb; ++w) t += red[w];
+    a.block_partials[blockIdx.x] = t;
+  }
+  if (last_block_done(a.ticket)) {
+    float t = 0.f;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) t += a.block_partials[b];
+    t = block_sum(t, red);
+    if (threadIdx.x == 0) *a.loss = t / (float)a.n_rows_global;
+  }
+}
+
+int launch_critic_head(const HeadArgs& a, cudaStream_t st) {
+  if (a.n_rows <= 0) return RECNN_OK;
+  const int64_t blocks = ceil_div(a.n_rows, 8);
+  const int grid = (int)(blocks < 2 * kNumSMs ? blocks : 2 * kNumSMs);
+  critic_head_kernel<<<grid, 256, 0, st>>>(a);
+  RECNN_CHECK_LAUNCH("critic_head_kernel");
+  return RECNN_OK;
+}
+
+__global__ void __launch_bounds__(256)
+critic_head_bwd_kernel(const float* __restrict__ dq, float dq_const, const float* __restrict__ w3,
+                       const float* __restrict__ h2, float gate_scale, float* __restrict__ dz2,
+                       long long total, int hidden) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / hidden;
+    const int c = (int)(i - n * hidden);
+    const float g = dq ? dq[n] : dq_const;
+    dz2[i] = h2[i] > 0.f ? __fmul_rn(__fmul_rn(g, __ldg(w3 + c)), gate_scale) : 0.f;
+  }
+}
+
+int launch_critic_head_bwd(const float* dq, float dq_const, const float* w3, const float* h2,
+                           float gate_scale, float* dz2, int64_t n_rows, int hidden, cudaStream_t st) {
+  const int64_t total = n_rows * hidden;
+  if (total <= 0) return RECNN_OK;
+  const int64_t blocks = ceil_div(total, 256);
+  const int grid = (int)(blocks < 8 * kNumSMs ? blocks : 8 * kNumSMs);
+  critic_head_bwd_kernel<<<grid, 256, 0, st>>>(dq, dq_const, w3, h2, gate_scale, dz2, total, hidden);
+  RECNN_CHECK_LAUNCH("critic_head_bwd_kernel");
+  return RECNN_OK;
+}
+
+// ---------------------------------------------------------------- split-K reduce
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const float* __restrict__ part, int splits, int C, int K1,
+                       float* __restrict__ w_dst, float* __restrict__ b_dst) {
+  const long long total = (long long)C * K1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += part[(long long)z * total + i];
+    const int c = (int)(i / K1), k = (int)(i - (long long)c * K1);
+    if (k < K1 - 1) w_dst[(long long)c * (K1 - 1) + k] = s;
+    else b_dst[c] = s;
+  }
+}
+
+int launch_reduce_partials(const float* part, int splits, int C, int K1, float* w_dst, float* b_dst,
+                           cudaStream_t st) {
+  const int64_t total = (int64_t)C * K1;
+  const int64_t blocks = ceil_div(total, 256);
+  const int grid = (int)(blocks < 8 * kNumSMs ? blocks : 8 * kNumSMs);
+  reduce_partials_kernel<<<grid, 256, 0, st>>>(part, splits, C, K1, w_dst, b_dst);
+  RECNN_CHECK_LAUNCH("reduce_partials_kernel");
+  return RECNN_OK;
+}
+
+// ---------------------------------------------------------------- L1 clip quirk
+__global__ void __launch_bounds__(256)
+l1_clip_coef_kernel(const float* __restrict__ g, long long count, float max_norm, float* coef, float* l1_out,
+                    float* block_partials, unsigned* ticket) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+       i += (long long)gridDim.x * blockDim.x)
+    s += fabsf(g[i]);
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) block_partials[blockIdx.x] = s;
+  if (last_block_done(ticket)) {
+    float t = 0.f;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) t += block_partials[b];
+    t = block_sum(t, red);
+    if (threadIdx.x == 0) {
+      // clip_coef = max_norm / (total_norm + 1e-6), clamped from above at 1.0
+      const float c = max_norm / (t + 1e-6f);
+      *coef = fminf(c, 1.0f);
+      if (l1_out) *l1_out = t;
+    }
+  }
+}
+
+int launch_l1_clip_coef(const float* grads, int64_t count, float max_norm, float* coef, float* l1_out,
+                        float* block_partials, unsigned* ticket, cudaStream_t st) {
+  const int64_t blocks = ceil_div(count, 256 * 8);
+  const int grid = (int)(blocks < 2 * kNumSMs ? (blocks > 0 ? blocks : 1) : 2 * kNumSMs);
+  l1_clip_coef_kernel<<<grid, 256, 0, st>>>(grads, count, max_norm, coef, l1_out, block_partials, ticket);
+  RECNN_CHECK_LAUNCH("l1_clip_coef_kernel");
+  return RECNN_OK;
+}
+
+__global__ void scale_inplace_kernel(float* x, long long count, const float* scale) {
+  const float s = *scale;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+       i += (long long)gridDim.x * blockDim.x)
+    x[i] = __fmul_rn(x[i], s);
+}
+
+int launch_scale_inplace(float* x, int64_t count, const float* scale, cudaStream_t st) {
+  const int64_t blocks = ceil_div(count, 256);
+  const int grid = (int)(blocks < 4 * kNumSMs ? (blocks > 0 ? blocks : 1) : 4 * kNumSMs);
+  scale_inplace_kernel<<<grid, 256, 0, st>>>(x, count, scale);
+  RECNN_CHECK_LAUNCH("scale_inplace_kernel");
+  return RECNN_OK;
+}
+
+// ---------------------------------------------------------------- optimizers
+// torch.optim.Adam / SGD (single-tensor CPU path of torch 2.11), one flat arena.
+struct OptConsts {
+  float lr, one_minus_b1, b2, one_minus_b2, eps, wd, momentum;
+};
+
+__global__ void __launch_bounds__(256)
+optimizer_kernel(int kind, OptConsts k, double beta1, double beta2, double lr, float* __restrict__ p,
+                 float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                 const int* __restrict__ t_ptr, const float* __restrict__ grad_scale, long long count) {
+  __shared__ float s_step_size, s_bc2_sqrt;
+  const int t = *t_ptr + 1;
+  if (threadIdx.x == 0 && kind == RECNN_OPT_ADAM) {
+    // python-float (double) scalars, cast where torch casts them
+    const double bc1 = 1.0 - pow(beta1, (double)t);
+    const double bc2 = 1.0 - pow(beta2, (double)t);
+    s_step_size = (float)(lr / bc1);
+    s_bc2_sqrt = (float)sqrt(bc2);
+  }
+  __syncthreads();
+  const float gs = grad_scale ? *grad_scale : 1.0f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+       i += (long long)gridDim.x * blockDim.x) {
+    float grad = g[i];
+    if (grad_scale) {
+      grad = __fmul_rn(grad, gs);
+      g[i] = grad;                      // the reference leaves the scaled grad in .grad
+    }
+    float w = p[i];
+    if (k.wd != 0.f) grad = __fadd_rn(grad, __fmul_rn(k.wd, w));
+    if (kind == RECNN_OPT_SGD) {
+      if (k.momentum != 0.f) {
+        const float buf = (t == 1) ? grad : __fadd_rn(__fmul_rn(k.momentum, m[i]), grad);
+        m[i] = buf;
+        grad = buf;
+      }
+      p[i] = __fsub_rn(w, __fmul_rn(k.lr, grad));
+    } else {
+      float mi = m[i], vi = v[i];
+      mi = __fadd_rn(mi, __fmul_rn(k.one_minus_b1, __fsub_rn(grad, mi)));       // lerp_
+      vi = __fadd_rn(__fmul_rn(vi, k.b2), __fmul_rn(__fmul_rn(k.one_minus_b2, grad), grad));
+      m[i] = mi;
+      v[i] = vi;
+      const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vi), s_bc2_sqrt), k.eps);
+      p[i] = __fsub_rn(w, __fmul_rn(s_step_size, __fdiv_rn(mi, denom)));
+    }
+  }
+}
+
+__global__ void bump_counter_kernel(int* t) { *t += 1; }
+
+int launch_optimizer(const recnn_optim& o, const recnn_net& net, int64_t count, const float* grad_scale,
+                     cudaStream_t st) {
+  RECNN_REQUIRE(o.kind == RECNN_OPT_SGD || o.kind == RECNN_OPT_ADAM, "built-in optimizer kind must be SGD or ADAM");
+  RECNN_REQUIRE(net.params && net.grads && net.opt_t, "optimizer needs params, grads and the step counter");
+  if (o.kind == RECNN_OPT_ADAM) RECNN_REQUIRE(net.opt_m && net.opt_v, "Adam needs exp_avg / exp_avg_sq arenas");
+  if (o.kind == RECNN_OPT_SGD && o.momentum != 0.f) RECNN_REQUIRE(net.opt_m, "SGD momentum needs a buffer arena");
+  OptConsts k;
+  k.lr = (float)o.lr;
+  k.one_minus_b1 = (float)(1.0 - o.beta1);
+  k.b2 = (float)o.beta2;
+  k.one_minus_b2 = (float)(1.0 - o.beta2);
+  k.eps = (float)o.eps;
+  k.wd = (float)o.weight_decay;
+  k.momentum = (float)o.momentum;
+  const int64_t blocks = ceil_div(count, 256 * 4);
+  const int grid = (int)(blocks < 4 * kNumSMs ? (blocks > 0 ? blocks : 1) : 4 * kNumSMs);
+  optimizer_kernel<<<grid, 256, 0, st>>>(o.kind, k, o.beta1, o.beta2, o.lr, net.params,
+                                         net.grads, net.opt_m, net.opt_v, net.opt_t, grad_scale, count);
+  RECNN_CHECK_LAUNCH("optimizer_kernel");
+  bump_counter_kernel<<<1, 1, 0, st>>>(net.opt_t);
+  RECNN_CHECK_LAUNCH("bump_counter_kernel");
+  return RECNN_OK;
+}
+
+// ---------------------------------------------------------------- Polyak
+__global__ void __launch_bounds__(256)
+polyak_kernel(float* __restrict__ target, const float* __restrict__ net, long long count, float one_minus_tau,
+              float tau) {
+  // target.data * (1.0 - soft_tau) + param.data * soft_tau   (recnn/utils/misc.py:3-5)
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+       i += (long long)gridDim.x * blockDim.x)
+    target[i] = __fadd_rn(__fmul_rn(target[i], one_minus_tau), __fmul_rn(net[i], tau));
+}
+
+int launch_polyak(float* target, const float* net, int64_t count, double tau, cudaStream_t st) {
+  const int64_t blocks = ceil_div(count, 256 * 4);
+  const int grid = (int)(blocks < 4 * kNumSMs ? (blocks > 0 ? blocks : 1) : 4 * kNumSMs);
+  polyak_kernel<<<grid, 256, 0, st>>>(target, net, count, (float)(1.0 - tau), (float)tau);
+  RECNN_CHECK_LAUNCH("polyak_kernel");
+  return RECNN_OK;
+}
+
+}  // namespace recnn
+
+using namespace recnn;
+
+extern "C" int recnn_polyak_update(float* target, const float* net, int64_t count, double tau, void* stream) {
+  RECNN_REQUIRE(target && net && count >= 0, "target/net must be non-null");
+  if (count == 0) return RECNN_OK;
+  return launch_polyak(target, net, count, tau, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int recnn_optimizer_step(const recnn_optim* o, const recnn_net* net, int64_t count,
+                                    const float* grad_scale, void* stream) {
+  RECNN_REQUIRE(o && net && count > 0, "optimizer/net must be non-null");
+  return launch_optimizer(*o, *net, count, grad_scale, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,57 @@
+// Declarations of the non-GEMM kernels' host launchers (pointwise.cu).
+#pragma once
+#include "common.cuh"
+
+namespace recnn {
+
+enum HeadMode {
+  HEAD_PLAIN = 0,        // out[n] = q
+  HEAD_TARGET_DDPG = 1,  // y[n] = clamp(r + (1-d)*gamma*q, min, max)            misc.py:30-35
+  HEAD_TARGET_TD3_A = 2, // tmp[n] = q                                            td3.py:81
+  HEAD_TARGET_TD3_B = 3, // y[n] = r + (1-d)*gamma*min(tmp[n], q)  (no clamp)     td3.py:82-86
+  HEAD_VALUE = 4,        // diff=q-y; dq[n]=2*diff/Ng; loss += diff^2/Ng          misc.py:37-39
+  HEAD_POLICY = 5        // loss += -q/Ng                                          ddpg.py:79,87
+};
+
+struct HeadArgs {
+  const float* h2;      // [N, H]
+  const float* w3;      // [H]
+  const float* b3;      // [1]
+  int64_t n_rows;
+  int64_t n_rows_global;
+  int hidden;
+  int mode;
+  const float* reward;  // [N]
+  const float* done;    // [N]
+  float gamma, min_value, max_value;
+  float* y;             // TD target in/out
+  float* tmp;           // TD3 first critic
+  float* out;           // HEAD_PLAIN / q copy (may be null)
+  float* dq;            // HEAD_VALUE
+  float* loss;          // device scalar to write (VALUE / POLICY)
+  float* block_partials;  // >= gridDim floats
+  unsigned* ticket;       // zero-initialised, self-resetting
+};
+int launch_critic_head(const HeadArgs& a, cudaStream_t st);
+
+// dz2[n,c] = dq_n * w3[c] * (h2[n,c] > 0 ? gate_scale : 0); dq_n = dq ? dq[n] : dq_const
+int launch_critic_head_bwd(const float* dq, float dq_const, const float* w3, const float* h2,
+                           float gate_scale, float* dz2, int64_t n_rows, int hidden, cudaStream_t st);
+
+// grad arena <- sum over split-K partials; part is [splits][C][K1] where column K1-1 is the
+// bias gradient: w_dst[c*(K1-1)+k] for k<K1-1, b_dst[c] for k==K1-1.
+int launch_reduce_partials(const float* part, int splits, int C, int K1, float* w_dst, float* b_dst,
+                           cudaStream_t st);
+
+// *coef = min(max_norm / (||g||_1 + 1e-6), 1)  (clip_grad_norm_(.., -1, 1): ddpg.py:92);  *l1_out = ||g||_1
+int launch_l1_clip_coef(const float* grads, int64_t count, float max_norm, float* coef, float* l1_out,
+                        float* block_partials, unsigned* ticket, cudaStream_t st);
+
+int launch_scale_inplace(float* x, int64_t count, const float* scale, cudaStream_t st);
+
+int launch_optimizer(const recnn_optim& o, const recnn_net& net, int64_t count, const float* grad_scale,
+                     cudaStream_t st);
+
+int launch_polyak(float* target, const float* net, int64_t count, double tau, cudaStream_t st);
+
+}  // namespace recnn

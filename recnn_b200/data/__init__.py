@@ -1,0 +1,3 @@
+from . import utils
+from .utils import (rolling_window, batch_tensor_embeddings, batch_frames, prepare_batch_static_size,
+                    make_items_tensor, get_base_batch)

@@ -1,0 +1,87 @@
+"""Algo / DDPG / TD3 wrappers with the reference's wiring (recnn/nn/algo.py:15-179).
+
+These are the dispatchers the update functions plug into (``Algo.algorithm``);
+they only hold state.  One deliberate difference: the reference builds
+``torch_optimizer.Ranger(lr=1e-5, weight_decay=1e-2)`` optimizers
+(algo.py:84-89), a third-party package that is not available here (SURVEY.md
+fact 4); the default is recnn_b200.optim.Adam with the same lr / weight_decay,
+and any optimizer can be supplied through ``self.optimizers`` as in the reference.
+"""
+from __future__ import annotations
+
+import copy
+
+import torch
+
+from .. import optim, utils
+from . import update
+
+
+class Algo:
+    def __init__(self):
+        self.nets = {"value_net": None, "policy_net": None}
+        self.optimizers = {"policy_optimizer": None, "value_optimizer": None}
+        self.params = {"Some parameters here": None}
+        self._step = 0
+        self.debug = {}
+        self.writer = utils.misc.DummyWriter()
+        self.device = torch.device("cpu")
+        self.loss_layout = {"test": {"value": [], "policy": [], "step": []},
+                            "train": {"value": [], "policy": [], "step": []}}
+        self.algorithm = None
+
+    def update(self, batch, learn=True):
+        return self.algorithm(batch, self.params, self.nets, self.optimizers, device=self.device,
+                              debug=self.debug, writer=self.writer, learn=learn, step=self._step)
+
+    def to(self, device):
+        self.nets = {k: v.to(device) for k, v in self.nets.items()}
+        self.device = device
+        return self
+
+    def step(self):
+        self._step += 1
+
+
+def _target_of(net):
+    target = copy.deepcopy(net)
+    target.__dict__.pop("_recnn_engines", None)
+    target.eval()
+    return target
+
+
+class DDPG(Algo):
+    def __init__(self, policy_net, value_net):
+        super().__init__()
+        self.algorithm = update.ddpg_update
+        target_policy_net = _target_of(policy_net)      # deepcopy == soft_update(tau=1.0), algo.py:73-81
+        target_value_net = _target_of(value_net)
+        self.nets = {"value_net": value_net, "target_value_net": target_value_net,
+                     "policy_net": policy_net, "target_policy_net": target_policy_net}
+        self.optimizers = {
+            "policy_optimizer": optim.Adam(policy_net.parameters(), lr=1e-5, weight_decay=1e-2),
+            "value_optimizer": optim.Adam(value_net.parameters(), lr=1e-5, weight_decay=1e-2),
+        }
+        self.params = {"gamma": 0.99, "min_value": -10, "max_value": 10, "policy_step": 10, "soft_tau": 0.001}
+        self.loss_layout = {"test": {"value": [], "policy": [], "step": []},
+                            "train": {"value": [], "policy": [], "step": []}}
+
+
+class TD3(Algo):
+    def __init__(self, policy_net, value_net1, value_net2):
+        super().__init__()
+        self.algorithm = update.td3_update
+        self.nets = {
+            "value_net1": value_net1, "target_value_net1": _target_of(value_net1),
+            "value_net2": value_net2, "target_value_net2": _target_of(value_net2),
+            "policy_net": policy_net, "target_policy_net": _target_of(policy_net),
+        }
+        self.optimizers = {
+            "policy_optimizer": optim.Adam(policy_net.parameters(), lr=1e-5, weight_decay=1e-2),
+            "value_optimizer1": optim.Adam(value_net1.parameters(), lr=1e-5, weight_decay=1e-2),
+            "value_optimizer2": optim.Adam(value_net2.parameters(), lr=1e-5, weight_decay=1e-2),
+        }
+        self.params = {"gamma": 0.99, "noise_std": 0.5, "noise_clip": 3, "soft_tau": 0.001, "policy_update": 10,
+                       "policy_lr": 1e-5, "value_lr": 1e-5, "actor_weight_init": 25e-2, "critic_weight_init": 6e-1}
+        self.loss_layout = {"test": {"value1": [], "value2": [], "policy": [], "step": []},
+                            "train": {"value1": [], "value2": [], "policy": [], "step": []}}

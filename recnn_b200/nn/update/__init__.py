@@ -1,0 +1,3 @@
+from .misc import temporal_difference, value_update
+from .ddpg import ddpg_update
+from .td3 import td3_update

@@ -1,0 +1,381 @@
+"""Host-side driver of the fused device step (one instance per set of nets).
+
+Responsibilities (all plumbing; the arithmetic is in recnn_b200/csrc):
+  * validate / (re)build the flat parameter, gradient and optimizer arenas;
+  * stage the batch into fixed device buffers (one async copy per tensor) so the
+    step is replayable as a CUDA graph;
+  * pick the phase split: one call (built-in optimizers, one GPU), or three
+    calls with gradient all-reduces / external ``optimizer.step()`` in between;
+  * read the 3-4 loss scalars back (the only synchronisation of a step -- the
+    reference API returns Python floats, recnn/nn/update/ddpg.py:102).
+"""
+from __future__ import annotations
+
+import os
+import warnings
+
+import torch
+
+from ... import _lib
+from ... import optim as _optim
+from ..arena import param_arena, grad_arena
+
+_USE_GRAPHS = os.environ.get("RECNN_B200_GRAPHS", "1") != "0"
+MASK_KEY = "dropout_masks"      # optional batch entries for bit-reproducible runs
+NOISE_KEY = "noise"
+
+DDPG_NETS = ("value_net", "target_value_net", "policy_net", "target_policy_net")
+TD3_NETS = ("value_net1", "target_value_net1", "value_net2", "target_value_net2", "policy_net",
+            "target_policy_net")
+
+
+def _as_device(t, device, dtype):
+    if not torch.is_tensor(t):
+        t = torch.as_tensor(t)
+    return t.detach()
+
+
+class StepEngine:
+    def __init__(self, algo, nets, device):
+        self.algo = algo
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.RecnnError("recnn_b200 update functions run on CUDA only (device=%s); there is no CPU path"
+                                  % self.device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.names = DDPG_NETS if algo == _lib.ALGO_DDPG else TD3_NETS
+        for k in self.names:
+            if k not in nets:
+                raise KeyError(k)
+        self.policy = nets["policy_net"]
+        pol = self.policy            # any module with linear1/2/3 works (also the reference's own classes)
+        self.dims = _lib.Dims(pol.linear1.in_features, pol.linear3.out_features, pol.linear1.out_features, 0)
+        crit = nets[self.names[0]]
+        if (crit.linear1.in_features != self.dims.state_dim + self.dims.action_dim
+                or crit.linear1.out_features != self.dims.hidden or crit.linear3.out_features != 1):
+            raise ValueError("critic shape does not match the actor (expects input state_dim+action_dim, same hidden, 1 output)")
+        self.n_rows = -1
+        self.form = None
+        self.graphs = {}
+        self.graph_sig = None
+        self.eager_runs = {}
+        self.group = None            # torch.distributed process group for data parallel
+        self.world = 1
+        self.seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
+        self.losses = torch.zeros(4, dtype=torch.float32, device=self.device)
+        self.losses_host = torch.zeros(4, dtype=torch.float32).pin_memory()
+        self.rng_step = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.buf = {}
+        self.kernels = 0             # kernels of this library launched by this engine (graph replays included)
+        self.last_call_kernels = 0
+
+    # ------------------------------------------------------------------ staging
+    def _buffer(self, name, shape, dtype):
+        b = self.buf.get(name)
+        if b is None or tuple(b.shape) != tuple(shape) or b.dtype != dtype:
+            b = torch.empty(shape, dtype=dtype, device=self.device)
+            self.buf[name] = b
+            self.graphs.clear()
+        return b
+
+    def _stage(self, name, src, dtype, shape=None):
+        src = src if torch.is_tensor(src) else torch.as_tensor(src)
+        src = src.detach()
+        if shape is not None:
+            src = src.reshape(shape)
+        dst = self._buffer(name, src.shape, dtype)
+        dst.copy_(src, non_blocking=True)
+        return dst
+
+    def _stage_batch(self, batch):
+        d = self.dims
+        if "items" in batch and batch.get("table") is not None:
+            form = "frames"
+            items = batch["items"]
+            n = int(items.shape[0])
+            table = batch["table"]
+            if table.device != self.device or table.dtype != torch.float32 or not table.is_contiguous():
+                raise _lib.RecnnError("batch['table'] must be a contiguous fp32 tensor on %s" % self.device)
+            frame = int(items.shape[1]) - 1
+            emb = int(table.shape[1])
+            if frame * emb + frame != d.state_dim or emb != d.action_dim:
+                raise ValueError("frame batch (frame=%d, dim=%d) does not match the nets (state_dim=%d, action_dim=%d)"
+                                 % (frame, emb, d.state_dim, d.action_dim))
+            st = dict(form=form, n=n, table=table, frame=frame, emb=emb,
+                      items=self._stage("items", items, torch.int64),
+                      ratings=self._stage("ratings", batch["ratings"], torch.float32))
+            if batch.get("done") is not None:
+                st["done"] = self._stage("done", batch["done"], torch.float32, (n,))
+            else:
+                sizes = self._stage("sizes", batch["sizes"], torch.int64)
+                done = self._buffer("done", (n,), torch.float32)
+                _lib.check(_lib.lib().recnn_done_from_sizes(sizes.data_ptr(), sizes.numel(), frame, done.data_ptr(),
+                                                            n, _lib.stream_ptr(self.device)))
+                st["done"] = done
+            st["reward"] = (self._stage("reward", batch["reward"], torch.float32, (n,))
+                            if batch.get("reward") is not None else None)
+        else:
+            form = "dense"
+            n = int(batch["state"].shape[0])
+            st = dict(form=form, n=n,
+                      state=self._stage("state", batch["state"], torch.float32),
+                      next_state=self._stage("next_state", batch["next_state"], torch.float32),
+                      action=self._stage("action", batch["action"], torch.float32),
+                      reward=self._stage("reward", batch["reward"], torch.float32, (n,)),
+                      done=self._stage("done", batch["done"], torch.float32, (n,)))
+            if st["state"].shape[1] != d.state_dim or st["action"].shape[1] != d.action_dim:
+                raise ValueError("batch shapes do not match the nets")
+        n_masks = 6 if self.algo == _lib.ALGO_DDPG else 8
+        masks = batch.get(MASK_KEY)
+        if masks is not None:
+            if len(masks) != n_masks:
+                raise ValueError("%s needs %d masks" % (MASK_KEY, n_masks))
+            st["masks"] = [self._stage("mask%d" % i, m, torch.uint8, (n, d.hidden)) for i, m in enumerate(masks)]
+        else:
+            st["masks"] = None
+        noise = batch.get(NOISE_KEY) if self.algo == _lib.ALGO_TD3 else None
+        st["noise"] = self._stage("noise", noise, torch.float32, (n, d.action_dim)) if noise is not None else None
+        if n != self.n_rows or form != self.form:
+            self.n_rows, self.form = n, form
+            self.graphs.clear()
+        return st
+
+    # ------------------------------------------------------------------ arenas / args
+    def _c_net(self, module, opt, with_grads):
+        flat = param_arena(module)
+        if flat.device != self.device:
+            raise _lib.RecnnError("net is on %s but the update runs on %s (call Algo.to(device) / net.cuda())"
+                                  % (flat.device, self.device))
+        if not with_grads:
+            return _lib.Net(flat.data_ptr(), None, None, None, None)
+        if isinstance(opt, _optim._ArenaOptimizer):
+            if opt._module is not module:
+                opt.bind(module)
+            return opt.c_net(module)
+        g = grad_arena(module)
+        return _lib.Net(flat.data_ptr(), g.data_ptr(), None, None, None)
+
+    @staticmethod
+    def _c_optim(opt):
+        if isinstance(opt, _optim._ArenaOptimizer):
+            return opt.c_optim()
+        return _lib.Optim(_lib.OPT_EXTERNAL, 0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0)
+
+    def _build_args(self, st, nets, optimizer, params, learn, do_policy):
+        a = _lib.StepArgs()
+        a.algo = self.algo
+        a.learn = int(bool(learn))
+        a.do_policy_step = int(bool(do_policy))
+        a.dims = self.dims
+        a.n_rows = st["n"]
+        a.n_rows_global = st["n"] * self.world
+        if st["form"] == "frames":
+            a.table = st["table"].data_ptr()
+            a.n_items = int(st["table"].shape[0])
+            a.frame = st["frame"]
+            a.emb_dim = st["emb"]
+            a.items = st["items"].data_ptr()
+            a.ratings = st["ratings"].data_ptr()
+        else:
+            a.state = st["state"].data_ptr()
+            a.next_state = st["next_state"].data_ptr()
+            a.action = st["action"].data_ptr()
+        a.reward = _lib.ptr(st["reward"])
+        a.done = st["done"].data_ptr()
+        td3 = self.algo == _lib.ALGO_TD3
+        pol_opt = optimizer.get("policy_optimizer") if learn else None
+        a.policy = self._c_net(nets["policy_net"], pol_opt, learn)
+        a.target_policy = self._c_net(nets["target_policy_net"], None, False)
+        a.policy_optim = self._c_optim(pol_opt)
+        val_opts = []
+        for i in range(2 if td3 else 1):
+            sfx = str(i + 1) if td3 else ""
+            vo = optimizer.get("value_optimizer" + sfx) if learn else None
+            val_opts.append(vo)
+            a.value[i] = self._c_net(nets["value_net" + sfx], vo, learn)
+            a.target_value[i] = self._c_net(nets["target_value_net" + sfx], None, False)
+        kinds = {type(v) for v in val_opts}
+        a.value_optim = self._c_optim(val_opts[0])
+        if td3 and isinstance(val_opts[0], _optim._ArenaOptimizer):
+            o0, o1 = val_opts[0].c_optim(), (val_opts[1].c_optim() if isinstance(val_opts[1], _optim._ArenaOptimizer) else None)
+            same = o1 is not None and all(getattr(o0, f) == getattr(o1, f) for f, _ in _lib.Optim._fields_)
+            if len(kinds) != 1 or not same:
+                raise ValueError("the two TD3 value optimizers must be the same built-in optimizer with equal hyper-parameters")
+        a.gamma = float(params["gamma"])
+        if not td3:
+            a.min_value = float(params["min_value"])
+            a.max_value = float(params["max_value"])
+        else:
+            a.noise_std = float(params["noise_std"])
+            a.noise_clip = float(params["noise_clip"])
+        a.soft_tau = float(params["soft_tau"])
+        a.dropout = int(bool(nets["policy_net"].training))
+        if st["masks"] is not None:
+            for i, m in enumerate(st["masks"]):
+                a.masks[i] = m.data_ptr()
+        a.noise = _lib.ptr(st["noise"])
+        a.seed = self.seed
+        a.rng_step = self.rng_step.data_ptr()
+        a.losses = self.losses.data_ptr()
+        nbytes = _lib.lib().recnn_step_workspace_bytes(self.dims, st["n"], self.algo)
+        ws = self.buf.get("workspace")
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+            self.buf["workspace"] = ws
+            self.graphs.clear()
+        a.workspace = ws.data_ptr()
+        a.workspace_bytes = ws.numel()
+        return a, pol_opt, val_opts
+
+    def _signature(self, a):
+        """Everything a captured graph baked in: pointers and scalars."""
+        return bytes(a)
+
+    def _launch(self, a, phases, want_debug=None):
+        a.phases = phases
+        if want_debug is not None:
+            a.next_action_out = _lib.ptr(want_debug.get("next_action"))
+            a.gen_action_out = _lib.ptr(want_debug.get("gen_action"))
+        L = _lib.lib()
+        fn = L.recnn_ddpg_step if self.algo == _lib.ALGO_DDPG else L.recnn_td3_step
+        before = L.recnn_b200_launch_count()
+        _lib.check(fn(a, _lib.stream_ptr(self.device)))
+        self.last_call_kernels = L.recnn_b200_launch_count() - before
+        self.kernels += self.last_call_kernels
+
+    def _run_fused(self, a):
+        """Whole step in one C call; replayed as a CUDA graph once the variant is warm."""
+        a.phases = _lib.PH_ALL
+        key = self._signature(a)
+        if not _USE_GRAPHS:
+            self._launch(a, _lib.PH_ALL)
+            return
+        g = self.graphs.get(key)
+        if g is not None:
+            g[0].replay()
+            self.kernels += g[1]
+            return
+        runs = self.eager_runs.get(key, 0)
+        self.eager_runs[key] = runs + 1
+        if runs < 1:                      # first time: plain launch (also warms lazy module loading)
+            self._launch(a, _lib.PH_ALL)
+            return
+        if len(self.graphs) > 16:
+            self.graphs.clear()
+            self.eager_runs.clear()
+        try:
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._launch(a, _lib.PH_ALL)
+            self.graphs[key] = (g, self.last_call_kernels)
+            g.replay()
+        except Exception as exc:      # capture unsupported in this context: stay on direct launches
+            warnings.warn("recnn_b200: CUDA graph capture failed (%s); using direct launches" % exc)
+            globals()["_USE_GRAPHS"] = False
+            self._launch(a, _lib.PH_ALL)
+
+    # ------------------------------------------------------------------ the step
+    def step(self, batch, params, nets, optimizer, learn, step, debug, policy_every_key):
+        with torch.cuda.device(self.device):
+            return self._step(batch, params, nets, optimizer, learn, step, debug, policy_every_key)
+
+    def _allreduce(self, t):
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+    def _step(self, batch, params, nets, optimizer, learn, step, debug, policy_every_key):
+        st = self._stage_batch(batch)
+        do_policy = bool(learn and step % params[policy_every_key] == 0)
+        a, pol_opt, val_opts = self._build_args(st, nets, optimizer, params, learn, do_policy)
+        td3 = self.algo == _lib.ALGO_TD3
+        builtin = (not learn) or (isinstance(pol_opt, _optim._ArenaOptimizer)
+                                  and all(isinstance(v, _optim._ArenaOptimizer) for v in val_opts))
+        want_debug = None
+        if not learn:
+            n, A = st["n"], self.dims.action_dim
+            want_debug = {"next_action": torch.empty(n, A, device=self.device),
+                          "gen_action": torch.empty(n, A, device=self.device)}
+        if builtin and self.world == 1 and want_debug is None:
+            self._run_fused(a)
+        else:
+            P = _lib
+            value_nets = [nets["value_net" + (str(i + 1) if td3 else "")] for i in range(2 if td3 else 1)]
+            self._launch(a, P.PH_GATHER | P.PH_VALUE_GRAD, want_debug)
+            if learn:
+                if self.world > 1:
+                    for vn in value_nets:
+                        self._allreduce(grad_arena(vn))
+                if builtin:
+                    self._launch(a, P.PH_VALUE_OPT, want_debug)
+                else:
+                    for vn, vo in zip(value_nets, val_opts):
+                        grad_arena(vn)          # re-attach p.grad views if zero_grad(set_to_none) dropped them
+                        vo.step()
+            self._launch(a, P.PH_POLICY_LOSS, want_debug)
+            if do_policy:
+                self._launch(a, P.PH_POLICY_GRAD, want_debug)
+                if self.world > 1:
+                    self._allreduce(grad_arena(nets["policy_net"]))
+                self._launch(a, P.PH_POLICY_OPT, want_debug)
+                if not builtin:
+                    grad_arena(nets["policy_net"])
+                    pol_opt.step()
+                self._launch(a, P.PH_SOFT_UPDATE, want_debug)
+            if self.world > 1:
+                self._allreduce(self.losses[:3])
+        # the Philox step advances once per update (perf-mode dropout / noise)
+        self.rng_step.add_(1)
+        self.losses_host.copy_(self.losses, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        vals = self.losses_host.tolist()
+        if want_debug is not None:
+            debug["next_action"] = want_debug["next_action"]
+            debug["gen_action"] = want_debug["gen_action"]
+        return vals
+
+
+def _value_only(self, batch, params, nets, optimizer, learn, debug):
+    """recnn/nn/update/misc.py:10-55 on its own: critic step without the policy half."""
+    with torch.cuda.device(self.device):
+        st = self._stage_batch(batch)
+        a, _, val_opts = self._build_args(st, nets, optimizer, params, learn, False)
+        want_debug = None
+        if not learn:
+            want_debug = {"next_action": torch.empty(st["n"], self.dims.action_dim, device=self.device)}
+        self._launch(a, _lib.PH_GATHER | _lib.PH_VALUE_GRAD, want_debug)
+        if learn:
+            vn = nets["value_net"]
+            if self.world > 1:
+                self._allreduce(grad_arena(vn))
+            if isinstance(val_opts[0], _optim._ArenaOptimizer):
+                self._launch(a, _lib.PH_VALUE_OPT, want_debug)
+            else:
+                grad_arena(vn)
+                val_opts[0].step()
+        self.rng_step.add_(1)
+        self.losses_host.copy_(self.losses, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        if want_debug is not None:
+            debug["next_action"] = want_debug["next_action"]
+        return self.losses_host.tolist()
+
+
+StepEngine.value_only = _value_only
+
+
+def get_engine(algo, nets, device) -> StepEngine:
+    """Engines are cached on the policy net (they own graphs and staging buffers)."""
+    policy = nets["policy_net"]
+    cache = policy.__dict__.setdefault("_recnn_engines", {})
+    dev = torch.device(device)
+    key = (algo, dev.type, dev.index)
+    eng = cache.get(key)
+    if eng is None:
+        eng = StepEngine(algo, nets, dev)
+        dp = policy.__dict__.get("_recnn_dp")
+        if dp is not None:
+            eng.group, eng.world = dp
+        cache[key] = eng
+    return eng

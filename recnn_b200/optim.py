@@ -1,0 +1,102 @@
+"""Built-in optimizers whose step is fused into the device update step.
+
+``recnn_b200.optim.Adam`` / ``SGD`` follow torch.optim.Adam / SGD (torch 2.11
+single-tensor semantics: lerp_ for exp_avg, bias corrections formed in double,
+L2-style weight_decay) but keep their state as flat arenas next to the net's
+parameter arena, so the update functions can run the optimizer as part of the
+same CUDA graph.  They are torch.optim.Optimizer subclasses: ``zero_grad``,
+``param_groups`` (lr can be edited between steps) and ``state_dict`` behave as
+usual, and ``step()`` may also be called on its own.
+
+Any other torch optimizer passed through the reference's ``optimizer`` dict is
+honoured too (the step is then split at the points where gradients are
+complete and ``optimizer.step()`` is called in between); the reference's default
+``torch_optimizer.Ranger`` is not reproducible here.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+
+class _ArenaOptimizer(torch.optim.Optimizer):
+    _recnn_kind = _lib.OPT_EXTERNAL
+
+    def __init__(self, params, defaults):
+        super().__init__(params, defaults)
+        if len(self.param_groups) != 1:
+            raise ValueError("recnn_b200 optimizers take a single parameter group (one net)")
+        self._m = self._v = self._t = None
+        self._module = None
+
+    # -- binding to a net -------------------------------------------------------
+    def bind(self, module):
+        """Associate with the Actor/Critic whose parameters this optimizer owns."""
+        from .nn.arena import _params
+        mine = [id(p) for p in self.param_groups[0]["params"]]
+        theirs = [id(p) for p in _params(module)]
+        if mine != theirs:
+            raise ValueError("optimizer parameters are not exactly this net's parameters()")
+        self._module = module
+        return self
+
+    def _state_arenas(self, flat):
+        if self._t is None or self._t.device != flat.device:
+            self._t = torch.zeros(1, dtype=torch.int32, device=flat.device)
+            self._m = torch.zeros_like(flat)
+            self._v = torch.zeros_like(flat) if self._recnn_kind == _lib.OPT_ADAM else None
+        return self._m, self._v, self._t
+
+    def c_optim(self) -> _lib.Optim:
+        raise NotImplementedError
+
+    def c_net(self, module=None) -> _lib.Net:
+        from .nn.arena import param_arena, grad_arena
+        module = module or self._module
+        if module is None:
+            raise _lib.RecnnError("optimizer is not bound to a net; call .bind(net) or pass it through an update function")
+        flat = param_arena(module)
+        g = grad_arena(module)
+        m, v, t = self._state_arenas(flat)
+        return _lib.Net(flat.data_ptr(), g.data_ptr(), _lib.ptr(m), _lib.ptr(v), t.data_ptr())
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        if closure is not None:
+            raise ValueError("closures are not supported")
+        from .nn.arena import param_arena
+        if self._module is None:
+            raise _lib.RecnnError("optimizer is not bound to a net; call .bind(net) first")
+        flat = param_arena(self._module)
+        net = self.c_net()
+        opt = self.c_optim()
+        with torch.cuda.device(flat.device):
+            _lib.check(_lib.lib().recnn_optimizer_step(opt, net, flat.numel(), None, _lib.stream_ptr(flat.device)))
+
+    def steps_taken(self) -> int:
+        return 0 if self._t is None else int(self._t.item())
+
+
+class Adam(_ArenaOptimizer):
+    _recnn_kind = _lib.OPT_ADAM
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+
+    def c_optim(self):
+        g = self.param_groups[0]
+        return _lib.Optim(_lib.OPT_ADAM, 0, float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]),
+                          float(g["eps"]), float(g["weight_decay"]), 0.0)
+
+
+class SGD(_ArenaOptimizer):
+    _recnn_kind = _lib.OPT_SGD
+
+    def __init__(self, params, lr=1e-3, momentum=0.0, weight_decay=0.0):
+        super().__init__(params, dict(lr=lr, momentum=momentum, weight_decay=weight_decay))
+
+    def c_optim(self):
+        g = self.param_groups[0]
+        return _lib.Optim(_lib.OPT_SGD, 0, float(g["lr"]), 0.0, 0.0, 0.0, float(g["weight_decay"]),
+                          float(g["momentum"]))

