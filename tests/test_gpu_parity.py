@@ -104,7 +104,7 @@ def test_actor_critic_forward_vs_oracle(n_rows, train):
     np.testing.assert_allclose(got_a, want_a, rtol=1e-5, atol=1e-5 * np.abs(want_a).max())
     np.testing.assert_allclose(got_q, want_q, rtol=1e-5, atol=1e-5 * np.abs(want_q).max())
     got_t = actor(torch.from_numpy(s), tanh=True, masks=tm).cpu().numpy()
-    np.testing.assert_allclose(got_t, np.tanh(want_a), rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(got_t, np.tanh(want_a), rtol=1e-5, atol=5e-6)   # tanhf vs libm tanh
 
 
 def test_train_mode_forward_uses_dropout():

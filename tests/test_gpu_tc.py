@@ -1,0 +1,92 @@
+"""tcgen05 3xTF32 GEMM (recnn_gemm_tf32x3) against float64 numpy and against the exact-fp32
+CUDA-core GEMM (recnn_gemm_fp32), all four operand-major combinations, ragged shapes."""
+import numpy as np
+import pytest
+import torch
+
+from recnn_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _pad4(n):
+    return (n + 3) // 4 * 4
+
+
+def _make(rows, cols, rng, scale=1.0):
+    """fp32 [rows, cols] stored with a row pitch that is a multiple of 4 floats (TMA)."""
+    ld = _pad4(cols)
+    host = (rng.standard_normal((rows, cols)) * scale).astype(np.float32)
+    dev = torch.zeros(rows, ld, device=DEV)
+    dev[:, :cols] = torch.from_numpy(host).to(DEV)
+    return host, dev, ld
+
+
+def _run(kind, M, N, K, a_mn, b_mn, seed=0, tile_n=0, scale_b=1.0):
+    rng = np.random.default_rng(seed)
+    a_h, a_d, lda = _make(K, M, rng) if a_mn else _make(M, K, rng)
+    b_h, b_d, ldb = _make(K, N, rng, scale_b) if b_mn else _make(N, K, rng, scale_b)
+    ldc = _pad4(N)
+    c_d = torch.full((M, ldc), float("nan"), device=DEV)
+    L = _lib.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    if kind == "tc":
+        _lib.check(L.recnn_gemm_tf32x3(M, N, K, a_d.data_ptr(), lda, int(a_mn), b_d.data_ptr(), ldb, int(b_mn),
+                                       c_d.data_ptr(), ldc, tile_n, st))
+    else:
+        _lib.check(L.recnn_gemm_fp32(M, N, K, a_d.data_ptr(), lda, int(a_mn), b_d.data_ptr(), ldb, int(b_mn),
+                                     c_d.data_ptr(), ldc, st))
+    torch.cuda.synchronize()
+    A = (a_h.T if a_mn else a_h).astype(np.float64)
+    B = (b_h.T if b_mn else b_h).astype(np.float64)
+    want = A @ B.T
+    got = c_d[:, :N].cpu().numpy().astype(np.float64)
+    return got, want
+
+
+SHAPES = [
+    (128, 256, 16), (128, 256, 64), (128, 64, 48), (128, 128, 200),
+    (300, 256, 1290),          # ragged M, K with a zero-filled tail block
+    (4096, 256, 1290), (4096, 256, 256), (4096, 128, 256), (1000, 100, 77),
+]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
+def test_tf32x3_matches_float64(M, N, K, a_mn, b_mn):
+    got, want = _run("tc", M, N, K, a_mn, b_mn, seed=M + N + K)
+    assert np.isfinite(got).all()
+    # error of an fp32-accumulated dot product of length K, relative to the result scale sqrt(K)
+    err = np.abs(got - want).max() / np.sqrt(K)
+    assert err < 2e-6, "max abs err / sqrt(K) = %.3g" % err
+    rel = np.abs(got - want).max() / np.abs(want).max()
+    assert rel < 3e-6, rel
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 256, 1290), (257, 130, 333)])
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
+def test_fp32_simt_matches_float64(M, N, K, a_mn, b_mn):
+    got, want = _run("simt", M, N, K, a_mn, b_mn, seed=1)
+    assert np.abs(got - want).max() / np.abs(want).max() < 3e-6
+
+
+def test_tf32_operand_truncation_semantics():
+    """The split assumes kind::tf32 reads a raw fp32 word by ignoring its low 13 mantissa bits.
+    If the hardware rounded instead, hi (as read) + lo (as computed) != x for about half of all
+    inputs and the error would be ~2^-11 (5e-4) relative, not ~1e-7."""
+    got, want = _run("tc", 256, 256, 512, False, False, seed=7)
+    rel = np.abs(got - want) / (np.abs(want) + 1e-3 * np.abs(want).max())
+    assert rel.max() < 1e-5, rel.max()
+
+
+@pytest.mark.parametrize("tile_n", [64, 128, 256])
+def test_tile_widths_agree(tile_n):
+    got, want = _run("tc", 512, 256, 320, False, False, seed=3, tile_n=tile_n)
+    assert np.abs(got - want).max() / np.abs(want).max() < 3e-6
+
+
+def test_wide_dynamic_range():
+    """gradient-like operand (1e-6 scale) times activation-like operand: relative accuracy holds."""
+    got, want = _run("tc", 256, 256, 4096, True, True, seed=5, scale_b=1e-6)
+    assert np.abs(got - want).max() / np.abs(want).max() < 3e-6
