@@ -2,6 +2,7 @@
 // configuration, and the generic C-ABI entry points recnn_gemm_tf32x3 / recnn_gemm_fp32.
 #include "tc_gemm.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -31,12 +32,13 @@ int make_tmap(CUtensorMap* out, const float* base, int64_t rows, int64_t cols, i
   }
   RECNN_REQUIRE(reinterpret_cast<uintptr_t>(base) % 16 == 0, "TMA base must be 16-byte aligned");
   RECNN_REQUIRE(ld % 4 == 0 && ld >= cols, "TMA row pitch must be a multiple of 4 floats");
-  RECNN_REQUIRE(box_cols * 4 <= swizzle_bytes && box_rows <= 256, "TMA box");
+  RECNN_REQUIRE(box_cols * 4 <= (swizzle_bytes == 1032 ? 128 : swizzle_bytes) && box_rows <= 256, "TMA box");
   const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
   const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
-  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+  const CUtensorMapSwizzle sw = swizzle_bytes == 1032 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                               : swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                                                      : CU_TENSOR_MAP_SWIZZLE_32B;
   const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
@@ -73,11 +75,11 @@ static int launch_cfg(const Operand& A0, const Operand& A1, const Operand& B, co
     else ma1 = ma0;
   } else {
     RECNN_REQUIRE(p.K1 == 0, "MN-major A cannot be a K-concat");
-    RECNN_PROPAGATE(make_tmap(&ma0, A0.ptr, p.K0, p.M, A0.ld, 32, C::BK, 128));
+    RECNN_PROPAGATE(make_tmap(&ma0, A0.ptr, p.K0, p.M, A0.ld, 32, C::BK, 1032));
     ma1 = ma0;
   }
   if (!C::B_MN) RECNN_PROPAGATE(make_tmap(&mb, B.ptr, B.rows, B.cols, B.ld, C::BK, C::BN, C::K_SWZ));
-  else RECNN_PROPAGATE(make_tmap(&mb, B.ptr, B.rows, B.cols, B.ld, 32, C::BK, 128));
+  else RECNN_PROPAGATE(make_tmap(&mb, B.ptr, B.rows, B.cols, B.ld, 32, C::BK, 1032));
   dim3 grid((unsigned)ceil_div(p.N, C::BN), (unsigned)ceil_div(p.M, C::BM), (unsigned)splits);
   tc_gemm_kernel<C, EPI><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(ma0, ma1, mb, p, epi);
   RECNN_CHECK_LAUNCH("tc_gemm_kernel");

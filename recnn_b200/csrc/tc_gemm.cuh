@@ -261,9 +261,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     if (lane == 0) {
       constexpr uint32_t idesc = instr_desc_tf32(BM, BN, C::A_MN, C::B_MN);
       // K-major: LBO unused (1), SBO = 8 rows * swizzle span.  MN-major: LBO = chunk stride, SBO = 1024.
-      constexpr uint64_t a_base = C::A_MN ? smem_desc_base(BK * 128, 1024, 2)
+      // K-major: rows of K_SWZ bytes, LBO unused (1), SBO = 8 rows.  MN-major fp32/tf32 operands must
+      // use the 128B_BASE32B layout (cute: "for mn-major tf32 operands, SW128_32B is the only available
+      // smem layout"): 128-byte rows of 32 MN elements, swizzle period 4 k-rows => SBO = 512 B between
+      // 4-row groups, LBO = pitch between 32-element MN chunks (BK rows * 128 B).
+      constexpr uint64_t a_base = C::A_MN ? smem_desc_base(BK * 128, 512, 1)
                                           : smem_desc_base(16, 8 * C::K_SWZ, C::K_SWZ == 128 ? 2 : 4);
-      constexpr uint64_t b_base = C::B_MN ? smem_desc_base(BK * 128, 1024, 2)
+      constexpr uint64_t b_base = C::B_MN ? smem_desc_base(BK * 128, 512, 1)
                                           : smem_desc_base(16, 8 * C::K_SWZ, C::K_SWZ == 128 ? 2 : 4);
       constexpr uint32_t a_kstep = C::A_MN ? 1024 : 32;     // bytes to advance per 8-wide k-slice
       constexpr uint32_t b_kstep = C::B_MN ? 1024 : 32;
@@ -346,6 +350,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn get_encode_fn();
 
 // 2-D fp32 tensor [rows, cols] with row pitch ld (floats, multiple of 4); box = {box_cols, box_rows}.
+// swizzle_bytes: 64 / 128 = the classic 16-byte-unit swizzles; 1032 = 128B span with 32-byte units
+// (CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, the partner of the UMMA 128B_BASE32B layout).
 int make_tmap(CUtensorMap* out, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_cols,
               int box_rows, int swizzle_bytes);
 
