@@ -20,7 +20,9 @@
  *     nn.Module.parameters() order: linear1.weight [H,in], linear1.bias [H],
  *     linear2.weight [H,H], linear2.bias [H], linear3.weight [out,H],
  *     linear3.bias [out]  (nn.Linear layout, y = x W^T + b;
- *     recnn/nn/models.py:41-57 Actor, :187-203 Critic).
+ *     recnn/nn/models.py:41-57 Actor, :187-203 Critic).  Every matrix row and every
+ *     segment is padded to a multiple of 4 floats (16 bytes, the TMA granule):
+ *     recnn_net_layout() returns the offsets and row pitches; pad elements are 0.
  */
 #ifndef RECNN_B200_H
 #define RECNN_B200_H
@@ -85,9 +87,13 @@ typedef struct recnn_dims {
   int32_t reserved;
 } recnn_dims;
 
-/* number of fp32 in an Actor / Critic arena for these dims */
+/* number of fp32 in an Actor / Critic arena for these dims (padding included) */
 RECNN_API int64_t recnn_actor_param_count(const recnn_dims* d);
 RECNN_API int64_t recnn_critic_param_count(const recnn_dims* d);
+
+/* arena geometry: offsets (in floats) of w1,b1,w2,b2,w3,b3 then the row pitches of w1,w2,w3,
+ * then the total count -> out[10].  is_critic selects in = S+A / out = 1. */
+RECNN_API int recnn_net_layout(const recnn_dims* d, int is_critic, int64_t* out);
 
 /* recnn/nn/models.py:59-73 Actor.forward.  masks: two uint8[n_rows,H] arrays
  * (train mode: h = relu(z) * mask * 2) or NULL,NULL for eval().  apply_tanh as

@@ -53,18 +53,28 @@ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 
 // ---- arena layout of one MLP (nn.Module.parameters() order) -----------------
+// Weight rows are padded to a multiple of 4 floats (16 bytes) so that every matrix in the arena is
+// a legal TMA tensor: linear1.weight of the Actor is [H, 1290] with row pitch 1292, of the Critic
+// [H, 1418] with pitch 1420.  The nn.Parameter objects on the Python side are strided views of the
+// arena, so the padding is invisible to state_dict / optimizers; pad elements stay 0 forever
+// (their gradient is never written, Adam/SGD/Polyak of 0 with 0 is 0).
 struct NetLayout {
   int in_dim, hidden, out_dim;
+  int ld1, ld2, ld3;                 // row pitches of w1 [H,in], w2 [H,H], w3 [out,H]
   int64_t w1, b1, w2, b2, w3, b3, count;
   __host__ __device__ NetLayout() {}
   __host__ __device__ NetLayout(int in_, int h, int out_) : in_dim(in_), hidden(h), out_dim(out_) {
+    ld1 = (in_ + 3) / 4 * 4;
+    ld2 = (h + 3) / 4 * 4;
+    ld3 = (h + 3) / 4 * 4;
+    const int64_t hb = (h + 3) / 4 * 4, ob = (out_ + 3) / 4 * 4;
     w1 = 0;
-    b1 = w1 + (int64_t)h * in_;
-    w2 = b1 + h;
-    b2 = w2 + (int64_t)h * h;
-    w3 = b2 + h;
-    b3 = w3 + (int64_t)out_ * h;
-    count = b3 + out_;
+    b1 = w1 + (int64_t)h * ld1;
+    w2 = b1 + hb;
+    b2 = w2 + (int64_t)h * ld2;
+    w3 = b2 + hb;
+    b3 = w3 + (int64_t)out_ * ld3;
+    count = b3 + ob;
   }
 };
 static inline NetLayout actor_layout(const recnn_dims& d) {
@@ -73,6 +83,7 @@ static inline NetLayout actor_layout(const recnn_dims& d) {
 static inline NetLayout critic_layout(const recnn_dims& d) {
   return NetLayout(d.state_dim + d.action_dim, d.hidden, 1);
 }
+static inline int pad4(int n) { return (n + 3) / 4 * 4; }
 
 // ---- warp helpers -----------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {

@@ -23,13 +23,13 @@ template <bool VEC>
 __global__ void __launch_bounds__(256)
 frame_gather_kernel(const float* __restrict__ table, long long n_items, int dim,
                     const long long* __restrict__ items, const float* __restrict__ ratings,
-                    long long n_rows, int frame,
+                    long long n_rows, int frame, long long s_ld,
                     float* __restrict__ state, float* __restrict__ next_state,
                     float* __restrict__ action, float* __restrict__ reward, int* __restrict__ oob) {
   const int lane = threadIdx.x & 31;
   const long long warps_per_grid = (long long)gridDim.x * (blockDim.x >> 5);
   const int f1 = frame + 1;
-  const long long s_dim = (long long)frame * dim + frame;
+  const long long s_dim = s_ld;       // row pitch of state / next_state (>= frame*dim + frame)
 
   for (long long n = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); n < n_rows;
        n += warps_per_grid) {
@@ -115,15 +115,15 @@ __global__ void done_from_sizes_kernel(const long long* __restrict__ sizes, long
 
 using namespace recnn;
 
-extern "C" int recnn_frame_gather(const float* table, int64_t n_items, int dim, const int64_t* items,
-                                  const float* ratings, int64_t n_rows, int frame, float* state,
-                                  float* next_state, float* action, float* reward, int* oob_flag,
-                                  void* stream) {
+namespace recnn {
+int launch_frame_gather(const float* table, int64_t n_items, int dim, const int64_t* items, const float* ratings,
+                        int64_t n_rows, int frame, int64_t s_ld, float* state, float* next_state, float* action,
+                        float* reward, int* oob_flag, cudaStream_t st) {
   RECNN_REQUIRE(table && items && ratings, "table/items/ratings must be non-null");
   RECNN_REQUIRE(n_items > 0 && dim > 0 && frame > 0 && n_rows >= 0, "sizes must be positive");
   if (n_rows == 0) return RECNN_OK;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const long long s_dim = (long long)frame * dim + frame;
+  const long long s_dim = s_ld;
+  RECNN_REQUIRE(s_ld >= (int64_t)frame * dim + frame, "state pitch too small");
   const bool aligned = (reinterpret_cast<uintptr_t>(table) % 16 == 0) &&
                        (!state || reinterpret_cast<uintptr_t>(state) % 8 == 0) &&
                        (!next_state || reinterpret_cast<uintptr_t>(next_state) % 8 == 0) &&
@@ -134,12 +134,22 @@ extern "C" int recnn_frame_gather(const float* table, int64_t n_items, int dim, 
   const int grid = (int)(blocks < (int64_t)kNumSMs * 8 ? blocks : (int64_t)kNumSMs * 8);
   if (vec)
     frame_gather_kernel<true><<<grid, 256, 0, st>>>(table, n_items, dim, (const long long*)items, ratings,
-                                                    n_rows, frame, state, next_state, action, reward, oob_flag);
+                                                    n_rows, frame, s_ld, state, next_state, action, reward, oob_flag);
   else
     frame_gather_kernel<false><<<grid, 256, 0, st>>>(table, n_items, dim, (const long long*)items, ratings,
-                                                     n_rows, frame, state, next_state, action, reward, oob_flag);
+                                                     n_rows, frame, s_ld, state, next_state, action, reward, oob_flag);
   RECNN_CHECK_LAUNCH("frame_gather_kernel");
   return RECNN_OK;
+}
+}  // namespace recnn
+
+extern "C" int recnn_frame_gather(const float* table, int64_t n_items, int dim, const int64_t* items,
+                                  const float* ratings, int64_t n_rows, int frame, float* state,
+                                  float* next_state, float* action, float* reward, int* oob_flag,
+                                  void* stream) {
+  return recnn::launch_frame_gather(table, n_items, dim, items, ratings, n_rows, frame,
+                                    (int64_t)frame * dim + frame, state, next_state, action, reward, oob_flag,
+                                    static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int recnn_done_from_sizes(const int64_t* sizes, int64_t n_users, int frame, float* done,

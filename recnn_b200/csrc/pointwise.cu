@@ -110,25 +110,56 @@ int launch_critic_head_bwd(const float* dq, float dq_const, const float* w3, con
 // ---------------------------------------------------------------- split-K reduce
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(const float* __restrict__ part, int splits, int C, int K1,
-                       float* __restrict__ w_dst, float* __restrict__ b_dst) {
+                       float* __restrict__ w_dst, long long ldw, float* __restrict__ b_dst) {
   const long long total = (long long)C * K1;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     float s = 0.f;
-    for (int z = 0; z < splits; ++z) s += part[(long long)z * total + i];
+    for (int z = 0; z < splits; ++z) s += part[(long long)z * total + i];     // fixed order: deterministic
     const int c = (int)(i / K1), k = (int)(i - (long long)c * K1);
-    if (k < K1 - 1) w_dst[(long long)c * (K1 - 1) + k] = s;
+    if (k < K1 - 1) w_dst[(long long)c * ldw + k] = s;
     else b_dst[c] = s;
   }
 }
 
-int launch_reduce_partials(const float* part, int splits, int C, int K1, float* w_dst, float* b_dst,
-                           cudaStream_t st) {
+int launch_reduce_partials(const float* part, int splits, int C, int K1, float* w_dst, long long ldw,
+                           float* b_dst, cudaStream_t st) {
   const int64_t total = (int64_t)C * K1;
   const int64_t blocks = ceil_div(total, 256);
   const int grid = (int)(blocks < 8 * kNumSMs ? blocks : 8 * kNumSMs);
-  reduce_partials_kernel<<<grid, 256, 0, st>>>(part, splits, C, K1, w_dst, b_dst);
+  reduce_partials_kernel<<<grid, 256, 0, st>>>(part, splits, C, K1, w_dst, ldw, b_dst);
   RECNN_CHECK_LAUNCH("reduce_partials_kernel");
+  return RECNN_OK;
+}
+
+// Column sums of dZ [n_rows, C] per row-split, written into column K1-1 of the split-K partial
+// buffer part[z][c][K1] (the bias-gradient column next to a tensor-core weight gradient).
+__global__ void __launch_bounds__(256)
+colsum_partials_kernel(const float* __restrict__ dz, long long n_rows, int C, long long rows_per_split,
+                       float* __restrict__ part, int K1) {
+  __shared__ float red[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx, z = blockIdx.y;
+  const long long r0 = (long long)z * rows_per_split;
+  const long long r1 = min(n_rows, r0 + rows_per_split);
+  float s = 0.f;
+  if (c < C)
+    for (long long r = r0 + ry; r < r1; r += 8) s += dz[r * C + c];
+  red[ry][cx] = s;
+  __syncthreads();
+  if (ry == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][cx];
+    part[((long long)z * C + c) * K1 + (K1 - 1)] = t;
+  }
+}
+
+int launch_colsum_partials(const float* dz, int64_t n_rows, int C, int64_t rows_per_split, int splits,
+                           float* part, int K1, cudaStream_t st) {
+  dim3 grid((unsigned)ceil_div(C, 32), (unsigned)splits);
+  colsum_partials_kernel<<<grid, 256, 0, st>>>(dz, n_rows, C, rows_per_split, part, K1);
+  RECNN_CHECK_LAUNCH("colsum_partials_kernel");
   return RECNN_OK;
 }
 

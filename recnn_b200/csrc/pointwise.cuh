@@ -39,9 +39,11 @@ int launch_critic_head_bwd(const float* dq, float dq_const, const float* w3, con
                            float gate_scale, float* dz2, int64_t n_rows, int hidden, cudaStream_t st);
 
 // grad arena <- sum over split-K partials; part is [splits][C][K1] where column K1-1 is the
-// bias gradient: w_dst[c*(K1-1)+k] for k<K1-1, b_dst[c] for k==K1-1.
-int launch_reduce_partials(const float* part, int splits, int C, int K1, float* w_dst, float* b_dst,
-                           cudaStream_t st);
+// bias gradient: w_dst[c*ldw+k] for k<K1-1 (ldw = arena row pitch), b_dst[c] for k==K1-1.
+int launch_reduce_partials(const float* part, int splits, int C, int K1, float* w_dst, long long ldw,
+                           float* b_dst, cudaStream_t st);
+int launch_colsum_partials(const float* dz, int64_t n_rows, int C, int64_t rows_per_split, int splits,
+                           float* part, int K1, cudaStream_t st);
 
 // *coef = min(max_norm / (||g||_1 + 1e-6), 1)  (clip_grad_norm_(.., -1, 1): ddpg.py:92);  *l1_out = ||g||_1
 int launch_l1_clip_coef(const float* grads, int64_t count, float max_norm, float* coef, float* l1_out,

@@ -4,17 +4,41 @@
 // synchronisation, no host read-back -- so the whole call is CUDA-graph
 // capturable.  Step-dependent scalars (Adam's t, the Philox step) live on the
 // device for the same reason.
+//
+// Every contraction goes through one of four helpers (hidden_layer, linear_out,
+// backprop_hidden, weight_grad).  Each has two back ends with identical
+// semantics: the tcgen05 3xTF32 tensor-core kernel (tc_gemm.cuh; default) and
+// the exact-fp32 CUDA-core kernel (gemm_simt.cuh; arbitrary shapes, and
+// RECNN_B200_MATH=simt forces it for A/B comparisons).
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "pointwise.cuh"
+#include "tc_gemm.cuh"
 
 namespace recnn {
 
+int launch_frame_gather(const float* table, int64_t n_items, int dim, const int64_t* items, const float* ratings,
+                        int64_t n_rows, int frame, int64_t s_ld, float* state, float* next_state, float* action,
+                        float* reward, int* oob_flag, cudaStream_t st);
+
+static bool math_tc() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RECNN_B200_MATH");
+    v = (e && strcmp(e, "simt") == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 // ---------------------------------------------------------------- workspace
 struct Workspace {
-  float* S;        // [N,S]  frame form only
-  float* S2;       // [N,S]
-  float* ACT;      // [N,A]
+  float* S;        // [N, ldS] state (frame form: gathered; dense form: re-pitched copy)
+  float* S2;       // [N, ldS]
+  float* ACT;      // [N,A]  frame form only
   float* REW;      // [N]
   float* hb[6];    // [N,H] activation / gradient buffers (lifetimes in DESIGN.md)
   float* ab[3];    // [N,A] next_action / gen_action / d gen_action
@@ -28,25 +52,33 @@ struct Workspace {
   int64_t bytes;
 };
 
-static int dw_splits(int C, int K1, int64_t n_rows) {
-  // enough (m,n,z) tiles for ~1.5 waves of 148 SMs, chunks of >= 256 rows
-  const int64_t tiles = ceil_div(C, 128) * ceil_div(K1, 128);
+// split count of a weight-gradient GEMM dW[C, K] = dZ^T X over n_rows (the contraction dim).
+// Must be a pure function of the shapes: the workspace size depends on it.
+static int dw_splits(int C, int K, int64_t n_rows, bool tc_path) {
+  if (tc_path) {
+    const int64_t tiles = ceil_div(C, 128) * ceil_div(K, 256);
+    int64_t s = ceil_div(192, tiles);
+    const int64_t max_s = ceil_div(n_rows, 16) / 8 > 0 ? ceil_div(n_rows, 16) / 8 : 1;   // >= 8 k-blocks per split
+    if (s > max_s) s = max_s;
+    return (int)(s < 1 ? 1 : s);
+  }
+  const int64_t tiles = ceil_div(C, 128) * ceil_div(K + 1, 128);
   int64_t s = ceil_div(220, tiles);
   const int64_t max_s = n_rows / 256 > 0 ? n_rows / 256 : 1;
   if (s > max_s) s = max_s;
-  if (s < 1) s = 1;
-  return (int)s;
+  return (int)(s < 1 ? 1 : s);
 }
 
 static int64_t partial_floats(const recnn_dims& d, int64_t n_rows) {
   const int in_c = d.state_dim + d.action_dim;
   int64_t best = 0;
-  const int shapes[5][2] = {{d.hidden, in_c + 1}, {d.hidden, d.state_dim + 1}, {d.hidden, d.hidden + 1},
-                            {d.action_dim, d.hidden + 1}, {1, d.hidden + 1}};
-  for (auto& s : shapes) {
-    const int64_t f = (int64_t)dw_splits(s[0], s[1], n_rows) * s[0] * s[1];
-    if (f > best) best = f;
-  }
+  const int shapes[5][2] = {{d.hidden, in_c}, {d.hidden, d.state_dim}, {d.hidden, d.hidden},
+                            {d.action_dim, d.hidden}, {1, d.hidden}};
+  for (auto& s : shapes)
+    for (int tcp = 0; tcp < 2; ++tcp) {
+      const int64_t f = (int64_t)dw_splits(s[0], s[1], n_rows, tcp != 0) * s[0] * (s[1] + 1);
+      if (f > best) best = f;
+    }
   return best;
 }
 
@@ -59,8 +91,9 @@ static Workspace carve(const recnn_dims& d, int64_t n, void* base) {
     off += round_up(floats * 4, 256);
     return r;
   };
-  w.S = take(n * d.state_dim);
-  w.S2 = take(n * d.state_dim);
+  const int ldS = pad4(d.state_dim);
+  w.S = take(n * ldS);
+  w.S2 = take(n * ldS);
   w.ACT = take(n * d.action_dim);
   w.REW = take(n);
   for (auto& b : w.hb) b = take(n * d.hidden);
@@ -85,27 +118,59 @@ struct Rng {
 
 static Epilogue base_epi() {
   Epilogue e;
-  e.out = nullptr; e.ldo = 0; e.bias = nullptr; e.mask = nullptr; e.train = 0; e.seed = 0;
-  e.rng_step = nullptr; e.stream_id = 0; e.h = nullptr; e.ldh = 0; e.gate_scale = 1.f;
-  e.apply_tanh = 0; e.noise = nullptr; e.noise_clip = 0.f; e.noise_std = 0.f; e.add_noise = 0;
+  memset(&e, 0, sizeof(e));
+  e.gate_scale = 1.f;
   return e;
 }
 
-// h = dropout(relu(X W^T + b))   X may be the virtual concat [x0 | x1]
-static int hidden_layer(const MatView& X, int K, const float* W, const float* b, int H, int64_t n,
-                        bool train, const uint8_t* mask, const Rng& rng, unsigned stream_id, float* out,
+// one K-contiguous input matrix [n, cols] with row pitch ld
+struct Seg {
+  const float* p;
+  int cols;
+  long long ld;
+};
+static const Seg kNoSeg = {nullptr, 0, 0};
+
+static int pick_bn(int64_t M, int N) {
+  // widest tile that still yields >= 96 CTAs; otherwise the narrowest (more CTAs, less reuse)
+  const int64_t mt = ceil_div(M, 128);
+  if (N > 128 && mt * ceil_div(N, 256) >= 96) return 256;
+  if (N > 64 && mt * ceil_div(N, 128) >= 96) return 128;
+  return 64;
+}
+
+// out[n, N] = epi( [x0 | x1] W^T )    W is [N, K0+K1] with row pitch ldw
+template <int EPI>
+static int gemm_nt(const Seg& x0, const Seg& x1, const float* W, long long ldw, int N, int64_t n, const Epilogue& e,
+                   cudaStream_t st) {
+  const int K = x0.cols + x1.cols;
+  const bool tc_ok = math_tc() && aligned16(x0.p) && (x1.cols == 0 || aligned16(x1.p)) && aligned16(W) &&
+                     x0.ld % 4 == 0 && (x1.cols == 0 || x1.ld % 4 == 0) && ldw % 4 == 0;
+  if (tc_ok) {
+    tc::Operand a0 = {x0.p, x0.ld, 0, 0}, a1 = {x1.p, x1.ld, 0, 0}, b = {W, ldw, N, K};
+    tc::Problem p = {(int)n, N, x0.cols, x1.cols, 0, x0.cols, 0, 0};
+    const int r = tc::launch<false, false, EPI>(a0, a1, b, p, 1, pick_bn(n, N), e, st);
+    return r < 0 ? r : RECNN_OK;
+  }
+  const MatView X = x1.cols ? mat_cat(x0.p, x0.ld, x0.cols, x1.p, x1.ld) : mat(x0.p, x0.ld);
+  return launch_gemm_simt<true, true, EPI>(X, mat(W, ldw), (int)n, N, K, 1, e, st);
+}
+
+// h = dropout(relu([x0|x1] W^T + b))
+static int hidden_layer(const Seg& x0, const Seg& x1, const float* W, long long ldw, const float* b, int H,
+                        int64_t n, bool train, const uint8_t* mask, const Rng& rng, unsigned stream_id, float* out,
                         cudaStream_t st) {
   Epilogue e = base_epi();
   e.out = out; e.ldo = H; e.bias = b;
   e.train = train ? 1 : 0; e.mask = mask; e.seed = rng.seed; e.rng_step = rng.step; e.stream_id = stream_id;
-  return launch_gemm_simt<true, true, EPI_HIDDEN>(X, mat(W, K), (int)n, H, K, 1, e, st);
+  return gemm_nt<EPI_HIDDEN>(x0, x1, W, ldw, H, n, e, st);
 }
 
 struct NoiseSpec {
   int add; const float* noise; float clip, std; unsigned long long seed; const long long* step; unsigned stream_id;
 };
 
-static int linear_out(const float* X, int K, const float* W, const float* b, int out_dim, int64_t n,
+static int linear_out(const Seg& x, const float* W, long long ldw, const float* b, int out_dim, int64_t n,
                       int apply_tanh, const NoiseSpec* nz, float* out, cudaStream_t st) {
   Epilogue e = base_epi();
   e.out = out; e.ldo = out_dim; e.bias = b; e.apply_tanh = apply_tanh;
@@ -113,31 +178,66 @@ static int linear_out(const float* X, int K, const float* W, const float* b, int
     e.add_noise = 1; e.noise = nz->noise; e.noise_clip = nz->clip; e.noise_std = nz->std;
     e.seed = nz->seed; e.rng_step = nz->step; e.stream_id = nz->stream_id;
   }
-  return launch_gemm_simt<true, true, EPI_LINEAR>(mat(X, K), mat(W, K), (int)n, out_dim, K, 1, e, st);
+  return gemm_nt<EPI_LINEAR>(x, kNoSeg, W, ldw, out_dim, n, e, st);
 }
 
-// dX = (dZ W) * gate(h)     dZ [n,C], W [C,K] (row-major, optionally a column window), out [n,K]
-static int backprop_hidden(const float* dZ, int C, const float* W, long long ldw, int K, int64_t n,
-                           const float* h, float gate_scale, float* out, cudaStream_t st) {
+// dX = (dZ W[:, col0:col0+K]) * gate(h)     dZ [n,C]; W [C, w_cols] row pitch ldw; out [n,K]
+static int backprop_hidden(const float* dZ, int C, const float* W, long long ldw, int w_cols, int col0, int K,
+                           int64_t n, const float* h, float gate_scale, float* out, cudaStream_t st) {
   Epilogue e = base_epi();
   e.out = out; e.ldo = K; e.h = h; e.ldh = K; e.gate_scale = gate_scale;
-  if (h) return launch_gemm_simt<true, false, EPI_GATE>(mat(dZ, C), mat(W, ldw), (int)n, K, C, 1, e, st);
-  return launch_gemm_simt<true, false, EPI_STORE>(mat(dZ, C), mat(W, ldw), (int)n, K, C, 1, e, st);
+  const bool tc_ok = math_tc() && aligned16(dZ) && aligned16(W) && C % 4 == 0 && ldw % 4 == 0;
+  if (tc_ok) {
+    tc::Operand a0 = {dZ, C, 0, 0}, a1 = {nullptr, 0, 0, 0}, b = {W, ldw, C, w_cols};
+    tc::Problem p = {(int)n, K, C, 0, 0, C, 0, col0};
+    const int bn = pick_bn(n, K);
+    const int r = h ? tc::launch<false, true, EPI_GATE>(a0, a1, b, p, 1, bn, e, st)
+                    : tc::launch<false, true, EPI_STORE>(a0, a1, b, p, 1, bn, e, st);
+    return r < 0 ? r : RECNN_OK;
+  }
+  if (h) return launch_gemm_simt<true, false, EPI_GATE>(mat(dZ, C), mat(W + col0, ldw), (int)n, K, C, 1, e, st);
+  return launch_gemm_simt<true, false, EPI_STORE>(mat(dZ, C), mat(W + col0, ldw), (int)n, K, C, 1, e, st);
 }
 
-// dW[c,k] = sum_n dZ[n,c] X[n,k];  db[c] = sum_n dZ[n,c]   (X may be a concat view)
-static int weight_grad(const float* dZ, int C, MatView X, int K, int64_t n, float* dW, float* db,
-                       const Workspace& ws, cudaStream_t st) {
-  X.ones_at = K;                        // virtual bias column
-  const int K1 = K + 1;
-  const int splits_req = dw_splits(C, K1, n);
+// dW[c,k] = sum_n dZ[n,c] [x0|x1][n,k];  db[c] = sum_n dZ[n,c].   dW has row pitch ldw.
+static int weight_grad(const float* dZ, int C, const Seg& x0, const Seg& x1, int64_t n, float* dW, long long ldw,
+                       float* db, const Workspace& ws, cudaStream_t st) {
+  const int K = x0.cols + x1.cols, K1 = K + 1;
   Epilogue e = base_epi();
   e.out = ws.partial; e.ldo = K1;
+  const bool tc_ok = math_tc() && C % 4 == 0 && C >= 32 && aligned16(dZ) && aligned16(x0.p) && x0.ld % 4 == 0 &&
+                     (x1.cols == 0 || (aligned16(x1.p) && x1.ld % 4 == 0));
+  if (tc_ok) {
+    const int req = dw_splits(C, K, n, true);
+    int k_chunk = 0;
+    const int splits = tc::split_plan((int)ceil_div(n, 16), req, &k_chunk);
+    tc::Operand a0 = {dZ, C, 0, 0}, a1 = {nullptr, 0, 0, 0};
+    const Seg* segs[2] = {&x0, &x1};
+    int col = 0;
+    for (const Seg* s : segs) {
+      if (s->cols == 0) continue;
+      tc::Operand b = {s->p, s->ld, n, s->cols};
+      tc::Problem p = {C, s->cols, (int)n, 0, 0, 0, col, 0};
+      const int bn = s->cols > 128 ? 256 : (s->cols > 64 ? 128 : 64);
+      const int r = tc::launch<true, true, EPI_PARTIAL>(a0, a1, b, p, req, bn, e, st);
+      if (r < 0) return r;
+      if (r != splits) {
+        set_error("internal: split plan mismatch (%d vs %d)", r, splits);
+        return RECNN_E_INVALID;
+      }
+      col += s->cols;
+    }
+    RECNN_PROPAGATE(launch_colsum_partials(dZ, n, C, k_chunk, splits, ws.partial, K1, st));
+    return launch_reduce_partials(ws.partial, splits, C, K1, dW, ldw, db, st);
+  }
+  MatView X = x1.cols ? mat_cat(x0.p, x0.ld, x0.cols, x1.p, x1.ld) : mat(x0.p, x0.ld);
+  X.ones_at = K;                        // virtual bias column
+  const int splits_req = dw_splits(C, K, n, false);
   // the launcher rounds the chunk; recompute the effective split count the same way
   const int k_chunk = (int)round_up(ceil_div(n, splits_req), 16);
   const int splits = (int)ceil_div(n, k_chunk);
   RECNN_PROPAGATE((launch_gemm_simt<false, false, EPI_PARTIAL>(mat(dZ, C), X, C, K1, (int)n, splits_req, e, st)));
-  return launch_reduce_partials(ws.partial, splits, C, K1, dW, db, st);
+  return launch_reduce_partials(ws.partial, splits, C, K1, dW, ldw, db, st);
 }
 
 struct Ctx {
@@ -146,6 +246,7 @@ struct Ctx {
   NetLayout la, lc;
   Workspace ws;
   const float *S, *S2, *ACT, *REW, *DONE;
+  long long ldS;
   int64_t n;
   cudaStream_t st;
   Rng rng;
@@ -157,12 +258,12 @@ struct Ctx {
 static int critic_hidden(const Ctx& c, const float* params, const float* s, const float* act, bool train,
                          int mask_base, float* out1, float* out2) {
   const int S = c.d.state_dim, A = c.d.action_dim, H = c.d.hidden;
-  const MatView X = mat_cat(s, S, S, act, A);
   const uint8_t* m1 = (train && c.rng.masks) ? c.rng.masks[mask_base] : nullptr;
   const uint8_t* m2 = (train && c.rng.masks) ? c.rng.masks[mask_base + 1] : nullptr;
-  RECNN_PROPAGATE(hidden_layer(X, S + A, params + c.lc.w1, params + c.lc.b1, H, c.n, train, m1, c.rng,
+  const Seg xs = {s, S, c.ldS}, xa = {act, A, A}, h1 = {out1, H, H};
+  RECNN_PROPAGATE(hidden_layer(xs, xa, params + c.lc.w1, c.lc.ld1, params + c.lc.b1, H, c.n, train, m1, c.rng,
                                mask_base, out1, c.st));
-  return hidden_layer(mat(out1, H), H, params + c.lc.w2, params + c.lc.b2, H, c.n, train, m2, c.rng,
+  return hidden_layer(h1, kNoSeg, params + c.lc.w2, c.lc.ld2, params + c.lc.b2, H, c.n, train, m2, c.rng,
                       mask_base + 1, out2, c.st);
 }
 
@@ -171,9 +272,10 @@ static int actor_hidden(const Ctx& c, const float* params, const float* s, bool 
   const int S = c.d.state_dim, H = c.d.hidden;
   const uint8_t* m1 = (train && c.rng.masks) ? c.rng.masks[mask_base] : nullptr;
   const uint8_t* m2 = (train && c.rng.masks) ? c.rng.masks[mask_base + 1] : nullptr;
-  RECNN_PROPAGATE(hidden_layer(mat(s, S), S, params + c.la.w1, params + c.la.b1, H, c.n, train, m1, c.rng,
+  const Seg xs = {s, S, c.ldS}, h1 = {out1, H, H};
+  RECNN_PROPAGATE(hidden_layer(xs, kNoSeg, params + c.la.w1, c.la.ld1, params + c.la.b1, H, c.n, train, m1, c.rng,
                                mask_base, out1, c.st));
-  return hidden_layer(mat(out1, H), H, params + c.la.w2, params + c.la.b2, H, c.n, train, m2, c.rng,
+  return hidden_layer(h1, kNoSeg, params + c.la.w2, c.la.ld2, params + c.la.b2, H, c.n, train, m2, c.rng,
                       mask_base + 1, out2, c.st);
 }
 
@@ -201,8 +303,9 @@ static int phase_value_grad(Ctx& c) {
   // target policy on next_state, eval mode (misc.py:28 / td3.py:73) (+ clipped noise, td3.py:74-78)
   RECNN_PROPAGATE(actor_hidden(c, a.target_policy.params, c.S2, false, 0, X0, X1));
   NoiseSpec nz = {td3 ? 1 : 0, a.noise, a.noise_clip, a.noise_std, a.seed, (const long long*)a.rng_step, 15u};
-  RECNN_PROPAGATE(linear_out(X1, H, a.target_policy.params + c.la.w3, a.target_policy.params + c.la.b3, A, c.n,
-                             0, &nz, a2, c.st));
+  const Seg x1s = {X1, H, H};
+  RECNN_PROPAGATE(linear_out(x1s, a.target_policy.params + c.la.w3, c.la.ld3, a.target_policy.params + c.la.b3, A,
+                             c.n, 0, &nz, a2, c.st));
   if (a.next_action_out)
     RECNN_CHECK_CUDA(cudaMemcpyAsync(a.next_action_out, a2, sizeof(float) * c.n * A, cudaMemcpyDeviceToDevice, c.st));
 
@@ -224,13 +327,13 @@ static int phase_value_grad(Ctx& c) {
     if (!a.learn) continue;
     float* G = a.value[i].grads;
     RECNN_REQUIRE(G != nullptr, "value net needs a grad arena when learn=1");
+    const Seg sc2 = {c2, H, H}, sc1 = {c1, H, H}, ss = {c.S, S, c.ldS}, sa = {c.ACT, A, A};
     // layer 3: dW3 = dq^T h2, db3 = sum dq ; dz2 = (dq w3) * gate(h2)
-    RECNN_PROPAGATE(weight_grad(c.ws.dq, 1, mat(c2, H), H, c.n, G + c.lc.w3, G + c.lc.b3, c.ws, c.st));
+    RECNN_PROPAGATE(weight_grad(c.ws.dq, 1, sc2, kNoSeg, c.n, G + c.lc.w3, c.lc.ld3, G + c.lc.b3, c.ws, c.st));
     RECNN_PROPAGATE(launch_critic_head_bwd(c.ws.dq, 0.f, P + c.lc.w3, c2, c.gate, dz2, c.n, H, c.st));
-    RECNN_PROPAGATE(weight_grad(dz2, H, mat(c1, H), H, c.n, G + c.lc.w2, G + c.lc.b2, c.ws, c.st));
-    RECNN_PROPAGATE(backprop_hidden(dz2, H, P + c.lc.w2, H, H, c.n, c1, c.gate, dz1, c.st));
-    RECNN_PROPAGATE(weight_grad(dz1, H, mat_cat(c.S, S, S, c.ACT, A), S + A, c.n, G + c.lc.w1, G + c.lc.b1,
-                                c.ws, c.st));
+    RECNN_PROPAGATE(weight_grad(dz2, H, sc1, kNoSeg, c.n, G + c.lc.w2, c.lc.ld2, G + c.lc.b2, c.ws, c.st));
+    RECNN_PROPAGATE(backprop_hidden(dz2, H, P + c.lc.w2, c.lc.ld2, H, 0, H, c.n, c1, c.gate, dz1, c.st));
+    RECNN_PROPAGATE(weight_grad(dz1, H, ss, sa, c.n, G + c.lc.w1, c.lc.ld1, G + c.lc.b1, c.ws, c.st));
   }
   return RECNN_OK;
 }
@@ -253,8 +356,9 @@ static int phase_policy_loss(Ctx& c) {
   float* gen = c.ws.ab[1];
   // gen_action = policy_net(state); policy_loss = -value_net(state, gen_action)  (ddpg.py:78-79, td3.py:116-118)
   RECNN_PROPAGATE(actor_hidden(c, a.policy.params, c.S, c.train, pm, p1, p2));
-  RECNN_PROPAGATE(linear_out(p2, H, a.policy.params + c.la.w3, a.policy.params + c.la.b3, A, c.n, 0, nullptr,
-                             gen, c.st));
+  const Seg sp2 = {p2, H, H};
+  RECNN_PROPAGATE(linear_out(sp2, a.policy.params + c.la.w3, c.la.ld3, a.policy.params + c.la.b3, A, c.n, 0,
+                             nullptr, gen, c.st));
   if (a.gen_action_out)
     RECNN_CHECK_CUDA(cudaMemcpyAsync(a.gen_action_out, gen, sizeof(float) * c.n * A, cudaMemcpyDeviceToDevice, c.st));
   RECNN_PROPAGATE(critic_hidden(c, a.value[0].params, c.S, gen, c.train, vm, v1, v2));
@@ -277,16 +381,17 @@ static int phase_policy_grad(Ctx& c) {
   const float dq = -1.0f / (float)a.n_rows_global;            // d(-mean q)/dq
   // through the critic, input-gradient only, and only the action slice of layer 1
   RECNN_PROPAGATE(launch_critic_head_bwd(nullptr, dq, Pc + c.lc.w3, v2, c.gate, dv2, c.n, H, c.st));
-  RECNN_PROPAGATE(backprop_hidden(dv2, H, Pc + c.lc.w2, H, H, c.n, v1, c.gate, dv1, c.st));
-  RECNN_PROPAGATE(backprop_hidden(dv1, H, Pc + c.lc.w1 + S, S + A, A, c.n, nullptr, 1.f, dgen, c.st));
+  RECNN_PROPAGATE(backprop_hidden(dv2, H, Pc + c.lc.w2, c.lc.ld2, H, 0, H, c.n, v1, c.gate, dv1, c.st));
+  RECNN_PROPAGATE(backprop_hidden(dv1, H, Pc + c.lc.w1, c.lc.ld1, S + A, S, A, c.n, nullptr, 1.f, dgen, c.st));
   // actor backward
-  RECNN_PROPAGATE(weight_grad(dgen, A, mat(p2, H), H, c.n, G + c.la.w3, G + c.la.b3, c.ws, c.st));
+  const Seg sp2 = {p2, H, H}, sp1 = {p1, H, H}, ss = {c.S, S, c.ldS};
+  RECNN_PROPAGATE(weight_grad(dgen, A, sp2, kNoSeg, c.n, G + c.la.w3, c.la.ld3, G + c.la.b3, c.ws, c.st));
   float* dp2 = dv2;   // dv2/dv1 are dead once dgen exists
   float* dp1 = dv1;
-  RECNN_PROPAGATE(backprop_hidden(dgen, A, Pa + c.la.w3, H, H, c.n, p2, c.gate, dp2, c.st));
-  RECNN_PROPAGATE(weight_grad(dp2, H, mat(p1, H), H, c.n, G + c.la.w2, G + c.la.b2, c.ws, c.st));
-  RECNN_PROPAGATE(backprop_hidden(dp2, H, Pa + c.la.w2, H, H, c.n, p1, c.gate, dp1, c.st));
-  RECNN_PROPAGATE(weight_grad(dp1, H, mat(c.S, S), S, c.n, G + c.la.w1, G + c.la.b1, c.ws, c.st));
+  RECNN_PROPAGATE(backprop_hidden(dgen, A, Pa + c.la.w3, c.la.ld3, H, 0, H, c.n, p2, c.gate, dp2, c.st));
+  RECNN_PROPAGATE(weight_grad(dp2, H, sp1, kNoSeg, c.n, G + c.la.w2, c.la.ld2, G + c.la.b2, c.ws, c.st));
+  RECNN_PROPAGATE(backprop_hidden(dp2, H, Pa + c.la.w2, c.la.ld2, H, 0, H, c.n, p1, c.gate, dp1, c.st));
+  RECNN_PROPAGATE(weight_grad(dp1, H, ss, kNoSeg, c.n, G + c.la.w1, c.la.ld1, G + c.la.b1, c.ws, c.st));
   return RECNN_OK;
 }
 
@@ -354,16 +459,29 @@ static int run_step(const recnn_step_args* a, int algo, void* stream) {
   c.train = a->dropout != 0;
   c.gate = c.train ? 2.0f : 1.0f;
   c.DONE = a->done;
+  c.ldS = pad4(c.d.state_dim);
+  const int S = c.d.state_dim;
   // tickets of the deterministic two-level reductions start at zero
   RECNN_CHECK_CUDA(cudaMemsetAsync(c.ws.tickets, 0, 8 * sizeof(unsigned), c.st));
+  // The step works on state / next_state images with a 16-byte-multiple row pitch (TMA); they are
+  // materialised into the workspace once per step (RECNN_PH_GATHER) from the frames or the dense batch.
+  c.S = c.ws.S;
+  c.S2 = c.ws.S2;
   if (frames) {
     if (a->phases & RECNN_PH_GATHER)
-    RECNN_PROPAGATE(recnn_frame_gather(a->table, a->n_items, a->emb_dim, a->items, a->ratings, c.n, a->frame,
-                                       c.ws.S, c.ws.S2, c.ws.ACT, c.ws.REW, nullptr, stream));
-    c.S = c.ws.S; c.S2 = c.ws.S2; c.ACT = c.ws.ACT;
+      RECNN_PROPAGATE(launch_frame_gather(a->table, a->n_items, a->emb_dim, a->items, a->ratings, c.n, a->frame,
+                                          c.ldS, c.ws.S, c.ws.S2, c.ws.ACT, c.ws.REW, nullptr, c.st));
+    c.ACT = c.ws.ACT;
     c.REW = a->reward ? a->reward : c.ws.REW;
   } else {
-    c.S = a->state; c.S2 = a->next_state; c.ACT = a->action; c.REW = a->reward;
+    if (a->phases & RECNN_PH_GATHER) {
+      RECNN_CHECK_CUDA(cudaMemcpy2DAsync(c.ws.S, c.ldS * 4, a->state, (size_t)S * 4, (size_t)S * 4, c.n,
+                                         cudaMemcpyDeviceToDevice, c.st));
+      RECNN_CHECK_CUDA(cudaMemcpy2DAsync(c.ws.S2, c.ldS * 4, a->next_state, (size_t)S * 4, (size_t)S * 4, c.n,
+                                         cudaMemcpyDeviceToDevice, c.st));
+    }
+    c.ACT = a->action;
+    c.REW = a->reward;
   }
   if (a->phases & RECNN_PH_VALUE_GRAD) RECNN_PROPAGATE(phase_value_grad(c));
   if (a->phases & RECNN_PH_VALUE_OPT) RECNN_PROPAGATE(phase_value_opt(c));
@@ -395,6 +513,16 @@ extern "C" int recnn_td3_step(const recnn_step_args* args, void* stream) {
 extern "C" int64_t recnn_actor_param_count(const recnn_dims* d) { return d ? actor_layout(*d).count : 0; }
 extern "C" int64_t recnn_critic_param_count(const recnn_dims* d) { return d ? critic_layout(*d).count : 0; }
 
+extern "C" int recnn_net_layout(const recnn_dims* d, int is_critic, int64_t* out) {
+  RECNN_REQUIRE(d && out, "null pointer");
+  const NetLayout l = is_critic ? critic_layout(*d) : actor_layout(*d);
+  const int64_t v[10] = {l.w1, l.b1, l.w2, l.b2, l.w3, l.b3, l.ld1, l.ld2, l.ld3, l.count};
+  for (int i = 0; i < 10; ++i) out[i] = v[i];
+  return RECNN_OK;
+}
+
+// Inference entry points take densely packed inputs ([n, S] / [n, A]); a row pitch that is not a
+// 16-byte multiple (S = 1290) sends layer 1 to the CUDA-core kernel, everything else to tcgen05.
 extern "C" int recnn_actor_forward(const recnn_dims* d, const float* params, const float* state, int64_t n_rows,
                                    const uint8_t* mask1, const uint8_t* mask2, int apply_tanh, float* action_out,
                                    float* scratch, void* stream) {
@@ -406,13 +534,12 @@ extern "C" int recnn_actor_forward(const recnn_dims* d, const float* params, con
   const int H = d->hidden;
   float* h1 = scratch;
   float* h2 = scratch + n_rows * H;
-  const uint8_t* masks[2] = {mask1, mask2};
-  Rng rng = {masks, 0, nullptr};
+  Rng rng = {nullptr, 0, nullptr};
   const bool train = mask1 != nullptr;
-  RECNN_PROPAGATE(hidden_layer(mat(state, d->state_dim), d->state_dim, params + l.w1, params + l.b1, H, n_rows,
-                               train, mask1, rng, 0, h1, st));
-  RECNN_PROPAGATE(hidden_layer(mat(h1, H), H, params + l.w2, params + l.b2, H, n_rows, train, mask2, rng, 1, h2, st));
-  return linear_out(h2, H, params + l.w3, params + l.b3, d->action_dim, n_rows, apply_tanh, nullptr, action_out, st);
+  const Seg xs = {state, d->state_dim, d->state_dim}, s1 = {h1, H, H}, s2 = {h2, H, H};
+  RECNN_PROPAGATE(hidden_layer(xs, kNoSeg, params + l.w1, l.ld1, params + l.b1, H, n_rows, train, mask1, rng, 0, h1, st));
+  RECNN_PROPAGATE(hidden_layer(s1, kNoSeg, params + l.w2, l.ld2, params + l.b2, H, n_rows, train, mask2, rng, 1, h2, st));
+  return linear_out(s2, params + l.w3, l.ld3, params + l.b3, d->action_dim, n_rows, apply_tanh, nullptr, action_out, st);
 }
 
 extern "C" int recnn_critic_forward(const recnn_dims* d, const float* params, const float* state,
@@ -426,12 +553,11 @@ extern "C" int recnn_critic_forward(const recnn_dims* d, const float* params, co
   const int H = d->hidden, S = d->state_dim, A = d->action_dim;
   float* h1 = scratch;
   float* h2 = scratch + n_rows * H;
-  const uint8_t* masks[2] = {mask1, mask2};
-  Rng rng = {masks, 0, nullptr};
+  Rng rng = {nullptr, 0, nullptr};
   const bool train = mask1 != nullptr;
-  RECNN_PROPAGATE(hidden_layer(mat_cat(state, S, S, action, A), S + A, params + l.w1, params + l.b1, H, n_rows,
-                               train, mask1, rng, 0, h1, st));
-  RECNN_PROPAGATE(hidden_layer(mat(h1, H), H, params + l.w2, params + l.b2, H, n_rows, train, mask2, rng, 1, h2, st));
+  const Seg xs = {state, S, S}, xa = {action, A, A}, s1 = {h1, H, H};
+  RECNN_PROPAGATE(hidden_layer(xs, xa, params + l.w1, l.ld1, params + l.b1, H, n_rows, train, mask1, rng, 0, h1, st));
+  RECNN_PROPAGATE(hidden_layer(s1, kNoSeg, params + l.w2, l.ld2, params + l.b2, H, n_rows, train, mask2, rng, 1, h2, st));
   HeadArgs h;
   h.h2 = h2; h.w3 = params + l.w3; h.b3 = params + l.b3; h.n_rows = n_rows; h.n_rows_global = n_rows;
   h.hidden = H; h.mode = HEAD_PLAIN; h.reward = nullptr; h.done = nullptr; h.gamma = 0; h.min_value = 0;
@@ -446,9 +572,10 @@ extern "C" int recnn_linear_forward(const float* x, int64_t n_rows, int in_dim, 
   RECNN_REQUIRE(in_dim > 0 && out_dim > 0 && n_rows >= 0, "sizes");
   if (n_rows == 0) return RECNN_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const Seg xs = {x, in_dim, in_dim};
   if (relu) {
     Rng rng = {nullptr, 0, nullptr};
-    return hidden_layer(mat(x, in_dim), in_dim, weight, bias, out_dim, n_rows, false, nullptr, rng, 0, out, st);
+    return hidden_layer(xs, kNoSeg, weight, in_dim, bias, out_dim, n_rows, false, nullptr, rng, 0, out, st);
   }
-  return linear_out(x, in_dim, weight, bias, out_dim, n_rows, 0, nullptr, out, st);
+  return linear_out(xs, weight, in_dim, bias, out_dim, n_rows, 0, nullptr, out, st);
 }

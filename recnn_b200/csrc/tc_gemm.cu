@@ -52,6 +52,13 @@ int make_tmap(CUtensorMap* out, const float* base, int64_t rows, int64_t cols, i
   return RECNN_OK;
 }
 
+int split_plan(int K_total_blocks, int splits_req, int* k_chunk) {
+  if (splits_req < 1) splits_req = 1;
+  const int kb_per = (int)ceil_div(K_total_blocks, splits_req);
+  *k_chunk = kb_per * 16;
+  return (int)ceil_div(K_total_blocks, kb_per);
+}
+
 template <class C, int EPI>
 static int launch_cfg(const Operand& A0, const Operand& A1, const Operand& B, const Problem& p_in, int splits,
                       const Epilogue& epi, cudaStream_t st) {
@@ -63,10 +70,7 @@ static int launch_cfg(const Operand& A0, const Operand& A1, const Operand& B, co
     attr_set = true;
   }
   const int nkb = (int)(ceil_div(p.K0, C::BK) + ceil_div(p.K1, C::BK));
-  if (splits < 1) splits = 1;
-  const int kb_per = (int)ceil_div(nkb, splits);
-  p.k_chunk = kb_per * C::BK;
-  splits = (int)ceil_div(nkb, kb_per);
+  splits = split_plan(nkb, splits, &p.k_chunk);
   CUtensorMap ma0, ma1, mb;
   // K-major operand: tensor [rows = M|N, cols = K], box {BK, tile rows}; MN-major: tensor [rows = K, cols = M|N], box {32, BK}
   if (!C::A_MN) {
@@ -90,9 +94,9 @@ template <bool A_MN, bool B_MN, int EPI>
 int launch(const Operand& A0, const Operand& A1, const Operand& B, const Problem& p, int splits, int bn,
            const Epilogue& epi, cudaStream_t st) {
   // stages chosen to fill ~190 KB of shared memory
-  if (bn >= 256) return launch_cfg<Cfg<256, 16, 4, A_MN, B_MN>, EPI>(A0, A1, B, p, splits, epi, st);
-  if (bn >= 128) return launch_cfg<Cfg<128, 16, 6, A_MN, B_MN>, EPI>(A0, A1, B, p, splits, epi, st);
-  return launch_cfg<Cfg<64, 16, 8, A_MN, B_MN>, EPI>(A0, A1, B, p, splits, epi, st);
+  if (bn >= 256) return launch_cfg<Cfg<256, 4, A_MN, B_MN>, EPI>(A0, A1, B, p, splits, epi, st);
+  if (bn >= 128) return launch_cfg<Cfg<128, 6, A_MN, B_MN>, EPI>(A0, A1, B, p, splits, epi, st);
+  return launch_cfg<Cfg<64, 8, A_MN, B_MN>, EPI>(A0, A1, B, p, splits, epi, st);
 }
 
 // explicit instantiations used by step.cu / the generic entry points
@@ -106,6 +110,7 @@ RECNN_TC_INST(false, true, EPI_STORE)
 RECNN_TC_INST(false, true, EPI_GATE)
 RECNN_TC_INST(true, true, EPI_STORE)
 RECNN_TC_INST(true, true, EPI_PARTIAL)
+RECNN_TC_INST(false, false, EPI_PARTIAL)
 RECNN_TC_INST(true, false, EPI_STORE)
 
 }  // namespace tc
@@ -127,7 +132,7 @@ extern "C" int recnn_gemm_tf32x3(int M, int N, int K, const float* A, int64_t ld
   e.ldo = ldc;
   tc::Operand a0 = {A, lda, 0, 0}, a1 = {nullptr, 0, 0, 0};
   tc::Operand b = {B, ldb, b_mn ? K : N, b_mn ? N : K};
-  tc::Problem p = {M, N, K, 0, 0, K, 0};
+  tc::Problem p = {M, N, K, 0, 0, K, 0, 0};
   if (tile_n <= 0) tile_n = N > 128 ? 256 : (N > 64 ? 128 : 64);
   int r;
   if (!a_mn && !b_mn) r = tc::launch<false, false, EPI_STORE>(a0, a1, b, p, 1, tile_n, e, st);

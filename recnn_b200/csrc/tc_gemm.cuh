@@ -1,28 +1,33 @@
 // tcgen05 (5th-gen tensor core) GEMM with fp32-grade accuracy: error-compensated
-// 3xTF32, accumulators in TMEM, operands staged by TMA, sm_100a only.
+// 3xTF32, operands staged by TMA, chunked accumulation in TMEM, sm_100a only.
 //
 //   C[m,n] = sum_k A(m,k) * B(n,k)            (+ fused epilogue)
 //
 // Why 3xTF32: the parity bar is the reference's fp32 CPU result to 1e-5
 // (BASELINE.json north_star); one TF32 pass has a 10-bit mantissa (~1e-3).  Each
 // fp32 operand x is split into  hi = x with the low 13 mantissa bits cleared
-// (what kind::tf32 reads from a raw fp32 word -- verified on device by
-// tests/test_gpu_tc.py::test_tf32_operand_truncation) and  lo = rna_tf32(x - hi)
-// (exact subtraction, then round-to-nearest).  Three MMAs per k-slice
-//   lo_a*hi_b + hi_a*lo_b + hi_a*hi_b
-// accumulate in fp32 in TMEM; the dropped lo*lo term is < 2^-20 relative.
+// (exactly what kind::tf32 reads from a raw fp32 word: measured on the device,
+// tests/test_gpu_tc.py) and  lo = rna_tf32(x - hi)  (exact subtraction, then
+// round-to-nearest).  Three MMAs per 8-wide k-slice,  lo_a*hi_b + hi_a*lo_b + hi_a*hi_b,
+// accumulate in TMEM; the dropped lo*lo term is < 2^-20 relative.
 //
-// Pipeline (one 128 x BN output tile per CTA, 192 threads):
-//   warp 0      TMA producer: raw fp32 tiles of A and B -> smem stage s        (full[s])
-//   warps 2-5   splitter: read raw tile, write the `lo` tile next to it         (split[s])
-//               (the raw tile itself is the `hi` operand; nothing is rewritten)
-//   warp 1      MMA issuer (one lane): 3 x BK/8 tcgen05.mma per stage, then
-//               tcgen05.commit -> empty[s]; after the last k-block -> accum_full
-//   warps 2-5   epilogue: tcgen05.ld the accumulator (warp w owns TMEM lanes
-//               32*(w%4)..), apply bias/relu/dropout/..., store.
-// Operand layouts in smem are the canonical UMMA layouts written by TMA with
-// hardware swizzle, so the splitter is swizzle-agnostic (same offset in the
-// `lo` buffer) and the same smem descriptors serve hi and lo.
+// Why chunked accumulation: the tensor core's fp32 accumulate TRUNCATES (measured:
+// all-positive operands lose 2.2e-8 of the sum per unit of K, i.e. -2.8e-5 at K=1290).
+// So a TMEM accumulator only ever sums CH k-blocks (K = 64): after each chunk the
+// worker warps pull it out with tcgen05.ld and add it to a register-resident running
+// sum with round-to-nearest FADDs, while the tensor core fills the other TMEM buffer.
+//
+// Warp roles (one 128 x BN output tile per CTA; BN=256 -> 10 warps):
+//   warp 0        TMA producer: raw fp32 tiles of A and B -> smem stage s             (full[s])
+//   warp 1        MMA issuer (one lane): per stage 3 x BK/8 tcgen05.mma, commit -> empty[s];
+//                 per chunk commit -> acc_full[buf]
+//   workers       4 per 128 columns.  (1) splitter: read the raw stage with ld.shared, write the
+//                 `lo` tile next to it (the raw tile itself is the `hi` operand)       (split[s])
+//                 (2) drain: TMEM chunk -> registers, running sum += chunk             (acc_empty[buf])
+//                 (3) epilogue on the register-resident row (bias/relu/dropout/...), store.
+// Operand tiles in smem are the canonical UMMA layouts written by TMA with hardware
+// swizzle, so the splitter is swizzle-agnostic (same offset in the `lo` buffer) and the
+// same smem descriptors serve hi and lo.
 #pragma once
 #include <cuda.h>
 
@@ -36,35 +41,35 @@ namespace tc {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.b32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(bar), "r"(parity)
       : "memory");
   return ok != 0;
 }
 // Bounded wait: a pipeline bug must not hang the GPU (a wedged box costs a whole lease), so
 // after ~2 s of polling the kernel traps and the launch surfaces as a CUDA error instead.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000ll) {
-      printf("recnn_b200: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z,
-             threadIdx.x);
+      printf("recnn_b200: mbarrier wait timed out (block %d,%d,%d thread %d bar %u)\n", blockIdx.x, blockIdx.y,
+             blockIdx.z, threadIdx.x, bar);
       __trap();
     }
   }
@@ -78,14 +83,14 @@ __device__ __forceinline__ void fence_proxy_async() {
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
                : "memory");
 }
 __device__ __forceinline__ void tmem_relinquish() {
@@ -106,9 +111,8 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint6
       : "memory");
 }
 // arrives on `bar` once every tcgen05.mma issued so far by this thread has completed
-__device__ __forceinline__ void mma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -123,6 +127,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
 
 __device__ __forceinline__ float tf32_lo(float x) {
   // x = hi + lo exactly, hi = x with the low 13 mantissa bits cleared; return rna_tf32(lo)
@@ -150,57 +163,147 @@ struct Problem {
   int k_chunk;           // k extent per split (multiple of BK), split index = blockIdx.z
   int b_k1_offset;       // B's k coordinate where the K1 segment starts (== K0 for a dense weight)
   int n_out_offset;      // column offset added when storing (C window)
+  int b_n_offset;        // B's n coordinate of output column 0 (window into a wider B, e.g. W1[:, S:S+A])
 };
 
-template <int BN_, int BK_, int STAGES_, bool A_MN_, bool B_MN_>
+template <int BN_, int STAGES_, bool A_MN_, bool B_MN_>
 struct Cfg {
-  static constexpr int BM = 128, BN = BN_, BK = BK_, STAGES = STAGES_;
+  static constexpr int BM = 128, BN = BN_, BK = 16, STAGES = STAGES_;
+  static constexpr int CH = 4;                                     // k-blocks per TMEM accumulation chunk (K = 64)
   static constexpr bool A_MN = A_MN_, B_MN = B_MN_;
   static constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);      // raw + lo
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-  static constexpr int THREADS = 192;
-  // K-major operand: rows of BK*4 bytes, swizzle span == row; MN-major: 128-byte rows of 32 elements
-  static constexpr int K_SWZ = BK * 4;                              // 64 or 128
-  static_assert(BK == 16 || BK == 32, "BK");
+  static constexpr int COLS_PER_WORKER = BN >= 128 ? 128 : BN;     // register-resident running sum per thread
+  static constexpr int WORKERS = 4 * (BN / COLS_PER_WORKER);       // warps
+  static constexpr int THREADS = 64 + 32 * WORKERS;
+  static constexpr int TMEM_COLS = 2 * BN;                         // double-buffered chunk accumulator (>= 128)
+  static constexpr int K_SWZ = BK * 4;                             // K-major rows: 64 B, SWIZZLE_64B
   static_assert(BN == 64 || BN == 128 || BN == 256, "BN");
   static_assert(SMEM_BYTES <= 227 * 1024, "smem");
 };
+
+// ------------------------------------------------------------------ epilogue on a register-resident row
+// acc[j] is C[m, nb + j] for j < NC.  Stores 16 bytes at a time when the destination allows it.
+template <int EPI, int NC>
+__device__ __forceinline__ void epilogue_row(const Epilogue& e, const Problem& p, int m, int nb, int z,
+                                             float (&acc)[NC]) {
+  const int N = p.N;
+  if (m >= p.M) return;
+  float* out_row;
+  if (EPI == EPI_PARTIAL) out_row = e.out + ((long long)z * p.M + m) * e.ldo + p.n_out_offset;
+  else out_row = e.out + (long long)m * e.ldo + p.n_out_offset;
+#pragma unroll
+  for (int j0 = 0; j0 < NC; j0 += 32) {
+    if (nb + j0 < N) {
+      uint32_t keep_bits = 0xFFFFFFFFu;
+      if (EPI == EPI_HIDDEN && e.train) {
+        if (e.mask) {
+          keep_bits = 0;
+          const uint8_t* mrow = e.mask + (long long)m * N + nb + j0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nb + j0 + j < N && mrow[j]) keep_bits |= 1u << j;
+        } else {
+          // same stream as the CUDA-core path: bit (idx & 31) of word idx >> 5, idx = m*N + n
+          const unsigned long long idx = (unsigned long long)m * N + nb + j0;
+          if ((idx & 31) == 0) {
+            keep_bits = philox_keep_bits32(e.seed, (unsigned long long)*e.rng_step, e.stream_id, idx >> 5);
+          } else {
+            keep_bits = 0;
+#pragma unroll 1
+            for (int j = 0; j < 32; ++j) {
+              const unsigned long long ij = idx + j;
+              const uint32_t w = philox_keep_bits32(e.seed, (unsigned long long)*e.rng_step, e.stream_id, ij >> 5);
+              keep_bits |= ((w >> (ij & 31)) & 1u) << j;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int j4 = 0; j4 < 32; j4 += 4) {
+        const int n = nb + j0 + j4;
+        if (n < N) {
+          float v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float x = acc[j0 + j4 + u];
+            const int nn = n + u;
+            if (nn < N) {
+              if (EPI == EPI_HIDDEN) {
+                x = fmaxf(x + __ldg(e.bias + nn), 0.f);
+                if (e.train) x = ((keep_bits >> (j4 + u)) & 1u) ? x * 2.0f : 0.f;
+              } else if (EPI == EPI_LINEAR) {
+                x = x + __ldg(e.bias + nn);
+                if (e.apply_tanh) x = tanhf(x);
+                if (e.add_noise) {
+                  float z0;
+                  if (e.noise) z0 = e.noise[(long long)m * N + nn];
+                  else {
+                    const unsigned long long idx = (unsigned long long)m * N + nn;
+                    Philox ph(e.seed);
+                    const uint4 r = ph(idx, ((unsigned long long)*e.rng_step << 8) | e.stream_id);
+                    const float u1 = (r.x + 1.0f) * 2.3283064365386963e-10f;
+                    const float u2 = r.y * 2.3283064365386963e-10f;
+                    z0 = sqrtf(-2.0f * __logf(u1)) * __cosf(6.283185307179586f * u2) * e.noise_std;
+                  }
+                  x += fminf(fmaxf(z0, -e.noise_clip), e.noise_clip);
+                }
+              } else if (EPI == EPI_GATE) {
+                x = e.h[(long long)m * e.ldh + nn] > 0.f ? x * e.gate_scale : 0.f;
+              }
+            }
+            v[u] = x;
+          }
+          float* dst = out_row + n;
+          if (n + 3 < N && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+          } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (n + u < N) dst[u] = v[u];
+          }
+        }
+      }
+    }
+  }
+}
 
 // ------------------------------------------------------------------ the kernel
 template <class C, int EPI>
 __global__ void __launch_bounds__(C::THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_b, Problem p, Epilogue epi) {
-  constexpr int BM = C::BM, BN = C::BN, BK = C::BK, STAGES = C::STAGES;
+  constexpr int BM = C::BM, BN = C::BN, BK = C::BK, STAGES = C::STAGES, CH = C::CH;
+  constexpr int NC = C::COLS_PER_WORKER, WORKERS = C::WORKERS;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  auto stage_ptr = [&](int s, int which) {   // 0 rawA, 1 rawB, 2 loA, 3 loB
-    uint8_t* base = smem + (size_t)s * C::STAGE_BYTES;
-    switch (which) {
-      case 0: return base;
-      case 1: return base + C::A_BYTES;
-      case 2: return base + C::A_BYTES + C::B_BYTES;
-      default: return base + 2 * C::A_BYTES + C::B_BYTES;
-    }
+  const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;       // shared-window address, 1 KB aligned
+  auto stage_addr = [&](int s, int which) -> uint32_t {              // 0 rawA, 1 rawB, 2 loA, 3 loB
+    const uint32_t base = smem + (uint32_t)s * C::STAGE_BYTES;
+    return which == 0 ? base
+         : which == 1 ? base + C::A_BYTES
+         : which == 2 ? base + C::A_BYTES + C::B_BYTES
+                      : base + 2 * C::A_BYTES + C::B_BYTES;
   };
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * C::STAGE_BYTES);
-  uint64_t* full = bars;                    // [STAGES] TMA -> splitter
-  uint64_t* split = bars + STAGES;          // [STAGES] splitter -> MMA
-  uint64_t* empty = bars + 2 * STAGES;      // [STAGES] MMA -> TMA
-  uint64_t* accum_full = bars + 3 * STAGES; // MMA -> epilogue
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
+  const uint32_t bars = smem + (uint32_t)STAGES * C::STAGE_BYTES;
+  auto full = [&](int s) { return bars + 8u * s; };                   // TMA -> workers
+  auto split = [&](int s) { return bars + 8u * (STAGES + s); };       // workers -> MMA
+  auto empty = [&](int s) { return bars + 8u * (2 * STAGES + s); };   // MMA -> TMA
+  auto acc_full = [&](int b) { return bars + 8u * (3 * STAGES + b); };       // MMA -> workers
+  auto acc_empty = [&](int b) { return bars + 8u * (3 * STAGES + 2 + b); };  // workers -> MMA
+  const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 4);
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM, z = blockIdx.z;
-  const int K = p.K0 + p.K1;
   // k-blocks: segment 0 then segment 1, each padded up to a multiple of BK (TMA zero-fills the tail)
   const int nkb0 = (p.K0 + BK - 1) / BK, nkb1 = (p.K1 + BK - 1) / BK;
   const int kb_per_split = p.k_chunk / BK;
   const int kb_begin = z * kb_per_split;
   const int kb_end = min(nkb0 + nkb1, kb_begin + kb_per_split);
   const int num_kb = max(kb_end - kb_begin, 0);
-  (void)K;
+  const int num_chunks = (num_kb + CH - 1) / CH;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a0);
@@ -209,21 +312,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&split[s], 4);      // one arrive per splitter warp
-      mbar_init(&empty[s], 1);
+      mbar_init(full(s), 1);
+      mbar_init(split(s), WORKERS);      // one arrive per worker warp
+      mbar_init(empty(s), 1);
     }
-    mbar_init(accum_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(acc_full(b), 1);
+      mbar_init(acc_empty(b), WORKERS);
+    }
     fence_barrier_init();
   }
-  if (warp == 1) {                  // whole warp: TMEM allocation (BN fp32 columns)
-    tmem_alloc(tmem_slot, BN);
+  if (warp == 1) {                       // whole warp: TMEM allocation
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = *tmem_slot_gen;
 
   if (warp == 0) {
     // ===================================================== TMA producer
@@ -231,28 +337,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       for (int i = 0; i < num_kb; ++i) {
         const int s = i % STAGES;
         const uint32_t ph = (i / STAGES) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        mbar_expect_tx(&full[s], C::A_BYTES + C::B_BYTES);
+        mbar_wait(empty(s), ph ^ 1);
+        mbar_expect_tx(full(s), C::A_BYTES + C::B_BYTES);
         const int kb = kb_begin + i;
         const bool seg1 = kb >= nkb0;
-        const int ka = seg1 ? (kb - nkb0) * BK : kb * BK;                   // k coordinate inside A's segment
+        const int ka = seg1 ? (kb - nkb0) * BK : kb * BK;                     // k coordinate inside A's segment
         const int kbcol = seg1 ? p.b_k1_offset + (kb - nkb0) * BK : kb * BK;  // k coordinate in B
         const CUtensorMap* ma = seg1 ? &map_a1 : &map_a0;
-        uint8_t* dst_a = stage_ptr(s, 0);
-        uint8_t* dst_b = stage_ptr(s, 1);
+        const uint32_t dst_a = stage_addr(s, 0), dst_b = stage_addr(s, 1);
         if (!C::A_MN) {
-          tma_load_2d(dst_a, ma, &full[s], ka, m0);                         // box {BK, 128}
+          tma_load_2d(dst_a, ma, full(s), ka, m0);                            // box {BK, 128}
         } else {
 #pragma unroll
-          for (int c = 0; c < BM / 32; ++c)                                 // box {32, BK} per 32-wide M chunk
-            tma_load_2d(dst_a + c * (BK * 128), ma, &full[s], m0 + 32 * c, ka);
+          for (int c = 0; c < BM / 32; ++c)                                   // box {32, BK} per 32-wide M chunk
+            tma_load_2d(dst_a + c * (BK * 128), ma, full(s), m0 + 32 * c, ka);
         }
         if (!C::B_MN) {
-          tma_load_2d(dst_b, &map_b, &full[s], kbcol, n0);                  // box {BK, BN}
+          tma_load_2d(dst_b, &map_b, full(s), kbcol, p.b_n_offset + n0);      // box {BK, BN}
         } else {
 #pragma unroll
           for (int c = 0; c < BN / 32; ++c)
-            tma_load_2d(dst_b + c * (BK * 128), &map_b, &full[s], n0 + 32 * c, kbcol);
+            tma_load_2d(dst_b + c * (BK * 128), &map_b, full(s), p.b_n_offset + n0 + 32 * c, kbcol);
         }
       }
     }
@@ -260,85 +365,99 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     // ===================================================== MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = instr_desc_tf32(BM, BN, C::A_MN, C::B_MN);
-      // K-major: LBO unused (1), SBO = 8 rows * swizzle span.  MN-major: LBO = chunk stride, SBO = 1024.
       // K-major: rows of K_SWZ bytes, LBO unused (1), SBO = 8 rows.  MN-major fp32/tf32 operands must
       // use the 128B_BASE32B layout (cute: "for mn-major tf32 operands, SW128_32B is the only available
       // smem layout"): 128-byte rows of 32 MN elements, swizzle period 4 k-rows => SBO = 512 B between
       // 4-row groups, LBO = pitch between 32-element MN chunks (BK rows * 128 B).
-      constexpr uint64_t a_base = C::A_MN ? smem_desc_base(BK * 128, 512, 1)
-                                          : smem_desc_base(16, 8 * C::K_SWZ, C::K_SWZ == 128 ? 2 : 4);
-      constexpr uint64_t b_base = C::B_MN ? smem_desc_base(BK * 128, 512, 1)
-                                          : smem_desc_base(16, 8 * C::K_SWZ, C::K_SWZ == 128 ? 2 : 4);
+      constexpr uint64_t a_base = C::A_MN ? smem_desc_base(BK * 128, 512, 1) : smem_desc_base(16, 8 * C::K_SWZ, 4);
+      constexpr uint64_t b_base = C::B_MN ? smem_desc_base(BK * 128, 512, 1) : smem_desc_base(16, 8 * C::K_SWZ, 4);
       constexpr uint32_t a_kstep = C::A_MN ? 1024 : 32;     // bytes to advance per 8-wide k-slice
       constexpr uint32_t b_kstep = C::B_MN ? 1024 : 32;
       for (int i = 0; i < num_kb; ++i) {
         const int s = i % STAGES;
         const uint32_t ph = (i / STAGES) & 1;
-        mbar_wait(&split[s], ph);
+        const int chunk = i / CH, buf = chunk & 1;
+        if (i % CH == 0) {                                   // new chunk: its TMEM buffer must have been drained
+          mbar_wait(acc_empty(buf), ((chunk >> 1) & 1) ^ 1);
+          tc_fence_after();
+        }
+        mbar_wait(split(s), ph);
         tc_fence_after();
-        const uint32_t a_hi = smem_u32(stage_ptr(s, 0)), b_hi = smem_u32(stage_ptr(s, 1));
-        const uint32_t a_lo = smem_u32(stage_ptr(s, 2)), b_lo = smem_u32(stage_ptr(s, 3));
+        const uint32_t d_tmem = tmem_base + (uint32_t)buf * BN;
+        const uint32_t a_hi = stage_addr(s, 0), b_hi = stage_addr(s, 1);
+        const uint32_t a_lo = stage_addr(s, 2), b_lo = stage_addr(s, 3);
 #pragma unroll
         for (int k = 0; k < BK / 8; ++k) {
           const uint64_t da_hi = a_base | uint64_t(((a_hi + k * a_kstep) & 0x3FFFF) >> 4);
           const uint64_t da_lo = a_base | uint64_t(((a_lo + k * a_kstep) & 0x3FFFF) >> 4);
           const uint64_t db_hi = b_base | uint64_t(((b_hi + k * b_kstep) & 0x3FFFF) >> 4);
           const uint64_t db_lo = b_base | uint64_t(((b_lo + k * b_kstep) & 0x3FFFF) >> 4);
-          mma_tf32(tmem_base, da_lo, db_hi, idesc, (i | k) != 0);   // small terms first
-          mma_tf32(tmem_base, da_hi, db_lo, idesc, 1);
-          mma_tf32(tmem_base, da_hi, db_hi, idesc, 1);
+          mma_tf32(d_tmem, da_lo, db_hi, idesc, ((i % CH) | k) != 0);   // small terms first
+          mma_tf32(d_tmem, da_hi, db_lo, idesc, 1);
+          mma_tf32(d_tmem, da_hi, db_hi, idesc, 1);
         }
-        mma_commit(&empty[s]);          // frees the stage once these MMAs have read it
+        mma_commit(empty(s));                                // frees the stage once these MMAs have read it
+        if (i % CH == CH - 1 || i == num_kb - 1) mma_commit(acc_full(buf));
       }
-      mma_commit(accum_full);
     }
   } else {
-    // ===================================================== splitter (warps 2..5), then epilogue
-    const int t = threadIdx.x - 64;     // 0..127
+    // ===================================================== workers: split, drain, epilogue
+    const int w = warp - 2;                  // 0 .. WORKERS-1
+    const int q = warp & 3;                  // TMEM lane quarter this warp may access
+    const int col_group = w >> 2;            // which NC-column slab of the tile this warp owns
+    const int t = threadIdx.x - 64;
+    constexpr int NT = 32 * WORKERS;
     constexpr int VEC_PER_STAGE = (C::A_BYTES + C::B_BYTES) / 16;
+    constexpr int VEC_PER_THREAD = VEC_PER_STAGE / NT;
+    static_assert(VEC_PER_STAGE % NT == 0, "stage must split evenly over the worker threads");
+    float acc[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) acc[j] = 0.f;
+    const uint32_t lane_base = tmem_base + (uint32_t(32 * q) << 16) + (uint32_t)col_group * NC;
+
+    auto drain = [&](int chunk) {
+      const int buf = chunk & 1;
+      mbar_wait(acc_full(buf), (chunk >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < NC; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(lane_base + (uint32_t)buf * BN + c0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[c0 + j] = __fadd_rn(acc[c0 + j], __uint_as_float(r[j]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(buf));
+    };
+
     for (int i = 0; i < num_kb; ++i) {
       const int s = i % STAGES;
       const uint32_t ph = (i / STAGES) & 1;
-      mbar_wait(&full[s], ph);
-      const float4* raw = reinterpret_cast<const float4*>(stage_ptr(s, 0));      // rawA|rawB contiguous
-      float4* lo = reinterpret_cast<float4*>(stage_ptr(s, 2));                   // loA|loB contiguous
-#pragma unroll 4
-      for (int v = t; v < VEC_PER_STAGE; v += 128) {
-        const float4 x = raw[v];
-        lo[v] = make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
-      }
+      mbar_wait(full(s), ph);
+      const uint32_t raw = stage_addr(s, 0);                  // rawA|rawB contiguous
+      const uint32_t lo = stage_addr(s, 2);                   // loA|loB contiguous
+      float4 x[VEC_PER_THREAD];
+#pragma unroll
+      for (int v = 0; v < VEC_PER_THREAD; ++v) x[v] = lds128(raw + 16u * (t + v * NT));
+#pragma unroll
+      for (int v = 0; v < VEC_PER_THREAD; ++v)
+        sts128(lo + 16u * (t + v * NT),
+               make_float4(tf32_lo(x[v].x), tf32_lo(x[v].y), tf32_lo(x[v].z), tf32_lo(x[v].w)));
       fence_proxy_async();              // generic-proxy writes -> visible to the tensor core (async proxy)
       __syncwarp();
-      if (lane == 0) mbar_arrive(&split[s]);
+      if (lane == 0) mbar_arrive(split(s));
+      // once the last k-block of chunk c has been split, chunk c-1 has long been accumulated: drain it
+      if (i % CH == CH - 1 && i / CH >= 1) drain(i / CH - 1);
     }
-    // ---- epilogue: this warp may touch TMEM lanes 32*(warp%4) .. +31
-    mbar_wait(accum_full, 0);
-    tc_fence_after();
-    const int q = warp & 3;
-    const int m = m0 + 32 * q + lane;
-    const uint32_t lane_base = tmem_base + (uint32_t(32 * q) << 16);
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      if (num_kb > 0) {
-        tmem_ld32(lane_base + c0, r);
-        tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = 0u;
-      }
-      if (m < p.M) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int n = n0 + c0 + j;
-          if (n < p.N) epi_store<EPI>(epi, p.M, p.N, m, n + p.n_out_offset, __uint_as_float(r[j]), z);
-        }
-      }
-    }
+    // chunks not drained inside the loop: the last full one (and a trailing partial one)
+    for (int c = max(num_kb / CH - 1, 0); c < num_chunks; ++c) drain(c);
+    epilogue_row<EPI, NC>(epi, p, m0 + 32 * q + lane, n0 + col_group * NC, z, acc);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, BN);
+  if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
 // ------------------------------------------------------------------ host side
@@ -362,6 +481,9 @@ struct Operand {
   long long ld;
   long long rows, cols;
 };
+
+// k-blocks (of 16) per split and the effective split count for a requested split count.
+int split_plan(int K_total_blocks, int splits_req, int* k_chunk);
 
 // Launch one GEMM.  Returns the effective number of k-splits (> 0) or a negative RECNN_E_* code.
 template <bool A_MN, bool B_MN, int EPI>

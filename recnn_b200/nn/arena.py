@@ -1,17 +1,23 @@
 """Flat parameter / gradient arenas behind Actor and Critic.
 
-The CUDA kernels address a net as ONE contiguous fp32 buffer in
-``nn.Module.parameters()`` order (include/recnn_b200.h, "net").  The modules keep
-ordinary ``nn.Parameter`` objects -- ``state_dict`` keys linear{1,2,3}.{weight,bias}
-stay loadable (examples/streamlit_demo.py:152-160 in the reference) and external
-torch optimizers keep working -- but their storage is a view into the arena.
+The CUDA kernels address a net as ONE fp32 buffer in ``nn.Module.parameters()`` order
+(include/recnn_b200.h, "net") whose matrix rows are padded to 16-byte multiples so that
+every weight is a legal TMA tensor (linear1.weight of the Actor: [256, 1290] with row
+pitch 1292).  The modules keep ordinary ``nn.Parameter`` objects -- ``state_dict`` keys
+linear{1,2,3}.{weight,bias} stay loadable (examples/streamlit_demo.py:152-160 in the
+reference) and external torch optimizers keep working -- but their storage is a (possibly
+strided) view into the arena; pad elements are zero and stay zero.
 ``module.to(device)``, ``load_state_dict`` into fresh tensors or
 ``zero_grad(set_to_none=True)`` can break that aliasing, so every kernel entry
 re-validates it (a few pointer compares) and rebuilds the arena if needed.
 """
 from __future__ import annotations
 
+import ctypes
+
 import torch
+
+from .. import _lib
 
 
 def _params(module):
@@ -19,54 +25,76 @@ def _params(module):
             module.linear3.weight, module.linear3.bias]
 
 
-def _is_view_of(flat, tensors):
+def net_layout(module):
+    """(offsets[6], pitches[3], count) of this module's arena, from the C library."""
+    s = module.linear1.in_features
+    h = module.linear1.out_features
+    out = module.linear3.out_features
+    is_critic = out == 1 and hasattr(module, "_action_dim")
+    if is_critic:
+        a = module._action_dim
+        dims = _lib.Dims(s - a, a, h, 0)
+    else:
+        is_critic = False
+        dims = _lib.Dims(s, out, h, 0)
+    buf = (ctypes.c_int64 * 10)()
+    _lib.check(_lib.lib().recnn_net_layout(dims, int(is_critic), buf))
+    v = list(buf)
+    return v[0:6], v[6:9], v[9]
+
+
+def _views(flat, module):
+    offs, lds, _ = net_layout(module)
+    ps = _params(module)
+    out = []
+    for i, p in enumerate(ps):
+        if p.dim() == 2:
+            rows, cols = p.shape
+            ld = lds[i // 2]
+            out.append(flat[offs[i]: offs[i] + rows * ld].view(rows, ld)[:, :cols])
+        else:
+            out.append(flat[offs[i]: offs[i] + p.numel()])
+    return out
+
+
+def _aliases(flat, module, tensors):
     if flat is None:
         return False
-    off = 0
-    base = flat.data_ptr()
-    for t in tensors:
-        if t is None or t.device != flat.device or t.dtype != torch.float32 or not t.is_contiguous():
+    for view, t in zip(_views(flat, module), tensors):
+        if t is None or t.device != flat.device or t.dtype != torch.float32:
             return False
-        if t.data_ptr() != base + 4 * off:
+        if t.data_ptr() != view.data_ptr() or t.stride() != view.stride() or t.shape != view.shape:
             return False
-        off += t.numel()
-    return off == flat.numel()
+    return True
 
 
 def param_arena(module) -> torch.Tensor:
-    """Flat fp32 view of all parameters of ``module`` (rebuilt if aliasing broke)."""
+    """Flat fp32 arena holding all parameters of ``module`` (rebuilt if aliasing broke)."""
     ps = _params(module)
     flat = getattr(module, "_recnn_flat", None)
-    if _is_view_of(flat, [p.data for p in ps]):
+    if flat is not None and flat.device == ps[0].device and _aliases(flat, module, [p.data for p in ps]):
         return flat
     dev = ps[0].device
-    count = sum(p.numel() for p in ps)
-    flat = torch.empty(count, dtype=torch.float32, device=dev)
-    off = 0
+    _, _, count = net_layout(module)
+    flat = torch.zeros(count, dtype=torch.float32, device=dev)
     with torch.no_grad():
-        for p in ps:
-            n = p.numel()
-            view = flat[off:off + n].view(p.shape)
+        for p, view in zip(ps, _views(flat, module)):
             view.copy_(p.data.to(device=dev, dtype=torch.float32))
             p.data = view
-            off += n
     object.__setattr__(module, "_recnn_flat", flat)
     object.__setattr__(module, "_recnn_flat_grad", None)
     return flat
 
 
 def grad_arena(module) -> torch.Tensor:
-    """Flat fp32 gradient buffer; ``p.grad`` of every parameter is a view into it."""
+    """Flat fp32 gradient arena (same geometry); ``p.grad`` of every parameter is a view into it."""
     ps = _params(module)
     flat = param_arena(module)
     g = getattr(module, "_recnn_flat_grad", None)
     if g is None or g.device != flat.device or g.numel() != flat.numel():
         g = torch.zeros_like(flat)
         object.__setattr__(module, "_recnn_flat_grad", g)
-    if not _is_view_of(g, [p.grad for p in ps]):
-        off = 0
-        for p in ps:
-            n = p.numel()
-            p.grad = g[off:off + n].view(p.shape)
-            off += n
+    if not _aliases(g, module, [p.grad for p in ps]):
+        for p, view in zip(ps, _views(g, module)):
+            p.grad = view
     return g

@@ -144,12 +144,10 @@ def test_builtin_optimizer_vs_torch(kind, kw):
     theirs = (torch.optim.Adam if kind == "adam" else torch.optim.SGD)(ref.parameters(), **kw)
     from recnn_b200.nn.arena import grad_arena
     for it in range(5):
-        g = grad_arena(net)
-        g.copy_(torch.randn_like(g) * 0.01)
-        off = 0
-        for p in ref.parameters():
-            p.grad = g[off:off + p.numel()].view(p.shape).clone()
-            off += p.numel()
+        grad_arena(net)                                   # p.grad are (strided) views of the arena
+        for p, q in zip(net.parameters(), ref.parameters()):
+            p.grad.copy_(torch.randn_like(p) * 0.01)
+            q.grad = p.grad.clone()
         mine.step()
         theirs.step()
     for (n1, p1), (n2, p2) in zip(net.named_parameters(), ref.named_parameters()):

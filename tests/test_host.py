@@ -35,8 +35,16 @@ def test_library_exports_every_declared_symbol():
 def test_param_counts_match_reference_shapes():
     L = _lib.lib()
     d = _lib.Dims(1290, 128, 256, 0)
-    assert L.recnn_actor_param_count(d) == 429184
-    assert L.recnn_critic_param_count(d) == 429313
+    # 429,184 / 429,313 parameters + 16-byte row padding of linear1.weight (1290 -> 1292,
+    # 1418 -> 1420) and of the critic's 1-element linear3.bias
+    assert L.recnn_actor_param_count(d) == 429184 + 256 * 2
+    assert L.recnn_critic_param_count(d) == 429313 + 256 * 2 + 3
+    a = recnn_b200.nn.Actor(1290, 128, 256)
+    c = recnn_b200.nn.Critic(1290, 128, 256)
+    assert sum(p.numel() for p in a.parameters()) == 429184 and sum(p.numel() for p in c.parameters()) == 429313
+    from recnn_b200.nn.arena import net_layout
+    offs, lds, count = net_layout(c)
+    assert lds == [1420, 256, 256] and count == 429313 + 515 and offs[0] == 0 and offs[1] == 256 * 1420
     assert L.recnn_step_workspace_bytes(d, 4096, 0) > 0
 
 
@@ -63,7 +71,8 @@ def test_arena_aliasing_survives_copies_and_moves():
     a = recnn_b200.nn.Actor(170, 16, 32)
     before = [p.detach().clone() for p in a.parameters()]
     flat = param_arena(a)
-    assert flat.numel() == sum(p.numel() for p in a.parameters())
+    assert flat.numel() >= sum(p.numel() for p in a.parameters())
+    assert a.linear1.weight.stride() == (172, 1) and a.linear1.weight.shape == (32, 170)   # 170 -> pitch 172
     for p, q in zip(a.parameters(), before):
         assert torch.equal(p, q)
     flat.mul_(2.0)                                           # writes through to the parameters
@@ -73,7 +82,8 @@ def test_arena_aliasing_survives_copies_and_moves():
     fb = param_arena(b)
     assert fb.data_ptr() != flat.data_ptr() and torch.equal(fb, flat)
     a.load_state_dict({k: v * 0 + 1 for k, v in a.state_dict().items()})
-    assert torch.equal(param_arena(a), torch.ones_like(flat))
+    assert param_arena(a).sum().item() == sum(p.numel() for p in a.parameters())          # pads stay 0
+    assert all(torch.equal(p, torch.ones_like(p)) for p in a.parameters())
     g = grad_arena(a)
     assert a.linear1.weight.grad.data_ptr() == g.data_ptr()
     torch.optim.SGD(a.parameters(), lr=0.1).zero_grad(set_to_none=True)
