@@ -118,7 +118,7 @@ RECNN_API int recnn_linear_forward(const float* x, int64_t n_rows, int in_dim, c
  * their autograd backward).  a_mn=0: A is [M,K] row-major, a_mn=1: A is stored [K,M];
  * same for B with N.  recnn_gemm_tf32x3 runs on the tcgen05 tensor cores with
  * error-compensated 3xTF32 (fp32-grade accuracy; pitches and bases must be 16-byte
- * multiples; tile_n in {0 (auto), 64, 128, 256}); recnn_gemm_fp32 is the exact-fp32
+ * multiples; tile_n in {0 (auto), 64, 128}); recnn_gemm_fp32 is the exact-fp32
  * CUDA-core path for arbitrary shapes. */
 RECNN_API int recnn_gemm_tf32x3(int M, int N, int K, const float* A, int64_t lda, int a_mn, const float* B,
                       int64_t ldb, int b_mn, float* C, int64_t ldc, int tile_n, void* stream);

@@ -15,10 +15,14 @@ F32 = np.float32
 
 # name -> spec.  "canon" = the reference's documented shapes:
 # D=128, F=10, S=1290, A=128, H=256, init_w as in .circleci/tests/learning.py:20-21.
+# Seeds are chosen by oracle/find_seeds.py so that, over all 12 steps and both optimizers, no kept
+# hidden unit has a pre-activation closer to 0 than GATE_GUARD: the ReLU gate decisions (where the
+# gradient is discontinuous) are then unambiguous at fp32 accuracy and a 1e-5 comparison is meaningful.
+GATE_GUARD = 2e-6
 CASES = {
-    "canon": dict(seed=1234, n_items=1000, dim=128, frame=10, hidden=256, n_rows=32,
+    "canon": dict(seeds={"ddpg": 9, "td3": 75}, n_items=1000, dim=128, frame=10, hidden=256, n_rows=32,
                   steps=12, actor_init_w=6e-1, critic_init_w=54e-2),
-    "tiny": dict(seed=77, n_items=50, dim=16, frame=4, hidden=32, n_rows=24,
+    "tiny": dict(seeds={"ddpg": 1, "td3": 3}, n_items=50, dim=16, frame=4, hidden=32, n_rows=24,
                  steps=12, actor_init_w=6e-1, critic_init_w=54e-2),
 }
 
@@ -33,7 +37,7 @@ def dims(spec):
 
 def make_inputs(spec, algo="ddpg"):
     """table, items, ratings, sizes, nets, masks per step (, noise per step)."""
-    rng = np.random.default_rng(spec["seed"] + (0 if algo == "ddpg" else 100003))
+    rng = np.random.default_rng(spec["seeds"][algo] + (0 if algo == "ddpg" else 100003))
     s_dim, a_dim, h = dims(spec)
     table, items, ratings, _ = O.synth_frames(rng, spec["n_rows"], spec["n_items"],
                                               spec["dim"], spec["frame"])

@@ -173,6 +173,11 @@ def run_update_case(recnn, case, algo, opt_kind):
     for name, p in inp["nets"].items():
         for k, v in C.net_digest(p).items():
             out["init.%s.%s" % (name, k)] = v
+    # gate margin of this case (numpy oracle on the same inputs; see oracle/cases.py GATE_GUARD)
+    from tests._golden import run_oracle_case
+    O.reset_gate_margin()
+    run_oracle_case(case, algo, opt_kind, golden=out if algo == "td3" else None)
+    out["gate_margin"] = np.float64(O.GATE_MARGIN["min"])
     if case == "tiny":           # small enough to store every final tensor verbatim
         for name, m in nets.items():
             for k, v in _dump(m).items():

@@ -23,7 +23,7 @@ template <bool VEC>
 __global__ void __launch_bounds__(256)
 frame_gather_kernel(const float* __restrict__ table, long long n_items, int dim,
                     const long long* __restrict__ items, const float* __restrict__ ratings,
-                    long long n_rows, int frame, long long s_ld,
+                    long long n_rows, int frame, long long s_ld, long long a_ld,
                     float* __restrict__ state, float* __restrict__ next_state,
                     float* __restrict__ action, float* __restrict__ reward, int* __restrict__ oob) {
   const int lane = threadIdx.x & 31;
@@ -75,7 +75,10 @@ frame_gather_kernel(const float* __restrict__ table, long long n_items, int dim,
                 d[0] = lo; d[1] = hi;
               }
               if (j == frame && action)
-                *reinterpret_cast<float4*>(action + n * dim + c) = v[u];
+                {
+                float2* d = reinterpret_cast<float2*>(action + n * a_ld + c);
+                d[0] = lo; d[1] = hi;
+              }
             }
           }
         } else {
@@ -87,7 +90,7 @@ frame_gather_kernel(const float* __restrict__ table, long long n_items, int dim,
               const float v = __ldg(table + id[u] * dim + c);
               if (j < frame && state) state[n * s_dim + (long long)j * dim + c] = v;
               if (j >= 1 && next_state) next_state[n * s_dim + (long long)(j - 1) * dim + c] = v;
-              if (j == frame && action) action[n * dim + c] = v;
+              if (j == frame && action) action[n * a_ld + c] = v;
             }
           }
         }
@@ -117,8 +120,8 @@ using namespace recnn;
 
 namespace recnn {
 int launch_frame_gather(const float* table, int64_t n_items, int dim, const int64_t* items, const float* ratings,
-                        int64_t n_rows, int frame, int64_t s_ld, float* state, float* next_state, float* action,
-                        float* reward, int* oob_flag, cudaStream_t st) {
+                        int64_t n_rows, int frame, int64_t s_ld, int64_t a_ld, float* state, float* next_state,
+                        float* action, float* reward, int* oob_flag, cudaStream_t st) {
   RECNN_REQUIRE(table && items && ratings, "table/items/ratings must be non-null");
   RECNN_REQUIRE(n_items > 0 && dim > 0 && frame > 0 && n_rows >= 0, "sizes must be positive");
   if (n_rows == 0) return RECNN_OK;
@@ -127,17 +130,17 @@ int launch_frame_gather(const float* table, int64_t n_items, int dim, const int6
   const bool aligned = (reinterpret_cast<uintptr_t>(table) % 16 == 0) &&
                        (!state || reinterpret_cast<uintptr_t>(state) % 8 == 0) &&
                        (!next_state || reinterpret_cast<uintptr_t>(next_state) % 8 == 0) &&
-                       (!action || reinterpret_cast<uintptr_t>(action) % 16 == 0);
-  const bool vec = aligned && (dim % 4 == 0) && (s_dim % 2 == 0);
+                       (!action || reinterpret_cast<uintptr_t>(action) % 8 == 0);
+  const bool vec = aligned && (dim % 4 == 0) && (s_dim % 2 == 0) && (a_ld % 2 == 0);
   const int warps_per_block = 8;
   const int64_t blocks = ceil_div(n_rows, warps_per_block);
   const int grid = (int)(blocks < (int64_t)kNumSMs * 8 ? blocks : (int64_t)kNumSMs * 8);
   if (vec)
     frame_gather_kernel<true><<<grid, 256, 0, st>>>(table, n_items, dim, (const long long*)items, ratings,
-                                                    n_rows, frame, s_ld, state, next_state, action, reward, oob_flag);
+                                                    n_rows, frame, s_ld, a_ld, state, next_state, action, reward, oob_flag);
   else
     frame_gather_kernel<false><<<grid, 256, 0, st>>>(table, n_items, dim, (const long long*)items, ratings,
-                                                     n_rows, frame, s_ld, state, next_state, action, reward, oob_flag);
+                                                     n_rows, frame, s_ld, a_ld, state, next_state, action, reward, oob_flag);
   RECNN_CHECK_LAUNCH("frame_gather_kernel");
   return RECNN_OK;
 }
@@ -148,7 +151,7 @@ extern "C" int recnn_frame_gather(const float* table, int64_t n_items, int dim, 
                                   float* next_state, float* action, float* reward, int* oob_flag,
                                   void* stream) {
   return recnn::launch_frame_gather(table, n_items, dim, items, ratings, n_rows, frame,
-                                    (int64_t)frame * dim + frame, state, next_state, action, reward, oob_flag,
+                                    (int64_t)frame * dim + frame, dim, state, next_state, action, reward, oob_flag,
                                     static_cast<cudaStream_t>(stream));
 }
 

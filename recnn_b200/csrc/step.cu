@@ -21,8 +21,8 @@
 namespace recnn {
 
 int launch_frame_gather(const float* table, int64_t n_items, int dim, const int64_t* items, const float* ratings,
-                        int64_t n_rows, int frame, int64_t s_ld, float* state, float* next_state, float* action,
-                        float* reward, int* oob_flag, cudaStream_t st);
+                        int64_t n_rows, int frame, int64_t s_ld, int64_t a_ld, float* state, float* next_state,
+                        float* action, float* reward, int* oob_flag, cudaStream_t st);
 
 static bool math_tc() {
   static int v = -1;
@@ -38,10 +38,10 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 struct Workspace {
   float* S;        // [N, ldS] state (frame form: gathered; dense form: re-pitched copy)
   float* S2;       // [N, ldS]
-  float* ACT;      // [N,A]  frame form only
+  float* ACT;      // [N, ldA] batch action, stored with `lead` zero columns in front (see Seg)
   float* REW;      // [N]
   float* hb[6];    // [N,H] activation / gradient buffers (lifetimes in DESIGN.md)
-  float* ab[3];    // [N,A] next_action / gen_action / d gen_action
+  float* ab[3];    // [N, ldA] next_action / gen_action (lead-padded) ; [N,A] d gen_action
   float* y;        // [N] TD target
   float* qtmp;     // [N]
   float* dq;       // [N]
@@ -56,7 +56,7 @@ struct Workspace {
 // Must be a pure function of the shapes: the workspace size depends on it.
 static int dw_splits(int C, int K, int64_t n_rows, bool tc_path) {
   if (tc_path) {
-    const int64_t tiles = ceil_div(C, 128) * ceil_div(K, 256);
+    const int64_t tiles = ceil_div(C, 128) * ceil_div(K, 128);
     int64_t s = ceil_div(192, tiles);
     const int64_t max_s = ceil_div(n_rows, 16) / 8 > 0 ? ceil_div(n_rows, 16) / 8 : 1;   // >= 8 k-blocks per split
     if (s > max_s) s = max_s;
@@ -92,12 +92,13 @@ static Workspace carve(const recnn_dims& d, int64_t n, void* base) {
     return r;
   };
   const int ldS = pad4(d.state_dim);
+  const int ldA = pad4(d.action_dim + d.state_dim % 4);
   w.S = take(n * ldS);
   w.S2 = take(n * ldS);
-  w.ACT = take(n * d.action_dim);
+  w.ACT = take(n * ldA);
   w.REW = take(n);
   for (auto& b : w.hb) b = take(n * d.hidden);
-  for (auto& b : w.ab) b = take(n * d.action_dim);
+  for (auto& b : w.ab) b = take(n * ldA);
   w.y = take(n);
   w.qtmp = take(n);
   w.dq = take(n);
@@ -123,19 +124,23 @@ static Epilogue base_epi() {
   return e;
 }
 
-// one K-contiguous input matrix [n, cols] with row pitch ld
+// one K-contiguous input matrix [n, cols] with row pitch ld.  `lead` of its columns are zero pads in
+// front of the data: TMA needs every box to start on a 16-byte boundary in BOTH operands, and the
+// critic's concat [state | action] puts the action block at weight column S = 1290 (8 mod 16 bytes).
+// Storing actions with S%4 leading zeros lets the second K-segment start at weight column S - lead,
+// which is aligned; the pad columns multiply state weights by zero.
 struct Seg {
   const float* p;
-  int cols;
+  int cols;          // including the lead pads
   long long ld;
+  int lead;
 };
-static const Seg kNoSeg = {nullptr, 0, 0};
+static const Seg kNoSeg = {nullptr, 0, 0, 0};
 
 static int pick_bn(int64_t M, int N) {
-  // widest tile that still yields >= 96 CTAs; otherwise the narrowest (more CTAs, less reuse)
+  // 128-wide tiles when they still yield >= 64 CTAs; otherwise 64-wide (more CTAs, less reuse)
   const int64_t mt = ceil_div(M, 128);
-  if (N > 128 && mt * ceil_div(N, 256) >= 96) return 256;
-  if (N > 64 && mt * ceil_div(N, 128) >= 96) return 128;
+  if (N > 64 && mt * ceil_div(N, 128) >= 64) return 128;
   return 64;
 }
 
@@ -143,16 +148,18 @@ static int pick_bn(int64_t M, int N) {
 template <int EPI>
 static int gemm_nt(const Seg& x0, const Seg& x1, const float* W, long long ldw, int N, int64_t n, const Epilogue& e,
                    cudaStream_t st) {
-  const int K = x0.cols + x1.cols;
+  const int K = x0.cols + x1.cols - x1.lead;             // logical contraction length == W's columns
   const bool tc_ok = math_tc() && aligned16(x0.p) && (x1.cols == 0 || aligned16(x1.p)) && aligned16(W) &&
-                     x0.ld % 4 == 0 && (x1.cols == 0 || x1.ld % 4 == 0) && ldw % 4 == 0;
+                     x0.ld % 4 == 0 && (x1.cols == 0 || x1.ld % 4 == 0) && ldw % 4 == 0 && x0.lead == 0 &&
+                     (x1.cols == 0 || (x0.cols - x1.lead) % 4 == 0);
   if (tc_ok) {
     tc::Operand a0 = {x0.p, x0.ld, 0, 0}, a1 = {x1.p, x1.ld, 0, 0}, b = {W, ldw, N, K};
-    tc::Problem p = {(int)n, N, x0.cols, x1.cols, 0, x0.cols, 0, 0};
+    tc::Problem p = {(int)n, N, x0.cols, x1.cols, 0, x0.cols - x1.lead, 0, 0};
     const int r = tc::launch<false, false, EPI>(a0, a1, b, p, 1, pick_bn(n, N), e, st);
     return r < 0 ? r : RECNN_OK;
   }
-  const MatView X = x1.cols ? mat_cat(x0.p, x0.ld, x0.cols, x1.p, x1.ld) : mat(x0.p, x0.ld);
+  const MatView X = x1.cols ? mat_cat(x0.p + x0.lead, x0.ld, x0.cols - x0.lead, x1.p + x1.lead, x1.ld)
+                            : mat(x0.p + x0.lead, x0.ld);
   return launch_gemm_simt<true, true, EPI>(X, mat(W, ldw), (int)n, N, K, 1, e, st);
 }
 
@@ -171,9 +178,9 @@ struct NoiseSpec {
 };
 
 static int linear_out(const Seg& x, const float* W, long long ldw, const float* b, int out_dim, int64_t n,
-                      int apply_tanh, const NoiseSpec* nz, float* out, cudaStream_t st) {
+                      int apply_tanh, const NoiseSpec* nz, float* out, long long ldo, cudaStream_t st) {
   Epilogue e = base_epi();
-  e.out = out; e.ldo = out_dim; e.bias = b; e.apply_tanh = apply_tanh;
+  e.out = out; e.ldo = ldo; e.bias = b; e.apply_tanh = apply_tanh;
   if (nz && nz->add) {
     e.add_noise = 1; e.noise = nz->noise; e.noise_clip = nz->clip; e.noise_std = nz->std;
     e.seed = nz->seed; e.rng_step = nz->step; e.stream_id = nz->stream_id;
@@ -186,7 +193,7 @@ static int backprop_hidden(const float* dZ, int C, const float* W, long long ldw
                            int64_t n, const float* h, float gate_scale, float* out, cudaStream_t st) {
   Epilogue e = base_epi();
   e.out = out; e.ldo = K; e.h = h; e.ldh = K; e.gate_scale = gate_scale;
-  const bool tc_ok = math_tc() && aligned16(dZ) && aligned16(W) && C % 4 == 0 && ldw % 4 == 0;
+  const bool tc_ok = math_tc() && aligned16(dZ) && aligned16(W) && C % 4 == 0 && ldw % 4 == 0 && col0 % 4 == 0;
   if (tc_ok) {
     tc::Operand a0 = {dZ, C, 0, 0}, a1 = {nullptr, 0, 0, 0}, b = {W, ldw, C, w_cols};
     tc::Problem p = {(int)n, K, C, 0, 0, C, 0, col0};
@@ -202,35 +209,38 @@ static int backprop_hidden(const float* dZ, int C, const float* W, long long ldw
 // dW[c,k] = sum_n dZ[n,c] [x0|x1][n,k];  db[c] = sum_n dZ[n,c].   dW has row pitch ldw.
 static int weight_grad(const float* dZ, int C, const Seg& x0, const Seg& x1, int64_t n, float* dW, long long ldw,
                        float* db, const Workspace& ws, cudaStream_t st) {
-  const int K = x0.cols + x1.cols, K1 = K + 1;
+  const int K = x0.cols + x1.cols - x1.lead, K1 = K + 1;
   Epilogue e = base_epi();
   e.out = ws.partial; e.ldo = K1;
   const bool tc_ok = math_tc() && C % 4 == 0 && C >= 32 && aligned16(dZ) && aligned16(x0.p) && x0.ld % 4 == 0 &&
-                     (x1.cols == 0 || (aligned16(x1.p) && x1.ld % 4 == 0));
+                     x0.lead == 0 && (x1.cols == 0 || (aligned16(x1.p) && x1.ld % 4 == 0));
   if (tc_ok) {
     const int req = dw_splits(C, K, n, true);
     int k_chunk = 0;
     const int splits = tc::split_plan((int)ceil_div(n, 16), req, &k_chunk);
     tc::Operand a0 = {dZ, C, 0, 0}, a1 = {nullptr, 0, 0, 0};
-    const Seg* segs[2] = {&x0, &x1};
-    int col = 0;
-    for (const Seg* s : segs) {
+    // the padded second segment goes first: its `lead` pad columns land (as zeros) on the last columns
+    // of the first segment's window, which the first segment's launch then overwrites with the real values
+    const Seg* segs[2] = {&x1, &x0};
+    const int cols0[2] = {x0.cols - x1.lead, 0};
+    for (int i = 0; i < 2; ++i) {
+      const Seg* s = segs[i];
       if (s->cols == 0) continue;
       tc::Operand b = {s->p, s->ld, n, s->cols};
-      tc::Problem p = {C, s->cols, (int)n, 0, 0, 0, col, 0};
-      const int bn = s->cols > 128 ? 256 : (s->cols > 64 ? 128 : 64);
+      tc::Problem p = {C, s->cols, (int)n, 0, 0, 0, cols0[i], 0};
+      const int bn = s->cols > 64 ? 128 : 64;
       const int r = tc::launch<true, true, EPI_PARTIAL>(a0, a1, b, p, req, bn, e, st);
       if (r < 0) return r;
       if (r != splits) {
         set_error("internal: split plan mismatch (%d vs %d)", r, splits);
         return RECNN_E_INVALID;
       }
-      col += s->cols;
     }
     RECNN_PROPAGATE(launch_colsum_partials(dZ, n, C, k_chunk, splits, ws.partial, K1, st));
     return launch_reduce_partials(ws.partial, splits, C, K1, dW, ldw, db, st);
   }
-  MatView X = x1.cols ? mat_cat(x0.p, x0.ld, x0.cols, x1.p, x1.ld) : mat(x0.p, x0.ld);
+  MatView X = x1.cols ? mat_cat(x0.p + x0.lead, x0.ld, x0.cols - x0.lead, x1.p + x1.lead, x1.ld)
+                      : mat(x0.p + x0.lead, x0.ld);
   X.ones_at = K;                        // virtual bias column
   const int splits_req = dw_splits(C, K, n, false);
   // the launcher rounds the chunk; recompute the effective split count the same way
@@ -246,7 +256,8 @@ struct Ctx {
   NetLayout la, lc;
   Workspace ws;
   const float *S, *S2, *ACT, *REW, *DONE;
-  long long ldS;
+  long long ldS, ldA;
+  int lead;          // zero columns in front of every action row (= state_dim % 4)
   int64_t n;
   cudaStream_t st;
   Rng rng;
@@ -260,7 +271,7 @@ static int critic_hidden(const Ctx& c, const float* params, const float* s, cons
   const int S = c.d.state_dim, A = c.d.action_dim, H = c.d.hidden;
   const uint8_t* m1 = (train && c.rng.masks) ? c.rng.masks[mask_base] : nullptr;
   const uint8_t* m2 = (train && c.rng.masks) ? c.rng.masks[mask_base + 1] : nullptr;
-  const Seg xs = {s, S, c.ldS}, xa = {act, A, A}, h1 = {out1, H, H};
+  const Seg xs = {s, S, c.ldS, 0}, xa = {act, A + c.lead, c.ldA, c.lead}, h1 = {out1, H, H, 0};
   RECNN_PROPAGATE(hidden_layer(xs, xa, params + c.lc.w1, c.lc.ld1, params + c.lc.b1, H, c.n, train, m1, c.rng,
                                mask_base, out1, c.st));
   return hidden_layer(h1, kNoSeg, params + c.lc.w2, c.lc.ld2, params + c.lc.b2, H, c.n, train, m2, c.rng,
@@ -272,7 +283,7 @@ static int actor_hidden(const Ctx& c, const float* params, const float* s, bool 
   const int S = c.d.state_dim, H = c.d.hidden;
   const uint8_t* m1 = (train && c.rng.masks) ? c.rng.masks[mask_base] : nullptr;
   const uint8_t* m2 = (train && c.rng.masks) ? c.rng.masks[mask_base + 1] : nullptr;
-  const Seg xs = {s, S, c.ldS}, h1 = {out1, H, H};
+  const Seg xs = {s, S, c.ldS, 0}, h1 = {out1, H, H, 0};
   RECNN_PROPAGATE(hidden_layer(xs, kNoSeg, params + c.la.w1, c.la.ld1, params + c.la.b1, H, c.n, train, m1, c.rng,
                                mask_base, out1, c.st));
   return hidden_layer(h1, kNoSeg, params + c.la.w2, c.la.ld2, params + c.la.b2, H, c.n, train, m2, c.rng,
@@ -303,11 +314,12 @@ static int phase_value_grad(Ctx& c) {
   // target policy on next_state, eval mode (misc.py:28 / td3.py:73) (+ clipped noise, td3.py:74-78)
   RECNN_PROPAGATE(actor_hidden(c, a.target_policy.params, c.S2, false, 0, X0, X1));
   NoiseSpec nz = {td3 ? 1 : 0, a.noise, a.noise_clip, a.noise_std, a.seed, (const long long*)a.rng_step, 15u};
-  const Seg x1s = {X1, H, H};
+  const Seg x1s = {X1, H, H, 0};
   RECNN_PROPAGATE(linear_out(x1s, a.target_policy.params + c.la.w3, c.la.ld3, a.target_policy.params + c.la.b3, A,
-                             c.n, 0, &nz, a2, c.st));
+                             c.n, 0, &nz, a2 + c.lead, c.ldA, c.st));
   if (a.next_action_out)
-    RECNN_CHECK_CUDA(cudaMemcpyAsync(a.next_action_out, a2, sizeof(float) * c.n * A, cudaMemcpyDeviceToDevice, c.st));
+    RECNN_CHECK_CUDA(cudaMemcpy2DAsync(a.next_action_out, (size_t)A * 4, a2 + c.lead, c.ldA * 4, (size_t)A * 4, c.n,
+                                       cudaMemcpyDeviceToDevice, c.st));
 
   // target critic(s) -> TD target y (misc.py:29-35 / td3.py:80-86)
   for (int i = 0; i < n_critics; ++i) {
@@ -327,7 +339,8 @@ static int phase_value_grad(Ctx& c) {
     if (!a.learn) continue;
     float* G = a.value[i].grads;
     RECNN_REQUIRE(G != nullptr, "value net needs a grad arena when learn=1");
-    const Seg sc2 = {c2, H, H}, sc1 = {c1, H, H}, ss = {c.S, S, c.ldS}, sa = {c.ACT, A, A};
+    const Seg sc2 = {c2, H, H, 0}, sc1 = {c1, H, H, 0}, ss = {c.S, S, c.ldS, 0},
+              sa = {c.ACT, A + c.lead, c.ldA, c.lead};
     // layer 3: dW3 = dq^T h2, db3 = sum dq ; dz2 = (dq w3) * gate(h2)
     RECNN_PROPAGATE(weight_grad(c.ws.dq, 1, sc2, kNoSeg, c.n, G + c.lc.w3, c.lc.ld3, G + c.lc.b3, c.ws, c.st));
     RECNN_PROPAGATE(launch_critic_head_bwd(c.ws.dq, 0.f, P + c.lc.w3, c2, c.gate, dz2, c.n, H, c.st));
@@ -356,11 +369,12 @@ static int phase_policy_loss(Ctx& c) {
   float* gen = c.ws.ab[1];
   // gen_action = policy_net(state); policy_loss = -value_net(state, gen_action)  (ddpg.py:78-79, td3.py:116-118)
   RECNN_PROPAGATE(actor_hidden(c, a.policy.params, c.S, c.train, pm, p1, p2));
-  const Seg sp2 = {p2, H, H};
+  const Seg sp2 = {p2, H, H, 0};
   RECNN_PROPAGATE(linear_out(sp2, a.policy.params + c.la.w3, c.la.ld3, a.policy.params + c.la.b3, A, c.n, 0,
-                             nullptr, gen, c.st));
+                             nullptr, gen + c.lead, c.ldA, c.st));
   if (a.gen_action_out)
-    RECNN_CHECK_CUDA(cudaMemcpyAsync(a.gen_action_out, gen, sizeof(float) * c.n * A, cudaMemcpyDeviceToDevice, c.st));
+    RECNN_CHECK_CUDA(cudaMemcpy2DAsync(a.gen_action_out, (size_t)A * 4, gen + c.lead, c.ldA * 4, (size_t)A * 4, c.n,
+                                       cudaMemcpyDeviceToDevice, c.st));
   RECNN_PROPAGATE(critic_hidden(c, a.value[0].params, c.S, gen, c.train, vm, v1, v2));
   HeadArgs h = head_args(c, a.value[0].params, v2, HEAD_POLICY);
   h.loss = a.losses + 2;
@@ -384,7 +398,7 @@ static int phase_policy_grad(Ctx& c) {
   RECNN_PROPAGATE(backprop_hidden(dv2, H, Pc + c.lc.w2, c.lc.ld2, H, 0, H, c.n, v1, c.gate, dv1, c.st));
   RECNN_PROPAGATE(backprop_hidden(dv1, H, Pc + c.lc.w1, c.lc.ld1, S + A, S, A, c.n, nullptr, 1.f, dgen, c.st));
   // actor backward
-  const Seg sp2 = {p2, H, H}, sp1 = {p1, H, H}, ss = {c.S, S, c.ldS};
+  const Seg sp2 = {p2, H, H, 0}, sp1 = {p1, H, H, 0}, ss = {c.S, S, c.ldS, 0};
   RECNN_PROPAGATE(weight_grad(dgen, A, sp2, kNoSeg, c.n, G + c.la.w3, c.la.ld3, G + c.la.b3, c.ws, c.st));
   float* dp2 = dv2;   // dv2/dv1 are dead once dgen exists
   float* dp1 = dv1;
@@ -460,18 +474,28 @@ static int run_step(const recnn_step_args* a, int algo, void* stream) {
   c.gate = c.train ? 2.0f : 1.0f;
   c.DONE = a->done;
   c.ldS = pad4(c.d.state_dim);
-  const int S = c.d.state_dim;
+  c.lead = c.d.state_dim % 4;
+  c.ldA = pad4(c.d.action_dim + c.lead);
+  const int S = c.d.state_dim, A = c.d.action_dim;
   // tickets of the deterministic two-level reductions start at zero
   RECNN_CHECK_CUDA(cudaMemsetAsync(c.ws.tickets, 0, 8 * sizeof(unsigned), c.st));
   // The step works on state / next_state images with a 16-byte-multiple row pitch (TMA); they are
   // materialised into the workspace once per step (RECNN_PH_GATHER) from the frames or the dense batch.
   c.S = c.ws.S;
   c.S2 = c.ws.S2;
+  c.ACT = c.ws.ACT;
+  if (a->phases & RECNN_PH_GATHER) {
+    // action buffers carry `lead` zero columns (and pitch padding) that the kernels never write
+    if (c.ldA != A) {
+      RECNN_CHECK_CUDA(cudaMemsetAsync(c.ws.ACT, 0, sizeof(float) * c.n * c.ldA, c.st));
+      RECNN_CHECK_CUDA(cudaMemsetAsync(c.ws.ab[0], 0, sizeof(float) * c.n * c.ldA, c.st));
+      RECNN_CHECK_CUDA(cudaMemsetAsync(c.ws.ab[1], 0, sizeof(float) * c.n * c.ldA, c.st));
+    }
+  }
   if (frames) {
     if (a->phases & RECNN_PH_GATHER)
       RECNN_PROPAGATE(launch_frame_gather(a->table, a->n_items, a->emb_dim, a->items, a->ratings, c.n, a->frame,
-                                          c.ldS, c.ws.S, c.ws.S2, c.ws.ACT, c.ws.REW, nullptr, c.st));
-    c.ACT = c.ws.ACT;
+                                          c.ldS, c.ldA, c.ws.S, c.ws.S2, c.ws.ACT + c.lead, c.ws.REW, nullptr, c.st));
     c.REW = a->reward ? a->reward : c.ws.REW;
   } else {
     if (a->phases & RECNN_PH_GATHER) {
@@ -479,8 +503,9 @@ static int run_step(const recnn_step_args* a, int algo, void* stream) {
                                          cudaMemcpyDeviceToDevice, c.st));
       RECNN_CHECK_CUDA(cudaMemcpy2DAsync(c.ws.S2, c.ldS * 4, a->next_state, (size_t)S * 4, (size_t)S * 4, c.n,
                                          cudaMemcpyDeviceToDevice, c.st));
+      RECNN_CHECK_CUDA(cudaMemcpy2DAsync(c.ws.ACT + c.lead, c.ldA * 4, a->action, (size_t)A * 4, (size_t)A * 4, c.n,
+                                         cudaMemcpyDeviceToDevice, c.st));
     }
-    c.ACT = a->action;
     c.REW = a->reward;
   }
   if (a->phases & RECNN_PH_VALUE_GRAD) RECNN_PROPAGATE(phase_value_grad(c));
@@ -536,10 +561,11 @@ extern "C" int recnn_actor_forward(const recnn_dims* d, const float* params, con
   float* h2 = scratch + n_rows * H;
   Rng rng = {nullptr, 0, nullptr};
   const bool train = mask1 != nullptr;
-  const Seg xs = {state, d->state_dim, d->state_dim}, s1 = {h1, H, H}, s2 = {h2, H, H};
+  const Seg xs = {state, d->state_dim, d->state_dim, 0}, s1 = {h1, H, H, 0}, s2 = {h2, H, H, 0};
   RECNN_PROPAGATE(hidden_layer(xs, kNoSeg, params + l.w1, l.ld1, params + l.b1, H, n_rows, train, mask1, rng, 0, h1, st));
   RECNN_PROPAGATE(hidden_layer(s1, kNoSeg, params + l.w2, l.ld2, params + l.b2, H, n_rows, train, mask2, rng, 1, h2, st));
-  return linear_out(s2, params + l.w3, l.ld3, params + l.b3, d->action_dim, n_rows, apply_tanh, nullptr, action_out, st);
+  return linear_out(s2, params + l.w3, l.ld3, params + l.b3, d->action_dim, n_rows, apply_tanh, nullptr, action_out,
+                    d->action_dim, st);
 }
 
 extern "C" int recnn_critic_forward(const recnn_dims* d, const float* params, const float* state,
@@ -555,7 +581,7 @@ extern "C" int recnn_critic_forward(const recnn_dims* d, const float* params, co
   float* h2 = scratch + n_rows * H;
   Rng rng = {nullptr, 0, nullptr};
   const bool train = mask1 != nullptr;
-  const Seg xs = {state, S, S}, xa = {action, A, A}, s1 = {h1, H, H};
+  const Seg xs = {state, S, S, 0}, xa = {action, A, A, 0}, s1 = {h1, H, H, 0};
   RECNN_PROPAGATE(hidden_layer(xs, xa, params + l.w1, l.ld1, params + l.b1, H, n_rows, train, mask1, rng, 0, h1, st));
   RECNN_PROPAGATE(hidden_layer(s1, kNoSeg, params + l.w2, l.ld2, params + l.b2, H, n_rows, train, mask2, rng, 1, h2, st));
   HeadArgs h;
@@ -572,10 +598,10 @@ extern "C" int recnn_linear_forward(const float* x, int64_t n_rows, int in_dim, 
   RECNN_REQUIRE(in_dim > 0 && out_dim > 0 && n_rows >= 0, "sizes");
   if (n_rows == 0) return RECNN_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const Seg xs = {x, in_dim, in_dim};
+  const Seg xs = {x, in_dim, in_dim, 0};
   if (relu) {
     Rng rng = {nullptr, 0, nullptr};
     return hidden_layer(xs, kNoSeg, weight, in_dim, bias, out_dim, n_rows, false, nullptr, rng, 0, out, st);
   }
-  return linear_out(xs, weight, in_dim, bias, out_dim, n_rows, 0, nullptr, out, st);
+  return linear_out(xs, weight, in_dim, bias, out_dim, n_rows, 0, nullptr, out, out_dim, st);
 }

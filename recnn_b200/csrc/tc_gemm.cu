@@ -85,8 +85,23 @@ static int launch_cfg(const Operand& A0, const Operand& A1, const Operand& B, co
   if (!C::B_MN) RECNN_PROPAGATE(make_tmap(&mb, B.ptr, B.rows, B.cols, B.ld, C::BK, C::BN, C::K_SWZ));
   else RECNN_PROPAGATE(make_tmap(&mb, B.ptr, B.rows, B.cols, B.ld, 32, C::BK, 1032));
   dim3 grid((unsigned)ceil_div(p.N, C::BN), (unsigned)ceil_div(p.M, C::BM), (unsigned)splits);
+  static const bool debug = getenv("RECNN_B200_DEBUG") != nullptr;
+  if (debug)
+    fprintf(stderr, "[tc_gemm] BN=%d A_MN=%d B_MN=%d EPI=%d M=%d N=%d K0=%d K1=%d k_chunk=%d bk1=%d nout=%d bn_off=%d "
+            "grid=%u,%u,%u a0=%p ld=%lld a1=%p ld=%lld b=%p ld=%lld rows=%lld cols=%lld out=%p ldo=%lld\n",
+            C::BN, (int)C::A_MN, (int)C::B_MN, EPI, p.M, p.N, p.K0, p.K1, p.k_chunk, p.b_k1_offset, p.n_out_offset,
+            p.b_n_offset, grid.x, grid.y, grid.z, (const void*)A0.ptr, A0.ld, (const void*)A1.ptr, A1.ld,
+            (const void*)B.ptr, B.ld, B.rows, B.cols, (void*)epi.out, epi.ldo);
   tc_gemm_kernel<C, EPI><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(ma0, ma1, mb, p, epi);
   RECNN_CHECK_LAUNCH("tc_gemm_kernel");
+  if (debug) {
+    const cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+      set_error("tc_gemm_kernel execution failed: %s", cudaGetErrorString(e));
+      fprintf(stderr, "[tc_gemm] FAILED: %s\n", cudaGetErrorString(e));
+      return RECNN_E_CUDA;
+    }
+  }
   return splits;
 }
 
@@ -94,7 +109,6 @@ template <bool A_MN, bool B_MN, int EPI>
 int launch(const Operand& A0, const Operand& A1, const Operand& B, const Problem& p, int splits, int bn,
            const Epilogue& epi, cudaStream_t st) {
   // stages chosen to fill ~190 KB of shared memory
-  if (bn >= 256) return launch_cfg<Cfg<256, 4, A_MN, B_MN>, EPI>(A0, A1, B, p, splits, epi, st);
   if (bn >= 128) return launch_cfg<Cfg<128, 6, A_MN, B_MN>, EPI>(A0, A1, B, p, splits, epi, st);
   return launch_cfg<Cfg<64, 8, A_MN, B_MN>, EPI>(A0, A1, B, p, splits, epi, st);
 }
@@ -133,7 +147,7 @@ extern "C" int recnn_gemm_tf32x3(int M, int N, int K, const float* A, int64_t ld
   tc::Operand a0 = {A, lda, 0, 0}, a1 = {nullptr, 0, 0, 0};
   tc::Operand b = {B, ldb, b_mn ? K : N, b_mn ? N : K};
   tc::Problem p = {M, N, K, 0, 0, K, 0, 0};
-  if (tile_n <= 0) tile_n = N > 128 ? 256 : (N > 64 ? 128 : 64);
+  if (tile_n <= 0) tile_n = N > 64 ? 128 : 64;
   int r;
   if (!a_mn && !b_mn) r = tc::launch<false, false, EPI_STORE>(a0, a1, b, p, 1, tile_n, e, st);
   else if (!a_mn && b_mn) r = tc::launch<false, true, EPI_STORE>(a0, a1, b, p, 1, tile_n, e, st);

@@ -5,24 +5,29 @@
 //
 // Why 3xTF32: the parity bar is the reference's fp32 CPU result to 1e-5
 // (BASELINE.json north_star); one TF32 pass has a 10-bit mantissa (~1e-3).  Each
-// fp32 operand x is split into  hi = x with the low 13 mantissa bits cleared
-// (exactly what kind::tf32 reads from a raw fp32 word: measured on the device,
-// tests/test_gpu_tc.py) and  lo = rna_tf32(x - hi)  (exact subtraction, then
-// round-to-nearest).  Three MMAs per 8-wide k-slice,  lo_a*hi_b + hi_a*lo_b + hi_a*hi_b,
-// accumulate in TMEM; the dropped lo*lo term is < 2^-20 relative.
+// fp32 operand x is split into  hi = rna_tf32(x)  and  lo = rna_tf32(x - hi)  (the
+// subtraction is exact).  Three MMAs per 8-wide k-slice,  lo_a*hi_b + hi_a*lo_b + hi_a*hi_b;
+// the dropped lo*lo term is < 2^-22 relative.
 //
-// Why chunked accumulation: the tensor core's fp32 accumulate TRUNCATES (measured:
-// all-positive operands lose 2.2e-8 of the sum per unit of K, i.e. -2.8e-5 at K=1290).
-// So a TMEM accumulator only ever sums CH k-blocks (K = 64): after each chunk the
-// worker warps pull it out with tcgen05.ld and add it to a register-resident running
-// sum with round-to-nearest FADDs, while the tensor core fills the other TMEM buffer.
+// Why chunked accumulation: the tensor core's fp32 accumulate TRUNCATES (measured: each
+// tcgen05.mma accumulate loses ~3.5e-8 of the running sum; unchunked, all-positive operands
+// are off by -2.8e-5 at K=1290).  So
+//   * the big hi*hi products of only CH k-blocks (K = 64, 8 accumulates) are summed in a TMEM
+//     chunk accumulator; after each chunk the worker warps pull it out with tcgen05.ld and add
+//     it to a register-resident running sum with round-to-nearest FADDs, while the tensor
+//     core fills the other chunk buffer;
+//   * the two small cross terms go to a separate TMEM accumulator D_lo that lives for the whole
+//     tile (its magnitude is 2^-11 of the result, so its truncation error is irrelevant) and is
+//     added once at the end.
+// hi is rounded to nearest (not truncated), so |lo| <= 2^-12 |x| is symmetric and the dropped
+// lo*lo term is unbiased.  Measured result: ~3e-7 worst-case systematic error, independent of K.
 //
-// Warp roles (one 128 x BN output tile per CTA; BN=256 -> 10 warps):
+// Warp roles (one 128 x BN output tile per CTA, BN in {64,128}; 6 warps):
 //   warp 0        TMA producer: raw fp32 tiles of A and B -> smem stage s             (full[s])
 //   warp 1        MMA issuer (one lane): per stage 3 x BK/8 tcgen05.mma, commit -> empty[s];
 //                 per chunk commit -> acc_full[buf]
-//   workers       4 per 128 columns.  (1) splitter: read the raw stage with ld.shared, write the
-//                 `lo` tile next to it (the raw tile itself is the `hi` operand)       (split[s])
+//   workers       4 warps.  (1) splitter: read the raw stage with ld.shared, write `hi` back in
+//                 place and the `lo` tile next to it                                   (split[s])
 //                 (2) drain: TMEM chunk -> registers, running sum += chunk             (acc_empty[buf])
 //                 (3) epilogue on the register-resident row (bias/relu/dropout/...), store.
 // Operand tiles in smem are the canonical UMMA layouts written by TMA with hardware
@@ -137,13 +142,21 @@ __device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
                : "memory");
 }
 
-__device__ __forceinline__ float tf32_lo(float x) {
-  // x = hi + lo exactly, hi = x with the low 13 mantissa bits cleared; return rna_tf32(lo)
-  const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-  const float lo = x - hi;
+__device__ __forceinline__ float tf32_rna(float x) {
   uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(lo));
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
+}
+// x = hi + lo (+ <= 2^-24 |x|): hi = rna_tf32(x), lo = rna_tf32(x - hi)
+__device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) {
+  hi = tf32_rna(x);
+  lo = tf32_rna(x - hi);
+}
+__device__ __forceinline__ void tf32_split4(const float4& x, float4& hi, float4& lo) {
+  tf32_split(x.x, hi.x, lo.x);
+  tf32_split(x.y, hi.y, lo.y);
+  tf32_split(x.z, hi.z, lo.z);
+  tf32_split(x.w, hi.w, lo.w);
 }
 
 // ------------------------------------------------------------------ descriptors
@@ -174,12 +187,12 @@ struct Cfg {
   static constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);      // raw + lo
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-  static constexpr int COLS_PER_WORKER = BN >= 128 ? 128 : BN;     // register-resident running sum per thread
-  static constexpr int WORKERS = 4 * (BN / COLS_PER_WORKER);       // warps
+  static constexpr int COLS_PER_WORKER = BN;                       // register-resident running sum per thread
+  static constexpr int WORKERS = 4;                                // warps (one per TMEM lane quarter)
   static constexpr int THREADS = 64 + 32 * WORKERS;
-  static constexpr int TMEM_COLS = 2 * BN;                         // double-buffered chunk accumulator (>= 128)
+  static constexpr int TMEM_COLS = 4 * BN;                         // D_hi chunk x2 | D_lo | (pad to a power of 2)
   static constexpr int K_SWZ = BK * 4;                             // K-major rows: 64 B, SWIZZLE_64B
-  static_assert(BN == 64 || BN == 128 || BN == 256, "BN");
+  static_assert(BN == 64 || BN == 128, "BN");
   static_assert(SMEM_BYTES <= 227 * 1024, "smem");
 };
 
@@ -383,7 +396,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         }
         mbar_wait(split(s), ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)buf * BN;
+        const uint32_t d_hi = tmem_base + (uint32_t)buf * BN;     // chunk accumulator (hi*hi)
+        const uint32_t d_lo = tmem_base + 2u * BN;                // tile-lifetime accumulator (cross terms)
         const uint32_t a_hi = stage_addr(s, 0), b_hi = stage_addr(s, 1);
         const uint32_t a_lo = stage_addr(s, 2), b_lo = stage_addr(s, 3);
 #pragma unroll
@@ -392,9 +406,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           const uint64_t da_lo = a_base | uint64_t(((a_lo + k * a_kstep) & 0x3FFFF) >> 4);
           const uint64_t db_hi = b_base | uint64_t(((b_hi + k * b_kstep) & 0x3FFFF) >> 4);
           const uint64_t db_lo = b_base | uint64_t(((b_lo + k * b_kstep) & 0x3FFFF) >> 4);
-          mma_tf32(d_tmem, da_lo, db_hi, idesc, ((i % CH) | k) != 0);   // small terms first
-          mma_tf32(d_tmem, da_hi, db_lo, idesc, 1);
-          mma_tf32(d_tmem, da_hi, db_hi, idesc, 1);
+          mma_tf32(d_lo, da_lo, db_hi, idesc, (i | k) != 0);
+          mma_tf32(d_lo, da_hi, db_lo, idesc, 1);
+          mma_tf32(d_hi, da_hi, db_hi, idesc, ((i % CH) | k) != 0);
         }
         mma_commit(empty(s));                                // frees the stage once these MMAs have read it
         if (i % CH == CH - 1 || i == num_kb - 1) mma_commit(acc_full(buf));
@@ -402,9 +416,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     }
   } else {
     // ===================================================== workers: split, drain, epilogue
-    const int w = warp - 2;                  // 0 .. WORKERS-1
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
-    const int col_group = w >> 2;            // which NC-column slab of the tile this warp owns
     const int t = threadIdx.x - 64;
     constexpr int NT = 32 * WORKERS;
     constexpr int VEC_PER_STAGE = (C::A_BYTES + C::B_BYTES) / 16;
@@ -413,7 +425,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     float acc[NC];
 #pragma unroll
     for (int j = 0; j < NC; ++j) acc[j] = 0.f;
-    const uint32_t lane_base = tmem_base + (uint32_t(32 * q) << 16) + (uint32_t)col_group * NC;
+    const uint32_t lane_base = tmem_base + (uint32_t(32 * q) << 16);
 
     auto drain = [&](int chunk) {
       const int buf = chunk & 1;
@@ -442,9 +454,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 #pragma unroll
       for (int v = 0; v < VEC_PER_THREAD; ++v) x[v] = lds128(raw + 16u * (t + v * NT));
 #pragma unroll
-      for (int v = 0; v < VEC_PER_THREAD; ++v)
-        sts128(lo + 16u * (t + v * NT),
-               make_float4(tf32_lo(x[v].x), tf32_lo(x[v].y), tf32_lo(x[v].z), tf32_lo(x[v].w)));
+      for (int v = 0; v < VEC_PER_THREAD; ++v) {
+        float4 xh, xl;
+        tf32_split4(x[v], xh, xl);
+        sts128(raw + 16u * (t + v * NT), xh);
+        sts128(lo + 16u * (t + v * NT), xl);
+      }
       fence_proxy_async();              // generic-proxy writes -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(split(s));
@@ -453,7 +468,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     }
     // chunks not drained inside the loop: the last full one (and a trailing partial one)
     for (int c = max(num_kb / CH - 1, 0); c < num_chunks; ++c) drain(c);
-    epilogue_row<EPI, NC>(epi, p, m0 + 32 * q + lane, n0 + col_group * NC, z, acc);
+    if (num_kb > 0) {
+      // the commit behind the last acc_full covers every MMA issued before it, D_lo's included
+#pragma unroll
+      for (int c0 = 0; c0 < NC; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(lane_base + 2u * BN + c0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[c0 + j] = __fadd_rn(acc[c0 + j], __uint_as_float(r[j]));
+      }
+    }
+    epilogue_row<EPI, NC>(epi, p, m0 + 32 * q + lane, n0, z, acc);
   }
   tc_fence_before();
   __syncthreads();

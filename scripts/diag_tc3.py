@@ -34,6 +34,6 @@ for (M, N, K, amn, bmn) in [(4096, 256, 1290, 0, 0), (4096, 256, 256, 0, 0), (16
     B, ldb = mk(K, N) if bmn else mk(N, K)
     ldc = (N + 3) // 4 * 4
     C = torch.empty(M, ldc, device=DEV)
-    for tile in (64, 128, 256):
+    for tile in (64, 128):
         ms = timeit(lambda: _lib.check(L.recnn_gemm_tf32x3(M, N, K, A.data_ptr(), lda, amn, B.data_ptr(), ldb, bmn, C.data_ptr(), ldc, tile, st)))
         print("tc   M%d N%d K%d amn%d bmn%d tile_n %3d: %.3f ms  %.1f TFLOP/s (x3: %.1f)" % (M, N, K, amn, bmn, tile, ms, 2.0 * M * N * K / ms / 1e9, 6.0 * M * N * K / ms / 1e9))

@@ -91,6 +91,7 @@ def compare_with_golden(got: dict, gold: dict, rtol=1e-5, floor_frac=1e-2, delta
     Grads: within ``grad_rtol`` of the largest gradient entry of the tensor."""
     np.testing.assert_allclose(got["input_checksums"], gold["input_checksums"], rtol=1e-12,
                                err_msg="regenerated inputs differ from the golden run's inputs")
+    assert float(gold["gate_margin"]) > C.GATE_GUARD, "golden case has an ambiguous ReLU gate"
     report = {}
     for key in sorted(k for k in gold if k.startswith("loss.")):
         e = rel_err(got[key], gold[key], loss_floor)

@@ -99,10 +99,10 @@ def test_accumulation_is_not_truncated_over_long_k():
                                                0, torch.cuda.current_stream().cuda_stream))
         want = a.astype(np.float64) @ b.astype(np.float64).T
         rel = (c_d.cpu().numpy() - want) / want
-        assert abs(rel.mean()) < 2e-6 and np.abs(rel).max() < 4e-6, (K, rel.mean(), np.abs(rel).max())
+        assert abs(rel.mean()) < 5e-7 and np.abs(rel).max() < 2e-6, (K, rel.mean(), np.abs(rel).max())
 
 
-@pytest.mark.parametrize("tile_n", [64, 128, 256])
+@pytest.mark.parametrize("tile_n", [64, 128])
 def test_tile_widths_agree(tile_n):
     got, want = _run("tc", 512, 256, 320, False, False, seed=3, tile_n=tile_n)
     assert np.abs(got - want).max() / np.abs(want).max() < 8e-6
