@@ -161,7 +161,8 @@ enum {
   RECNN_PH_SOFT_UPDATE = 32, /* Polyak target updates (policy steps only)              */
   RECNN_PH_GATHER = 64,      /* frame form: materialise state/next_state/action into the
                               * workspace (split-phase callers pass it once per step)  */
-  RECNN_PH_ALL = 127
+  RECNN_PH_FINISH = 128,     /* end of step: copy losses to losses_host (if set), ++*rng_step */
+  RECNN_PH_ALL = 255
 };
 
 enum { RECNN_ALGO_DDPG = 0, RECNN_ALGO_TD3 = 1 };
@@ -206,10 +207,11 @@ typedef struct recnn_step_args {
   const uint8_t* masks[8];
   const float* noise;
   uint64_t seed;
-  const int64_t* rng_step;   /* device int64 counter, read (not written) by the step */
+  int64_t* rng_step;         /* device int64 counter; read by every phase, incremented by RECNN_PH_FINISH */
 
   /* outputs */
   float* losses;           /* device fp32[4]: value(1), value2, policy, ||actor grad||_1 */
+  float* losses_host;      /* optional PINNED host fp32[4]: RECNN_PH_FINISH copies `losses` here (async) */
   float* next_action_out;  /* optional fp32[n_rows,A] (debug["next_action"]) */
   float* gen_action_out;   /* optional fp32[n_rows,A] (debug["gen_action"])  */
 

@@ -14,7 +14,8 @@ from . import build as _build
 
 PH_VALUE_GRAD, PH_VALUE_OPT, PH_POLICY_LOSS, PH_POLICY_GRAD, PH_POLICY_OPT, PH_SOFT_UPDATE, PH_GATHER = \
     1, 2, 4, 8, 16, 32, 64
-PH_ALL = 127
+PH_FINISH = 128
+PH_ALL = 255
 ALGO_DDPG, ALGO_TD3 = 0, 1
 OPT_EXTERNAL, OPT_SGD, OPT_ADAM = 0, 1, 2
 
@@ -49,7 +50,7 @@ class StepArgs(C.Structure):
         ("noise_std", C.c_float), ("noise_clip", C.c_float), ("dropout", C.c_int32),
         ("soft_tau", C.c_double),
         ("masks", C.c_void_p * 8), ("noise", C.c_void_p), ("seed", C.c_uint64), ("rng_step", C.c_void_p),
-        ("losses", C.c_void_p), ("next_action_out", C.c_void_p), ("gen_action_out", C.c_void_p),
+        ("losses", C.c_void_p), ("losses_host", C.c_void_p), ("next_action_out", C.c_void_p), ("gen_action_out", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
     ]
 

@@ -155,6 +155,40 @@ colsum_partials_kernel(const float* __restrict__ dz, long long n_rows, int C, lo
   }
 }
 
+// Critic head weight gradient (the 256 -> 1 layer): part[z][0][c] = sum_r dq[r] * h2[r, c] over the
+// rows of split z, part[z][0][H] = sum_r dq[r]   (dW3 = dq^T h2, db3 = sum dq; misc.py:43 backward).
+__global__ void __launch_bounds__(256)
+head_grad_partials_kernel(const float* __restrict__ dq, const float* __restrict__ h2, long long n_rows, int H,
+                          long long rows_per_split, float* __restrict__ part) {
+  __shared__ float red[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx, z = blockIdx.y;
+  const long long r0 = (long long)z * rows_per_split;
+  const long long r1 = min(n_rows, r0 + rows_per_split);
+  float s = 0.f;
+  if (c < H) {
+    for (long long r = r0 + ry; r < r1; r += 8) s = fmaf(dq[r], h2[r * H + c], s);
+  } else if (c == H) {
+    for (long long r = r0 + ry; r < r1; r += 8) s += dq[r];
+  }
+  red[ry][cx] = s;
+  __syncthreads();
+  if (ry == 0 && c <= H) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][cx];
+    part[(long long)z * (H + 1) + c] = t;
+  }
+}
+
+int launch_head_grad_partials(const float* dq, const float* h2, int64_t n_rows, int H, int64_t rows_per_split,
+                              int splits, float* part, cudaStream_t st) {
+  dim3 grid((unsigned)ceil_div(H + 1, 32), (unsigned)splits);
+  head_grad_partials_kernel<<<grid, 256, 0, st>>>(dq, h2, n_rows, H, rows_per_split, part);
+  RECNN_CHECK_LAUNCH("head_grad_partials_kernel");
+  return RECNN_OK;
+}
+
 int launch_colsum_partials(const float* dz, int64_t n_rows, int C, int64_t rows_per_split, int splits,
                            float* part, int K1, cudaStream_t st) {
   dim3 grid((unsigned)ceil_div(C, 32), (unsigned)splits);
@@ -261,6 +295,13 @@ optimizer_kernel(int kind, OptConsts k, double beta1, double beta2, double lr, f
 }
 
 __global__ void bump_counter_kernel(int* t) { *t += 1; }
+__global__ void bump_counter64_kernel(long long* t) { *t += 1; }
+
+int launch_bump64(long long* t, cudaStream_t st) {
+  bump_counter64_kernel<<<1, 1, 0, st>>>(t);
+  RECNN_CHECK_LAUNCH("bump_counter64_kernel");
+  return RECNN_OK;
+}
 
 int launch_optimizer(const recnn_optim& o, const recnn_net& net, int64_t count, const float* grad_scale,
                      cudaStream_t st) {

@@ -42,6 +42,8 @@ int launch_critic_head_bwd(const float* dq, float dq_const, const float* w3, con
 // bias gradient: w_dst[c*ldw+k] for k<K1-1 (ldw = arena row pitch), b_dst[c] for k==K1-1.
 int launch_reduce_partials(const float* part, int splits, int C, int K1, float* w_dst, long long ldw,
                            float* b_dst, cudaStream_t st);
+int launch_head_grad_partials(const float* dq, const float* h2, int64_t n_rows, int H, int64_t rows_per_split,
+                              int splits, float* part, cudaStream_t st);
 int launch_colsum_partials(const float* dz, int64_t n_rows, int C, int64_t rows_per_split, int splits,
                            float* part, int K1, cudaStream_t st);
 
@@ -54,6 +56,7 @@ int launch_scale_inplace(float* x, int64_t count, const float* scale, cudaStream
 int launch_optimizer(const recnn_optim& o, const recnn_net& net, int64_t count, const float* grad_scale,
                      cudaStream_t st);
 
+int launch_bump64(long long* t, cudaStream_t st);
 int launch_polyak(float* target, const float* net, int64_t count, double tau, cudaStream_t st);
 
 }  // namespace recnn

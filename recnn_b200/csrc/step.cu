@@ -34,13 +34,45 @@ static bool math_tc() {
 }
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// ---------------------------------------------------------------- intra-step concurrency
+// The three forward chains at the head of a step are independent: (T) target policy -> target critic
+// -> TD target, (V) online critic forward, (P) online policy forward.  Each GEMM fills at most 64-128
+// of the 148 SMs, so they are issued on three streams (fork/join with events; capturable into the
+// step's CUDA graph).  RECNN_B200_OVERLAP=0 serialises everything on the caller's stream.
+struct AuxStreams {
+  cudaStream_t sv, sp;
+  cudaEvent_t fork, v_done, p_done;
+  bool ok;
+};
+static AuxStreams* aux_streams() {
+  static AuxStreams per_dev[64];
+  static bool init[64] = {false};
+  static const bool enabled = !(getenv("RECNN_B200_OVERLAP") && strcmp(getenv("RECNN_B200_OVERLAP"), "0") == 0);
+  if (!enabled) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  AuxStreams& a = per_dev[dev];
+  if (!init[dev]) {
+    // never created while a capture is in flight: the first call of a shape is always a direct launch
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    (void)cs;
+    a.ok = cudaStreamCreateWithFlags(&a.sv, cudaStreamNonBlocking) == cudaSuccess &&
+           cudaStreamCreateWithFlags(&a.sp, cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&a.v_done, cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&a.p_done, cudaEventDisableTiming) == cudaSuccess;
+    init[dev] = true;
+  }
+  return a.ok ? &a : nullptr;
+}
+
 // ---------------------------------------------------------------- workspace
 struct Workspace {
   float* S;        // [N, ldS] state (frame form: gathered; dense form: re-pitched copy)
   float* S2;       // [N, ldS]
   float* ACT;      // [N, ldA] batch action, stored with `lead` zero columns in front (see Seg)
   float* REW;      // [N]
-  float* hb[6];    // [N,H] activation / gradient buffers (lifetimes in DESIGN.md)
+  float* hb[8];    // [N,H] activation / gradient buffers (lifetimes in DESIGN.md)
   float* ab[3];    // [N, ldA] next_action / gen_action (lead-padded) ; [N,A] d gen_action
   float* y;        // [N] TD target
   float* qtmp;     // [N]
@@ -154,7 +186,7 @@ static int gemm_nt(const Seg& x0, const Seg& x1, const float* W, long long ldw, 
                      (x1.cols == 0 || (x0.cols - x1.lead) % 4 == 0);
   if (tc_ok) {
     tc::Operand a0 = {x0.p, x0.ld, 0, 0}, a1 = {x1.p, x1.ld, 0, 0}, b = {W, ldw, N, K};
-    tc::Problem p = {(int)n, N, x0.cols, x1.cols, 0, x0.cols - x1.lead, 0, 0};
+    tc::Problem p = {(int)n, N, x0.cols, x1.cols, 0, x0.cols - x1.lead, 0, 0, nullptr, nullptr};
     const int r = tc::launch<false, false, EPI>(a0, a1, b, p, 1, pick_bn(n, N), e, st);
     return r < 0 ? r : RECNN_OK;
   }
@@ -196,7 +228,7 @@ static int backprop_hidden(const float* dZ, int C, const float* W, long long ldw
   const bool tc_ok = math_tc() && aligned16(dZ) && aligned16(W) && C % 4 == 0 && ldw % 4 == 0 && col0 % 4 == 0;
   if (tc_ok) {
     tc::Operand a0 = {dZ, C, 0, 0}, a1 = {nullptr, 0, 0, 0}, b = {W, ldw, C, w_cols};
-    tc::Problem p = {(int)n, K, C, 0, 0, C, 0, col0};
+    tc::Problem p = {(int)n, K, C, 0, 0, C, 0, col0, nullptr, nullptr};
     const int bn = pick_bn(n, K);
     const int r = h ? tc::launch<false, true, EPI_GATE>(a0, a1, b, p, 1, bn, e, st)
                     : tc::launch<false, true, EPI_STORE>(a0, a1, b, p, 1, bn, e, st);
@@ -227,7 +259,7 @@ static int weight_grad(const float* dZ, int C, const Seg& x0, const Seg& x1, int
       const Seg* s = segs[i];
       if (s->cols == 0) continue;
       tc::Operand b = {s->p, s->ld, n, s->cols};
-      tc::Problem p = {C, s->cols, (int)n, 0, 0, 0, cols0[i], 0};
+      tc::Problem p = {C, s->cols, (int)n, 0, 0, 0, cols0[i], 0, nullptr, nullptr};
       const int bn = s->cols > 64 ? 128 : 64;
       const int r = tc::launch<true, true, EPI_PARTIAL>(a0, a1, b, p, req, bn, e, st);
       if (r < 0) return r;
@@ -263,31 +295,33 @@ struct Ctx {
   Rng rng;
   bool train;
   float gate;
+  AuxStreams* aux;       // non-null: chains V and P run on side streams
+  bool v_prefetched, p_prefetched;
 };
 
 // Critic hidden layers on (s, act):  h1 -> out1, h2 -> out2
 static int critic_hidden(const Ctx& c, const float* params, const float* s, const float* act, bool train,
-                         int mask_base, float* out1, float* out2) {
+                         int mask_base, float* out1, float* out2, cudaStream_t st) {
   const int S = c.d.state_dim, A = c.d.action_dim, H = c.d.hidden;
   const uint8_t* m1 = (train && c.rng.masks) ? c.rng.masks[mask_base] : nullptr;
   const uint8_t* m2 = (train && c.rng.masks) ? c.rng.masks[mask_base + 1] : nullptr;
   const Seg xs = {s, S, c.ldS, 0}, xa = {act, A + c.lead, c.ldA, c.lead}, h1 = {out1, H, H, 0};
   RECNN_PROPAGATE(hidden_layer(xs, xa, params + c.lc.w1, c.lc.ld1, params + c.lc.b1, H, c.n, train, m1, c.rng,
-                               mask_base, out1, c.st));
+                               mask_base, out1, st));
   return hidden_layer(h1, kNoSeg, params + c.lc.w2, c.lc.ld2, params + c.lc.b2, H, c.n, train, m2, c.rng,
-                      mask_base + 1, out2, c.st);
+                      mask_base + 1, out2, st);
 }
 
 static int actor_hidden(const Ctx& c, const float* params, const float* s, bool train, int mask_base,
-                        float* out1, float* out2) {
+                        float* out1, float* out2, cudaStream_t st) {
   const int S = c.d.state_dim, H = c.d.hidden;
   const uint8_t* m1 = (train && c.rng.masks) ? c.rng.masks[mask_base] : nullptr;
   const uint8_t* m2 = (train && c.rng.masks) ? c.rng.masks[mask_base + 1] : nullptr;
   const Seg xs = {s, S, c.ldS, 0}, h1 = {out1, H, H, 0};
   RECNN_PROPAGATE(hidden_layer(xs, kNoSeg, params + c.la.w1, c.la.ld1, params + c.la.b1, H, c.n, train, m1, c.rng,
-                               mask_base, out1, c.st));
+                               mask_base, out1, st));
   return hidden_layer(h1, kNoSeg, params + c.la.w2, c.la.ld2, params + c.la.b2, H, c.n, train, m2, c.rng,
-                      mask_base + 1, out2, c.st);
+                      mask_base + 1, out2, st);
 }
 
 static HeadArgs head_args(const Ctx& c, const float* params, const float* h2, int mode) {
@@ -312,7 +346,7 @@ static int phase_value_grad(Ctx& c) {
   float* a2 = c.ws.ab[0];
 
   // target policy on next_state, eval mode (misc.py:28 / td3.py:73) (+ clipped noise, td3.py:74-78)
-  RECNN_PROPAGATE(actor_hidden(c, a.target_policy.params, c.S2, false, 0, X0, X1));
+  RECNN_PROPAGATE(actor_hidden(c, a.target_policy.params, c.S2, false, 0, X0, X1, c.st));
   NoiseSpec nz = {td3 ? 1 : 0, a.noise, a.noise_clip, a.noise_std, a.seed, (const long long*)a.rng_step, 15u};
   const Seg x1s = {X1, H, H, 0};
   RECNN_PROPAGATE(linear_out(x1s, a.target_policy.params + c.la.w3, c.la.ld3, a.target_policy.params + c.la.b3, A,
@@ -323,7 +357,7 @@ static int phase_value_grad(Ctx& c) {
 
   // target critic(s) -> TD target y (misc.py:29-35 / td3.py:80-86)
   for (int i = 0; i < n_critics; ++i) {
-    RECNN_PROPAGATE(critic_hidden(c, a.target_value[i].params, c.S2, a2, false, 0, X0, X1));
+    RECNN_PROPAGATE(critic_hidden(c, a.target_value[i].params, c.S2, a2, false, 0, X0, X1, c.st));
     HeadArgs h = head_args(c, a.target_value[i].params, X1,
                            td3 ? (i == 0 ? HEAD_TARGET_TD3_A : HEAD_TARGET_TD3_B) : HEAD_TARGET_DDPG);
     RECNN_PROPAGATE(launch_critic_head(h, c.st));
@@ -332,17 +366,25 @@ static int phase_value_grad(Ctx& c) {
   // online critic(s): value, loss, backward (misc.py:37-43 / td3.py:88-101)
   for (int i = 0; i < n_critics; ++i) {
     const float* P = a.value[i].params;
-    RECNN_PROPAGATE(critic_hidden(c, P, c.S, c.ACT, c.train, 2 * i, c1, c2));
+    if (i == 0 && c.v_prefetched) {
+      RECNN_CHECK_CUDA(cudaStreamWaitEvent(c.st, c.aux->v_done, 0));      // chain V ran on the side stream
+    } else {
+      RECNN_PROPAGATE(critic_hidden(c, P, c.S, c.ACT, c.train, 2 * i, c1, c2, c.st));
+    }
     HeadArgs h = head_args(c, P, c2, HEAD_VALUE);
     h.loss = a.losses + i;
     RECNN_PROPAGATE(launch_critic_head(h, c.st));
     if (!a.learn) continue;
     float* G = a.value[i].grads;
     RECNN_REQUIRE(G != nullptr, "value net needs a grad arena when learn=1");
-    const Seg sc2 = {c2, H, H, 0}, sc1 = {c1, H, H, 0}, ss = {c.S, S, c.ldS, 0},
-              sa = {c.ACT, A + c.lead, c.ldA, c.lead};
+    const Seg sc1 = {c1, H, H, 0}, ss = {c.S, S, c.ldS, 0}, sa = {c.ACT, A + c.lead, c.ldA, c.lead};
     // layer 3: dW3 = dq^T h2, db3 = sum dq ; dz2 = (dq w3) * gate(h2)
-    RECNN_PROPAGATE(weight_grad(c.ws.dq, 1, sc2, kNoSeg, c.n, G + c.lc.w3, c.lc.ld3, G + c.lc.b3, c.ws, c.st));
+    {
+      const int64_t rows_per = 256;
+      const int splits = (int)ceil_div(c.n, rows_per);       // <= dw_splits(1, H, n, false): fits ws.partial
+      RECNN_PROPAGATE(launch_head_grad_partials(c.ws.dq, c2, c.n, H, rows_per, splits, c.ws.partial, c.st));
+      RECNN_PROPAGATE(launch_reduce_partials(c.ws.partial, splits, 1, H + 1, G + c.lc.w3, c.lc.ld3, G + c.lc.b3, c.st));
+    }
     RECNN_PROPAGATE(launch_critic_head_bwd(c.ws.dq, 0.f, P + c.lc.w3, c2, c.gate, dz2, c.n, H, c.st));
     RECNN_PROPAGATE(weight_grad(dz2, H, sc1, kNoSeg, c.n, G + c.lc.w2, c.lc.ld2, G + c.lc.b2, c.ws, c.st));
     RECNN_PROPAGATE(backprop_hidden(dz2, H, P + c.lc.w2, c.lc.ld2, H, 0, H, c.n, c1, c.gate, dz1, c.st));
@@ -360,22 +402,33 @@ static int phase_value_opt(Ctx& c) {
   return RECNN_OK;
 }
 
-static int phase_policy_loss(Ctx& c) {
+// pi(s): hidden activations p1,p2 (kept for the actor backward) and gen_action
+static int policy_actor_forward(const Ctx& c, cudaStream_t st) {
   const recnn_step_args& a = *c.a;
   const int H = c.d.hidden, A = c.d.action_dim;
+  const int pm = a.algo == RECNN_ALGO_TD3 ? 4 : 2;
+  float *p1 = c.ws.hb[6], *p2 = c.ws.hb[7];
+  float* gen = c.ws.ab[1];
+  RECNN_PROPAGATE(actor_hidden(c, a.policy.params, c.S, c.train, pm, p1, p2, st));
+  const Seg sp2 = {p2, H, H, 0};
+  return linear_out(sp2, a.policy.params + c.la.w3, c.la.ld3, a.policy.params + c.la.b3, A, c.n, 0, nullptr,
+                    gen + c.lead, c.ldA, st);
+}
+
+static int phase_policy_loss(Ctx& c) {
+  const recnn_step_args& a = *c.a;
+  const int A = c.d.action_dim;
   const bool td3 = a.algo == RECNN_ALGO_TD3;
-  const int pm = td3 ? 4 : 2, vm = td3 ? 6 : 4;     // mask slots (header: call order)
-  float *p1 = c.ws.hb[0], *p2 = c.ws.hb[1], *v1 = c.ws.hb[2], *v2 = c.ws.hb[3];
+  const int vm = td3 ? 6 : 4;                       // mask slots (header: call order)
+  float *v1 = c.ws.hb[0], *v2 = c.ws.hb[1];
   float* gen = c.ws.ab[1];
   // gen_action = policy_net(state); policy_loss = -value_net(state, gen_action)  (ddpg.py:78-79, td3.py:116-118)
-  RECNN_PROPAGATE(actor_hidden(c, a.policy.params, c.S, c.train, pm, p1, p2));
-  const Seg sp2 = {p2, H, H, 0};
-  RECNN_PROPAGATE(linear_out(sp2, a.policy.params + c.la.w3, c.la.ld3, a.policy.params + c.la.b3, A, c.n, 0,
-                             nullptr, gen + c.lead, c.ldA, c.st));
+  if (c.p_prefetched) RECNN_CHECK_CUDA(cudaStreamWaitEvent(c.st, c.aux->p_done, 0));
+  else RECNN_PROPAGATE(policy_actor_forward(c, c.st));
   if (a.gen_action_out)
     RECNN_CHECK_CUDA(cudaMemcpy2DAsync(a.gen_action_out, (size_t)A * 4, gen + c.lead, c.ldA * 4, (size_t)A * 4, c.n,
                                        cudaMemcpyDeviceToDevice, c.st));
-  RECNN_PROPAGATE(critic_hidden(c, a.value[0].params, c.S, gen, c.train, vm, v1, v2));
+  RECNN_PROPAGATE(critic_hidden(c, a.value[0].params, c.S, gen, c.train, vm, v1, v2, c.st));
   HeadArgs h = head_args(c, a.value[0].params, v2, HEAD_POLICY);
   h.loss = a.losses + 2;
   return launch_critic_head(h, c.st);
@@ -385,7 +438,7 @@ static int phase_policy_grad(Ctx& c) {
   const recnn_step_args& a = *c.a;
   if (!a.do_policy_step) return RECNN_OK;
   const int S = c.d.state_dim, A = c.d.action_dim, H = c.d.hidden;
-  float *p1 = c.ws.hb[0], *p2 = c.ws.hb[1], *v1 = c.ws.hb[2], *v2 = c.ws.hb[3], *dv2 = c.ws.hb[4],
+  float *p1 = c.ws.hb[6], *p2 = c.ws.hb[7], *v1 = c.ws.hb[0], *v2 = c.ws.hb[1], *dv2 = c.ws.hb[4],
         *dv1 = c.ws.hb[5];
   float* dgen = c.ws.ab[2];
   const float* Pc = a.value[0].params;
@@ -508,12 +561,33 @@ static int run_step(const recnn_step_args* a, int algo, void* stream) {
     }
     c.REW = a->reward;
   }
+  // fork: chain V (online critic forward) and chain P (online policy forward) on side streams
+  c.aux = nullptr;
+  c.v_prefetched = c.p_prefetched = false;
+  if ((a->phases & RECNN_PH_VALUE_GRAD) && (c.aux = aux_streams()) != nullptr) {
+    RECNN_CHECK_CUDA(cudaEventRecord(c.aux->fork, c.st));
+    RECNN_CHECK_CUDA(cudaStreamWaitEvent(c.aux->sv, c.aux->fork, 0));
+    RECNN_PROPAGATE(critic_hidden(c, a->value[0].params, c.S, c.ACT, c.train, 0, c.ws.hb[2], c.ws.hb[3], c.aux->sv));
+    RECNN_CHECK_CUDA(cudaEventRecord(c.aux->v_done, c.aux->sv));
+    c.v_prefetched = true;
+    if (a->phases & RECNN_PH_POLICY_LOSS) {
+      RECNN_CHECK_CUDA(cudaStreamWaitEvent(c.aux->sp, c.aux->fork, 0));
+      RECNN_PROPAGATE(policy_actor_forward(c, c.aux->sp));
+      RECNN_CHECK_CUDA(cudaEventRecord(c.aux->p_done, c.aux->sp));
+      c.p_prefetched = true;
+    }
+  }
   if (a->phases & RECNN_PH_VALUE_GRAD) RECNN_PROPAGATE(phase_value_grad(c));
   if (a->phases & RECNN_PH_VALUE_OPT) RECNN_PROPAGATE(phase_value_opt(c));
   if (a->phases & RECNN_PH_POLICY_LOSS) RECNN_PROPAGATE(phase_policy_loss(c));
   if (a->phases & RECNN_PH_POLICY_GRAD) RECNN_PROPAGATE(phase_policy_grad(c));
   if (a->phases & RECNN_PH_POLICY_OPT) RECNN_PROPAGATE(phase_policy_opt(c));
   if (a->phases & RECNN_PH_SOFT_UPDATE) RECNN_PROPAGATE(phase_soft_update(c));
+  if (a->phases & RECNN_PH_FINISH) {
+    if (a->rng_step) RECNN_PROPAGATE(launch_bump64((long long*)a->rng_step, c.st));
+    if (a->losses_host)
+      RECNN_CHECK_CUDA(cudaMemcpyAsync(a->losses_host, a->losses, 4 * sizeof(float), cudaMemcpyDeviceToHost, c.st));
+  }
   return RECNN_OK;
 }
 

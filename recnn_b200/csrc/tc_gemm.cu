@@ -59,6 +59,19 @@ int split_plan(int K_total_blocks, int splits_req, int* k_chunk) {
   return (int)ceil_div(K_total_blocks, kb_per);
 }
 
+// Step-timeline tracing (debugging aid): when a span buffer is installed, launch number i of this
+// process writes {first CTA entry, last CTA exit} to span[2*i ..] (shape/config via recnn_debug_span_meta); the slot index is baked into the kernel parameters, so CUDA-graph replays refresh it.
+static unsigned long long* g_span = nullptr;
+static int g_span_cap = 0, g_span_next = 0;
+static long long g_span_meta[4096][4];
+extern "C" RECNN_API void recnn_debug_set_span(unsigned long long* buf, int capacity) {
+  g_span = buf; g_span_cap = capacity < 4096 ? capacity : 4096; g_span_next = 0;
+}
+extern "C" RECNN_API int recnn_debug_span_count(void) { return g_span_next; }
+extern "C" RECNN_API void recnn_debug_span_meta(int i, long long* out4) {
+  for (int j = 0; j < 4; ++j) out4[j] = g_span_meta[i][j];
+}
+
 template <class C, int EPI>
 static int launch_cfg(const Operand& A0, const Operand& A1, const Operand& B, const Problem& p_in, int splits,
                       const Epilogue& epi, cudaStream_t st) {
@@ -85,6 +98,15 @@ static int launch_cfg(const Operand& A0, const Operand& A1, const Operand& B, co
   if (!C::B_MN) RECNN_PROPAGATE(make_tmap(&mb, B.ptr, B.rows, B.cols, B.ld, C::BK, C::BN, C::K_SWZ));
   else RECNN_PROPAGATE(make_tmap(&mb, B.ptr, B.rows, B.cols, B.ld, 32, C::BK, 1032));
   dim3 grid((unsigned)ceil_div(p.N, C::BN), (unsigned)ceil_div(p.M, C::BM), (unsigned)splits);
+  if (g_span && g_span_next < g_span_cap) {
+    g_span_meta[g_span_next][0] = C::BN | (C::A_MN << 12) | (C::B_MN << 13) | (EPI << 16);
+    g_span_meta[g_span_next][1] = p.M;
+    g_span_meta[g_span_next][2] = p.N;
+    g_span_meta[g_span_next][3] = (long long)(p.K0 + p.K1) | ((long long)splits << 32);
+    p.span = g_span + 2 * g_span_next++;
+  } else {
+    p.span = nullptr;
+  }
   static const bool debug = getenv("RECNN_B200_DEBUG") != nullptr;
   if (debug)
     fprintf(stderr, "[tc_gemm] BN=%d A_MN=%d B_MN=%d EPI=%d M=%d N=%d K0=%d K1=%d k_chunk=%d bk1=%d nout=%d bn_off=%d "
@@ -132,6 +154,10 @@ RECNN_TC_INST(true, false, EPI_STORE)
 
 using namespace recnn;
 
+static unsigned long long* g_trace = nullptr;
+// debugging aid: device buffer (8 u64 per CTA) that recnn_gemm_tf32x3 fills with %globaltimer stamps
+extern "C" RECNN_API void recnn_debug_set_trace(unsigned long long* buf) { g_trace = buf; }
+
 // C[M,N] (row pitch ldc) = A . B^T in 3xTF32 on the tensor cores.
 //   a_mn = 0: A is [M,K] row-major (pitch lda)   a_mn = 1: A is [K,M] row-major
 //   b_mn = 0: B is [N,K] row-major (pitch ldb)   b_mn = 1: B is [K,N] row-major
@@ -146,7 +172,7 @@ extern "C" int recnn_gemm_tf32x3(int M, int N, int K, const float* A, int64_t ld
   e.ldo = ldc;
   tc::Operand a0 = {A, lda, 0, 0}, a1 = {nullptr, 0, 0, 0};
   tc::Operand b = {B, ldb, b_mn ? K : N, b_mn ? N : K};
-  tc::Problem p = {M, N, K, 0, 0, K, 0, 0};
+  tc::Problem p = {M, N, K, 0, 0, K, 0, 0, g_trace, nullptr};
   if (tile_n <= 0) tile_n = N > 64 ? 128 : 64;
   int r;
   if (!a_mn && !b_mn) r = tc::launch<false, false, EPI_STORE>(a0, a1, b, p, 1, tile_n, e, st);

@@ -177,7 +177,19 @@ struct Problem {
   int b_k1_offset;       // B's k coordinate where the K1 segment starts (== K0 for a dense weight)
   int n_out_offset;      // column offset added when storing (C window)
   int b_n_offset;        // B's n coordinate of output column 0 (window into a wider B, e.g. W1[:, S:S+A])
+  unsigned long long* trace;   // optional: per-CTA %globaltimer stamps (8 per CTA) for pipeline analysis
+  unsigned long long* span;    // optional: {min entry, max exit} of this launch (timeline of a whole step)
 };
+
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define RECNN_TRACE(slot)                                                                          \
+  do {                                                                                             \
+    if (p.trace) p.trace[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + (slot)] = gtimer(); \
+  } while (0)
 
 template <int BN_, int STAGES_, bool A_MN_, bool B_MN_>
 struct Cfg {
@@ -310,6 +322,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM, z = blockIdx.z;
+  if (threadIdx.x == 0) RECNN_TRACE(0);                       // kernel entry
+  if (threadIdx.x == 0 && p.span) atomicMin(p.span, gtimer());
   // k-blocks: segment 0 then segment 1, each padded up to a multiple of BK (TMA zero-fills the tail)
   const int nkb0 = (p.K0 + BK - 1) / BK, nkb1 = (p.K1 + BK - 1) / BK;
   const int kb_per_split = p.k_chunk / BK;
@@ -343,6 +357,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  if (threadIdx.x == 0) RECNN_TRACE(1);                       // prologue done
 
   if (warp == 0) {
     // ===================================================== TMA producer
@@ -396,6 +411,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         }
         mbar_wait(split(s), ph);
         tc_fence_after();
+        if (i == 0) RECNN_TRACE(2);                           // first stage loaded + split
         const uint32_t d_hi = tmem_base + (uint32_t)buf * BN;     // chunk accumulator (hi*hi)
         const uint32_t d_lo = tmem_base + 2u * BN;                // tile-lifetime accumulator (cross terms)
         const uint32_t a_hi = stage_addr(s, 0), b_hi = stage_addr(s, 1);
@@ -413,6 +429,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         mma_commit(empty(s));                                // frees the stage once these MMAs have read it
         if (i % CH == CH - 1 || i == num_kb - 1) mma_commit(acc_full(buf));
       }
+      RECNN_TRACE(3);                                         // last MMA issued
     }
   } else {
     // ===================================================== workers: split, drain, epilogue
@@ -466,8 +483,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       // once the last k-block of chunk c has been split, chunk c-1 has long been accumulated: drain it
       if (i % CH == CH - 1 && i / CH >= 1) drain(i / CH - 1);
     }
+    if (t == 0) RECNN_TRACE(4);                               // last stage split
     // chunks not drained inside the loop: the last full one (and a trailing partial one)
     for (int c = max(num_kb / CH - 1, 0); c < num_chunks; ++c) drain(c);
+    if (t == 0) RECNN_TRACE(5);                               // all chunks drained (MMAs complete)
     if (num_kb > 0) {
       // the commit behind the last acc_full covers every MMA issued before it, D_lo's included
 #pragma unroll
@@ -480,10 +499,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       }
     }
     epilogue_row<EPI, NC>(epi, p, m0 + 32 * q + lane, n0, z, acc);
+    if (t == 0) RECNN_TRACE(6);                               // epilogue stored
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+  if (threadIdx.x == 0) RECNN_TRACE(7);
+  if (threadIdx.x == 0 && p.span) atomicMax(p.span + 1, gtimer());
 }
 
 // ------------------------------------------------------------------ host side
