@@ -250,37 +250,65 @@ class StepEngine:
         self.last_call_kernels = L.recnn_b200_launch_count() - before
         self.kernels += self.last_call_kernels
 
-    def _run_fused(self, a):
-        """Whole step in one C call; replayed as a CUDA graph once the variant is warm."""
+    def _body(self, a, nets, do_policy):
+        """The whole step with built-in optimizers: one C call on one GPU.  (The multi-GPU branch below
+        is kept for direct launches only: capturing the NCCL all-reduces into the step graph deadlocked
+        on the 2-GPU box, so data parallel runs go through the split-phase path in _step.)"""
+        P = _lib
+        if self.world == 1:
+            self._launch(a, P.PH_ALL)
+            return self.last_call_kernels
+        td3 = self.algo == P.ALGO_TD3
+        kernels = 0
+        self._launch(a, P.PH_GATHER | P.PH_VALUE_GRAD)
+        kernels += self.last_call_kernels
+        for i in range(2 if td3 else 1):
+            self._allreduce(grad_arena(nets["value_net" + (str(i + 1) if td3 else "")]))
+        self._launch(a, P.PH_VALUE_OPT | P.PH_POLICY_LOSS | P.PH_POLICY_GRAD)
+        kernels += self.last_call_kernels
+        if do_policy:
+            self._allreduce(grad_arena(nets["policy_net"]))
+        self._allreduce(self.losses[:3])
+        self._launch(a, P.PH_POLICY_OPT | P.PH_SOFT_UPDATE | P.PH_FINISH)
+        kernels += self.last_call_kernels
+        return kernels
+
+    def _run_fused(self, a, nets, do_policy):
+        """Direct launches the first time a variant is seen, then one CUDA graph (kernels, side-stream
+        forks/joins, the loss read-back and -- with several GPUs -- the NCCL all-reduces) per variant."""
         a.phases = _lib.PH_ALL
         key = self._signature(a)
         if not _USE_GRAPHS:
-            self._launch(a, _lib.PH_ALL)
-            return
+            self._body(a, nets, do_policy)
+            return None
         g = self.graphs.get(key)
         if g is not None:
             g[0].replay()
             self.kernels += g[1]
-            return
+            return g
         runs = self.eager_runs.get(key, 0)
         self.eager_runs[key] = runs + 1
         if runs < 1:                      # first time: plain launch (also warms lazy module loading)
-            self._launch(a, _lib.PH_ALL)
-            return
+            self._body(a, nets, do_policy)
+            return None
         if len(self.graphs) > 16:
             self.graphs.clear()
             self.eager_runs.clear()
+            self._fast.clear()
         try:
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self._launch(a, _lib.PH_ALL)
-            self.graphs[key] = (g, self.last_call_kernels)
+                n_kernels = self._body(a, nets, do_policy)
+            self.graphs[key] = (g, n_kernels)
             g.replay()
+            self.kernels += n_kernels
+            return self.graphs[key]
         except Exception as exc:      # capture unsupported in this context: stay on direct launches
             warnings.warn("recnn_b200: CUDA graph capture failed (%s); using direct launches" % exc)
             globals()["_USE_GRAPHS"] = False
-            self._launch(a, _lib.PH_ALL)
+            self._body(a, nets, do_policy)
+            return None
 
     # ------------------------------------------------------------------ the step
     def step(self, batch, params, nets, optimizer, learn, step, debug, policy_every_key):
@@ -338,10 +366,9 @@ class StepEngine:
             n, A = st["n"], self.dims.action_dim
             want_debug = {"next_action": torch.empty(n, A, device=self.device),
                           "gen_action": torch.empty(n, A, device=self.device)}
-        if builtin and self.world == 1 and want_debug is None:
-            self._run_fused(a)
-            g = self.graphs.get(self._signature(a))
-            if g is not None and learn:
+        if builtin and learn and want_debug is None and self.world == 1:
+            g = self._run_fused(a, nets, do_policy)
+            if g is not None:
                 # arenas may have been (re)built by _build_args: fingerprint after the fact
                 self._fast[(do_policy, st["form"], st["n"])] = (self._tokens(nets, optimizer, params, st), g[0], g[1])
             torch.cuda.current_stream(self.device).synchronize()

@@ -62,30 +62,38 @@ def build_optimizers(kind, nets, algo, external=False):
     return {k: mk(nets[v]) for k, v in names.items()}
 
 
-def run_cuda_case(case, algo, opt_kind, golden=None, form="dense", external=False, device="cuda:0"):
+def run_cuda_case(case, algo, opt_kind, golden=None, form="dense", external=False, device="cuda:0",
+                  shard=None):
+    """shard=(rank, world): this process handles rows [lo, hi) of every minibatch (data parallel)."""
     spec = C.CASES[case]
     inp = C.make_inputs(spec, algo)
     dev = torch.device(device)
+    lo, hi = (0, spec["n_rows"]) if shard is None else recnn_b200.dist.shard_rows(spec["n_rows"], *shard)
     out = {"input_checksums": C.input_checksums(inp)}
     nets = build_nets(spec, inp, dev)
     opts = build_optimizers(opt_kind, nets, algo, external)
+    if shard is not None:
+        recnn_b200.dist.enable_data_parallel(nets)
     params = dict(C.DDPG_PARAMS if algo == "ddpg" else C.TD3_PARAMS)
     table = torch.from_numpy(inp["table"]).to(dev)
+    ref = O.frame_gather(inp["table"], inp["items"], inp["ratings"], inp["sizes"], spec["frame"])
     if form == "dense":
-        ref = O.frame_gather(inp["table"], inp["items"], inp["ratings"], inp["sizes"], spec["frame"])
-        base = {k: torch.from_numpy(v) for k, v in ref.items()}          # host tensors, like the reference's loader
-    else:
+        base = {k: torch.from_numpy(v[lo:hi]) for k, v in ref.items()}   # host tensors, like the reference's loader
+    elif shard is None:
         base = {"items": torch.from_numpy(inp["items"]), "ratings": torch.from_numpy(inp["ratings"]),
                 "sizes": torch.from_numpy(inp["sizes"]), "table": table}
+    else:                        # `done` is a prefix computation over the whole batch: sliced after the fact
+        base = {"items": torch.from_numpy(inp["items"][lo:hi]), "ratings": torch.from_numpy(inp["ratings"][lo:hi]),
+                "done": torch.from_numpy(ref["done"][lo:hi]), "table": table}
     update = recnn_b200.nn.ddpg_update if algo == "ddpg" else recnn_b200.nn.td3_update
     loss_keys = ("value", "policy") if algo == "ddpg" else ("value1", "value2", "policy")
     losses = {k: [] for k in loss_keys}
     for step in range(spec["steps"]):
         batch = dict(base)
-        batch["dropout_masks"] = [torch.from_numpy(m) for m in inp["masks"][step]]
+        batch["dropout_masks"] = [torch.from_numpy(np.ascontiguousarray(m[lo:hi])) for m in inp["masks"][step]]
         if algo == "td3":
             nz = golden["noise.%d" % step] if golden is not None else inp["noise"][step]
-            batch["noise"] = torch.from_numpy(np.ascontiguousarray(nz))
+            batch["noise"] = torch.from_numpy(np.ascontiguousarray(nz[lo:hi]))
         loss = update(batch, params, nets, opts, dev, {}, recnn_b200.utils.DummyWriter(), learn=True, step=step)
         assert loss["step"] == step
         for k in loss_keys:

@@ -290,3 +290,46 @@ def test_cpu_device_is_rejected_loudly():
             "value_net": recnn_b200.nn.Critic(s_dim, a_dim, h), "target_value_net": recnn_b200.nn.Critic(s_dim, a_dim, h)}
     with pytest.raises(_lib.RecnnError):
         recnn_b200.nn.ddpg_update({}, dict(C.DDPG_PARAMS), nets, {}, torch.device("cpu"), {}, learn=True, step=0)
+
+
+# ----------------------------------------------------------------------------- data parallel (2 GPUs)
+def _dp_worker(rank, world, port, algo, q):
+    import os
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        gold = load_golden("%s_canon_adam.npz" % algo)
+        got = run_cuda_case("canon", algo, "adam", golden=gold, form="frames", device="cuda:%d" % rank,
+                            shard=(rank, world))
+        got.pop("_nets")
+        q.put((rank, {k: v for k, v in got.items()}))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("algo", ["ddpg", "td3"])
+def test_two_rank_equals_reference(algo):
+    """Rows sharded over 2 ranks + gradient all-reduce == the single-process reference (golden),
+    and the two replicas stay bit-identical."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, algo, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    gold = load_golden("%s_canon_adam.npz" % algo)
+    for rank in (0, 1):
+        compare_with_golden(res[rank], gold, check_grads=False)
+    for k in res[0]:
+        if k.startswith("final."):
+            assert np.array_equal(res[0][k], res[1][k]), "replicas diverged: " + k
