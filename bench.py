@@ -109,124 +109,110 @@ def synth_step_inputs(seed, n_rows, n_steps):
 
 # =============================================================================== reference arm
 def run_reference(args):
-    """The reference algorithm (gather + ddpg_update) on the host CPU: numpy port in oracle/."""
+    """`--impl reference`: the reference algorithm on the host CPU (numpy port in oracle/; /root/reference is
+    Python and is not on the GPU box).  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    limiter, threads = pick_blas_threads()
-    if limiter is not None:
-        with limiter(limits=threads):
-            return _run_reference(args, threads)
-    return _run_reference(args, threads)
-
-
-def _run_reference(args, threads):
-    from oracle import recnn_oracle as O
-    from oracle import cases as C
-    rng = np.random.default_rng(0)
-    table = rng.standard_normal((N_ITEMS, DIM), dtype=np.float32)
     n_rows = ROWS_PER_GPU * args.gpus
-    total = args.steps + args.warmup
-    items, ratings, done = synth_step_inputs(1, n_rows, total)
-    nets = {"policy_net": O.make_actor(rng, S_DIM, DIM, HIDDEN, 6e-1),
-            "value_net": O.make_critic(rng, S_DIM, DIM, HIDDEN, 54e-2)}
-    nets["target_policy_net"] = O.copy_net(nets["policy_net"])
-    nets["target_value_net"] = O.copy_net(nets["value_net"])
-    opts = {"policy_optimizer": O.make_optimizer("adam", lr=1e-5),
-            "value_optimizer": O.make_optimizer("adam", lr=1e-5)}
-    params = dict(C.DDPG_PARAMS)
-    sizes = np.asarray([n_rows + FRAME], dtype=np.int64)
-    t_total = 0.0
-    for step in range(total):
-        masks = O.synth_masks(rng, 6, n_rows, HIDDEN)          # dropout draw (not timed: RNG differs per impl)
-        t0 = time.perf_counter()
-        batch = O.frame_gather(table, items[step], ratings[step], sizes, FRAME)
-        O.ddpg_update(batch, params, nets, opts, masks, step, learn=True)
-        dt = time.perf_counter() - t0
-        if step >= args.warmup:
-            t_total += dt
+    stepper = _OracleStepper(n_rows)
+    limiter, threads = pick_blas_threads(stepper)
+    ctx = limiter(limits=threads) if limiter is not None else None
+    if ctx is not None:
+        ctx.__enter__()
+    try:
+        for _ in range(args.warmup):
+            stepper.run()
+        t_total = sum(stepper.run() for _ in range(args.steps))
+    finally:
+        if ctx is not None:
+            ctx.__exit__(None, None, None)
     value = args.steps / t_total
-    cores = threads
     line = {
         "impl": "reference", "metric": "ddpg_update_steps_per_sec", "value": value, "unit": "steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "DDPG batch %d rows, 128-d embeddings, 26744 items, frame 10" % n_rows,
                    "rows_per_step": n_rows, "optimizer": "adam lr=1e-5", "policy_step": POLICY_STEP},
-        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port",
-                         "sample": "%d full steps (gather + ddpg_update, numpy/OpenBLAS fp32, best-of thread count; host has %d cpus)" % (args.steps, os.cpu_count() or 1)},
+        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": threads, "host_cpus": os.cpu_count() or 1,
+                         "kind": "port",
+                         "sample": "%d full steps (gather + ddpg_update, numpy/OpenBLAS fp32, best-of thread count)" % args.steps},
         "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
 
 
-def pick_blas_threads():
-    """OpenBLAS with one thread per hardware thread is far from its best on a 100+ core box
-    (this workload's GEMMs are small); give the CPU arm the thread count that maximises ITS
-    throughput: time one 4096x1290x256 GEMM at a few counts and keep the best."""
+class _OracleStepper:
+    """Reference algorithm (gather + ddpg_update) on the host: numpy port in oracle/."""
+
+    def __init__(self, n_rows):
+        from oracle import recnn_oracle as O
+        from oracle import cases as C
+        self.O, self.C, self.n = O, C, n_rows
+        rng = np.random.default_rng(0)
+        self.rng = rng
+        self.table = rng.standard_normal((N_ITEMS, DIM), dtype=np.float32)
+        self.nets = {"policy_net": O.make_actor(rng, S_DIM, DIM, HIDDEN, 6e-1),
+                     "value_net": O.make_critic(rng, S_DIM, DIM, HIDDEN, 54e-2)}
+        self.nets["target_policy_net"] = O.copy_net(self.nets["policy_net"])
+        self.nets["target_value_net"] = O.copy_net(self.nets["value_net"])
+        self.opts = {"policy_optimizer": O.make_optimizer("adam", lr=1e-5),
+                     "value_optimizer": O.make_optimizer("adam", lr=1e-5)}
+        self.sizes = np.asarray([n_rows + FRAME], dtype=np.int64)
+        self.items, self.ratings, _ = synth_step_inputs(1, n_rows, 4)
+        self.step = 0
+
+    def run(self):
+        """One step; returns its wall time (the dropout draw is not timed: RNGs differ per implementation)."""
+        masks = self.O.synth_masks(self.rng, 6, self.n, HIDDEN)
+        i = self.step % 4
+        t0 = time.perf_counter()
+        batch = self.O.frame_gather(self.table, self.items[i], self.ratings[i], self.sizes, FRAME)
+        self.O.ddpg_update(batch, dict(self.C.DDPG_PARAMS), self.nets, self.opts, masks, self.step, learn=True)
+        dt = time.perf_counter() - t0
+        self.step += 1
+        return dt
+
+
+def pick_blas_threads(stepper):
+    """One BLAS thread per hardware thread is far from OpenBLAS's best on a 100+ core box for GEMMs of this
+    size; give the CPU arm the thread count that maximises ITS step rate (2 steps at each candidate)."""
     try:
         from threadpoolctl import threadpool_limits
     except Exception:
         return None, os.cpu_count() or 1
-    a = np.random.default_rng(0).standard_normal((ROWS_PER_GPU, S_DIM), dtype=np.float32)
-    b = np.random.default_rng(1).standard_normal((S_DIM, HIDDEN), dtype=np.float32)
     ncpu = os.cpu_count() or 1
     best, best_t = ncpu, None
-    for n in sorted({c for c in (4, 8, 16, 32, 64, ncpu) if c <= ncpu}):
+    for n in sorted({c for c in (8, 16, 32, 64, ncpu) if c <= ncpu}):
         with threadpool_limits(limits=n):
-            a @ b
-            t0 = time.perf_counter()
-            for _ in range(5):
-                a @ b
-            t = time.perf_counter() - t0
+            stepper.run()
+            t = min(stepper.run(), stepper.run())
         if best_t is None or t < best_t:
             best, best_t = n, t
     return threadpool_limits, best
 
 
-def cpu_baseline_sample(seconds_budget=20.0):
+def cpu_baseline_sample(seconds_budget=15.0):
     """Oracle port on the host cores, bounded: N=4096 DDPG steps until ~budget is used."""
-    limiter, threads = pick_blas_threads()
-    if limiter is not None:
-        with limiter(limits=threads):
-            out = _cpu_baseline_sample(seconds_budget)
-    else:
-        out = _cpu_baseline_sample(seconds_budget)
-    out["cores"] = threads
-    out["host_cpus"] = os.cpu_count() or 1
-    return out
-
-
-def _cpu_baseline_sample(seconds_budget=20.0):
-    from oracle import recnn_oracle as O
-    from oracle import cases as C
-    rng = np.random.default_rng(0)
-    table = rng.standard_normal((N_ITEMS, DIM), dtype=np.float32)
-    n_rows = ROWS_PER_GPU
-    nets = {"policy_net": O.make_actor(rng, S_DIM, DIM, HIDDEN, 6e-1),
-            "value_net": O.make_critic(rng, S_DIM, DIM, HIDDEN, 54e-2)}
-    nets["target_policy_net"] = O.copy_net(nets["policy_net"])
-    nets["target_value_net"] = O.copy_net(nets["value_net"])
-    opts = {"policy_optimizer": O.make_optimizer("adam", lr=1e-5),
-            "value_optimizer": O.make_optimizer("adam", lr=1e-5)}
-    sizes = np.asarray([n_rows + FRAME], dtype=np.int64)
-    items, ratings, _ = synth_step_inputs(2, n_rows, 4)
-    timed, t_total, step = 0, 0.0, 0
-    t_start = time.perf_counter()
-    while True:
-        masks = O.synth_masks(rng, 6, n_rows, HIDDEN)
-        t0 = time.perf_counter()
-        batch = O.frame_gather(table, items[step % 4], ratings[step % 4], sizes, FRAME)
-        O.ddpg_update(batch, dict(C.DDPG_PARAMS), nets, opts, masks, step, learn=True)
-        dt = time.perf_counter() - t0
-        if step >= 2:
+    stepper = _OracleStepper(ROWS_PER_GPU)
+    limiter, threads = pick_blas_threads(stepper)
+    ctx = limiter(limits=threads) if limiter is not None else None
+    if ctx is not None:
+        ctx.__enter__()
+    try:
+        timed, t_total = 0, 0.0
+        t_start = time.perf_counter()
+        while True:
+            t_total += stepper.run()
             timed += 1
-            t_total += dt
-        step += 1
-        if (timed >= 10 and time.perf_counter() - t_start > seconds_budget) or timed >= 60:
-            break
-    return {"value": timed / t_total, "unit": "steps/s", "cores": os.cpu_count() or 1, "kind": "port",
+            if (timed >= 10 and time.perf_counter() - t_start > seconds_budget) or timed >= 60:
+                break
+    finally:
+        if ctx is not None:
+            ctx.__exit__(None, None, None)
+    return {"value": timed / t_total, "unit": "steps/s", "cores": threads, "host_cpus": os.cpu_count() or 1,
+            "kind": "port",
             "sample": "%d DDPG steps at 4096 rows (gather + update, numpy/OpenBLAS fp32, best-of thread count)" % timed}
 
 

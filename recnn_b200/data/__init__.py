@@ -1,3 +1,4 @@
-from . import utils
+from . import utils, env
 from .utils import (rolling_window, batch_tensor_embeddings, batch_frames, prepare_batch_static_size,
                     make_items_tensor, get_base_batch)
+from .env import UserDataset, EnvBase, DataPath, Env, FrameEnv

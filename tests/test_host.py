@@ -161,3 +161,28 @@ def test_algo_wrappers_keep_reference_wiring():
     assert ddpg._step == 0
     ddpg.step()
     assert ddpg._step == 1
+
+
+def test_frame_env_feed_matches_oracle_collate():
+    """FrameEnv (in-memory constructor) -> DataLoader -> collate -> frame-form batch."""
+    rng = np.random.default_rng(3)
+    table = torch.from_numpy(rng.standard_normal((40, 8), dtype=np.float32))
+    user_dict = {u: {"items": rng.integers(0, 40, size=n, dtype=np.int64),
+                     "ratings": rng.integers(-4, 6, size=n).astype(np.float64)}
+                 for u, n in enumerate((14, 30, 11, 12, 9, 25))}          # user 4 is too short for frame 10
+    env = recnn_b200.data.FrameEnv.from_user_dict(table, user_dict, frame_size=10, batch_size=3, num_workers=0,
+                                                  test_size=0.0, embed_batch=recnn_b200.data.batch_frames)
+    assert len(env.base.train_user_dataset) == 5
+    seen = 0
+    for batch in env.train_dataloader:
+        users = batch["users"].tolist()
+        want = O.collate_users([{"items": user_dict[u]["items"], "rates": user_dict[u]["ratings"],
+                                 "sizes": len(user_dict[u]["items"]), "users": u} for u in users], 10)
+        assert np.array_equal(batch["items"].numpy(), want["items"])
+        assert np.array_equal(batch["ratings"].numpy(), want["ratings"])
+        assert batch["items"].shape[0] == sum(len(user_dict[u]["items"]) - 10 for u in users)
+        seen += len(users)
+    assert seen == 5
+    from recnn_b200.data.env import DataPath
+    p = DataPath("/tmp/", "r.csv", "e.pkl", "c.pkl", use_cache=False)
+    assert p.ratings == "/tmp/r.csv" and p.cache == "/tmp/c.pkl"
