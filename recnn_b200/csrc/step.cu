@@ -40,8 +40,9 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // of the 148 SMs, so they are issued on three streams (fork/join with events; capturable into the
 // step's CUDA graph).  RECNN_B200_OVERLAP=0 serialises everything on the caller's stream.
 struct AuxStreams {
-  cudaStream_t sv, sp;
+  cudaStream_t sv, sp, sw;
   cudaEvent_t fork, v_done, p_done;
+  cudaEvent_t ev[6];       // fork/join pairs for the concurrent weight-gradient GEMMs
   bool ok;
 };
 static AuxStreams* aux_streams() {
@@ -58,9 +59,11 @@ static AuxStreams* aux_streams() {
     (void)cs;
     a.ok = cudaStreamCreateWithFlags(&a.sv, cudaStreamNonBlocking) == cudaSuccess &&
            cudaStreamCreateWithFlags(&a.sp, cudaStreamNonBlocking) == cudaSuccess &&
+           cudaStreamCreateWithFlags(&a.sw, cudaStreamNonBlocking) == cudaSuccess &&
            cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) == cudaSuccess &&
            cudaEventCreateWithFlags(&a.v_done, cudaEventDisableTiming) == cudaSuccess &&
            cudaEventCreateWithFlags(&a.p_done, cudaEventDisableTiming) == cudaSuccess;
+    for (auto& e : a.ev) a.ok = a.ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
     init[dev] = true;
   }
   return a.ok ? &a : nullptr;
@@ -78,6 +81,7 @@ struct Workspace {
   float* qtmp;     // [N]
   float* dq;       // [N]
   float* partial;  // split-K partials of the largest weight gradient
+  float* partial2; // second partial buffer (hidden x hidden sized) so two weight gradients can be in flight
   float* block_partials;  // [1024]
   float* scalars;         // [8]: 0 = clip coef
   unsigned* tickets;      // [8]
@@ -135,6 +139,16 @@ static Workspace carve(const recnn_dims& d, int64_t n, void* base) {
   w.qtmp = take(n);
   w.dq = take(n);
   w.partial = take(partial_floats(d, n));
+  {
+    int64_t f2 = 0;
+    const int shp[2][2] = {{d.hidden, d.hidden}, {d.action_dim, d.hidden}};
+    for (auto& s2 : shp)
+      for (int tcp = 0; tcp < 2; ++tcp) {
+        const int64_t f = (int64_t)dw_splits(s2[0], s2[1], n, tcp != 0) * s2[0] * (s2[1] + 1);
+        if (f > f2) f2 = f;
+      }
+    w.partial2 = take(f2);
+  }
   w.block_partials = take(1024);
   w.scalars = take(8);
   w.tickets = reinterpret_cast<unsigned*>(take(8));
@@ -169,9 +183,18 @@ struct Seg {
 };
 static const Seg kNoSeg = {nullptr, 0, 0, 0};
 
+// GEMMs that run alone on the GPU (nothing to overlap with) prefer 64-wide tiles: twice the CTAs.
+static thread_local bool t_alone = false;
+struct AloneScope {
+  bool prev;
+  explicit AloneScope(bool on) : prev(t_alone) { t_alone = on; }
+  ~AloneScope() { t_alone = prev; }
+};
+
 static int pick_bn(int64_t M, int N) {
   // 128-wide tiles when they still yield >= 64 CTAs; otherwise 64-wide (more CTAs, less reuse)
   const int64_t mt = ceil_div(M, 128);
+  if (t_alone && mt * ceil_div(N, 64) <= 2 * kNumSMs) return 64;
   if (N > 64 && mt * ceil_div(N, 128) >= 64) return 128;
   return 64;
 }
@@ -186,7 +209,7 @@ static int gemm_nt(const Seg& x0, const Seg& x1, const float* W, long long ldw, 
                      (x1.cols == 0 || (x0.cols - x1.lead) % 4 == 0);
   if (tc_ok) {
     tc::Operand a0 = {x0.p, x0.ld, 0, 0}, a1 = {x1.p, x1.ld, 0, 0}, b = {W, ldw, N, K};
-    tc::Problem p = {(int)n, N, x0.cols, x1.cols, 0, x0.cols - x1.lead, 0, 0, nullptr, nullptr};
+    tc::Problem p = {(int)n, N, x0.cols, x1.cols, 0, x0.cols - x1.lead, 0, 0, 0, nullptr, nullptr};
     const int r = tc::launch<false, false, EPI>(a0, a1, b, p, 1, pick_bn(n, N), e, st);
     return r < 0 ? r : RECNN_OK;
   }
@@ -228,7 +251,7 @@ static int backprop_hidden(const float* dZ, int C, const float* W, long long ldw
   const bool tc_ok = math_tc() && aligned16(dZ) && aligned16(W) && C % 4 == 0 && ldw % 4 == 0 && col0 % 4 == 0;
   if (tc_ok) {
     tc::Operand a0 = {dZ, C, 0, 0}, a1 = {nullptr, 0, 0, 0}, b = {W, ldw, C, w_cols};
-    tc::Problem p = {(int)n, K, C, 0, 0, C, 0, col0, nullptr, nullptr};
+    tc::Problem p = {(int)n, K, C, 0, 0, C, 0, col0, 0, nullptr, nullptr};
     const int bn = pick_bn(n, K);
     const int r = h ? tc::launch<false, true, EPI_GATE>(a0, a1, b, p, 1, bn, e, st)
                     : tc::launch<false, true, EPI_STORE>(a0, a1, b, p, 1, bn, e, st);
@@ -239,11 +262,16 @@ static int backprop_hidden(const float* dZ, int C, const float* W, long long ldw
 }
 
 // dW[c,k] = sum_n dZ[n,c] [x0|x1][n,k];  db[c] = sum_n dZ[n,c].   dW has row pitch ldw.
+struct SideLaunch {        // run the second K-segment's GEMM on `stream`, fork/join with these events
+  cudaStream_t stream;
+  cudaEvent_t fork, join;
+};
+
 static int weight_grad(const float* dZ, int C, const Seg& x0, const Seg& x1, int64_t n, float* dW, long long ldw,
-                       float* db, const Workspace& ws, cudaStream_t st) {
+                       float* db, float* partial, cudaStream_t st, const SideLaunch* side = nullptr) {
   const int K = x0.cols + x1.cols - x1.lead, K1 = K + 1;
   Epilogue e = base_epi();
-  e.out = ws.partial; e.ldo = K1;
+  e.out = partial; e.ldo = K1;
   const bool tc_ok = math_tc() && C % 4 == 0 && C >= 32 && aligned16(dZ) && aligned16(x0.p) && x0.ld % 4 == 0 &&
                      x0.lead == 0 && (x1.cols == 0 || (aligned16(x1.p) && x1.ld % 4 == 0));
   if (tc_ok) {
@@ -251,25 +279,34 @@ static int weight_grad(const float* dZ, int C, const Seg& x0, const Seg& x1, int
     int k_chunk = 0;
     const int splits = tc::split_plan((int)ceil_div(n, 16), req, &k_chunk);
     tc::Operand a0 = {dZ, C, 0, 0}, a1 = {nullptr, 0, 0, 0};
-    // the padded second segment goes first: its `lead` pad columns land (as zeros) on the last columns
-    // of the first segment's window, which the first segment's launch then overwrites with the real values
+    // the padded second segment's window starts `lead` columns inside the first segment's; those pad
+    // columns are computed (as zeros) but not stored (n_skip), so the two GEMMs are independent
     const Seg* segs[2] = {&x1, &x0};
     const int cols0[2] = {x0.cols - x1.lead, 0};
+    const bool use_side = side && x1.cols > 0;
+    if (use_side) {
+      RECNN_CHECK_CUDA(cudaEventRecord(side->fork, st));
+      RECNN_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+    }
     for (int i = 0; i < 2; ++i) {
       const Seg* s = segs[i];
       if (s->cols == 0) continue;
       tc::Operand b = {s->p, s->ld, n, s->cols};
-      tc::Problem p = {C, s->cols, (int)n, 0, 0, 0, cols0[i], 0, nullptr, nullptr};
+      tc::Problem p = {C, s->cols, (int)n, 0, 0, 0, cols0[i], 0, i == 0 ? x1.lead : 0, nullptr, nullptr};
       const int bn = s->cols > 64 ? 128 : 64;
-      const int r = tc::launch<true, true, EPI_PARTIAL>(a0, a1, b, p, req, bn, e, st);
+      const int r = tc::launch<true, true, EPI_PARTIAL>(a0, a1, b, p, req, bn, e, (i == 0 && use_side) ? side->stream : st);
       if (r < 0) return r;
       if (r != splits) {
         set_error("internal: split plan mismatch (%d vs %d)", r, splits);
         return RECNN_E_INVALID;
       }
     }
-    RECNN_PROPAGATE(launch_colsum_partials(dZ, n, C, k_chunk, splits, ws.partial, K1, st));
-    return launch_reduce_partials(ws.partial, splits, C, K1, dW, ldw, db, st);
+    if (use_side) {
+      RECNN_CHECK_CUDA(cudaEventRecord(side->join, side->stream));
+      RECNN_CHECK_CUDA(cudaStreamWaitEvent(st, side->join, 0));
+    }
+    RECNN_PROPAGATE(launch_colsum_partials(dZ, n, C, k_chunk, splits, partial, K1, st));
+    return launch_reduce_partials(partial, splits, C, K1, dW, ldw, db, st);
   }
   MatView X = x1.cols ? mat_cat(x0.p + x0.lead, x0.ld, x0.cols - x0.lead, x1.p + x1.lead, x1.ld)
                       : mat(x0.p + x0.lead, x0.ld);
@@ -279,7 +316,7 @@ static int weight_grad(const float* dZ, int C, const Seg& x0, const Seg& x1, int
   const int k_chunk = (int)round_up(ceil_div(n, splits_req), 16);
   const int splits = (int)ceil_div(n, k_chunk);
   RECNN_PROPAGATE((launch_gemm_simt<false, false, EPI_PARTIAL>(mat(dZ, C), X, C, K1, (int)n, splits_req, e, st)));
-  return launch_reduce_partials(ws.partial, splits, C, K1, dW, ldw, db, st);
+  return launch_reduce_partials(partial, splits, C, K1, dW, ldw, db, st);
 }
 
 struct Ctx {
@@ -357,6 +394,7 @@ static int phase_value_grad(Ctx& c) {
 
   // target critic(s) -> TD target y (misc.py:29-35 / td3.py:80-86)
   for (int i = 0; i < n_critics; ++i) {
+    AloneScope alone(c.aux != nullptr);       // the side chains have usually drained by now
     RECNN_PROPAGATE(critic_hidden(c, a.target_value[i].params, c.S2, a2, false, 0, X0, X1, c.st));
     HeadArgs h = head_args(c, a.target_value[i].params, X1,
                            td3 ? (i == 0 ? HEAD_TARGET_TD3_A : HEAD_TARGET_TD3_B) : HEAD_TARGET_DDPG);
@@ -386,9 +424,22 @@ static int phase_value_grad(Ctx& c) {
       RECNN_PROPAGATE(launch_reduce_partials(c.ws.partial, splits, 1, H + 1, G + c.lc.w3, c.lc.ld3, G + c.lc.b3, c.st));
     }
     RECNN_PROPAGATE(launch_critic_head_bwd(c.ws.dq, 0.f, P + c.lc.w3, c2, c.gate, dz2, c.n, H, c.st));
-    RECNN_PROPAGATE(weight_grad(dz2, H, sc1, kNoSeg, c.n, G + c.lc.w2, c.lc.ld2, G + c.lc.b2, c.ws, c.st));
-    RECNN_PROPAGATE(backprop_hidden(dz2, H, P + c.lc.w2, c.lc.ld2, H, 0, H, c.n, c1, c.gate, dz1, c.st));
-    RECNN_PROPAGATE(weight_grad(dz1, H, ss, sa, c.n, G + c.lc.w1, c.lc.ld1, G + c.lc.b1, c.ws, c.st));
+    if (c.aux) {
+      // dW2 (needs dz2, c1) on the side stream while the main stream back-propagates to dz1;
+      // dW1's action segment on a third stream next to its state segment
+      RECNN_CHECK_CUDA(cudaEventRecord(c.aux->ev[0], c.st));
+      RECNN_CHECK_CUDA(cudaStreamWaitEvent(c.aux->sv, c.aux->ev[0], 0));
+      RECNN_PROPAGATE(weight_grad(dz2, H, sc1, kNoSeg, c.n, G + c.lc.w2, c.lc.ld2, G + c.lc.b2, c.ws.partial2, c.aux->sv));
+      RECNN_CHECK_CUDA(cudaEventRecord(c.aux->ev[1], c.aux->sv));
+      RECNN_PROPAGATE(backprop_hidden(dz2, H, P + c.lc.w2, c.lc.ld2, H, 0, H, c.n, c1, c.gate, dz1, c.st));
+      const SideLaunch side = {c.aux->sw, c.aux->ev[2], c.aux->ev[3]};
+      RECNN_PROPAGATE(weight_grad(dz1, H, ss, sa, c.n, G + c.lc.w1, c.lc.ld1, G + c.lc.b1, c.ws.partial, c.st, &side));
+      RECNN_CHECK_CUDA(cudaStreamWaitEvent(c.st, c.aux->ev[1], 0));
+    } else {
+      RECNN_PROPAGATE(weight_grad(dz2, H, sc1, kNoSeg, c.n, G + c.lc.w2, c.lc.ld2, G + c.lc.b2, c.ws.partial, c.st));
+      RECNN_PROPAGATE(backprop_hidden(dz2, H, P + c.lc.w2, c.lc.ld2, H, 0, H, c.n, c1, c.gate, dz1, c.st));
+      RECNN_PROPAGATE(weight_grad(dz1, H, ss, sa, c.n, G + c.lc.w1, c.lc.ld1, G + c.lc.b1, c.ws.partial, c.st));
+    }
   }
   return RECNN_OK;
 }
@@ -428,7 +479,10 @@ static int phase_policy_loss(Ctx& c) {
   if (a.gen_action_out)
     RECNN_CHECK_CUDA(cudaMemcpy2DAsync(a.gen_action_out, (size_t)A * 4, gen + c.lead, c.ldA * 4, (size_t)A * 4, c.n,
                                        cudaMemcpyDeviceToDevice, c.st));
-  RECNN_PROPAGATE(critic_hidden(c, a.value[0].params, c.S, gen, c.train, vm, v1, v2, c.st));
+  {
+    AloneScope alone(true);
+    RECNN_PROPAGATE(critic_hidden(c, a.value[0].params, c.S, gen, c.train, vm, v1, v2, c.st));
+  }
   HeadArgs h = head_args(c, a.value[0].params, v2, HEAD_POLICY);
   h.loss = a.losses + 2;
   return launch_critic_head(h, c.st);
@@ -452,13 +506,13 @@ static int phase_policy_grad(Ctx& c) {
   RECNN_PROPAGATE(backprop_hidden(dv1, H, Pc + c.lc.w1, c.lc.ld1, S + A, S, A, c.n, nullptr, 1.f, dgen, c.st));
   // actor backward
   const Seg sp2 = {p2, H, H, 0}, sp1 = {p1, H, H, 0}, ss = {c.S, S, c.ldS, 0};
-  RECNN_PROPAGATE(weight_grad(dgen, A, sp2, kNoSeg, c.n, G + c.la.w3, c.la.ld3, G + c.la.b3, c.ws, c.st));
+  RECNN_PROPAGATE(weight_grad(dgen, A, sp2, kNoSeg, c.n, G + c.la.w3, c.la.ld3, G + c.la.b3, c.ws.partial, c.st));
   float* dp2 = dv2;   // dv2/dv1 are dead once dgen exists
   float* dp1 = dv1;
   RECNN_PROPAGATE(backprop_hidden(dgen, A, Pa + c.la.w3, c.la.ld3, H, 0, H, c.n, p2, c.gate, dp2, c.st));
-  RECNN_PROPAGATE(weight_grad(dp2, H, sp1, kNoSeg, c.n, G + c.la.w2, c.la.ld2, G + c.la.b2, c.ws, c.st));
+  RECNN_PROPAGATE(weight_grad(dp2, H, sp1, kNoSeg, c.n, G + c.la.w2, c.la.ld2, G + c.la.b2, c.ws.partial, c.st));
   RECNN_PROPAGATE(backprop_hidden(dp2, H, Pa + c.la.w2, c.la.ld2, H, 0, H, c.n, p1, c.gate, dp1, c.st));
-  RECNN_PROPAGATE(weight_grad(dp1, H, ss, kNoSeg, c.n, G + c.la.w1, c.la.ld1, G + c.la.b1, c.ws, c.st));
+  RECNN_PROPAGATE(weight_grad(dp1, H, ss, kNoSeg, c.n, G + c.la.w1, c.la.ld1, G + c.la.b1, c.ws.partial, c.st));
   return RECNN_OK;
 }
 

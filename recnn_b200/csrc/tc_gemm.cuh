@@ -177,6 +177,7 @@ struct Problem {
   int b_k1_offset;       // B's k coordinate where the K1 segment starts (== K0 for a dense weight)
   int n_out_offset;      // column offset added when storing (C window)
   int b_n_offset;        // B's n coordinate of output column 0 (window into a wider B, e.g. W1[:, S:S+A])
+  int n_skip;            // the first n_skip output columns are computed but not stored (operand lead pads)
   unsigned long long* trace;   // optional: per-CTA %globaltimer stamps (8 per CTA) for pipeline analysis
   unsigned long long* span;    // optional: {min entry, max exit} of this launch (timeline of a whole step)
 };
@@ -281,12 +282,12 @@ __device__ __forceinline__ void epilogue_row(const Epilogue& e, const Problem& p
             v[u] = x;
           }
           float* dst = out_row + n;
-          if (n + 3 < N && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+          if (n + 3 < N && n >= p.n_skip && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
             *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
           } else {
 #pragma unroll
             for (int u = 0; u < 4; ++u)
-              if (n + u < N) dst[u] = v[u];
+              if (n + u < N && n + u >= p.n_skip) dst[u] = v[u];
           }
         }
       }

@@ -58,6 +58,7 @@ class StepEngine:
         self.n_rows = -1
         self.form = None
         self.graphs = {}
+        self.seg_graphs = {}
         self._fast = {}
         self.graph_sig = None
         self.eager_runs = {}
@@ -310,6 +311,49 @@ class StepEngine:
             self._body(a, nets, do_policy)
             return None
 
+    def _run_segments(self, a, nets, do_policy, vkey):
+        """Data parallel: the step is cut where gradients are complete.  Each cut piece is its own CUDA
+        graph (kernels only); the NCCL all-reduces run between the replays on the same stream."""
+        P = _lib
+        td3 = self.algo == P.ALGO_TD3
+        segs = (P.PH_GATHER | P.PH_VALUE_GRAD, P.PH_VALUE_OPT | P.PH_POLICY_LOSS | P.PH_POLICY_GRAD,
+                P.PH_POLICY_OPT | P.PH_SOFT_UPDATE | P.PH_FINISH)
+        a.phases = 0
+        key = self._signature(a)
+        ent = self.seg_graphs.get(key)
+        runs = self.eager_runs.get(key, 0)
+        self.eager_runs[key] = runs + 1
+        if ent is None and _USE_GRAPHS and runs >= 1:
+            try:
+                torch.cuda.synchronize(self.device)
+                ent = []
+                for ph in segs:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._launch(a, ph)
+                    ent.append((g, self.last_call_kernels))
+                self.seg_graphs[key] = ent
+            except Exception as exc:
+                warnings.warn("recnn_b200: CUDA graph capture failed (%s); using direct launches" % exc)
+                globals()["_USE_GRAPHS"] = False
+                ent = None
+
+        def run(i):
+            if ent is not None:
+                ent[i][0].replay()
+                self.kernels += ent[i][1]
+            else:
+                self._launch(a, segs[i])
+
+        run(0)
+        for i in range(2 if td3 else 1):
+            self._allreduce(grad_arena(nets["value_net" + (str(i + 1) if td3 else "")]))
+        run(1)
+        if do_policy:
+            self._allreduce(grad_arena(nets["policy_net"]))
+        self._allreduce(self.losses[:3])
+        run(2)
+
     # ------------------------------------------------------------------ the step
     def step(self, batch, params, nets, optimizer, learn, step, debug, policy_every_key):
         with torch.cuda.device(self.device):
@@ -366,6 +410,10 @@ class StepEngine:
             n, A = st["n"], self.dims.action_dim
             want_debug = {"next_action": torch.empty(n, A, device=self.device),
                           "gen_action": torch.empty(n, A, device=self.device)}
+        if builtin and learn and want_debug is None and self.world > 1:
+            self._run_segments(a, nets, do_policy, None)
+            torch.cuda.current_stream(self.device).synchronize()
+            return self.losses_host.tolist()
         if builtin and learn and want_debug is None and self.world == 1:
             g = self._run_fused(a, nets, do_policy)
             if g is not None:
