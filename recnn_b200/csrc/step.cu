@@ -333,7 +333,7 @@ struct Ctx {
   bool train;
   float gate;
   AuxStreams* aux;       // non-null: chains V and P run on side streams
-  bool v_prefetched, p_prefetched;
+  bool v_prefetched, p_prefetched, p_deferred;
 };
 
 // Critic hidden layers on (s, act):  h1 -> out1, h2 -> out2
@@ -373,6 +373,8 @@ static HeadArgs head_args(const Ctx& c, const float* params, const float* h2, in
 }
 
 // ---------------------------------------------------------------- phases
+static int policy_actor_forward(const Ctx& c, cudaStream_t st);
+
 static int phase_value_grad(Ctx& c) {
   const recnn_step_args& a = *c.a;
   const int S = c.d.state_dim, A = c.d.action_dim, H = c.d.hidden;
@@ -384,6 +386,13 @@ static int phase_value_grad(Ctx& c) {
 
   // target policy on next_state, eval mode (misc.py:28 / td3.py:73) (+ clipped noise, td3.py:74-78)
   RECNN_PROPAGATE(actor_hidden(c, a.target_policy.params, c.S2, false, 0, X0, X1, c.st));
+  if (c.aux && c.p_deferred) {
+    RECNN_CHECK_CUDA(cudaEventRecord(c.aux->ev[4], c.st));
+    RECNN_CHECK_CUDA(cudaStreamWaitEvent(c.aux->sp, c.aux->ev[4], 0));
+    RECNN_PROPAGATE(policy_actor_forward(c, c.aux->sp));
+    RECNN_CHECK_CUDA(cudaEventRecord(c.aux->p_done, c.aux->sp));
+    c.p_prefetched = true;
+  }
   NoiseSpec nz = {td3 ? 1 : 0, a.noise, a.noise_clip, a.noise_std, a.seed, (const long long*)a.rng_step, 15u};
   const Seg x1s = {X1, H, H, 0};
   RECNN_PROPAGATE(linear_out(x1s, a.target_policy.params + c.la.w3, c.la.ld3, a.target_policy.params + c.la.b3, A,
@@ -394,7 +403,7 @@ static int phase_value_grad(Ctx& c) {
 
   // target critic(s) -> TD target y (misc.py:29-35 / td3.py:80-86)
   for (int i = 0; i < n_critics; ++i) {
-    AloneScope alone(c.aux != nullptr);       // the side chains have usually drained by now
+    AloneScope alone(c.aux != nullptr && !c.p_prefetched);   // alone unless chain P runs alongside
     RECNN_PROPAGATE(critic_hidden(c, a.target_value[i].params, c.S2, a2, false, 0, X0, X1, c.st));
     HeadArgs h = head_args(c, a.target_value[i].params, X1,
                            td3 ? (i == 0 ? HEAD_TARGET_TD3_A : HEAD_TARGET_TD3_B) : HEAD_TARGET_DDPG);
@@ -617,19 +626,16 @@ static int run_step(const recnn_step_args* a, int algo, void* stream) {
   }
   // fork: chain V (online critic forward) and chain P (online policy forward) on side streams
   c.aux = nullptr;
-  c.v_prefetched = c.p_prefetched = false;
+  c.v_prefetched = c.p_prefetched = c.p_deferred = false;
   if ((a->phases & RECNN_PH_VALUE_GRAD) && (c.aux = aux_streams()) != nullptr) {
     RECNN_CHECK_CUDA(cudaEventRecord(c.aux->fork, c.st));
     RECNN_CHECK_CUDA(cudaStreamWaitEvent(c.aux->sv, c.aux->fork, 0));
     RECNN_PROPAGATE(critic_hidden(c, a->value[0].params, c.S, c.ACT, c.train, 0, c.ws.hb[2], c.ws.hb[3], c.aux->sv));
     RECNN_CHECK_CUDA(cudaEventRecord(c.aux->v_done, c.aux->sv));
     c.v_prefetched = true;
-    if (a->phases & RECNN_PH_POLICY_LOSS) {
-      RECNN_CHECK_CUDA(cudaStreamWaitEvent(c.aux->sp, c.aux->fork, 0));
-      RECNN_PROPAGATE(policy_actor_forward(c, c.aux->sp));
-      RECNN_CHECK_CUDA(cudaEventRecord(c.aux->p_done, c.aux->sp));
-      c.p_prefetched = true;
-    }
+    // chain P is forked later (after the target policy's hidden layers, see phase_value_grad): three
+    // concurrent layer-1 GEMMs are 192 CTAs = two waves on 148 SMs, two are one wave
+    c.p_deferred = (a->phases & RECNN_PH_POLICY_LOSS) != 0;
   }
   if (a->phases & RECNN_PH_VALUE_GRAD) RECNN_PROPAGATE(phase_value_grad(c));
   if (a->phases & RECNN_PH_VALUE_OPT) RECNN_PROPAGATE(phase_value_opt(c));

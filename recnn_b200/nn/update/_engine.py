@@ -393,13 +393,16 @@ class StepEngine:
         do_policy = bool(learn and step % params[policy_every_key] == 0)
         td3 = self.algo == _lib.ALGO_TD3
         # ---- fast path: same variant as a previous step -> replay its graph
-        if learn and self.world == 1 and _USE_GRAPHS:
+        if learn and _USE_GRAPHS:
             vkey = (do_policy, st["form"], st["n"])
             ent = self._fast.get(vkey)
             tok = self._tokens(nets, optimizer, params, st)
             if ent is not None and ent[0] == tok:
-                ent[1].replay()
-                self.kernels += ent[2]
+                if self.world == 1:
+                    ent[1].replay()
+                    self.kernels += ent[2]
+                else:
+                    self._run_segments(ent[1], nets, do_policy, None)      # cached StepArgs
                 torch.cuda.current_stream(self.device).synchronize()
                 return self.losses_host.tolist()
         a, pol_opt, val_opts = self._build_args(st, nets, optimizer, params, learn, do_policy)
@@ -412,6 +415,8 @@ class StepEngine:
                           "gen_action": torch.empty(n, A, device=self.device)}
         if builtin and learn and want_debug is None and self.world > 1:
             self._run_segments(a, nets, do_policy, None)
+            if _USE_GRAPHS:
+                self._fast[(do_policy, st["form"], st["n"])] = (self._tokens(nets, optimizer, params, st), a, 0)
             torch.cuda.current_stream(self.device).synchronize()
             return self.losses_host.tolist()
         if builtin and learn and want_debug is None and self.world == 1:
