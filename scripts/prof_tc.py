@@ -5,7 +5,7 @@ import torch
 from recnn_b200 import _lib
 L = _lib.lib(); DEV = "cuda:0"
 M, N, K = 4096, 256, 1290
-tile = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+tile = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 ld = (K + 3) // 4 * 4
 A = torch.randn(M, ld, device=DEV); B = torch.randn(N, ld, device=DEV); C = torch.empty(M, N, device=DEV)
 st = torch.cuda.current_stream().cuda_stream
