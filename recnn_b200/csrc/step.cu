@@ -209,7 +209,7 @@ static int gemm_nt(const Seg& x0, const Seg& x1, const float* W, long long ldw, 
                      (x1.cols == 0 || (x0.cols - x1.lead) % 4 == 0);
   if (tc_ok) {
     tc::Operand a0 = {x0.p, x0.ld, 0, 0}, a1 = {x1.p, x1.ld, 0, 0}, b = {W, ldw, N, K};
-    tc::Problem p = {(int)n, N, x0.cols, x1.cols, 0, x0.cols - x1.lead, 0, 0, 0, nullptr, nullptr};
+    tc::Problem p = {(int)n, N, x0.cols, x1.cols, 0, x0.cols - x1.lead, 0, 0, 0, 0, nullptr, nullptr};
     const int r = tc::launch<false, false, EPI>(a0, a1, b, p, 1, pick_bn(n, N), e, st);
     return r < 0 ? r : RECNN_OK;
   }
@@ -251,7 +251,7 @@ static int backprop_hidden(const float* dZ, int C, const float* W, long long ldw
   const bool tc_ok = math_tc() && aligned16(dZ) && aligned16(W) && C % 4 == 0 && ldw % 4 == 0 && col0 % 4 == 0;
   if (tc_ok) {
     tc::Operand a0 = {dZ, C, 0, 0}, a1 = {nullptr, 0, 0, 0}, b = {W, ldw, C, w_cols};
-    tc::Problem p = {(int)n, K, C, 0, 0, C, 0, col0, 0, nullptr, nullptr};
+    tc::Problem p = {(int)n, K, C, 0, 0, C, 0, col0, 0, 0, nullptr, nullptr};
     const int bn = pick_bn(n, K);
     const int r = h ? tc::launch<false, true, EPI_GATE>(a0, a1, b, p, 1, bn, e, st)
                     : tc::launch<false, true, EPI_STORE>(a0, a1, b, p, 1, bn, e, st);
@@ -292,7 +292,7 @@ static int weight_grad(const float* dZ, int C, const Seg& x0, const Seg& x1, int
       const Seg* s = segs[i];
       if (s->cols == 0) continue;
       tc::Operand b = {s->p, s->ld, n, s->cols};
-      tc::Problem p = {C, s->cols, (int)n, 0, 0, 0, cols0[i], 0, i == 0 ? x1.lead : 0, nullptr, nullptr};
+      tc::Problem p = {C, s->cols, (int)n, 0, 0, 0, cols0[i], 0, i == 0 ? x1.lead : 0, 0, nullptr, nullptr};
       const int bn = s->cols > 64 ? 128 : 64;
       const int r = tc::launch<true, true, EPI_PARTIAL>(a0, a1, b, p, req, bn, e, (i == 0 && use_side) ? side->stream : st);
       if (r < 0) return r;

@@ -172,7 +172,7 @@ extern "C" int recnn_gemm_tf32x3(int M, int N, int K, const float* A, int64_t ld
   e.ldo = ldc;
   tc::Operand a0 = {A, lda, 0, 0}, a1 = {nullptr, 0, 0, 0};
   tc::Operand b = {B, ldb, b_mn ? K : N, b_mn ? N : K};
-  tc::Problem p = {M, N, K, 0, 0, K, 0, 0, 0, g_trace, nullptr};
+  tc::Problem p = {M, N, K, 0, 0, K, 0, 0, 0, getenv("RECNN_TC_DBG") ? atoi(getenv("RECNN_TC_DBG")) : 0, g_trace, nullptr};
   if (tile_n <= 0) tile_n = N > 64 ? 128 : 64;
   int r;
   if (!a_mn && !b_mn) r = tc::launch<false, false, EPI_STORE>(a0, a1, b, p, 1, tile_n, e, st);

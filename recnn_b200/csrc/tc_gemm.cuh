@@ -178,6 +178,7 @@ struct Problem {
   int n_out_offset;      // column offset added when storing (C window)
   int b_n_offset;        // B's n coordinate of output column 0 (window into a wider B, e.g. W1[:, S:S+A])
   int n_skip;            // the first n_skip output columns are computed but not stored (operand lead pads)
+  int dbg;               // timing experiments only (results become wrong): 1 no split, 2 no MMA, 4 no hi store, 8 no fence
   unsigned long long* trace;   // optional: per-CTA %globaltimer stamps (8 per CTA) for pipeline analysis
   unsigned long long* span;    // optional: {min entry, max exit} of this launch (timeline of a whole step)
 };
@@ -419,6 +420,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         const uint32_t a_lo = stage_addr(s, 2), b_lo = stage_addr(s, 3);
 #pragma unroll
         for (int k = 0; k < BK / 8; ++k) {
+          if (p.dbg & 2) break;
           const uint64_t da_hi = a_base | uint64_t(((a_hi + k * a_kstep) & 0x3FFFF) >> 4);
           const uint64_t da_lo = a_base | uint64_t(((a_lo + k * a_kstep) & 0x3FFFF) >> 4);
           const uint64_t db_hi = b_base | uint64_t(((b_hi + k * b_kstep) & 0x3FFFF) >> 4);
@@ -468,17 +470,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       mbar_wait(full(s), ph);
       const uint32_t raw = stage_addr(s, 0);                  // rawA|rawB contiguous
       const uint32_t lo = stage_addr(s, 2);                   // loA|loB contiguous
-      float4 x[VEC_PER_THREAD];
+      if (!(p.dbg & 1)) {
+        float4 x[VEC_PER_THREAD];
 #pragma unroll
-      for (int v = 0; v < VEC_PER_THREAD; ++v) x[v] = lds128(raw + 16u * (t + v * NT));
+        for (int v = 0; v < VEC_PER_THREAD; ++v) x[v] = lds128(raw + 16u * (t + v * NT));
 #pragma unroll
-      for (int v = 0; v < VEC_PER_THREAD; ++v) {
-        float4 xh, xl;
-        tf32_split4(x[v], xh, xl);
-        sts128(raw + 16u * (t + v * NT), xh);
-        sts128(lo + 16u * (t + v * NT), xl);
+        for (int v = 0; v < VEC_PER_THREAD; ++v) {
+          float4 xh, xl;
+          tf32_split4(x[v], xh, xl);
+          if (!(p.dbg & 4)) sts128(raw + 16u * (t + v * NT), xh);
+          sts128(lo + 16u * (t + v * NT), xl);
+        }
       }
-      fence_proxy_async();              // generic-proxy writes -> visible to the tensor core (async proxy)
+      if (!(p.dbg & 8)) fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(split(s));
       // once the last k-block of chunk c has been split, chunk c-1 has long been accumulated: drain it
