@@ -131,8 +131,9 @@ template <bool A_MN, bool B_MN, int EPI>
 int launch(const Operand& A0, const Operand& A1, const Operand& B, const Problem& p, int splits, int bn,
            const Epilogue& epi, cudaStream_t st) {
   // stages chosen to fill ~190 KB of shared memory
-  if (bn >= 128) return launch_cfg<Cfg<128, 6, A_MN, B_MN>, EPI>(A0, A1, B, p, splits, epi, st);
-  return launch_cfg<Cfg<64, 8, A_MN, B_MN>, EPI>(A0, A1, B, p, splits, epi, st);
+  // stage bytes: K-major A (split into tensor memory) 8+2*BN/16 KB, MN-major A 16+2*BN/16 KB
+  if (bn >= 128) return launch_cfg<Cfg<128, A_MN ? 6 : 8, A_MN, B_MN>, EPI>(A0, A1, B, p, splits, epi, st);
+  return launch_cfg<Cfg<64, A_MN ? 8 : 10, A_MN, B_MN>, EPI>(A0, A1, B, p, splits, epi, st);
 }
 
 // explicit instantiations used by step.cu / the generic entry points

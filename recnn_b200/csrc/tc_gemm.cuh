@@ -132,6 +132,25 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]),
+        "f"(v[8]), "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// A operand read from tensor memory (128 lanes = rows, 8 fp32 columns = one k-slice), B from shared memory
+__device__ __forceinline__ void mma_tf32_ta(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
@@ -198,13 +217,18 @@ struct Cfg {
   static constexpr int BM = 128, BN = BN_, BK = 16, STAGES = STAGES_;
   static constexpr int CH = 4;                                     // k-blocks per TMEM accumulation chunk (K = 64)
   static constexpr bool A_MN = A_MN_, B_MN = B_MN_;
+  // K-major A: the split A tile goes to TENSOR memory (tcgen05.st) and the MMA reads it from there, so
+  // A costs shared memory one TMA write + one read instead of write + read + 2 writes + 6 MMA reads.
+  static constexpr bool A_TM = !A_MN_;
+  static constexpr int A_SLOTS = 4, A_SLOT_COLS = 2 * BK;          // TMEM ring for A: hi | lo per k-block
   static constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
-  static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);      // raw + lo
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int STAGE_BYTES = (A_TM ? A_BYTES : 2 * A_BYTES) + 2 * B_BYTES;   // raw A (+lo A) | raw B | lo B
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
   static constexpr int COLS_PER_WORKER = BN;                       // register-resident running sum per thread
   static constexpr int WORKERS = 4;                                // warps (one per TMEM lane quarter)
   static constexpr int THREADS = 64 + 32 * WORKERS;
-  static constexpr int TMEM_COLS = 4 * BN;                         // D_hi chunk x2 | D_lo | (pad to a power of 2)
+  static constexpr int TMEM_COLS = 512;                            // D_hi chunk x2 | D_lo | A ring (3*BN + 128 <= 512)
+  static constexpr int A_COL0 = 3 * BN;
   static constexpr int K_SWZ = BK * 4;                             // K-major rows: 64 B, SWIZZLE_64B
   static_assert(BN == 64 || BN == 128, "BN");
   static_assert(SMEM_BYTES <= 227 * 1024, "smem");
@@ -310,7 +334,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     return which == 0 ? base
          : which == 1 ? base + C::A_BYTES
          : which == 2 ? base + C::A_BYTES + C::B_BYTES
-                      : base + 2 * C::A_BYTES + C::B_BYTES;
+                      : base + (C::A_TM ? C::A_BYTES : 2 * C::A_BYTES) + C::B_BYTES;
   };
   const uint32_t bars = smem + (uint32_t)STAGES * C::STAGE_BYTES;
   auto full = [&](int s) { return bars + 8u * s; };                   // TMA -> workers
@@ -318,7 +342,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   auto empty = [&](int s) { return bars + 8u * (2 * STAGES + s); };   // MMA -> TMA
   auto acc_full = [&](int b) { return bars + 8u * (3 * STAGES + b); };       // MMA -> workers
   auto acc_empty = [&](int b) { return bars + 8u * (3 * STAGES + 2 + b); };  // workers -> MMA
-  const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 4);
+  auto a_free = [&](int i) { return bars + 8u * (3 * STAGES + 4 + i); };    // MMA -> workers (A TMEM ring)
+  const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 4 + C::A_SLOTS);
   volatile uint32_t* tmem_slot_gen =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -349,6 +374,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       mbar_init(acc_full(b), 1);
       mbar_init(acc_empty(b), WORKERS);
     }
+    for (int i = 0; i < C::A_SLOTS; ++i) mbar_init(a_free(i), 1);
     fence_barrier_init();
   }
   if (warp == 1) {                       // whole warp: TMEM allocation
@@ -418,18 +444,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         const uint32_t d_lo = tmem_base + 2u * BN;                // tile-lifetime accumulator (cross terms)
         const uint32_t a_hi = stage_addr(s, 0), b_hi = stage_addr(s, 1);
         const uint32_t a_lo = stage_addr(s, 2), b_lo = stage_addr(s, 3);
+        const int slot = i % C::A_SLOTS;
 #pragma unroll
         for (int k = 0; k < BK / 8; ++k) {
           if (p.dbg & 2) break;
-          const uint64_t da_hi = a_base | uint64_t(((a_hi + k * a_kstep) & 0x3FFFF) >> 4);
-          const uint64_t da_lo = a_base | uint64_t(((a_lo + k * a_kstep) & 0x3FFFF) >> 4);
           const uint64_t db_hi = b_base | uint64_t(((b_hi + k * b_kstep) & 0x3FFFF) >> 4);
           const uint64_t db_lo = b_base | uint64_t(((b_lo + k * b_kstep) & 0x3FFFF) >> 4);
-          mma_tf32(d_lo, da_lo, db_hi, idesc, (i | k) != 0);
-          mma_tf32(d_lo, da_hi, db_lo, idesc, 1);
-          mma_tf32(d_hi, da_hi, db_hi, idesc, ((i % CH) | k) != 0);
+          if (C::A_TM) {
+            const uint32_t ta_hi = tmem_base + C::A_COL0 + slot * C::A_SLOT_COLS + k * 8;
+            const uint32_t ta_lo = ta_hi + BK;
+            mma_tf32_ta(d_lo, ta_lo, db_hi, idesc, (i | k) != 0);
+            mma_tf32_ta(d_lo, ta_hi, db_lo, idesc, 1);
+            mma_tf32_ta(d_hi, ta_hi, db_hi, idesc, ((i % CH) | k) != 0);
+          } else {
+            const uint64_t da_hi = a_base | uint64_t(((a_hi + k * a_kstep) & 0x3FFFF) >> 4);
+            const uint64_t da_lo = a_base | uint64_t(((a_lo + k * a_kstep) & 0x3FFFF) >> 4);
+            mma_tf32(d_lo, da_lo, db_hi, idesc, (i | k) != 0);
+            mma_tf32(d_lo, da_hi, db_lo, idesc, 1);
+            mma_tf32(d_hi, da_hi, db_hi, idesc, ((i % CH) | k) != 0);
+          }
         }
         mma_commit(empty(s));                                // frees the stage once these MMAs have read it
+        if (C::A_TM) mma_commit(a_free(slot));               // ... and the A slot in tensor memory
         if (i % CH == CH - 1 || i == num_kb - 1) mma_commit(acc_full(buf));
       }
       RECNN_TRACE(3);                                         // last MMA issued
@@ -439,7 +475,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
     const int t = threadIdx.x - 64;
     constexpr int NT = 32 * WORKERS;
-    constexpr int VEC_PER_STAGE = (C::A_BYTES + C::B_BYTES) / 16;
+    // shared-memory part of the split: the whole stage, or only B when A goes to tensor memory
+    constexpr int VEC_PER_STAGE = (C::A_TM ? C::B_BYTES : C::A_BYTES + C::B_BYTES) / 16;
     constexpr int VEC_PER_THREAD = VEC_PER_STAGE / NT;
     static_assert(VEC_PER_STAGE % NT == 0, "stage must split evenly over the worker threads");
     float acc[NC];
@@ -468,8 +505,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       const int s = i % STAGES;
       const uint32_t ph = (i / STAGES) & 1;
       mbar_wait(full(s), ph);
-      const uint32_t raw = stage_addr(s, 0);                  // rawA|rawB contiguous
-      const uint32_t lo = stage_addr(s, 2);                   // loA|loB contiguous
+      const uint32_t raw = stage_addr(s, C::A_TM ? 1 : 0);    // (rawA|)rawB contiguous
+      const uint32_t lo = stage_addr(s, C::A_TM ? 3 : 2);     // (loA|)loB contiguous
+      if (C::A_TM && !(p.dbg & 1)) {
+        // my row of the K-major A tile (64-byte rows, 16-byte chunks XOR-swizzled by (row>>1)&3) -> hi/lo in TMEM
+        const int slot = i % C::A_SLOTS;
+        mbar_wait(a_free(slot), ((i / C::A_SLOTS) & 1) ^ 1);
+        tc_fence_after();
+        const int row = 32 * q + lane;
+        const uint32_t rbase = stage_addr(s, 0) + (uint32_t)row * 64u;
+        const uint32_t sw = (uint32_t)(row >> 1) & 3u;
+        float hi[16], lw[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 x = lds128(rbase + ((j ^ sw) << 4));
+          tf32_split(x.x, hi[4 * j + 0], lw[4 * j + 0]);
+          tf32_split(x.y, hi[4 * j + 1], lw[4 * j + 1]);
+          tf32_split(x.z, hi[4 * j + 2], lw[4 * j + 2]);
+          tf32_split(x.w, hi[4 * j + 3], lw[4 * j + 3]);
+        }
+        const uint32_t ta = tmem_base + (uint32_t(32 * q) << 16) + C::A_COL0 + slot * C::A_SLOT_COLS;
+        tmem_st16(ta, hi);
+        tmem_st16(ta + BK, lw);
+      }
       if (!(p.dbg & 1)) {
         float4 x[VEC_PER_THREAD];
 #pragma unroll
@@ -483,6 +541,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         }
       }
       if (!(p.dbg & 8)) fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
+      if (C::A_TM) {
+        tmem_st_wait();
+        tc_fence_before();
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive(split(s));
       // once the last k-block of chunk c has been split, chunk c-1 has long been accumulated: drain it
