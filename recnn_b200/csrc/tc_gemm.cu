@@ -52,10 +52,10 @@ int make_tmap(CUtensorMap* out, const float* base, int64_t rows, int64_t cols, i
   return RECNN_OK;
 }
 
-int split_plan(int K_total_blocks, int splits_req, int* k_chunk) {
+int split_plan(int K_total_blocks, int splits_req, int* k_chunk, int bk) {
   if (splits_req < 1) splits_req = 1;
   const int kb_per = (int)ceil_div(K_total_blocks, splits_req);
-  *k_chunk = kb_per * 16;
+  *k_chunk = kb_per * bk;
   return (int)ceil_div(K_total_blocks, kb_per);
 }
 
@@ -83,7 +83,7 @@ static int launch_cfg(const Operand& A0, const Operand& A1, const Operand& B, co
     attr_set = true;
   }
   const int nkb = (int)(ceil_div(p.K0, C::BK) + ceil_div(p.K1, C::BK));
-  splits = split_plan(nkb, splits, &p.k_chunk);
+  splits = split_plan(nkb, splits, &p.k_chunk, C::BK);
   CUtensorMap ma0, ma1, mb;
   // K-major operand: tensor [rows = M|N, cols = K], box {BK, tile rows}; MN-major: tensor [rows = K, cols = M|N], box {32, BK}
   if (!C::A_MN) {
@@ -131,9 +131,10 @@ template <bool A_MN, bool B_MN, int EPI>
 int launch(const Operand& A0, const Operand& A1, const Operand& B, const Problem& p, int splits, int bn,
            const Epilogue& epi, cudaStream_t st) {
   // stages chosen to fill ~190 KB of shared memory
-  // stage bytes: K-major A (split into tensor memory) 8+2*BN/16 KB, MN-major A 16+2*BN/16 KB
-  if (bn >= 128) return launch_cfg<Cfg<128, A_MN ? 6 : 8, A_MN, B_MN>, EPI>(A0, A1, B, p, splits, epi, st);
-  return launch_cfg<Cfg<64, A_MN ? 8 : 10, A_MN, B_MN>, EPI>(A0, A1, B, p, splits, epi, st);
+  // K-major A: BK = 32 (128-byte TMA rows), A split into tensor memory: stage = 16 KB + 2 * BN/8 KB.
+  // MN-major A: BK = 16, A split in shared memory: stage = 16 KB + 2 * BN/16 KB.
+  if (bn >= 128) return launch_cfg<Cfg<128, A_MN ? 16 : 32, A_MN ? 6 : 4, A_MN, B_MN>, EPI>(A0, A1, B, p, splits, epi, st);
+  return launch_cfg<Cfg<64, A_MN ? 16 : 32, A_MN ? 8 : 6, A_MN, B_MN>, EPI>(A0, A1, B, p, splits, epi, st);
 }
 
 // explicit instantiations used by step.cu / the generic entry points

@@ -22,11 +22,11 @@
 // hi is rounded to nearest (not truncated), so |lo| <= 2^-12 |x| is symmetric and the dropped
 // lo*lo term is unbiased.  Measured result: ~3e-7 worst-case systematic error, independent of K.
 //
-// Warp roles (one 128 x BN output tile per CTA, BN in {64,128}; 6 warps):
+// Warp roles (one 128 x BN output tile per CTA, BN in {64,128}; 10 warps):
 //   warp 0        TMA producer: raw fp32 tiles of A and B -> smem stage s             (full[s])
 //   warp 1        MMA issuer (one lane): per stage 3 x BK/8 tcgen05.mma, commit -> empty[s];
 //                 per chunk commit -> acc_full[buf]
-//   workers       4 warps.  (1) splitter: read the raw stage with ld.shared, write `hi` back in
+//   workers       8 warps.  (1) splitter: read the raw stage with ld.shared, write `hi` back in
 //                 place and the `lo` tile next to it                                   (split[s])
 //                 (2) drain: TMEM chunk -> registers, running sum += chunk             (acc_empty[buf])
 //                 (3) epilogue on the register-resident row (bias/relu/dropout/...), store.
@@ -161,10 +161,11 @@ __device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
                : "memory");
 }
 
+// Round-to-nearest (ties away) to TF32 = add half a TF32 ulp to the magnitude bits, clear the low 13.
+// Bit-identical to cvt.rna.tf32.f32 for finite inputs, but two full-rate integer ops instead of a
+// quarter-rate conversion (the splitter was bound by the conversion pipe: 16 K cvt per k-block per SM).
 __device__ __forceinline__ float tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 // x = hi + lo (+ <= 2^-24 |x|): hi = rna_tf32(x), lo = rna_tf32(x - hi)
 __device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) {
@@ -212,25 +213,28 @@ __device__ __forceinline__ unsigned long long gtimer() {
     if (p.trace) p.trace[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + (slot)] = gtimer(); \
   } while (0)
 
-template <int BN_, int STAGES_, bool A_MN_, bool B_MN_>
+template <int BN_, int BK_, int STAGES_, bool A_MN_, bool B_MN_>
 struct Cfg {
-  static constexpr int BM = 128, BN = BN_, BK = 16, STAGES = STAGES_;
-  static constexpr int CH = 4;                                     // k-blocks per TMEM accumulation chunk (K = 64)
+  // BK = 32 (128-byte K-major rows) when A is K-major: TMA moves 64-byte rows at half the rate of
+  // 128-byte rows (measured: 31 B/clk/SM with BK = 16), and the operand stream is the kernel's bottleneck.
+  static constexpr int BM = 128, BN = BN_, BK = BK_, STAGES = STAGES_;
+  static constexpr int CH = 64 / BK;                               // k-blocks per TMEM accumulation chunk (K = 64)
   static constexpr bool A_MN = A_MN_, B_MN = B_MN_;
   // K-major A: the split A tile goes to TENSOR memory (tcgen05.st) and the MMA reads it from there, so
   // A costs shared memory one TMA write + one read instead of write + read + 2 writes + 6 MMA reads.
   static constexpr bool A_TM = !A_MN_;
-  static constexpr int A_SLOTS = 4, A_SLOT_COLS = 2 * BK;          // TMEM ring for A: hi | lo per k-block
+  static constexpr int A_SLOT_COLS = 2 * BK, A_SLOTS = 128 / A_SLOT_COLS;   // TMEM ring for A: hi | lo per k-block
   static constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = (A_TM ? A_BYTES : 2 * A_BYTES) + 2 * B_BYTES;   // raw A (+lo A) | raw B | lo B
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
-  static constexpr int COLS_PER_WORKER = BN;                       // register-resident running sum per thread
-  static constexpr int WORKERS = 4;                                // warps (one per TMEM lane quarter)
+  static constexpr int WORKERS = 8;                                // warps: two per TMEM lane quarter
+  static constexpr int COLS_PER_WORKER = BN / (WORKERS / 4);       // register-resident running sum per thread
   static constexpr int THREADS = 64 + 32 * WORKERS;
   static constexpr int TMEM_COLS = 512;                            // D_hi chunk x2 | D_lo | A ring (3*BN + 128 <= 512)
   static constexpr int A_COL0 = 3 * BN;
-  static constexpr int K_SWZ = BK * 4;                             // K-major rows: 64 B, SWIZZLE_64B
+  static constexpr int K_SWZ = BK * 4;                             // K-major rows: 64 B (SWIZZLE_64B) or 128 B (SWIZZLE_128B)
   static_assert(BN == 64 || BN == 128, "BN");
+  static_assert(BK == 16 || BK == 32, "BK");
   static_assert(SMEM_BYTES <= 227 * 1024, "smem");
 };
 
@@ -425,8 +429,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       // use the 128B_BASE32B layout (cute: "for mn-major tf32 operands, SW128_32B is the only available
       // smem layout"): 128-byte rows of 32 MN elements, swizzle period 4 k-rows => SBO = 512 B between
       // 4-row groups, LBO = pitch between 32-element MN chunks (BK rows * 128 B).
-      constexpr uint64_t a_base = C::A_MN ? smem_desc_base(BK * 128, 512, 1) : smem_desc_base(16, 8 * C::K_SWZ, 4);
-      constexpr uint64_t b_base = C::B_MN ? smem_desc_base(BK * 128, 512, 1) : smem_desc_base(16, 8 * C::K_SWZ, 4);
+      constexpr uint32_t k_layout = C::K_SWZ == 128 ? 2 : 4;     // SWIZZLE_128B : SWIZZLE_64B
+      constexpr uint64_t a_base = C::A_MN ? smem_desc_base(BK * 128, 512, 1) : smem_desc_base(16, 8 * C::K_SWZ, k_layout);
+      constexpr uint64_t b_base = C::B_MN ? smem_desc_base(BK * 128, 512, 1) : smem_desc_base(16, 8 * C::K_SWZ, k_layout);
       constexpr uint32_t a_kstep = C::A_MN ? 1024 : 32;     // bytes to advance per 8-wide k-slice
       constexpr uint32_t b_kstep = C::B_MN ? 1024 : 32;
       for (int i = 0; i < num_kb; ++i) {
@@ -473,6 +478,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   } else {
     // ===================================================== workers: split, drain, epilogue
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
+    const int g = (warp - 2) >> 2;           // which column slab (drain/epilogue) / k-half (A split) it owns
     const int t = threadIdx.x - 64;
     constexpr int NT = 32 * WORKERS;
     // shared-memory part of the split: the whole stage, or only B when A goes to tensor memory
@@ -482,7 +488,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     float acc[NC];
 #pragma unroll
     for (int j = 0; j < NC; ++j) acc[j] = 0.f;
-    const uint32_t lane_base = tmem_base + (uint32_t(32 * q) << 16);
+    const uint32_t lane_base = tmem_base + (uint32_t(32 * q) << 16) + (uint32_t)g * NC;
 
     auto drain = [&](int chunk) {
       const int buf = chunk & 1;
@@ -508,25 +514,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       const uint32_t raw = stage_addr(s, C::A_TM ? 1 : 0);    // (rawA|)rawB contiguous
       const uint32_t lo = stage_addr(s, C::A_TM ? 3 : 2);     // (loA|)loB contiguous
       if (C::A_TM && !(p.dbg & 1)) {
-        // my row of the K-major A tile (64-byte rows, 16-byte chunks XOR-swizzled by (row>>1)&3) -> hi/lo in TMEM
+        // my row of the K-major A tile -> hi/lo in TMEM.  Rows are K_SWZ bytes; TMA's swizzle XORs the
+        // 16-byte chunk index with address bits [7, 7+log2(K_SWZ/16)): (row>>1)&3 for 64-byte rows, row&7 for 128.
         const int slot = i % C::A_SLOTS;
         mbar_wait(a_free(slot), ((i / C::A_SLOTS) & 1) ^ 1);
         tc_fence_after();
         const int row = 32 * q + lane;
-        const uint32_t rbase = stage_addr(s, 0) + (uint32_t)row * 64u;
-        const uint32_t sw = (uint32_t)(row >> 1) & 3u;
-        float hi[16], lw[16];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 x = lds128(rbase + ((j ^ sw) << 4));
-          tf32_split(x.x, hi[4 * j + 0], lw[4 * j + 0]);
-          tf32_split(x.y, hi[4 * j + 1], lw[4 * j + 1]);
-          tf32_split(x.z, hi[4 * j + 2], lw[4 * j + 2]);
-          tf32_split(x.w, hi[4 * j + 3], lw[4 * j + 3]);
-        }
+        const uint32_t rbase = stage_addr(s, 0) + (uint32_t)row * (uint32_t)C::K_SWZ;
+        const uint32_t sw = C::K_SWZ == 128 ? ((uint32_t)row & 7u) : (((uint32_t)row >> 1) & 3u);
         const uint32_t ta = tmem_base + (uint32_t(32 * q) << 16) + C::A_COL0 + slot * C::A_SLOT_COLS;
-        tmem_st16(ta, hi);
-        tmem_st16(ta + BK, lw);
+        // BK = 32: the two warps of a lane quarter take 16 k-values each; BK = 16: warp group 0 takes the row
+        for (int half = (BK == 32 ? g : 0); half < (BK == 32 ? g + 1 : (g == 0 ? 1 : 0)); ++half) {
+          float hi[16], lw[16];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 x = lds128(rbase + (((4 * half + j) ^ sw) << 4));
+            tf32_split(x.x, hi[4 * j + 0], lw[4 * j + 0]);
+            tf32_split(x.y, hi[4 * j + 1], lw[4 * j + 1]);
+            tf32_split(x.z, hi[4 * j + 2], lw[4 * j + 2]);
+            tf32_split(x.w, hi[4 * j + 3], lw[4 * j + 3]);
+          }
+          tmem_st16(ta + 16 * half, hi);
+          tmem_st16(ta + BK + 16 * half, lw);
+        }
       }
       if (!(p.dbg & 1)) {
         float4 x[VEC_PER_THREAD];
@@ -565,7 +575,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         for (int j = 0; j < 32; ++j) acc[c0 + j] = __fadd_rn(acc[c0 + j], __uint_as_float(r[j]));
       }
     }
-    epilogue_row<EPI, NC>(epi, p, m0 + 32 * q + lane, n0, z, acc);
+    epilogue_row<EPI, NC>(epi, p, m0 + 32 * q + lane, n0 + g * NC, z, acc);
     if (t == 0) RECNN_TRACE(6);                               // epilogue stored
   }
   tc_fence_before();
@@ -597,8 +607,8 @@ struct Operand {
   long long rows, cols;
 };
 
-// k-blocks (of 16) per split and the effective split count for a requested split count.
-int split_plan(int K_total_blocks, int splits_req, int* k_chunk);
+// k-blocks (of bk) per split and the effective split count for a requested split count.
+int split_plan(int K_total_blocks, int splits_req, int* k_chunk, int bk = 16);
 
 // Launch one GEMM.  Returns the effective number of k-splits (> 0) or a negative RECNN_E_* code.
 template <bool A_MN, bool B_MN, int EPI>
