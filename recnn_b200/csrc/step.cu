@@ -94,7 +94,7 @@ static int dw_splits(int C, int K, int64_t n_rows, bool tc_path) {
   if (tc_path) {
     const int64_t tiles = ceil_div(C, 128) * ceil_div(K, 128);
     int64_t s = ceil_div(192, tiles);
-    const int64_t max_s = ceil_div(n_rows, 16) / 8 > 0 ? ceil_div(n_rows, 16) / 8 : 1;   // >= 8 k-blocks per split
+    const int64_t max_s = ceil_div(n_rows, 32) / 4 > 0 ? ceil_div(n_rows, 32) / 4 : 1;   // >= 4 k-blocks (128 rows) per split
     if (s > max_s) s = max_s;
     return (int)(s < 1 ? 1 : s);
   }
@@ -277,7 +277,7 @@ static int weight_grad(const float* dZ, int C, const Seg& x0, const Seg& x1, int
   if (tc_ok) {
     const int req = dw_splits(C, K, n, true);
     int k_chunk = 0;
-    const int splits = tc::split_plan((int)ceil_div(n, 16), req, &k_chunk);
+    const int splits = tc::split_plan((int)ceil_div(n, 32), req, &k_chunk, 32);
     tc::Operand a0 = {dZ, C, 0, 0}, a1 = {nullptr, 0, 0, 0};
     // the padded second segment's window starts `lead` columns inside the first segment's; those pad
     // columns are computed (as zeros) but not stored (n_skip), so the two GEMMs are independent

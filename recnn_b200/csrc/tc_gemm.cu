@@ -131,10 +131,9 @@ template <bool A_MN, bool B_MN, int EPI>
 int launch(const Operand& A0, const Operand& A1, const Operand& B, const Problem& p, int splits, int bn,
            const Epilogue& epi, cudaStream_t st) {
   // stages chosen to fill ~190 KB of shared memory
-  // K-major A: BK = 32 (128-byte TMA rows), A split into tensor memory: stage = 16 KB + 2 * BN/8 KB.
-  // MN-major A: BK = 16, A split in shared memory: stage = 16 KB + 2 * BN/16 KB.
-  if (bn >= 128) return launch_cfg<Cfg<128, A_MN ? 16 : 32, A_MN ? 6 : 4, A_MN, B_MN>, EPI>(A0, A1, B, p, splits, epi, st);
-  return launch_cfg<Cfg<64, A_MN ? 16 : 32, A_MN ? 8 : 6, A_MN, B_MN>, EPI>(A0, A1, B, p, splits, epi, st);
+  // BK = 32 (128-byte TMA rows), A split into tensor memory: stage = 16 KB (raw A) + 2 * BN/8 KB (B hi | B lo)
+  if (bn >= 128) return launch_cfg<Cfg<128, 32, 4, A_MN, B_MN>, EPI>(A0, A1, B, p, splits, epi, st);
+  return launch_cfg<Cfg<64, 32, 6, A_MN, B_MN>, EPI>(A0, A1, B, p, splits, epi, st);
 }
 
 // explicit instantiations used by step.cu / the generic entry points

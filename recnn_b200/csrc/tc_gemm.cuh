@@ -220,9 +220,9 @@ struct Cfg {
   static constexpr int BM = 128, BN = BN_, BK = BK_, STAGES = STAGES_;
   static constexpr int CH = 64 / BK;                               // k-blocks per TMEM accumulation chunk (K = 64)
   static constexpr bool A_MN = A_MN_, B_MN = B_MN_;
-  // K-major A: the split A tile goes to TENSOR memory (tcgen05.st) and the MMA reads it from there, so
-  // A costs shared memory one TMA write + one read instead of write + read + 2 writes + 6 MMA reads.
-  static constexpr bool A_TM = !A_MN_;
+  // The split A tile goes to TENSOR memory (tcgen05.st) and the MMA reads it from there, so A costs
+  // shared memory one TMA write + one read instead of write + read + 2 writes + 6 MMA reads.
+  static constexpr bool A_TM = true;
   static constexpr int A_SLOT_COLS = 2 * BK, A_SLOTS = 128 / A_SLOT_COLS;   // TMEM ring for A: hi | lo per k-block
   static constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = (A_TM ? A_BYTES : 2 * A_BYTES) + 2 * B_BYTES;   // raw A (+lo A) | raw B | lo B
@@ -424,7 +424,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   } else if (warp == 1) {
     // ===================================================== MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = instr_desc_tf32(BM, BN, C::A_MN, C::B_MN);
+      // A read from tensor memory is always [M lanes, K columns] = K-major, whatever its layout in global memory
+      constexpr uint32_t idesc = instr_desc_tf32(BM, BN, C::A_TM ? false : C::A_MN, C::B_MN);
       // K-major: rows of K_SWZ bytes, LBO unused (1), SBO = 8 rows.  MN-major fp32/tf32 operands must
       // use the 128B_BASE32B layout (cute: "for mn-major tf32 operands, SW128_32B is the only available
       // smem layout"): 128-byte rows of 32 MN elements, swizzle period 4 k-rows => SBO = 512 B between
@@ -513,7 +514,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       mbar_wait(full(s), ph);
       const uint32_t raw = stage_addr(s, C::A_TM ? 1 : 0);    // (rawA|)rawB contiguous
       const uint32_t lo = stage_addr(s, C::A_TM ? 3 : 2);     // (loA|)loB contiguous
-      if (C::A_TM && !(p.dbg & 1)) {
+      if (C::A_TM && C::A_MN && !(p.dbg & 1)) {
+        // MN-major A tile: 4 chunks (32 rows of M each) x BK k-rows of 128 bytes; TMA's 128B_ATOM_32B swizzle
+        // XORs the 32-byte unit index with (k & 3).  My TMEM lane is row m = 32*q + lane: chunk q, element `lane`
+        // of every k-row -> one conflict-free 128-byte wavefront per k for the warp.
+        const int slot = i % C::A_SLOTS;
+        mbar_wait(a_free(slot), ((i / C::A_SLOTS) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t cbase = stage_addr(s, 0) + (uint32_t)q * (BK * 128u) + (((uint32_t)lane & 7u) << 2);
+        const uint32_t unit = (uint32_t)lane >> 3;
+        const uint32_t ta = tmem_base + (uint32_t(32 * q) << 16) + C::A_COL0 + slot * C::A_SLOT_COLS;
+        float hi[16], lw[16];
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+          const uint32_t k = 16u * g + kk;
+          float x;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(cbase + k * 128u + ((unit ^ (k & 3u)) << 5)));
+          tf32_split(x, hi[kk], lw[kk]);
+        }
+        tmem_st16(ta + 16 * g, hi);
+        tmem_st16(ta + BK + 16 * g, lw);
+      } else if (C::A_TM && !(p.dbg & 1)) {
         // my row of the K-major A tile -> hi/lo in TMEM.  Rows are K_SWZ bytes; TMA's swizzle XORs the
         // 16-byte chunk index with address bits [7, 7+log2(K_SWZ/16)): (row>>1)&3 for 64-byte rows, row&7 for 128.
         const int slot = i % C::A_SLOTS;
