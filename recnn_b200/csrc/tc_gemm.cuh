@@ -116,6 +116,17 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint6
       : "memory");
 }
 // arrives on `bar` once every tcgen05.mma issued so far by this thread has completed
+// One lane of a fully converged warp (elect.sync); the compiler then knows the guarded tcgen05/TMA
+// instructions run in a single thread and emits them without a per-lane serialisation loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -208,6 +219,22 @@ __device__ __forceinline__ unsigned long long gtimer() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
+// stall accounting (dbg bit 16): cycles spent inside a wait, written behind the stamps of all CTAs
+#define RECNN_TIMED(counter, stmt)                         \
+  do {                                                     \
+    if (prof) {                                            \
+      const long long c0__ = clock64();                    \
+      stmt;                                                \
+      counter += clock64() - c0__;                         \
+    } else {                                               \
+      stmt;                                                \
+    }                                                      \
+  } while (0)
+#define RECNN_PROF_OUT(slot, v)                                                                    \
+  do {                                                                                             \
+    if (prof && p.trace)                                                                           \
+      p.trace[((gridDim.z * gridDim.y * gridDim.x) + (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + (slot)] = (unsigned long long)(v); \
+  } while (0)
 #define RECNN_TRACE(slot)                                                                          \
   do {                                                                                             \
     if (p.trace) p.trace[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + (slot)] = gtimer(); \
@@ -234,7 +261,7 @@ struct Cfg {
   static constexpr int A_COL0 = 3 * BN;
   static constexpr int K_SWZ = BK * 4;                             // K-major rows: 64 B (SWIZZLE_64B) or 128 B (SWIZZLE_128B)
   static_assert(BN == 64 || BN == 128, "BN");
-  static_assert(BK == 16 || BK == 32, "BK");
+  static_assert(BK == 32, "BK: 128-byte operand rows");
   static_assert(SMEM_BYTES <= 227 * 1024, "smem");
 };
 
@@ -329,7 +356,8 @@ template <class C, int EPI>
 __global__ void __launch_bounds__(C::THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_b, Problem p, Epilogue epi) {
-  constexpr int BM = C::BM, BN = C::BN, BK = C::BK, STAGES = C::STAGES, CH = C::CH;
+  constexpr int BM = C::BM, BN = C::BN, BK = C::BK, STAGES = C::STAGES;
+  const int CH = ((p.dbg >> 8) & 15) ? ((p.dbg >> 8) & 15) : C::CH;   // experiment hook: chunk length override
   constexpr int NC = C::COLS_PER_WORKER, WORKERS = C::WORKERS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;       // shared-window address, 1 KB aligned
@@ -362,6 +390,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   const int kb_end = min(nkb0 + nkb1, kb_begin + kb_per_split);
   const int num_kb = max(kb_end - kb_begin, 0);
   const int num_chunks = (num_kb + CH - 1) / CH;
+  const bool prof = (p.dbg & 16) != 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a0);
@@ -371,7 +400,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full(s), 1);
-      mbar_init(split(s), WORKERS);      // one arrive per worker warp
+      mbar_init(split(s), (p.dbg & 32) ? WORKERS : WORKERS / 2);   // one arrive per worker warp that split the stage
       mbar_init(empty(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -392,19 +421,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   if (threadIdx.x == 0) RECNN_TRACE(1);                       // prologue done
 
   if (warp == 0) {
-    // ===================================================== TMA producer
-    if (lane == 0) {
-      for (int i = 0; i < num_kb; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        mbar_wait(empty(s), ph ^ 1);
+    // ===================================================== TMA producer (whole warp walks, one elected lane issues)
+    const bool leader = elect_one();
+    long long w0 = 0;
+    for (int i = 0; i < num_kb; ++i) {
+      const int s = i % STAGES;
+      const uint32_t ph = (i / STAGES) & 1;
+      RECNN_TIMED(w0, mbar_wait(empty(s), ph ^ 1));
+      const int kb = kb_begin + i;
+      const bool seg1 = kb >= nkb0;
+      const int ka = seg1 ? (kb - nkb0) * BK : kb * BK;                     // k coordinate inside A's segment
+      const int kbcol = seg1 ? p.b_k1_offset + (kb - nkb0) * BK : kb * BK;  // k coordinate in B
+      const CUtensorMap* ma = seg1 ? &map_a1 : &map_a0;
+      const uint32_t dst_a = stage_addr(s, 0), dst_b = stage_addr(s, 1);
+      if (leader) {
         mbar_expect_tx(full(s), C::A_BYTES + C::B_BYTES);
-        const int kb = kb_begin + i;
-        const bool seg1 = kb >= nkb0;
-        const int ka = seg1 ? (kb - nkb0) * BK : kb * BK;                     // k coordinate inside A's segment
-        const int kbcol = seg1 ? p.b_k1_offset + (kb - nkb0) * BK : kb * BK;  // k coordinate in B
-        const CUtensorMap* ma = seg1 ? &map_a1 : &map_a0;
-        const uint32_t dst_a = stage_addr(s, 0), dst_b = stage_addr(s, 1);
         if (!C::A_MN) {
           tma_load_2d(dst_a, ma, full(s), ka, m0);                            // box {BK, 128}
         } else {
@@ -420,61 +451,63 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             tma_load_2d(dst_b + c * (BK * 128), &map_b, full(s), p.b_n_offset + n0 + 32 * c, kbcol);
         }
       }
+      __syncwarp();
     }
+    if (lane == 0) RECNN_PROF_OUT(6, w0);
   } else if (warp == 1) {
     // ===================================================== MMA issuer
-    if (lane == 0) {
-      // A read from tensor memory is always [M lanes, K columns] = K-major, whatever its layout in global memory
-      constexpr uint32_t idesc = instr_desc_tf32(BM, BN, C::A_TM ? false : C::A_MN, C::B_MN);
-      // K-major: rows of K_SWZ bytes, LBO unused (1), SBO = 8 rows.  MN-major fp32/tf32 operands must
-      // use the 128B_BASE32B layout (cute: "for mn-major tf32 operands, SW128_32B is the only available
-      // smem layout"): 128-byte rows of 32 MN elements, swizzle period 4 k-rows => SBO = 512 B between
-      // 4-row groups, LBO = pitch between 32-element MN chunks (BK rows * 128 B).
-      constexpr uint32_t k_layout = C::K_SWZ == 128 ? 2 : 4;     // SWIZZLE_128B : SWIZZLE_64B
-      constexpr uint64_t a_base = C::A_MN ? smem_desc_base(BK * 128, 512, 1) : smem_desc_base(16, 8 * C::K_SWZ, k_layout);
-      constexpr uint64_t b_base = C::B_MN ? smem_desc_base(BK * 128, 512, 1) : smem_desc_base(16, 8 * C::K_SWZ, k_layout);
-      constexpr uint32_t a_kstep = C::A_MN ? 1024 : 32;     // bytes to advance per 8-wide k-slice
-      constexpr uint32_t b_kstep = C::B_MN ? 1024 : 32;
-      for (int i = 0; i < num_kb; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        const int chunk = i / CH, buf = chunk & 1;
-        if (i % CH == 0) {                                   // new chunk: its TMEM buffer must have been drained
-          mbar_wait(acc_empty(buf), ((chunk >> 1) & 1) ^ 1);
-          tc_fence_after();
-        }
-        mbar_wait(split(s), ph);
-        tc_fence_after();
-        if (i == 0) RECNN_TRACE(2);                           // first stage loaded + split
-        const uint32_t d_hi = tmem_base + (uint32_t)buf * BN;     // chunk accumulator (hi*hi)
-        const uint32_t d_lo = tmem_base + 2u * BN;                // tile-lifetime accumulator (cross terms)
-        const uint32_t a_hi = stage_addr(s, 0), b_hi = stage_addr(s, 1);
-        const uint32_t a_lo = stage_addr(s, 2), b_lo = stage_addr(s, 3);
-        const int slot = i % C::A_SLOTS;
+    // The whole warp walks the pipeline (so every value below is warp-uniform and lives in uniform
+    // registers); one elected lane issues the MMAs and commits.  Issuing under `if (lane == 0)` instead makes
+    // the compiler wrap every tcgen05 instruction in an ELECT/BRA.U.ANY loop, which made the issue stream,
+    // not the tensor pipe, the limiter (~130 clk per MMA against a 64 clk floor).
+    // A read from tensor memory is always [M lanes, K columns] = K-major, whatever its layout in global memory.
+    constexpr uint32_t idesc = instr_desc_tf32(BM, BN, false, C::B_MN);
+    // K-major B: rows of 128 bytes, LBO unused (1), SBO = 8 rows.  MN-major fp32/tf32 operands must
+    // use the 128B_BASE32B layout (cute: "for mn-major tf32 operands, SW128_32B is the only available
+    // smem layout"): 128-byte rows of 32 MN elements, swizzle period 4 k-rows => SBO = 512 B between
+    // 4-row groups, LBO = pitch between 32-element MN chunks (BK rows * 128 B).
+    constexpr uint64_t b_base = C::B_MN ? smem_desc_base(BK * 128, 512, 1) : smem_desc_base(16, 8 * C::K_SWZ, 2);
+    constexpr uint32_t b_kstep = C::B_MN ? 1024 : 32;        // bytes to advance per 8-wide k-slice
+    const bool leader = elect_one();
+    long long w_split = 0, w_acc = 0;
+    for (int i = 0; i < num_kb; ++i) {
+      const int s = i % STAGES;
+      const uint32_t ph = (i / STAGES) & 1;
+      const int chunk = i / CH, buf = chunk & 1;
+      if (i % CH == 0) {                                     // new chunk: its TMEM buffer must have been drained
+        RECNN_TIMED(w_acc, mbar_wait(acc_empty(buf), ((chunk >> 1) & 1) ^ 1));
+      }
+      RECNN_TIMED(w_split, mbar_wait(split(s), ph));
+      tc_fence_after();
+      if (i == 0 && lane == 0) RECNN_TRACE(2);               // first stage loaded + split
+      const uint32_t d_hi = tmem_base + (uint32_t)buf * BN;  // chunk accumulator (hi*hi)
+      const uint32_t d_lo = tmem_base + 2u * BN;             // tile-lifetime accumulator (cross terms)
+      const uint64_t db_hi0 = b_base | uint64_t((stage_addr(s, 1) & 0x3FFFF) >> 4);
+      const uint64_t db_lo0 = b_base | uint64_t((stage_addr(s, 3) & 0x3FFFF) >> 4);
+      const int slot = i % C::A_SLOTS;
+      const uint32_t ta0 = tmem_base + C::A_COL0 + slot * C::A_SLOT_COLS;
+      if (leader && !(p.dbg & 2)) {
 #pragma unroll
         for (int k = 0; k < BK / 8; ++k) {
-          if (p.dbg & 2) break;
-          const uint64_t db_hi = b_base | uint64_t(((b_hi + k * b_kstep) & 0x3FFFF) >> 4);
-          const uint64_t db_lo = b_base | uint64_t(((b_lo + k * b_kstep) & 0x3FFFF) >> 4);
-          if (C::A_TM) {
-            const uint32_t ta_hi = tmem_base + C::A_COL0 + slot * C::A_SLOT_COLS + k * 8;
-            const uint32_t ta_lo = ta_hi + BK;
-            mma_tf32_ta(d_lo, ta_lo, db_hi, idesc, (i | k) != 0);
-            mma_tf32_ta(d_lo, ta_hi, db_lo, idesc, 1);
-            mma_tf32_ta(d_hi, ta_hi, db_hi, idesc, ((i % CH) | k) != 0);
-          } else {
-            const uint64_t da_hi = a_base | uint64_t(((a_hi + k * a_kstep) & 0x3FFFF) >> 4);
-            const uint64_t da_lo = a_base | uint64_t(((a_lo + k * a_kstep) & 0x3FFFF) >> 4);
-            mma_tf32(d_lo, da_lo, db_hi, idesc, (i | k) != 0);
-            mma_tf32(d_lo, da_hi, db_lo, idesc, 1);
-            mma_tf32(d_hi, da_hi, db_hi, idesc, ((i % CH) | k) != 0);
-          }
+          const uint64_t db_hi = db_hi0 + uint64_t((k * b_kstep) >> 4);
+          const uint64_t db_lo = db_lo0 + uint64_t((k * b_kstep) >> 4);
+          const uint32_t ta_hi = ta0 + k * 8, ta_lo = ta_hi + BK;
+          mma_tf32_ta(d_lo, ta_lo, db_hi, idesc, (i | k) != 0);
+          mma_tf32_ta(d_lo, ta_hi, db_lo, idesc, 1);
+          mma_tf32_ta(d_hi, ta_hi, db_hi, idesc, ((i % CH) | k) != 0);
         }
+      }
+      if (leader) {
         mma_commit(empty(s));                                // frees the stage once these MMAs have read it
-        if (C::A_TM) mma_commit(a_free(slot));               // ... and the A slot in tensor memory
+        mma_commit(a_free(slot));                            // ... and the A slot in tensor memory
         if (i % CH == CH - 1 || i == num_kb - 1) mma_commit(acc_full(buf));
       }
+      __syncwarp();
+    }
+    if (lane == 0) {
       RECNN_TRACE(3);                                         // last MMA issued
+      RECNN_PROF_OUT(4, w_split);
+      RECNN_PROF_OUT(5, w_acc);
     }
   } else {
     // ===================================================== workers: split, drain, epilogue
@@ -482,19 +515,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     const int g = (warp - 2) >> 2;           // which column slab (drain/epilogue) / k-half (A split) it owns
     const int t = threadIdx.x - 64;
     constexpr int NT = 32 * WORKERS;
-    // shared-memory part of the split: the whole stage, or only B when A goes to tensor memory
-    constexpr int VEC_PER_STAGE = (C::A_TM ? C::B_BYTES : C::A_BYTES + C::B_BYTES) / 16;
-    constexpr int VEC_PER_THREAD = VEC_PER_STAGE / NT;
-    static_assert(VEC_PER_STAGE % NT == 0, "stage must split evenly over the worker threads");
     float acc[NC];
 #pragma unroll
     for (int j = 0; j < NC; ++j) acc[j] = 0.f;
     const uint32_t lane_base = tmem_base + (uint32_t(32 * q) << 16) + (uint32_t)g * NC;
+    long long w_full = 0, w_afree = 0, w_drain = 0, w_ld = 0;
+    const long long loop0 = clock64();
 
     auto drain = [&](int chunk) {
       const int buf = chunk & 1;
-      mbar_wait(acc_full(buf), (chunk >> 1) & 1);
+      RECNN_TIMED(w_drain, mbar_wait(acc_full(buf), (chunk >> 1) & 1));
       tc_fence_after();
+      const long long ld0 = prof ? clock64() : 0;
 #pragma unroll
       for (int c0 = 0; c0 < NC; c0 += 32) {
         uint32_t r[32];
@@ -503,88 +535,104 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[c0 + j] = __fadd_rn(acc[c0 + j], __uint_as_float(r[j]));
       }
+      if (prof) w_ld += clock64() - ld0;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty(buf));
     };
 
-    for (int i = 0; i < num_kb; ++i) {
+    // The two warp groups (one warp per TMEM lane quarter each) take alternate k-blocks, so one group's
+    // publish latency (membar + proxy fence + tcgen05.wait::st) hides behind the other group's arithmetic.
+    // dbg bit 32 (experiments): all 8 warps share every k-block instead (half a row / an eighth of B each).
+    const int ng = (p.dbg & 32) ? 1 : 2;
+    const int tg = ng == 2 ? (t & 127) : t;                   // index among the threads sharing one k-block
+    const uint32_t ntg = ng == 2 ? 128u : 256u;
+    constexpr int VB = C::B_BYTES / 16 / NT;                  // float4s per thread per batch (all 256 threads = 1 batch)
+    static_assert(C::B_BYTES / 16 % NT == 0 && VB >= 1, "B tile must split evenly over the worker threads");
+    int next_drain = 0;
+    for (int i = (ng == 2 ? g : 0); i < num_kb; i += ng) {
       const int s = i % STAGES;
       const uint32_t ph = (i / STAGES) & 1;
-      mbar_wait(full(s), ph);
-      const uint32_t raw = stage_addr(s, C::A_TM ? 1 : 0);    // (rawA|)rawB contiguous
-      const uint32_t lo = stage_addr(s, C::A_TM ? 3 : 2);     // (loA|)loB contiguous
-      if (C::A_TM && C::A_MN && !(p.dbg & 1)) {
-        // MN-major A tile: 4 chunks (32 rows of M each) x BK k-rows of 128 bytes; TMA's 128B_ATOM_32B swizzle
-        // XORs the 32-byte unit index with (k & 3).  My TMEM lane is row m = 32*q + lane: chunk q, element `lane`
-        // of every k-row -> one conflict-free 128-byte wavefront per k for the warp.
-        const int slot = i % C::A_SLOTS;
-        mbar_wait(a_free(slot), ((i / C::A_SLOTS) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t cbase = stage_addr(s, 0) + (uint32_t)q * (BK * 128u) + (((uint32_t)lane & 7u) << 2);
-        const uint32_t unit = (uint32_t)lane >> 3;
-        const uint32_t ta = tmem_base + (uint32_t(32 * q) << 16) + C::A_COL0 + slot * C::A_SLOT_COLS;
-        float hi[16], lw[16];
-#pragma unroll
-        for (int kk = 0; kk < 16; ++kk) {
-          const uint32_t k = 16u * g + kk;
-          float x;
-          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(cbase + k * 128u + ((unit ^ (k & 3u)) << 5)));
-          tf32_split(x, hi[kk], lw[kk]);
-        }
-        tmem_st16(ta + 16 * g, hi);
-        tmem_st16(ta + BK + 16 * g, lw);
-      } else if (C::A_TM && !(p.dbg & 1)) {
-        // my row of the K-major A tile -> hi/lo in TMEM.  Rows are K_SWZ bytes; TMA's swizzle XORs the
-        // 16-byte chunk index with address bits [7, 7+log2(K_SWZ/16)): (row>>1)&3 for 64-byte rows, row&7 for 128.
-        const int slot = i % C::A_SLOTS;
-        mbar_wait(a_free(slot), ((i / C::A_SLOTS) & 1) ^ 1);
-        tc_fence_after();
-        const int row = 32 * q + lane;
-        const uint32_t rbase = stage_addr(s, 0) + (uint32_t)row * (uint32_t)C::K_SWZ;
-        const uint32_t sw = C::K_SWZ == 128 ? ((uint32_t)row & 7u) : (((uint32_t)row >> 1) & 3u);
-        const uint32_t ta = tmem_base + (uint32_t(32 * q) << 16) + C::A_COL0 + slot * C::A_SLOT_COLS;
-        // BK = 32: the two warps of a lane quarter take 16 k-values each; BK = 16: warp group 0 takes the row
-        for (int half = (BK == 32 ? g : 0); half < (BK == 32 ? g + 1 : (g == 0 ? 1 : 0)); ++half) {
-          float hi[16], lw[16];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 x = lds128(rbase + (((4 * half + j) ^ sw) << 4));
-            tf32_split(x.x, hi[4 * j + 0], lw[4 * j + 0]);
-            tf32_split(x.y, hi[4 * j + 1], lw[4 * j + 1]);
-            tf32_split(x.z, hi[4 * j + 2], lw[4 * j + 2]);
-            tf32_split(x.w, hi[4 * j + 3], lw[4 * j + 3]);
-          }
-          tmem_st16(ta + 16 * half, hi);
-          tmem_st16(ta + BK + 16 * half, lw);
-        }
-      }
+      RECNN_TIMED(w_full, mbar_wait(full(s), ph));
+      const uint32_t raw = stage_addr(s, 1);                  // raw B, split in place into hi
+      const uint32_t lo = stage_addr(s, 3);                   // lo B
+      const int slot = i % C::A_SLOTS;
+      const uint32_t ta = tmem_base + (uint32_t(32 * q) << 16) + C::A_COL0 + slot * C::A_SLOT_COLS;
+      const int half0 = ng == 2 ? 0 : g, half1 = ng == 2 ? 2 : g + 1;
       if (!(p.dbg & 1)) {
-        float4 x[VEC_PER_THREAD];
+        RECNN_TIMED(w_afree, mbar_wait(a_free(slot), ((i / C::A_SLOTS) & 1) ^ 1));
+        tc_fence_after();
+        if (C::A_MN) {
+          // MN-major A tile: 4 chunks (32 rows of M each) x BK k-rows of 128 bytes; TMA's 128B_ATOM_32B swizzle
+          // XORs the 32-byte unit index with (k & 3).  My TMEM lane is row m = 32*q + lane: chunk q, element `lane`
+          // of every k-row -> one conflict-free 128-byte wavefront per k for the warp.
+          const uint32_t cbase = stage_addr(s, 0) + (uint32_t)q * (BK * 128u) + (((uint32_t)lane & 7u) << 2);
+          const uint32_t unit = (uint32_t)lane >> 3;
+          for (int half = half0; half < half1; ++half) {
+            float hi[16], lw[16];
 #pragma unroll
-        for (int v = 0; v < VEC_PER_THREAD; ++v) x[v] = lds128(raw + 16u * (t + v * NT));
+            for (int kk = 0; kk < 16; ++kk) {
+              const uint32_t k = 16u * half + kk;
+              float x;
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(cbase + k * 128u + ((unit ^ (k & 3u)) << 5)));
+              tf32_split(x, hi[kk], lw[kk]);
+            }
+            tmem_st16(ta + 16 * half, hi);
+            tmem_st16(ta + BK + 16 * half, lw);
+          }
+        } else {
+          // my row of the K-major A tile -> hi/lo in TMEM.  Rows are 128 bytes; TMA's SWIZZLE_128B XORs the
+          // 16-byte chunk index with address bits [7, 10) = row & 7.
+          const int row = 32 * q + lane;
+          const uint32_t rbase = stage_addr(s, 0) + (uint32_t)row * 128u;
+          const uint32_t sw = (uint32_t)row & 7u;
+          for (int half = half0; half < half1; ++half) {
+            float hi[16], lw[16];
 #pragma unroll
-        for (int v = 0; v < VEC_PER_THREAD; ++v) {
-          float4 xh, xl;
-          tf32_split4(x[v], xh, xl);
-          if (!(p.dbg & 4)) sts128(raw + 16u * (t + v * NT), xh);
-          sts128(lo + 16u * (t + v * NT), xl);
+            for (int j = 0; j < 4; ++j) {
+              const float4 x = lds128(rbase + (((4 * half + j) ^ sw) << 4));
+              tf32_split(x.x, hi[4 * j + 0], lw[4 * j + 0]);
+              tf32_split(x.y, hi[4 * j + 1], lw[4 * j + 1]);
+              tf32_split(x.z, hi[4 * j + 2], lw[4 * j + 2]);
+              tf32_split(x.w, hi[4 * j + 3], lw[4 * j + 3]);
+            }
+            tmem_st16(ta + 16 * half, hi);
+            tmem_st16(ta + BK + 16 * half, lw);
+          }
+        }
+        for (uint32_t b = 0; b < 256u / ntg; ++b) {
+          float4 x[VB];
+          const uint32_t v0 = (uint32_t)tg + b * (uint32_t)VB * ntg;
+#pragma unroll
+          for (int v = 0; v < VB; ++v) x[v] = lds128(raw + 16u * (v0 + v * ntg));
+#pragma unroll
+          for (int v = 0; v < VB; ++v) {
+            float4 xh, xl;
+            tf32_split4(x[v], xh, xl);
+            if (!(p.dbg & 4)) sts128(raw + 16u * (v0 + v * ntg), xh);
+            sts128(lo + 16u * (v0 + v * ntg), xl);
+          }
         }
       }
       if (!(p.dbg & 8)) fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
-      if (C::A_TM) {
-        tmem_st_wait();
-        tc_fence_before();
-      }
+      tmem_st_wait();
+      tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(split(s));
-      // once the last k-block of chunk c has been split, chunk c-1 has long been accumulated: drain it
-      if (i % CH == CH - 1 && i / CH >= 1) drain(i / CH - 1);
+      // after my last k-block of chunk c, chunk c-1 has long been accumulated: drain it
+      if ((i + ng) / CH != i / CH)
+        while (next_drain < i / CH) drain(next_drain++);
     }
     if (t == 0) RECNN_TRACE(4);                               // last stage split
-    // chunks not drained inside the loop: the last full one (and a trailing partial one)
-    for (int c = max(num_kb / CH - 1, 0); c < num_chunks; ++c) drain(c);
+    while (next_drain < num_chunks) drain(next_drain++);      // the last full chunk (and a trailing partial one)
     if (t == 0) RECNN_TRACE(5);                               // all chunks drained (MMAs complete)
+    if (t == 0) {
+      RECNN_PROF_OUT(0, w_full);
+      RECNN_PROF_OUT(1, w_afree);
+      RECNN_PROF_OUT(2, w_drain);
+      RECNN_PROF_OUT(3, clock64() - loop0);
+      RECNN_PROF_OUT(7, w_ld);
+    }
     if (num_kb > 0) {
       // the commit behind the last acc_full covers every MMA issued before it, D_lo's included
 #pragma unroll
