@@ -167,6 +167,9 @@ enum {
 
 enum { RECNN_ALGO_DDPG = 0, RECNN_ALGO_TD3 = 1 };
 
+/* Peer-memory communicator of the data-parallel step (see "data parallel" below); opaque. */
+typedef struct recnn_comm recnn_comm;
+
 typedef struct recnn_step_args {
   int32_t algo;            /* RECNN_ALGO_* */
   int32_t phases;          /* RECNN_PH_* mask */
@@ -217,6 +220,12 @@ typedef struct recnn_step_args {
 
   void* workspace;
   int64_t workspace_bytes;
+
+  /* data parallel (optional, NULL on one GPU): when set, the step all-reduces (sums) the gradient
+   * arenas over the communicator's ranks before each optimizer update, and the three loss scalars
+   * before RECNN_PH_FINISH, with kernels on `stream` -- no host-side collective between phases.
+   * Each rank passes its shard (n_rows local, n_rows_global = total). */
+  const recnn_comm* comm;
 } recnn_step_args;
 
 /* bytes of scratch a step with these shapes needs (frame form included). */
@@ -232,6 +241,25 @@ RECNN_API int recnn_td3_step(const recnn_step_args* args, void* stream);
  * grad_scale: optional device scalar the gradient is multiplied by first. */
 RECNN_API int recnn_optimizer_step(const recnn_optim* o, const recnn_net* net, int64_t count,
                          const float* grad_scale, void* stream);
+
+/* ---- data parallel: all-reduce over NVLink peer memory ------------------------------------------
+ * BASELINE north_star: "partition the embedding gather + update across the 8 GPUs of one box with
+ * an allreduce of the Actor/Critic gradients over NVLink".  The reference itself is single-process
+ * (recnn/nn/update/ddpg.py:82-100 is where the gradients are complete and consumed), so these entry
+ * points have no reference counterpart; they are what a torch.distributed launcher binds:
+ *   every rank:  recnn_comm_create -> recnn_comm_local_handle -> (all-gather the handles with any
+ *   host transport) -> recnn_comm_connect -> put the communicator in recnn_step_args.comm.
+ * One process per GPU, at most 8 ranks on one node; the staging buffers are cudaMalloc memory shared
+ * with cudaIpc and read by the peers' kernels directly (no NCCL call on the step's path). */
+RECNN_API int recnn_comm_create(int32_t rank, int32_t world, int64_t capacity_floats, recnn_comm** out);
+RECNN_API int32_t recnn_comm_handle_bytes(void);
+RECNN_API int recnn_comm_local_handle(const recnn_comm* comm, void* out_handle);
+/* all_handles: `world` handles of recnn_comm_handle_bytes() each, in rank order */
+RECNN_API int recnn_comm_connect(recnn_comm* comm, const void* all_handles);
+/* buf[i] <- sum over ranks of buf[i], in place, identical bits on every rank (n <= capacity_floats);
+ * every rank must issue the same sequence of collectives on ONE stream. */
+RECNN_API int recnn_comm_allreduce(const recnn_comm* comm, float* buf, int64_t n, void* stream);
+RECNN_API int recnn_comm_destroy(recnn_comm* comm);
 
 #ifdef __cplusplus
 }

@@ -52,11 +52,12 @@ class StepArgs(C.Structure):
         ("masks", C.c_void_p * 8), ("noise", C.c_void_p), ("seed", C.c_uint64), ("rng_step", C.c_void_p),
         ("losses", C.c_void_p), ("losses_host", C.c_void_p), ("next_action_out", C.c_void_p), ("gen_action_out", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+        ("comm", C.c_void_p),
     ]
 
 
 _PROBE_FIELDS = ["dims", "n_rows", "table", "policy", "policy_optim", "gamma", "soft_tau", "masks", "seed",
-                 "losses", "workspace_bytes"]
+                 "losses", "workspace_bytes", "comm"]
 
 # name -> (restype, argtypes); every symbol include/recnn_b200.h declares
 SIGNATURES = {
@@ -86,6 +87,12 @@ SIGNATURES = {
     "recnn_ddpg_step": (C.c_int, [C.POINTER(StepArgs), C.c_void_p]),
     "recnn_td3_step": (C.c_int, [C.POINTER(StepArgs), C.c_void_p]),
     "recnn_optimizer_step": (C.c_int, [C.POINTER(Optim), C.POINTER(Net), C.c_int64, C.c_void_p, C.c_void_p]),
+    "recnn_comm_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.POINTER(C.c_void_p)]),
+    "recnn_comm_handle_bytes": (C.c_int32, []),
+    "recnn_comm_local_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "recnn_comm_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "recnn_comm_allreduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "recnn_comm_destroy": (C.c_int, [C.c_void_p]),
 }
 
 _LIB = None

@@ -38,6 +38,7 @@ extern "C" RECNN_API int64_t recnn_offsetof_step_args(int field) {
     case 8: return offsetof(recnn_step_args, seed);
     case 9: return offsetof(recnn_step_args, losses);
     case 10: return offsetof(recnn_step_args, workspace_bytes);
+    case 11: return offsetof(recnn_step_args, comm);
     default: return -1;
   }
 }

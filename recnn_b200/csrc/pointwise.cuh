@@ -51,6 +51,11 @@ int launch_colsum_partials(const float* dz, int64_t n_rows, int C, int64_t rows_
 int launch_l1_clip_coef(const float* grads, int64_t count, float max_norm, float* coef, float* l1_out,
                         float* block_partials, unsigned* ticket, cudaStream_t st);
 
+// comm.cu: buf <- sum over the communicator's ranks (in place, rank order).  With coef != nullptr also the
+// L1 norm of the summed gradient and its clip coefficient, as launch_l1_clip_coef would give them.
+int launch_comm_allreduce(const recnn_comm* comm, float* buf, int64_t n, float max_norm, float* coef, float* l1_out,
+                          float* block_partials, cudaStream_t st);
+
 int launch_scale_inplace(float* x, int64_t count, const float* scale, cudaStream_t st);
 
 int launch_optimizer(const recnn_optim& o, const recnn_net& net, int64_t count, const float* grad_scale,

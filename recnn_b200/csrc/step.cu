@@ -457,8 +457,11 @@ static int phase_value_opt(Ctx& c) {
   const recnn_step_args& a = *c.a;
   if (!a.learn || a.value_optim.kind == RECNN_OPT_EXTERNAL) return RECNN_OK;
   const int n_critics = a.algo == RECNN_ALGO_TD3 ? 2 : 1;
-  for (int i = 0; i < n_critics; ++i)
+  for (int i = 0; i < n_critics; ++i) {
+    if (a.comm)     // data parallel: every rank's shard gradient -> the global-batch gradient, over NVLink
+      RECNN_PROPAGATE(launch_comm_allreduce(a.comm, a.value[i].grads, c.lc.count, 0.f, nullptr, nullptr, nullptr, c.st));
     RECNN_PROPAGATE(launch_optimizer(a.value_optim, a.value[i], c.lc.count, nullptr, c.st));
+  }
   return RECNN_OK;
 }
 
@@ -530,8 +533,12 @@ static int phase_policy_opt(Ctx& c) {
   if (!a.do_policy_step) return RECNN_OK;
   float* coef = c.ws.scalars;
   // clip_grad_norm_(policy params, max_norm=-1, norm_type=1)   (ddpg.py:92, td3.py:133)
-  RECNN_PROPAGATE(launch_l1_clip_coef(a.policy.grads, c.la.count, -1.0f, coef, a.losses + 3,
-                                      c.ws.block_partials, c.ws.tickets + 1, c.st));
+  if (a.comm)       // all-reduce fused with the L1 norm of the summed gradient
+    RECNN_PROPAGATE(launch_comm_allreduce(a.comm, a.policy.grads, c.la.count, -1.0f, coef, a.losses + 3,
+                                          c.ws.block_partials, c.st));
+  else
+    RECNN_PROPAGATE(launch_l1_clip_coef(a.policy.grads, c.la.count, -1.0f, coef, a.losses + 3,
+                                        c.ws.block_partials, c.ws.tickets + 1, c.st));
   if (a.policy_optim.kind == RECNN_OPT_EXTERNAL)
     return launch_scale_inplace(a.policy.grads, c.la.count, coef, c.st);
   return launch_optimizer(a.policy_optim, a.policy, c.la.count, coef, c.st);
@@ -644,6 +651,8 @@ static int run_step(const recnn_step_args* a, int algo, void* stream) {
   if (a->phases & RECNN_PH_POLICY_OPT) RECNN_PROPAGATE(phase_policy_opt(c));
   if (a->phases & RECNN_PH_SOFT_UPDATE) RECNN_PROPAGATE(phase_soft_update(c));
   if (a->phases & RECNN_PH_FINISH) {
+    if (a->comm)      // losses are shard sums / n_rows_global: the sum over ranks is the global mean
+      RECNN_PROPAGATE(launch_comm_allreduce(a->comm, a->losses, 3, 0.f, nullptr, nullptr, nullptr, c.st));
     if (a->rng_step) RECNN_PROPAGATE(launch_bump64((long long*)a->rng_step, c.st));
     if (a->losses_host)
       RECNN_CHECK_CUDA(cudaMemcpyAsync(a->losses_host, a->losses, 4 * sizeof(float), cudaMemcpyDeviceToHost, c.st));

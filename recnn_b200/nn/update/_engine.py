@@ -64,6 +64,7 @@ class StepEngine:
         self.eager_runs = {}
         self.group = None            # torch.distributed process group for data parallel
         self.world = 1
+        self.comm = None             # recnn_b200.dist.PeerComm: in-kernel all-reduce over NVLink peer memory
         self.seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
         self.losses = torch.zeros(4, dtype=torch.float32, device=self.device)
         self.losses_host = torch.zeros(4, dtype=torch.float32).pin_memory()
@@ -256,7 +257,7 @@ class StepEngine:
         is kept for direct launches only: capturing the NCCL all-reduces into the step graph deadlocked
         on the 2-GPU box, so data parallel runs go through the split-phase path in _step.)"""
         P = _lib
-        if self.world == 1:
+        if self.world == 1 or a.comm:      # with a peer communicator the gradient all-reduces are kernels of the step
             self._launch(a, P.PH_ALL)
             return self.last_call_kernels
         td3 = self.algo == P.ALGO_TD3
@@ -398,7 +399,7 @@ class StepEngine:
             ent = self._fast.get(vkey)
             tok = self._tokens(nets, optimizer, params, st)
             if ent is not None and ent[0] == tok:
-                if self.world == 1:
+                if self.world == 1 or self.comm is not None:
                     ent[1].replay()
                     self.kernels += ent[2]
                 else:
@@ -413,13 +414,16 @@ class StepEngine:
             n, A = st["n"], self.dims.action_dim
             want_debug = {"next_action": torch.empty(n, A, device=self.device),
                           "gen_action": torch.empty(n, A, device=self.device)}
-        if builtin and learn and want_debug is None and self.world > 1:
+        fused = builtin and learn and want_debug is None
+        if fused and self.comm is not None:
+            a.comm = self.comm.ptr
+        if fused and self.world > 1 and self.comm is None:
             self._run_segments(a, nets, do_policy, None)
             if _USE_GRAPHS:
                 self._fast[(do_policy, st["form"], st["n"])] = (self._tokens(nets, optimizer, params, st), a, 0)
             torch.cuda.current_stream(self.device).synchronize()
             return self.losses_host.tolist()
-        if builtin and learn and want_debug is None and self.world == 1:
+        if fused:
             g = self._run_fused(a, nets, do_policy)
             if g is not None:
                 # arenas may have been (re)built by _build_args: fingerprint after the fact
@@ -500,6 +504,6 @@ def get_engine(algo, nets, device) -> StepEngine:
         eng = StepEngine(algo, nets, dev)
         dp = policy.__dict__.get("_recnn_dp")
         if dp is not None:
-            eng.group, eng.world = dp
+            eng.group, eng.world, eng.comm = dp
         cache[key] = eng
     return eng

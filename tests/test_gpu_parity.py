@@ -293,34 +293,49 @@ def test_cpu_device_is_rejected_loudly():
 
 
 # ----------------------------------------------------------------------------- data parallel (2 GPUs)
-def _dp_worker(rank, world, port, algo, q):
+def _dp_worker(rank, world, port, algo, transport, q):
     import os
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    os.environ["RECNN_B200_COMM"] = transport
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         gold = load_golden("%s_canon_adam.npz" % algo)
         got = run_cuda_case("canon", algo, "adam", golden=gold, form="frames", device="cuda:%d" % rank,
                             shard=(rank, world))
-        got.pop("_nets")
+        nets = got.pop("_nets")
+        comm = nets["policy_net"].__dict__["_recnn_dp"][2]
+        got["_peer_comm"] = np.asarray(comm is not None)
+        if comm is not None:
+            # the collective on its own: odd sizes (scalar path), the arena size (float4 path), repeated calls
+            gen = torch.Generator(device="cuda:%d" % rank).manual_seed(100 + rank)
+            for n in (3, 1001, 429828, 3, 4096):
+                x = torch.randn(n, device="cuda:%d" % rank, generator=gen)
+                want = x.clone()
+                dist.all_reduce(want)
+                comm.all_reduce(x)
+                torch.cuda.synchronize()
+                assert torch.equal(x, want), "peer all-reduce != NCCL all-reduce (n=%d)" % n
         q.put((rank, {k: v for k, v in got.items()}))
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("transport", ["peer", "nccl"])
 @pytest.mark.parametrize("algo", ["ddpg", "td3"])
-def test_two_rank_equals_reference(algo):
+def test_two_rank_equals_reference(algo, transport):
     """Rows sharded over 2 ranks + gradient all-reduce == the single-process reference (golden),
-    and the two replicas stay bit-identical."""
+    and the two replicas stay bit-identical.  transport: the in-graph NVLink peer-memory all-reduce
+    (recnn_comm_*) or NCCL calls between the phases."""
     import socket
     import torch.multiprocessing as mp
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, algo, q)) for r in range(2)]
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, algo, transport, q)) for r in range(2)]
     for p in procs:
         p.start()
     res = dict(q.get(timeout=300) for _ in range(2))
@@ -329,6 +344,7 @@ def test_two_rank_equals_reference(algo):
         assert p.exitcode == 0
     gold = load_golden("%s_canon_adam.npz" % algo)
     for rank in (0, 1):
+        assert bool(res[rank].pop("_peer_comm")) == (transport == "peer"), "wrong all-reduce transport was used"
         compare_with_golden(res[rank], gold, check_grads=False)
     for k in res[0]:
         if k.startswith("final."):
