@@ -304,8 +304,12 @@ def run_native(args):
     warm_ms, _, _, _ = run_loop(False, args.steps, 3, flush_l2=False)
 
     rows_global = n_rows * world
-    value = args.steps / (dev_ms / 1e3)
-    e2e_value = args.steps / (e2e_ms / 1e3)
+    # One unit = one 4096-row minibatch through the update step.  Data parallel is weak scaling: every rank
+    # takes its own 4096 rows per step and the gradients are all-reduced, so a global step consumes `world`
+    # units; `value` counts units/s over the whole job (= optimizer updates/s * n_gpus).
+    global_steps_per_sec = args.steps / (dev_ms / 1e3)
+    value = global_steps_per_sec * world
+    e2e_value = args.steps / (e2e_ms / 1e3) * world
     line = None
     if rank == 0:
         L = _lib.lib()
@@ -353,13 +357,20 @@ def run_native(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "DDPG batch 4096 rows/GPU, 128-d embeddings, 26744 items, frame 10 (BASELINE configs[1])",
                        "rows_per_gpu": n_rows, "global_rows": rows_global, "parallelism": "dp%d" % world,
+                       "unit_def": "4096-row minibatches through the update step per second, whole job "
+                                   "(each data-parallel step consumes n_gpus of them; optimizer updates/s = value / n_gpus)",
+                       "grad_allreduce": ("none" if world == 1 else
+                                          "in-graph NVLink peer-memory kernels (recnn_comm_*)" if getattr(
+                                              agent.nets["policy_net"], "_recnn_dp", (0, 0, None))[2] is not None
+                                          else "NCCL between the step's phases"),
                        "optimizer": "adam lr=1e-5 (fused)", "policy_step": POLICY_STEP,
                        "dropout": "on (device Philox)", "l2": "flushed between timed steps (256 MB write)",
                        "inputs": "items/ratings/done resident in HBM; frames gathered on device inside the step",
                        "matmul": "tcgen05 3xTF32 (error-compensated, fp32-grade) with fp32 CUDA-core fallbacks for the 256->1 head"},
-            "rows_per_sec": value * rows_global,
-            "update_tflops": flop_step * value / 1e12,
-            "value_warm_l2": args.steps / (warm_ms / 1e3),
+            "optimizer_updates_per_sec": global_steps_per_sec,
+            "rows_per_sec": global_steps_per_sec * rows_global,
+            "update_tflops": flop_step * global_steps_per_sec / 1e12,
+            "value_warm_l2": args.steps / (warm_ms / 1e3) * world,
             "wall_s": wall_s,
             "e2e": {"value": e2e_value, "unit": "steps/s",
                     "h2d_bytes_per_step": int(n_rows * ((FRAME + 1) * 12 + 4)), "d2h_bytes_per_step": 16,

@@ -250,14 +250,14 @@ struct Cfg {
   // The split A tile goes to TENSOR memory (tcgen05.st) and the MMA reads it from there, so A costs
   // shared memory one TMA write + one read instead of write + read + 2 writes + 6 MMA reads.
   static constexpr bool A_TM = true;
-  static constexpr int A_SLOT_COLS = 2 * BK, A_SLOTS = 128 / A_SLOT_COLS;   // TMEM ring for A: hi | lo per k-block
+  static constexpr int A_SLOT_COLS = 2 * BK, A_SLOTS = (512 - 3 * BN) / A_SLOT_COLS;   // TMEM ring for A (hi | lo per k-block): 2 slots at BN = 128, 5 at BN = 64
   static constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = (A_TM ? A_BYTES : 2 * A_BYTES) + 2 * B_BYTES;   // raw A (+lo A) | raw B | lo B
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
   static constexpr int WORKERS = 8;                                // warps: two per TMEM lane quarter
   static constexpr int COLS_PER_WORKER = BN / (WORKERS / 4);       // register-resident running sum per thread
   static constexpr int THREADS = 64 + 32 * WORKERS;
-  static constexpr int TMEM_COLS = 512;                            // D_hi chunk x2 | D_lo | A ring (3*BN + 128 <= 512)
+  static constexpr int TMEM_COLS = 512;                            // D_hi chunk x2 | D_lo | A ring
   static constexpr int A_COL0 = 3 * BN;
   static constexpr int K_SWZ = BK * 4;                             // K-major rows: 64 B (SWIZZLE_64B) or 128 B (SWIZZLE_128B)
   static_assert(BN == 64 || BN == 128, "BN");

@@ -31,6 +31,6 @@ if len(sys.argv) > 1:
         out.append("K%d/t%d: span %.1f cta %.1f main %.1f" % (K, tile, s[0], s[1], s[2]))
     print("dbg=%-2s  %s" % (os.environ.get("RECNN_TC_DBG", "0"), "   ".join(out)))
     sys.exit(0)
-for dbg in ("0", "32", "1", "2", "3"):
+for dbg in ("0",):
     r = subprocess.run([sys.executable, __file__, "child"], env=dict(os.environ, RECNN_TC_DBG=dbg), capture_output=True, text=True, timeout=120)
     print(r.stdout.strip() or r.stderr[-300:])
