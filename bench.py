@@ -338,6 +338,19 @@ def run_native(args):
             table.data_ptr(), N_ITEMS, DIM, items_d[0].data_ptr(), ratings_d[0].data_ptr(), n_rows, FRAME,
             g_state.data_ptr(), g_next.data_ptr(), g_act.data_ptr(), g_rew.data_ptr(), None, st)))
         gather_gbs = n_rows * GATHER_BYTES_PER_ROW / (gather_ms * 1e-3) / 1e9
+        # the same kernel on a batch whose output does not fit in L2 (16x the rows): its HBM-bound regime
+        big = 16 * n_rows
+        gb_items = torch.randint(0, N_ITEMS, (big, FRAME + 1), device=dev, dtype=torch.int64)
+        gb_ratings = torch.rand(big, FRAME + 1, device=dev)
+        gb_state = torch.empty(big, S_DIM, device=dev)
+        gb_next = torch.empty(big, S_DIM, device=dev)
+        gb_act = torch.empty(big, DIM, device=dev)
+        gb_rew = torch.empty(big, device=dev)
+        gather_big_ms = time_kernel(lambda: _lib.check(L.recnn_frame_gather(
+            table.data_ptr(), N_ITEMS, DIM, gb_items.data_ptr(), gb_ratings.data_ptr(), big, FRAME,
+            gb_state.data_ptr(), gb_next.data_ptr(), gb_act.data_ptr(), gb_rew.data_ptr(), None, st)), iters=10)
+        gather_big_gbs = big * GATHER_BYTES_PER_ROW / (gather_big_ms * 1e-3) / 1e9
+        del gb_state, gb_next, gb_act, gb_rew, gb_items, gb_ratings
         # (2) the dominant kernel of the step: layer-1 forward GEMM [4096,1290] x [1290,256]
         #     (same tcgen05 3xTF32 kernel and operand pitches as inside the step; plain-store epilogue)
         ld_s = (S_DIM + 3) // 4 * 4
@@ -385,7 +398,12 @@ def run_native(args):
                                 "peak": peaks["hbm"], "unit": "GB/s", "frac": gather_gbs / peaks["hbm"],
                                 "traffic": 12083712, "traffic_source": "dram__bytes_read+write per launch, profiles/README.md: the 44 MB of "
                                 "output is absorbed by the 126 MB L2 inside the kernel, so DRAM traffic << algorithmic bytes", "peak_source": peaks["source"], "ms": gather_ms,
-                                "bytes_per_launch": n_rows * GATHER_BYTES_PER_ROW},
+                                "bytes_per_launch": n_rows * GATHER_BYTES_PER_ROW,
+                                "at_16x_rows": {"rows": big, "ms": gather_big_ms, "algorithmic_gbs": gather_big_gbs,
+                                                "dram_gbs_est": (big * 10840 + N_ITEMS * DIM * 4) / (gather_big_ms * 1e-3) / 1e9,
+                                                "dram_frac_est": (big * 10840 + N_ITEMS * DIM * 4) / (gather_big_ms * 1e-3) / 1e9 / peaks["hbm"],
+                                                "note": "same kernel, 16x the rows: the 710 MB of output no longer fits in L2 and goes to HBM, "
+                                                        "the 13.7 MB table is still served by L2, so DRAM traffic ~ output + table once"}},
             "clocks": clocks,
             "last_loss": last_loss,
         }

@@ -83,6 +83,103 @@ int launch_critic_head(const HeadArgs& a, cudaStream_t st) {
   return RECNN_OK;
 }
 
+// ---------------------------------------------------------------- fused critic head (value step)
+template <int HC>   // hidden = 32 * HC
+__global__ void __launch_bounds__(256) value_head_fused_kernel(ValueHeadArgs a) {
+  constexpr int H = 32 * HC;
+  __shared__ float red[8][H + 2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float w3r[HC], tw3r[HC], gw[HC];
+#pragma unroll
+  for (int j = 0; j < HC; ++j) {
+    w3r[j] = __ldg(a.w3 + lane + 32 * j);
+    tw3r[j] = a.th2 ? __ldg(a.tw3 + lane + 32 * j) : 0.f;
+    gw[j] = 0.f;
+  }
+  const float b3 = a.b3[0], tb3 = a.th2 ? a.tb3[0] : 0.f;
+  const float inv_n = 1.0f / (float)a.n_rows_global;
+  float gb = 0.f, lacc = 0.f;
+  for (long long n = (long long)blockIdx.x * 8 + warp; n < a.n_rows; n += (long long)gridDim.x * 8) {
+    float h[HC];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < HC; ++j) {
+      h[j] = a.h2[n * H + lane + 32 * j];
+      s = fmaf(h[j], w3r[j], s);
+    }
+    const float q = warp_sum(s) + b3;
+    float y;
+    if (a.th2) {
+      float t = 0.f;
+#pragma unroll
+      for (int j = 0; j < HC; ++j) t = fmaf(a.th2[n * H + lane + 32 * j], tw3r[j], t);
+      const float tq = warp_sum(t) + tb3;
+      // reward + (1.0 - done) * gamma * target, then clamp   (misc.py:6-7, :33-35)
+      const float e = __fadd_rn(a.reward[n], __fmul_rn(__fmul_rn(__fsub_rn(1.0f, a.done[n]), a.gamma), tq));
+      y = fminf(fmaxf(e, a.min_value), a.max_value);
+      if (lane == 0) a.y[n] = y;
+    } else {
+      y = a.y[n];
+    }
+    const float diff = __fsub_rn(q, y);
+    const float dq = __fmul_rn(__fmul_rn(2.0f, diff), inv_n);
+    lacc = __fadd_rn(lacc, __fmul_rn(diff, diff));
+    if (a.learn) {
+#pragma unroll
+      for (int j = 0; j < HC; ++j) {
+        a.dz2[n * H + lane + 32 * j] = h[j] > 0.f ? __fmul_rn(__fmul_rn(dq, w3r[j]), a.gate_scale) : 0.f;
+        gw[j] = fmaf(dq, h[j], gw[j]);
+      }
+      gb += dq;
+    }
+  }
+  // warps in order, then blocks in order: deterministic
+#pragma unroll
+  for (int j = 0; j < HC; ++j) red[warp][lane + 32 * j] = gw[j];
+  if (lane == 0) {
+    red[warp][H] = gb;
+    red[warp][H + 1] = lacc;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < H + 2; c += blockDim.x) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][c];
+    a.block_partials[(long long)blockIdx.x * (H + 2) + c] = t;
+  }
+  if (last_block_done(a.ticket)) {
+    for (int c = threadIdx.x; c < H + 2; c += blockDim.x) {
+      float t = 0.f;
+      for (unsigned b = 0; b < gridDim.x; ++b) t += a.block_partials[(long long)b * (H + 2) + c];
+      if (c < H) {
+        if (a.learn) a.gw3[c] = t;
+      } else if (c == H) {
+        if (a.learn) a.gb3[0] = t;
+      } else {
+        *a.loss = t / (float)a.n_rows_global;
+      }
+    }
+  }
+}
+
+bool value_head_fusable(int hidden) { return hidden % 32 == 0 && hidden >= 32 && hidden <= 256; }
+
+int launch_value_head_fused(const ValueHeadArgs& a, cudaStream_t st) {
+  if (a.n_rows <= 0) return RECNN_OK;
+  RECNN_REQUIRE(value_head_fusable(a.hidden), "fused value head needs hidden = 32..256, multiple of 32");
+  const int64_t blocks = ceil_div(a.n_rows, 8);
+  const int grid = (int)(blocks < kNumSMs ? blocks : kNumSMs);
+  switch (a.hidden / 32) {
+#define RECNN_VH_CASE(HC) case HC: value_head_fused_kernel<HC><<<grid, 256, 0, st>>>(a); break;
+    RECNN_VH_CASE(1) RECNN_VH_CASE(2) RECNN_VH_CASE(3) RECNN_VH_CASE(4)
+    RECNN_VH_CASE(5) RECNN_VH_CASE(6) RECNN_VH_CASE(7) RECNN_VH_CASE(8)
+#undef RECNN_VH_CASE
+    default: break;
+  }
+  RECNN_CHECK_LAUNCH("value_head_fused_kernel");
+  return RECNN_OK;
+}
+
 __global__ void __launch_bounds__(256)
 critic_head_bwd_kernel(const float* __restrict__ dq, float dq_const, const float* __restrict__ w3,
                        const float* __restrict__ h2, float gate_scale, float* __restrict__ dz2,
@@ -254,7 +351,7 @@ struct OptConsts {
 __global__ void __launch_bounds__(256)
 optimizer_kernel(int kind, OptConsts k, double beta1, double beta2, double lr, float* __restrict__ p,
                  float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                 const int* __restrict__ t_ptr, const float* __restrict__ grad_scale, long long count) {
+                 int* __restrict__ t_ptr, const float* __restrict__ grad_scale, long long count, unsigned* ticket) {
   __shared__ float s_step_size, s_bc2_sqrt;
   const int t = *t_ptr + 1;
   if (threadIdx.x == 0 && kind == RECNN_OPT_ADAM) {
@@ -292,6 +389,11 @@ optimizer_kernel(int kind, OptConsts k, double beta1, double beta2, double lr, f
       p[i] = __fsub_rn(w, __fmul_rn(s_step_size, __fdiv_rn(mi, denom)));
     }
   }
+  // ++t by the block that finishes last (every block has read t by then); without a ticket the
+  // launcher appends a one-thread kernel instead
+  if (ticket) {
+    if (last_block_done(ticket) && threadIdx.x == 0) *t_ptr = t;
+  }
 }
 
 __global__ void bump_counter_kernel(int* t) { *t += 1; }
@@ -304,7 +406,7 @@ int launch_bump64(long long* t, cudaStream_t st) {
 }
 
 int launch_optimizer(const recnn_optim& o, const recnn_net& net, int64_t count, const float* grad_scale,
-                     cudaStream_t st) {
+                     cudaStream_t st, unsigned* ticket) {
   RECNN_REQUIRE(o.kind == RECNN_OPT_SGD || o.kind == RECNN_OPT_ADAM, "built-in optimizer kind must be SGD or ADAM");
   RECNN_REQUIRE(net.params && net.grads && net.opt_t, "optimizer needs params, grads and the step counter");
   if (o.kind == RECNN_OPT_ADAM) RECNN_REQUIRE(net.opt_m && net.opt_v, "Adam needs exp_avg / exp_avg_sq arenas");
@@ -320,10 +422,12 @@ int launch_optimizer(const recnn_optim& o, const recnn_net& net, int64_t count, 
   const int64_t blocks = ceil_div(count, 256 * 4);
   const int grid = (int)(blocks < 4 * kNumSMs ? (blocks > 0 ? blocks : 1) : 4 * kNumSMs);
   optimizer_kernel<<<grid, 256, 0, st>>>(o.kind, k, o.beta1, o.beta2, o.lr, net.params,
-                                         net.grads, net.opt_m, net.opt_v, net.opt_t, grad_scale, count);
+                                         net.grads, net.opt_m, net.opt_v, net.opt_t, grad_scale, count, ticket);
   RECNN_CHECK_LAUNCH("optimizer_kernel");
-  bump_counter_kernel<<<1, 1, 0, st>>>(net.opt_t);
-  RECNN_CHECK_LAUNCH("bump_counter_kernel");
+  if (!ticket) {
+    bump_counter_kernel<<<1, 1, 0, st>>>(net.opt_t);
+    RECNN_CHECK_LAUNCH("bump_counter_kernel");
+  }
   return RECNN_OK;
 }
 

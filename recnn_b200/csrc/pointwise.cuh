@@ -34,6 +34,30 @@ struct HeadArgs {
 };
 int launch_critic_head(const HeadArgs& a, cudaStream_t st);
 
+// Everything between the critic's last hidden layer and its backward GEMMs in ONE kernel (was five launches
+// on the step's critical path): q = h2 w3 + b3; TD target y from the target critic's hidden layer (DDPG,
+// misc.py:28-35) or a precomputed y (TD3's min of two targets); MSE loss; dq = 2 (q - y) / N_global;
+// dz2 = dq w3 * gate(h2); dW3 = dq^T h2 and db3 = sum dq (deterministic two-level reductions).
+struct ValueHeadArgs {
+  const float *h2, *w3, *b3;         // online critic: hidden2 [N, H], head weights
+  const float *th2, *tw3, *tb3;      // target critic (fused TD target) or null (y is an input)
+  const float *reward, *done;
+  float gamma, min_value, max_value;
+  float* y;                          // [N] TD target: written when th2 != null, read otherwise
+  int64_t n_rows, n_rows_global;
+  int hidden;
+  int learn;                         // 0: loss only
+  float gate_scale;
+  float* dz2;                        // [N, H]
+  float* gw3;                        // [H] gradient of the head weights
+  float* gb3;                        // [1]
+  float* loss;
+  float* block_partials;             // >= 148 * (H + 2) floats
+  unsigned* ticket;
+};
+bool value_head_fusable(int hidden);
+int launch_value_head_fused(const ValueHeadArgs& a, cudaStream_t st);
+
 // dz2[n,c] = dq_n * w3[c] * (h2[n,c] > 0 ? gate_scale : 0); dq_n = dq ? dq[n] : dq_const
 int launch_critic_head_bwd(const float* dq, float dq_const, const float* w3, const float* h2,
                            float gate_scale, float* dz2, int64_t n_rows, int hidden, cudaStream_t st);
@@ -58,8 +82,9 @@ int launch_comm_allreduce(const recnn_comm* comm, float* buf, int64_t n, float m
 
 int launch_scale_inplace(float* x, int64_t count, const float* scale, cudaStream_t st);
 
+// ticket: zero-initialised self-resetting counter; when given, the kernel itself increments *net.opt_t
 int launch_optimizer(const recnn_optim& o, const recnn_net& net, int64_t count, const float* grad_scale,
-                     cudaStream_t st);
+                     cudaStream_t st, unsigned* ticket = nullptr);
 
 int launch_bump64(long long* t, cudaStream_t st);
 int launch_polyak(float* target, const float* net, int64_t count, double tau, cudaStream_t st);

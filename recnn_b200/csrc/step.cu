@@ -115,7 +115,8 @@ static int64_t partial_floats(const recnn_dims& d, int64_t n_rows) {
       const int64_t f = (int64_t)dw_splits(s[0], s[1], n_rows, tcp != 0) * s[0] * (s[1] + 1);
       if (f > best) best = f;
     }
-  return best;
+  const int64_t head = (int64_t)kNumSMs * (d.hidden + 2);     // block partials of the fused value-head kernel
+  return best > head ? best : head;
 }
 
 static Workspace carve(const recnn_dims& d, int64_t n, void* base) {
@@ -383,6 +384,8 @@ static int phase_value_grad(Ctx& c) {
   float *X0 = c.ws.hb[0], *X1 = c.ws.hb[1], *c1 = c.ws.hb[2], *c2 = c.ws.hb[3], *dz2 = c.ws.hb[4],
         *dz1 = c.ws.hb[5];
   float* a2 = c.ws.ab[0];
+  static const bool fuse_env = [] { const char* e = getenv("RECNN_B200_FUSE_HEAD"); return !(e && e[0] == '0'); }();
+  const bool fuse_head = fuse_env && value_head_fusable(H);
 
   // target policy on next_state, eval mode (misc.py:28 / td3.py:73) (+ clipped noise, td3.py:74-78)
   RECNN_PROPAGATE(actor_hidden(c, a.target_policy.params, c.S2, false, 0, X0, X1, c.st));
@@ -405,6 +408,7 @@ static int phase_value_grad(Ctx& c) {
   for (int i = 0; i < n_critics; ++i) {
     AloneScope alone(c.aux != nullptr && !c.p_prefetched);   // alone unless chain P runs alongside
     RECNN_PROPAGATE(critic_hidden(c, a.target_value[i].params, c.S2, a2, false, 0, X0, X1, c.st));
+    if (fuse_head && !td3) continue;       // DDPG: the TD target is formed inside the fused value-head kernel
     HeadArgs h = head_args(c, a.target_value[i].params, X1,
                            td3 ? (i == 0 ? HEAD_TARGET_TD3_A : HEAD_TARGET_TD3_B) : HEAD_TARGET_DDPG);
     RECNN_PROPAGATE(launch_critic_head(h, c.st));
@@ -418,21 +422,37 @@ static int phase_value_grad(Ctx& c) {
     } else {
       RECNN_PROPAGATE(critic_hidden(c, P, c.S, c.ACT, c.train, 2 * i, c1, c2, c.st));
     }
-    HeadArgs h = head_args(c, P, c2, HEAD_VALUE);
-    h.loss = a.losses + i;
-    RECNN_PROPAGATE(launch_critic_head(h, c.st));
-    if (!a.learn) continue;
     float* G = a.value[i].grads;
-    RECNN_REQUIRE(G != nullptr, "value net needs a grad arena when learn=1");
-    const Seg sc1 = {c1, H, H, 0}, ss = {c.S, S, c.ldS, 0}, sa = {c.ACT, A + c.lead, c.ldA, c.lead};
-    // layer 3: dW3 = dq^T h2, db3 = sum dq ; dz2 = (dq w3) * gate(h2)
-    {
+    RECNN_REQUIRE(!a.learn || G != nullptr, "value net needs a grad arena when learn=1");
+    if (fuse_head) {
+      // loss, dq, dz2 = (dq w3) * gate(h2), dW3 = dq^T h2, db3 = sum dq (and DDPG's TD target) in one launch
+      ValueHeadArgs v;
+      v.h2 = c2; v.w3 = P + c.lc.w3; v.b3 = P + c.lc.b3;
+      v.th2 = td3 ? nullptr : X1;
+      v.tw3 = a.target_value[0].params + c.lc.w3; v.tb3 = a.target_value[0].params + c.lc.b3;
+      v.reward = c.REW; v.done = c.DONE;
+      v.gamma = a.gamma; v.min_value = a.min_value; v.max_value = a.max_value;
+      v.y = c.ws.y; v.n_rows = c.n; v.n_rows_global = a.n_rows_global; v.hidden = H;
+      v.learn = a.learn ? 1 : 0; v.gate_scale = c.gate; v.dz2 = dz2;
+      v.gw3 = a.learn ? G + c.lc.w3 : nullptr; v.gb3 = a.learn ? G + c.lc.b3 : nullptr;
+      v.loss = a.losses + i;
+      v.block_partials = c.ws.partial;       // free here: the weight-gradient GEMMs come later
+      v.ticket = c.ws.tickets + 2;
+      RECNN_PROPAGATE(launch_value_head_fused(v, c.st));
+      if (!a.learn) continue;
+    } else {
+      HeadArgs h = head_args(c, P, c2, HEAD_VALUE);
+      h.loss = a.losses + i;
+      RECNN_PROPAGATE(launch_critic_head(h, c.st));
+      if (!a.learn) continue;
+      // layer 3: dW3 = dq^T h2, db3 = sum dq ; dz2 = (dq w3) * gate(h2)
       const int64_t rows_per = 256;
       const int splits = (int)ceil_div(c.n, rows_per);       // <= dw_splits(1, H, n, false): fits ws.partial
       RECNN_PROPAGATE(launch_head_grad_partials(c.ws.dq, c2, c.n, H, rows_per, splits, c.ws.partial, c.st));
       RECNN_PROPAGATE(launch_reduce_partials(c.ws.partial, splits, 1, H + 1, G + c.lc.w3, c.lc.ld3, G + c.lc.b3, c.st));
+      RECNN_PROPAGATE(launch_critic_head_bwd(c.ws.dq, 0.f, P + c.lc.w3, c2, c.gate, dz2, c.n, H, c.st));
     }
-    RECNN_PROPAGATE(launch_critic_head_bwd(c.ws.dq, 0.f, P + c.lc.w3, c2, c.gate, dz2, c.n, H, c.st));
+    const Seg sc1 = {c1, H, H, 0}, ss = {c.S, S, c.ldS, 0}, sa = {c.ACT, A + c.lead, c.ldA, c.lead};
     if (c.aux) {
       // dW2 (needs dz2, c1) on the side stream while the main stream back-propagates to dz1;
       // dW1's action segment on a third stream next to its state segment
@@ -460,7 +480,7 @@ static int phase_value_opt(Ctx& c) {
   for (int i = 0; i < n_critics; ++i) {
     if (a.comm)     // data parallel: every rank's shard gradient -> the global-batch gradient, over NVLink
       RECNN_PROPAGATE(launch_comm_allreduce(a.comm, a.value[i].grads, c.lc.count, 0.f, nullptr, nullptr, nullptr, c.st));
-    RECNN_PROPAGATE(launch_optimizer(a.value_optim, a.value[i], c.lc.count, nullptr, c.st));
+    RECNN_PROPAGATE(launch_optimizer(a.value_optim, a.value[i], c.lc.count, nullptr, c.st, c.ws.tickets + 3));
   }
   return RECNN_OK;
 }
@@ -541,7 +561,7 @@ static int phase_policy_opt(Ctx& c) {
                                         c.ws.block_partials, c.ws.tickets + 1, c.st));
   if (a.policy_optim.kind == RECNN_OPT_EXTERNAL)
     return launch_scale_inplace(a.policy.grads, c.la.count, coef, c.st);
-  return launch_optimizer(a.policy_optim, a.policy, c.la.count, coef, c.st);
+  return launch_optimizer(a.policy_optim, a.policy, c.la.count, coef, c.st, c.ws.tickets + 3);
 }
 
 static int phase_soft_update(Ctx& c) {
