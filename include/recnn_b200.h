@@ -78,6 +78,46 @@ RECNN_API int recnn_frame_gather(const float* table, int64_t n_items, int dim,
 RECNN_API int recnn_done_from_sizes(const int64_t* sizes, int64_t n_users, int frame,
                           float* done, int64_t n_rows, void* stream);
 
+/* Device-resident FrameEnv feed.  The reference builds every minibatch on the host, inside a
+ * DataLoader worker: UserDataset.__getitem__ (recnn/data/env.py:47-64) hands out one user's
+ * time-ordered items / ratings, and the collate function cuts ALL length-(frame+1) sliding
+ * windows of every user of the batch and concatenates them (rolling_window, recnn/data/utils.py:7-10;
+ * prepare_batch_static_size, :161-181; ratings cast with .float(), :178).  Here the histories stay in
+ * HBM as a CSR over users
+ *     hist_items int64[total]   hist_ratings fp32[total] (the .float() cast, done once)
+ *     hist_offsets int64[n_users+1]
+ * and the windows are cut on the device: the only per-minibatch input is the list of users.
+ * Outputs are exactly what the collate hands to embed_batch: items int64[n_rows, frame+1],
+ * ratings fp32[n_rows, frame+1] (feed them to recnn_frame_gather or to the frame form of
+ * recnn_ddpg_step / recnn_td3_step), plus done fp32[n_rows] (recnn/data/utils.py:70-71:
+ * 1 on the last window of every user) and sizes int64[n_batch] (history lengths, :171).
+ * Any output pointer may be NULL.  Bit-exact (copies only).
+ *   batch_users int64[n_batch]    positions of the minibatch's users in the CSR, in batch order
+ *   row_offsets int64[n_batch+1]  exclusive prefix sum of (length - frame) over batch_users;
+ *                                 n_rows == row_offsets[n_batch] (host-side plan: lengths are
+ *                                 known to the caller, so no device->host sync is needed)
+ * A user index out of range, or a plan that disagrees with the resident lengths, sets *err_flag
+ * (device int32, may be NULL) and zero-fills the affected rows. */
+RECNN_API int recnn_window_gather_users(const int64_t* hist_items, const float* hist_ratings,
+                              const int64_t* hist_offsets, int64_t n_users,
+                              const int64_t* batch_users, const int64_t* row_offsets, int64_t n_batch,
+                              int frame, int64_t n_rows,
+                              int64_t* items, float* ratings, float* done, int64_t* sizes,
+                              int* err_flag, void* stream);
+
+/* Fixed-size minibatch over the same CSR: row n is the window with GLOBAL id window_ids[n], windows
+ * being numbered user by user in storage order (win_offsets int64[n_users+1] = exclusive prefix sum
+ * of max(length - frame, 0)).  Equals rows window_ids of the reference collate over ALL users
+ * (prepare_batch_static_size over the whole UserDataset, recnn/data/utils.py:161-181), so a
+ * replay-style sampler can draw a constant number of rows per step (constant shapes keep the update
+ * step one CUDA graph).  users_out int64[n_rows] (optional) = CSR position of each row's user;
+ * done = 1 where the window is its user's last.  Out-of-range ids set *err_flag and zero-fill. */
+RECNN_API int recnn_window_gather_ids(const int64_t* hist_items, const float* hist_ratings,
+                            const int64_t* hist_offsets, const int64_t* win_offsets, int64_t n_users,
+                            const int64_t* window_ids, int frame, int64_t n_rows,
+                            int64_t* items, float* ratings, float* done, int64_t* users_out,
+                            int* err_flag, void* stream);
+
 /* ------------------------------------------------------------------ networks */
 
 typedef struct recnn_dims {

@@ -9,6 +9,12 @@ are produced here by differential execution of its own functions):
 
 * gather.npz  -- recnn.data.utils.prepare_batch_static_size + batch_tensor_embeddings
                  on three synthetic users (full inputs and outputs, bit-exact).
+* collate.npz -- recnn.data.utils.prepare_batch_static_size up to (not including) the embedding
+                 gather: the [N, F+1] item-id / rating windows, sizes and users it hands to
+                 ``embed_batch`` (captured by passing an identity ``embed_batch``), plus ``done``
+                 from batch_tensor_embeddings, for (i) all 14 synthetic users in storage order and
+                 (ii) a shuffled 6-user minibatch.  Ragged lengths incl. the minimum F+1, float64
+                 ratings that are not fp32-representable (pins the ``.float()`` rounding).
 * ddpg_<case>.npz / td3_<case>.npz -- recnn.nn.update.ddpg_update / td3_update,
                  12 consecutive steps (policy steps 0 and 10 included), torch.optim
                  Adam(lr=1e-5) and SGD(lr=1e-3) passed through the reference's
@@ -208,12 +214,63 @@ def run_gather_case(recnn):
     return out
 
 
+COLLATE_LENGTHS = (11, 12, 30, 11, 57, 13, 100, 25, 11, 19, 64, 33, 12, 47)
+COLLATE_MINIBATCH = (9, 0, 13, 4, 3, 6)      # positions in storage order, as a shuffling DataLoader would pick
+
+
+def collate_case_users(frame=10, n_items=500):
+    """Synthetic user histories of the collate fixture (shared with the tests through the stored arrays)."""
+    rng = np.random.default_rng(77)
+    users = []
+    for pos, length in enumerate(COLLATE_LENGTHS):
+        rates = 2.0 * (rng.integers(1, 11, size=length) / 2.0 - 2.5)          # ML-20M half stars -> 2(r-2.5)
+        rates = rates + (rng.random(length) < 0.3) * rng.standard_normal(length) * 0.1   # some non-representable
+        users.append({"items": rng.integers(0, n_items, size=length, dtype=np.int64),
+                      "rates": rates.astype(np.float64), "sizes": length, "users": 1000 + 7 * pos})
+    return users
+
+
+def run_collate_case(recnn):
+    frame = 10
+    users = collate_case_users(frame)
+    table = np.random.default_rng(78).standard_normal((500, 4), dtype=np.float32)
+    ident = lambda batch, item_embeddings_tensor, frame_size: batch      # noqa: E731  (captures embed_batch's input)
+    out = {"frame_size": np.int64(frame), "n_users": np.int64(len(users)),
+           "minibatch": np.asarray(COLLATE_MINIBATCH, dtype=np.int64)}
+    for i, u in enumerate(users):
+        out["user%d.items" % i] = u["items"]
+        out["user%d.rates" % i] = u["rates"]
+        out["user%d.id" % i] = np.int64(u["users"])
+    for tag, sel in (("all", list(range(len(users)))), ("mini", list(COLLATE_MINIBATCH))):
+        picked = [copy.deepcopy(users[i]) for i in sel]
+        got = recnn.data.utils.prepare_batch_static_size(copy.deepcopy(picked), torch.from_numpy(table),
+                                                         frame_size=frame, embed_batch=ident)
+        emb = recnn.data.utils.prepare_batch_static_size(copy.deepcopy(picked), torch.from_numpy(table),
+                                                         frame_size=frame)
+        out[tag + ".items"] = got["items"].numpy()
+        out[tag + ".ratings"] = got["ratings"].numpy()
+        out[tag + ".sizes"] = got["sizes"].numpy()
+        out[tag + ".users"] = got["users"].numpy()
+        out[tag + ".done"] = emb["done"].numpy()
+        assert out[tag + ".ratings"].dtype == np.float32 and out[tag + ".items"].dtype == np.int64
+    return out
+
+
 def main():
     torch.set_num_threads(max(1, min(8, os.cpu_count() or 1)))
     recnn = import_reference()
     os.makedirs(GOLDEN_DIR, exist_ok=True)
-    np.savez_compressed(os.path.join(GOLDEN_DIR, "gather.npz"), **run_gather_case(recnn))
-    print("wrote gather.npz")
+    only = set(sys.argv[1:])
+    if not only or "collate" in only:
+        np.savez_compressed(os.path.join(GOLDEN_DIR, "collate.npz"), **run_collate_case(recnn))
+        print("wrote collate.npz")
+    if only and "gather" not in only and "update" not in only:
+        return
+    if not only or "gather" in only:
+        np.savez_compressed(os.path.join(GOLDEN_DIR, "gather.npz"), **run_gather_case(recnn))
+        print("wrote gather.npz")
+    if only and "update" not in only:
+        return
     for case in C.CASES:
         for algo in ("ddpg", "td3"):
             for opt_kind in ("adam", "sgd"):

@@ -45,6 +45,17 @@ def collate_users(users: list, frame_size: int):
             "sizes": sizes, "users": uid}
 
 
+def collate_rows(users: list, frame_size: int, window_ids: np.ndarray):
+    """Rows ``window_ids`` of the collate of ALL ``users`` (storage order): the fixed-size minibatch form
+    of the device-resident feed.  Nothing new is computed: it is recnn/data/utils.py:161-181 over every
+    user followed by row selection, and ``done`` is recnn/data/utils.py:70-71 of that full collate."""
+    full = collate_users(users, frame_size)
+    done = done_from_sizes(full["sizes"], frame_size, full["items"].shape[0])
+    owner = np.repeat(full["users"], full["sizes"] - frame_size)       # user id of every row
+    w = np.asarray(window_ids, dtype=np.int64)
+    return {"items": full["items"][w], "ratings": full["ratings"][w], "done": done[w], "users": owner[w]}
+
+
 def done_from_sizes(sizes: np.ndarray, frame_size: int, n_rows: int) -> np.ndarray:
     """recnn/data/utils.py:70-71: done[cumsum(sizes - F) - 1] = 1."""
     done = np.zeros(n_rows, dtype=F32)

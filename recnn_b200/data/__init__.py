@@ -1,4 +1,5 @@
-from . import utils, env
+from . import utils, env, feed
 from .utils import (rolling_window, batch_tensor_embeddings, batch_frames, prepare_batch_static_size,
                     make_items_tensor, get_base_batch)
 from .env import UserDataset, EnvBase, DataPath, Env, FrameEnv
+from .feed import HistoryCSR, DeviceFrameFeed

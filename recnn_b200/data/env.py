@@ -156,5 +156,14 @@ class FrameEnv(Env):
     def train_batch(self):
         return next(iter(self.train_dataloader))
 
+    def device_feed(self, device="cuda", split="train"):
+        """The same users and table as the DataLoaders, resident on ``device``: a
+        ``recnn_b200.data.DeviceFrameFeed`` whose ``epoch(batch_size)`` / ``batch(...)`` yield the
+        minibatches ``train_dataloader`` would (frame form; windows cut by a kernel instead of a
+        DataLoader worker), and whose ``sample(n_rows)`` draws constant-size minibatches."""
+        from .feed import HistoryCSR, DeviceFrameFeed
+        ds = self.base.train_user_dataset if split == "train" else self.base.test_user_dataset
+        return DeviceFrameFeed(HistoryCSR.from_dataset(ds, self.frame_size), self.base.embeddings, device)
+
     def test_batch(self):
         return next(iter(self.test_dataloader))

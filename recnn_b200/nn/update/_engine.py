@@ -289,6 +289,8 @@ class StepEngine:
             self.kernels += g[1]
             return g
         runs = self.eager_runs.get(key, 0)
+        if len(self.eager_runs) > 256:    # variable-size minibatches (reference-style FrameEnv batches): every step is
+            self.eager_runs.clear()       # a new variant; do not let the bookkeeping grow with the run
         self.eager_runs[key] = runs + 1
         if runs < 1:                      # first time: plain launch (also warms lazy module loading)
             self._body(a, nets, do_policy)
