@@ -1,6 +1,8 @@
 // Error plumbing + version of the C ABI (include/recnn_b200.h).
 #include <stdarg.h>
 #include <stddef.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include <atomic>
 
@@ -17,7 +19,40 @@ void set_error(const char* fmt, ...) {
 }
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// Runtime switches.  Defaults are the measured-best variants (profiles/README.md); the environment
+// variables are read once, recnn_debug_set_option() overrides them at any time (used by the A/B
+// legs of bench.py and by tests that check the variants against each other).
+static std::atomic<int> g_options[OPT_COUNT];
+static std::atomic<bool> g_options_init{false};
+static void init_options() {
+  if (g_options_init.load(std::memory_order_acquire)) return;
+  const struct { Option o; const char* env; int def; } table[] = {
+      {OPT_GATHER_VARIANT, "RECNN_B200_GATHER", 0},      // 0: one warp per row   1: balanced (row, slot) units
+      {OPT_PRESPLIT, "RECNN_B200_PRESPLIT", 0},          // 1: weights pre-split into TF32 hi/lo planes
+  };
+  for (const auto& t : table) {
+    const char* e = getenv(t.env);
+    g_options[t.o].store(e && *e ? atoi(e) : t.def, std::memory_order_relaxed);
+  }
+  g_options_init.store(true, std::memory_order_release);
+}
+int option(Option o) {
+  init_options();
+  return g_options[o].load(std::memory_order_relaxed);
+}
 }  // namespace recnn
+
+// name in {"gather_variant", "presplit"}; returns the previous value, or -1 for an unknown name
+extern "C" RECNN_API int recnn_debug_set_option(const char* name, int value) {
+  recnn::init_options();
+  if (!name) return -1;
+  int idx = -1;
+  if (strcmp(name, "gather_variant") == 0) idx = recnn::OPT_GATHER_VARIANT;
+  else if (strcmp(name, "presplit") == 0) idx = recnn::OPT_PRESPLIT;
+  if (idx < 0) return -1;
+  return recnn::g_options[idx].exchange(value);
+}
 
 extern "C" RECNN_API int64_t recnn_b200_launch_count(void) { return recnn::g_launches.load(); }
 extern "C" int recnn_b200_abi_version(void) { return RECNN_B200_ABI_VERSION; }

@@ -47,6 +47,10 @@ void count_launch();   // every kernel launch of this library bumps a process-wi
     if (_s != RECNN_OK) return _s;                                                    \
   } while (0)
 
+// ---- runtime switches (A/B experiments and regression fallbacks; recnn_debug_set_option) --------
+enum Option { OPT_GATHER_VARIANT = 0, OPT_PRESPLIT = 1, OPT_COUNT = 2 };
+int option(Option o);          // current value (initialised from RECNN_B200_GATHER / RECNN_B200_PRESPLIT)
+
 constexpr int kNumSMs = 148;   // B200
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

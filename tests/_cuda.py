@@ -65,7 +65,7 @@ def build_optimizers(kind, nets, algo, external=False):
 def run_cuda_case(case, algo, opt_kind, golden=None, form="dense", external=False, device="cuda:0",
                   shard=None):
     """shard=(rank, world): this process handles rows [lo, hi) of every minibatch (data parallel)."""
-    spec = C.CASES[case]
+    spec = C.CASES[case] if isinstance(case, str) else case      # a name or a spec dict
     inp = C.make_inputs(spec, algo)
     dev = torch.device(device)
     lo, hi = (0, spec["n_rows"]) if shard is None else recnn_b200.dist.shard_rows(spec["n_rows"], *shard)

@@ -28,7 +28,7 @@ def oracle_optimizers(kind, algo):
 
 def run_oracle_case(case, algo, opt_kind, golden=None):
     """Same bookkeeping as oracle/make_golden.py:run_update_case, numpy oracle."""
-    spec = C.CASES[case]
+    spec = C.CASES[case] if isinstance(case, str) else case      # a name or a spec dict
     inp = C.make_inputs(spec, algo)
     out = {"input_checksums": C.input_checksums(inp)}
     nets = {k: O.copy_net(v) for k, v in inp["nets"].items()}
