@@ -233,6 +233,12 @@ def run_native(args):
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
 
+    opts = {}
+    for kv in args.opt:
+        name, _, val = kv.partition("=")
+        _lib.set_option(name, int(val))
+        opts[name] = int(val)
+
     torch.manual_seed(1234)                       # same weights on every rank
     rng = np.random.default_rng(0)
     table = torch.from_numpy(rng.standard_normal((N_ITEMS, DIM), dtype=np.float32)).to(dev)
@@ -364,7 +370,7 @@ def run_native(args):
         tf32_peak = peaks["bf16"] / 2.0           # dense TF32 = half the dense bf16 rate
         flop_step = rows_global * (DDPG_FLOP_POLICY + (POLICY_STEP - 1) * DDPG_FLOP_NONPOLICY) / POLICY_STEP
         feed_info = bench_device_feed(agent, table, dev, flush, time_kernel, args) if world == 1 else None
-        cpu = cpu_baseline_sample() if world == 1 else None
+        cpu = cpu_baseline_sample() if (world == 1 and not args.no_cpu_baseline) else None
         line = {
             "metric": "ddpg_update_steps_per_sec", "value": value, "unit": "steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
@@ -408,6 +414,8 @@ def run_native(args):
             "clocks": clocks,
             "last_loss": last_loss,
         }
+        if opts:
+            line["config"]["options"] = opts
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if feed_info is not None:
@@ -467,6 +475,9 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
+                    help="library A/B switch (recnn_debug_set_option), e.g. --opt presplit=1 --opt gather_variant=1")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (A/B runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps > 40:          # bounded: the CPU port does ~3-10 steps/s

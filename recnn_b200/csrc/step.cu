@@ -85,8 +85,66 @@ struct Workspace {
   float* block_partials;  // [1024]
   float* scalars;         // [8]: 0 = clip coef
   unsigned* tickets;      // [8]
+  // TF32 hi / lo planes of the six nets' arenas (pre-split weights for the B_PRE GEMMs), same geometry
+  // as the arenas: 0 policy, 1 target policy (actor layout); 2,3 value[0..1]; 4,5 target value[0..1]
+  float* plane_hi[6];
+  float* plane_lo[6];
   int64_t bytes;
 };
+
+// ---------------------------------------------------------------- pre-split weight planes
+// Forward and input-gradient GEMMs take a WEIGHT matrix as their B operand.  Splitting it into TF32
+// hi/lo inside every GEMM costs the split warps a shared-memory read + two writes of the B tile and a
+// proxy fence per k-block -- for a matrix that only changes at an optimizer / Polyak step.  Instead one
+// small kernel splits the nets' whole arenas at the start of the call (and the online critic again after
+// its optimizer step), and the GEMMs fetch hi and lo straight from those planes (tc::Cfg::B_PRE).
+// A plane is only used while `valid`: any path that changes an arena inside the call clears the flag,
+// and a GEMM whose weights have no valid plane silently uses the in-kernel split (identical results).
+struct PlaneEntry {
+  const float* base;       // arena
+  float* hi;
+  float* lo;
+  int64_t count;
+  bool valid;
+};
+struct PlaneTable {
+  PlaneEntry e[6];
+  bool enabled;
+};
+static thread_local PlaneTable* t_planes = nullptr;
+struct PlaneScope {
+  PlaneTable* prev;
+  explicit PlaneScope(PlaneTable* t) : prev(t_planes) { t_planes = t; }
+  ~PlaneScope() { t_planes = prev; }
+};
+// hi/lo plane addresses of the weight matrix at `W` (inside one of the registered arenas), or false
+static bool planes_for(const float* W, const float** hi, const float** lo) {
+  const PlaneTable* t = t_planes;
+  if (!t || !t->enabled) return false;
+  for (const PlaneEntry& e : t->e) {
+    if (e.valid && e.base && W >= e.base && W < e.base + e.count) {
+      *hi = e.hi + (W - e.base);
+      *lo = e.lo + (W - e.base);
+      return true;
+    }
+  }
+  return false;
+}
+// (re)split the listed entries that are not valid; one launch
+static int split_planes(PlaneTable& t, const int* which, int n, cudaStream_t st) {
+  if (!t.enabled) return RECNN_OK;
+  tc::SplitJob jobs[6];
+  int nj = 0;
+  for (int i = 0; i < n; ++i) {
+    PlaneEntry& e = t.e[which[i]];
+    if (!e.base || e.valid) continue;
+    bool dup = false;                       // the same arena registered twice (a net used in two roles)
+    for (int k = 0; k < nj; ++k) dup = dup || jobs[k].src == e.base;
+    if (!dup) jobs[nj++] = tc::SplitJob{e.base, e.hi, e.lo, (long long)e.count};
+    e.valid = true;
+  }
+  return tc::launch_split_planes(jobs, nj, st);
+}
 
 // split count of a weight-gradient GEMM dW[C, K] = dZ^T X over n_rows (the contraction dim).
 // Must be a pure function of the shapes: the workspace size depends on it.
@@ -153,6 +211,13 @@ static Workspace carve(const recnn_dims& d, int64_t n, void* base) {
   w.block_partials = take(1024);
   w.scalars = take(8);
   w.tickets = reinterpret_cast<unsigned*>(take(8));
+  {
+    const int64_t ca = actor_layout(d).count, cc = critic_layout(d).count;
+    for (int i = 0; i < 6; ++i) {
+      w.plane_hi[i] = take(i < 2 ? ca : cc);
+      w.plane_lo[i] = take(i < 2 ? ca : cc);
+    }
+  }
   w.bytes = off;
   return w;
 }
@@ -210,6 +275,8 @@ static int gemm_nt(const Seg& x0, const Seg& x1, const float* W, long long ldw, 
                      (x1.cols == 0 || (x0.cols - x1.lead) % 4 == 0);
   if (tc_ok) {
     tc::Operand a0 = {x0.p, x0.ld, 0, 0}, a1 = {x1.p, x1.ld, 0, 0}, b = {W, ldw, N, K};
+    const float *whi, *wlo;
+    if (planes_for(W, &whi, &wlo)) { b.ptr = whi; b.lo = wlo; }
     tc::Problem p = {(int)n, N, x0.cols, x1.cols, 0, x0.cols - x1.lead, 0, 0, 0, 0, nullptr, nullptr};
     const int r = tc::launch<false, false, EPI>(a0, a1, b, p, 1, pick_bn(n, N), e, st);
     return r < 0 ? r : RECNN_OK;
@@ -252,6 +319,8 @@ static int backprop_hidden(const float* dZ, int C, const float* W, long long ldw
   const bool tc_ok = math_tc() && aligned16(dZ) && aligned16(W) && C % 4 == 0 && ldw % 4 == 0 && col0 % 4 == 0;
   if (tc_ok) {
     tc::Operand a0 = {dZ, C, 0, 0}, a1 = {nullptr, 0, 0, 0}, b = {W, ldw, C, w_cols};
+    const float *whi, *wlo;
+    if (planes_for(W, &whi, &wlo)) { b.ptr = whi; b.lo = wlo; }
     tc::Problem p = {(int)n, K, C, 0, 0, C, 0, col0, 0, 0, nullptr, nullptr};
     const int bn = pick_bn(n, K);
     const int r = h ? tc::launch<false, true, EPI_GATE>(a0, a1, b, p, 1, bn, e, st)
@@ -335,7 +404,9 @@ struct Ctx {
   float gate;
   AuxStreams* aux;       // non-null: chains V and P run on side streams
   bool v_prefetched, p_prefetched, p_deferred;
+  PlaneTable planes;     // pre-split weight planes of this call (indices as in Workspace::plane_hi)
 };
+enum { PL_POLICY = 0, PL_TARGET_POLICY = 1, PL_VALUE0 = 2, PL_VALUE1 = 3, PL_TVALUE0 = 4, PL_TVALUE1 = 5 };
 
 // Critic hidden layers on (s, act):  h1 -> out1, h2 -> out2
 static int critic_hidden(const Ctx& c, const float* params, const float* s, const float* act, bool train,
@@ -481,6 +552,7 @@ static int phase_value_opt(Ctx& c) {
     if (a.comm)     // data parallel: every rank's shard gradient -> the global-batch gradient, over NVLink
       RECNN_PROPAGATE(launch_comm_allreduce(a.comm, a.value[i].grads, c.lc.count, 0.f, nullptr, nullptr, nullptr, c.st));
     RECNN_PROPAGATE(launch_optimizer(a.value_optim, a.value[i], c.lc.count, nullptr, c.st, c.ws.tickets + 3));
+    c.planes.e[PL_VALUE0 + i].valid = false;       // weights changed: the planes are stale
   }
   return RECNN_OK;
 }
@@ -505,6 +577,14 @@ static int phase_policy_loss(Ctx& c) {
   const int vm = td3 ? 6 : 4;                       // mask slots (header: call order)
   float *v1 = c.ws.hb[0], *v2 = c.ws.hb[1];
   float* gen = c.ws.ab[1];
+  {
+    // the critic was stepped since the value phase (built-in optimizer above, or an external optimizer /
+    // all-reduce between two calls): its planes are re-split here; the actor's only if this call did not
+    // already split them for the prefetched chain P
+    if (!(a.phases & RECNN_PH_VALUE_OPT) || a.value_optim.kind == RECNN_OPT_EXTERNAL) c.planes.e[PL_VALUE0].valid = false;
+    const int need[2] = {PL_VALUE0, PL_POLICY};
+    RECNN_PROPAGATE(split_planes(c.planes, need, 2, c.st));
+  }
   // gen_action = policy_net(state); policy_loss = -value_net(state, gen_action)  (ddpg.py:78-79, td3.py:116-118)
   if (c.p_prefetched) RECNN_CHECK_CUDA(cudaStreamWaitEvent(c.st, c.aux->p_done, 0));
   else RECNN_PROPAGATE(policy_actor_forward(c, c.st));
@@ -559,6 +639,7 @@ static int phase_policy_opt(Ctx& c) {
   else
     RECNN_PROPAGATE(launch_l1_clip_coef(a.policy.grads, c.la.count, -1.0f, coef, a.losses + 3,
                                         c.ws.block_partials, c.ws.tickets + 1, c.st));
+  c.planes.e[PL_POLICY].valid = false;
   if (a.policy_optim.kind == RECNN_OPT_EXTERNAL)
     return launch_scale_inplace(a.policy.grads, c.la.count, coef, c.st);
   return launch_optimizer(a.policy_optim, a.policy, c.la.count, coef, c.st, c.ws.tickets + 3);
@@ -650,6 +731,21 @@ static int run_step(const recnn_step_args* a, int algo, void* stream) {
                                          cudaMemcpyDeviceToDevice, c.st));
     }
     c.REW = a->reward;
+  }
+  // pre-split weight planes (see PlaneTable): registered for the whole call, filled before the fork so that
+  // the side-stream chains see them through the fork event
+  {
+    const float* bases[6] = {a->policy.params, a->target_policy.params, a->value[0].params,
+                             n_critics > 1 ? a->value[1].params : nullptr, a->target_value[0].params,
+                             n_critics > 1 ? a->target_value[1].params : nullptr};
+    for (int i = 0; i < 6; ++i)
+      c.planes.e[i] = PlaneEntry{bases[i], c.ws.plane_hi[i], c.ws.plane_lo[i], i < 2 ? c.la.count : c.lc.count, false};
+    c.planes.enabled = math_tc() && option(OPT_PRESPLIT) != 0;
+  }
+  PlaneScope plane_scope(&c.planes);
+  if (a->phases & RECNN_PH_VALUE_GRAD) {
+    const int all[6] = {PL_POLICY, PL_TARGET_POLICY, PL_VALUE0, PL_VALUE1, PL_TVALUE0, PL_TVALUE1};
+    RECNN_PROPAGATE(split_planes(c.planes, all, 6, c.st));
   }
   // fork: chain V (online critic forward) and chain P (online policy forward) on side streams
   c.aux = nullptr;

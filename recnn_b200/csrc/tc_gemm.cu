@@ -84,7 +84,7 @@ static int launch_cfg(const Operand& A0, const Operand& A1, const Operand& B, co
   }
   const int nkb = (int)(ceil_div(p.K0, C::BK) + ceil_div(p.K1, C::BK));
   splits = split_plan(nkb, splits, &p.k_chunk, C::BK);
-  CUtensorMap ma0, ma1, mb;
+  CUtensorMap ma0, ma1, mb, mb_lo;
   // K-major operand: tensor [rows = M|N, cols = K], box {BK, tile rows}; MN-major: tensor [rows = K, cols = M|N], box {32, BK}
   if (!C::A_MN) {
     RECNN_PROPAGATE(make_tmap(&ma0, A0.ptr, p.M, p.K0, A0.ld, C::BK, C::BM, C::K_SWZ));
@@ -97,9 +97,16 @@ static int launch_cfg(const Operand& A0, const Operand& A1, const Operand& B, co
   }
   if (!C::B_MN) RECNN_PROPAGATE(make_tmap(&mb, B.ptr, B.rows, B.cols, B.ld, C::BK, C::BN, C::K_SWZ));
   else RECNN_PROPAGATE(make_tmap(&mb, B.ptr, B.rows, B.cols, B.ld, 32, C::BK, 1032));
+  if (C::B_PRE) {
+    RECNN_REQUIRE(B.lo != nullptr, "pre-split B needs its lo plane");
+    if (!C::B_MN) RECNN_PROPAGATE(make_tmap(&mb_lo, B.lo, B.rows, B.cols, B.ld, C::BK, C::BN, C::K_SWZ));
+    else RECNN_PROPAGATE(make_tmap(&mb_lo, B.lo, B.rows, B.cols, B.ld, 32, C::BK, 1032));
+  } else {
+    mb_lo = mb;
+  }
   dim3 grid((unsigned)ceil_div(p.N, C::BN), (unsigned)ceil_div(p.M, C::BM), (unsigned)splits);
   if (g_span && g_span_next < g_span_cap) {
-    g_span_meta[g_span_next][0] = C::BN | (C::A_MN << 12) | (C::B_MN << 13) | (EPI << 16);
+    g_span_meta[g_span_next][0] = C::BN | (C::A_MN << 12) | (C::B_MN << 13) | (C::B_PRE << 14) | (EPI << 16);
     g_span_meta[g_span_next][1] = p.M;
     g_span_meta[g_span_next][2] = p.N;
     g_span_meta[g_span_next][3] = (long long)(p.K0 + p.K1) | ((long long)splits << 32);
@@ -114,7 +121,7 @@ static int launch_cfg(const Operand& A0, const Operand& A1, const Operand& B, co
             C::BN, (int)C::A_MN, (int)C::B_MN, EPI, p.M, p.N, p.K0, p.K1, p.k_chunk, p.b_k1_offset, p.n_out_offset,
             p.b_n_offset, grid.x, grid.y, grid.z, (const void*)A0.ptr, A0.ld, (const void*)A1.ptr, A1.ld,
             (const void*)B.ptr, B.ld, B.rows, B.cols, (void*)epi.out, epi.ldo);
-  tc_gemm_kernel<C, EPI><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(ma0, ma1, mb, p, epi);
+  tc_gemm_kernel<C, EPI><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(ma0, ma1, mb, mb_lo, p, epi);
   RECNN_CHECK_LAUNCH("tc_gemm_kernel");
   if (debug) {
     const cudaError_t e = cudaStreamSynchronize(st);
@@ -132,8 +139,57 @@ int launch(const Operand& A0, const Operand& A1, const Operand& B, const Problem
            const Epilogue& epi, cudaStream_t st) {
   // stages chosen to fill ~190 KB of shared memory
   // BK = 32 (128-byte TMA rows), A split into tensor memory: stage = 16 KB (raw A) + 2 * BN/8 KB (B hi | B lo)
+  // Pre-split B (weights as hi/lo planes) exists for the forward and input-gradient GEMMs: A K-major,
+  // every epilogue but the split-K partial.
+  if constexpr (!A_MN && EPI != EPI_PARTIAL) {
+    if (B.lo != nullptr) {
+      if (bn >= 128) return launch_cfg<Cfg<128, 32, 4, A_MN, B_MN, true>, EPI>(A0, A1, B, p, splits, epi, st);
+      return launch_cfg<Cfg<64, 32, 6, A_MN, B_MN, true>, EPI>(A0, A1, B, p, splits, epi, st);
+    }
+  }
+  RECNN_REQUIRE(B.lo == nullptr, "pre-split B is not available for this GEMM form");
   if (bn >= 128) return launch_cfg<Cfg<128, 32, 4, A_MN, B_MN>, EPI>(A0, A1, B, p, splits, epi, st);
   return launch_cfg<Cfg<64, 32, 6, A_MN, B_MN>, EPI>(A0, A1, B, p, splits, epi, st);
+}
+
+// ---- TF32 hi/lo planes of whole arrays (weights) -------------------------------------------------
+struct SplitJobs {
+  SplitJob j[8];
+};
+__global__ void __launch_bounds__(256) split_planes_kernel(SplitJobs jobs) {
+  const SplitJob job = jobs.j[blockIdx.y];
+  const long long n4 = job.count >> 2;
+  const float4* __restrict__ src = reinterpret_cast<const float4*>(job.src);
+  float4* __restrict__ hi = reinterpret_cast<float4*>(job.hi);
+  float4* __restrict__ lo = reinterpret_cast<float4*>(job.lo);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 h, l;
+    tf32_split4(src[i], h, l);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
+int launch_split_planes(const SplitJob* jobs, int n_jobs, cudaStream_t st) {
+  RECNN_REQUIRE(jobs && n_jobs >= 0 && n_jobs <= 8, "at most 8 arrays per launch");
+  if (n_jobs == 0) return RECNN_OK;
+  SplitJobs js;
+  long long longest = 0;
+  for (int i = 0; i < n_jobs; ++i) {
+    const SplitJob& j = jobs[i];
+    RECNN_REQUIRE(j.src && j.hi && j.lo && j.count > 0 && j.count % 4 == 0, "split job");
+    RECNN_REQUIRE(((reinterpret_cast<uintptr_t>(j.src) | reinterpret_cast<uintptr_t>(j.hi) |
+                    reinterpret_cast<uintptr_t>(j.lo)) & 15) == 0, "split planes must be 16-byte aligned");
+    js.j[i] = j;
+    if (j.count > longest) longest = j.count;
+  }
+  for (int i = n_jobs; i < 8; ++i) js.j[i] = SplitJob{nullptr, nullptr, nullptr, 0};
+  // 1.7 MB per arena: two float4 per thread, so the launch is a single wave however many arenas it covers
+  const long long blocks = ceil_div(longest >> 2, 256 * 2);
+  dim3 grid((unsigned)(blocks < 1 ? 1 : blocks), (unsigned)n_jobs);
+  split_planes_kernel<<<grid, 256, 0, st>>>(js);
+  RECNN_CHECK_LAUNCH("split_planes_kernel");
+  return RECNN_OK;
 }
 
 // explicit instantiations used by step.cu / the generic entry points
@@ -180,6 +236,31 @@ extern "C" int recnn_gemm_tf32x3(int M, int N, int K, const float* A, int64_t ld
   else if (!a_mn && b_mn) r = tc::launch<false, true, EPI_STORE>(a0, a1, b, p, 1, tile_n, e, st);
   else if (a_mn && b_mn) r = tc::launch<true, true, EPI_STORE>(a0, a1, b, p, 1, tile_n, e, st);
   else r = tc::launch<true, false, EPI_STORE>(a0, a1, b, p, 1, tile_n, e, st);
+  return r < 0 ? r : RECNN_OK;
+}
+
+// Test hook (not part of the product ABI): the same GEMM with B first split into hi/lo planes (caller
+// scratch, same geometry as B) and consumed by the B_PRE kernels.  A must be K-major.  Results must be
+// bit-identical to recnn_gemm_tf32x3.
+extern "C" RECNN_API int recnn_debug_gemm_tf32x3_presplit(int M, int N, int K, const float* A, int64_t lda,
+                                                          const float* B, int64_t ldb, int b_mn, float* C,
+                                                          int64_t ldc, int tile_n, float* b_hi, float* b_lo,
+                                                          void* stream) {
+  RECNN_REQUIRE(A && B && C && b_hi && b_lo && M > 0 && N > 0 && K > 0, "null pointer / sizes");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long b_rows = b_mn ? K : N;
+  const tc::SplitJob job = {B, b_hi, b_lo, b_rows * ldb};
+  RECNN_PROPAGATE(tc::launch_split_planes(&job, 1, st));
+  Epilogue e;
+  memset(&e, 0, sizeof(e));
+  e.out = C;
+  e.ldo = ldc;
+  tc::Operand a0 = {A, lda, 0, 0}, a1 = {nullptr, 0, 0, 0};
+  tc::Operand b = {b_hi, ldb, b_mn ? K : N, b_mn ? N : K, b_lo};
+  tc::Problem p = {M, N, K, 0, 0, K, 0, 0, 0, 0, nullptr, nullptr};
+  if (tile_n <= 0) tile_n = N > 64 ? 128 : 64;
+  const int r = b_mn ? tc::launch<false, true, EPI_STORE>(a0, a1, b, p, 1, tile_n, e, st)
+                     : tc::launch<false, false, EPI_STORE>(a0, a1, b, p, 1, tile_n, e, st);
   return r < 0 ? r : RECNN_OK;
 }
 

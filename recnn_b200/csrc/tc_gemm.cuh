@@ -240,13 +240,19 @@ __device__ __forceinline__ unsigned long long gtimer() {
     if (p.trace) p.trace[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + (slot)] = gtimer(); \
   } while (0)
 
-template <int BN_, int BK_, int STAGES_, bool A_MN_, bool B_MN_>
+template <int BN_, int BK_, int STAGES_, bool A_MN_, bool B_MN_, bool B_PRE_ = false>
 struct Cfg {
   // BK = 32 (128-byte K-major rows) when A is K-major: TMA moves 64-byte rows at half the rate of
   // 128-byte rows (measured: 31 B/clk/SM with BK = 16), and the operand stream is the kernel's bottleneck.
   static constexpr int BM = 128, BN = BN_, BK = BK_, STAGES = STAGES_;
   static constexpr int CH = 64 / BK;                               // k-blocks per TMEM accumulation chunk (K = 64)
   static constexpr bool A_MN = A_MN_, B_MN = B_MN_;
+  // B_PRE: B arrives already split into TF32 hi / lo planes in global memory (weights: split once per
+  // optimizer step by split_planes_kernel).  TMA then fills both B slots of the stage and the worker
+  // warps never touch B: per k-block that removes a 128*BN-byte shared-memory read, a 256*BN-byte write
+  // and the generic->async proxy fence from the split warps' critical path, at the price of fetching
+  // B twice from L2.  Same hi/lo values as the in-kernel split => bit-identical results.
+  static constexpr bool B_PRE = B_PRE_;
   // The split A tile goes to TENSOR memory (tcgen05.st) and the MMA reads it from there, so A costs
   // shared memory one TMA write + one read instead of write + read + 2 writes + 6 MMA reads.
   static constexpr bool A_TM = true;
@@ -355,7 +361,8 @@ __device__ __forceinline__ void epilogue_row(const Epilogue& e, const Problem& p
 template <class C, int EPI>
 __global__ void __launch_bounds__(C::THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
-               const __grid_constant__ CUtensorMap map_b, Problem p, Epilogue epi) {
+               const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_b_lo, Problem p,
+               Epilogue epi) {
   constexpr int BM = C::BM, BN = C::BN, BK = C::BK, STAGES = C::STAGES;
   const int CH = ((p.dbg >> 8) & 15) ? ((p.dbg >> 8) & 15) : C::CH;   // experiment hook: chunk length override
   constexpr int NC = C::COLS_PER_WORKER, WORKERS = C::WORKERS;
@@ -396,6 +403,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     tma_prefetch_desc(&map_a0);
     tma_prefetch_desc(&map_b);
     if (p.K1 > 0) tma_prefetch_desc(&map_a1);
+    if (C::B_PRE) tma_prefetch_desc(&map_b_lo);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -433,9 +441,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       const int ka = seg1 ? (kb - nkb0) * BK : kb * BK;                     // k coordinate inside A's segment
       const int kbcol = seg1 ? p.b_k1_offset + (kb - nkb0) * BK : kb * BK;  // k coordinate in B
       const CUtensorMap* ma = seg1 ? &map_a1 : &map_a0;
-      const uint32_t dst_a = stage_addr(s, 0), dst_b = stage_addr(s, 1);
+      const uint32_t dst_a = stage_addr(s, 0), dst_b = stage_addr(s, 1), dst_b_lo = stage_addr(s, 3);
       if (leader) {
-        mbar_expect_tx(full(s), C::A_BYTES + C::B_BYTES);
+        mbar_expect_tx(full(s), C::A_BYTES + (C::B_PRE ? 2 : 1) * C::B_BYTES);
         if (!C::A_MN) {
           tma_load_2d(dst_a, ma, full(s), ka, m0);                            // box {BK, 128}
         } else {
@@ -445,10 +453,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         }
         if (!C::B_MN) {
           tma_load_2d(dst_b, &map_b, full(s), kbcol, p.b_n_offset + n0);      // box {BK, BN}
+          if (C::B_PRE) tma_load_2d(dst_b_lo, &map_b_lo, full(s), kbcol, p.b_n_offset + n0);
         } else {
 #pragma unroll
-          for (int c = 0; c < BN / 32; ++c)
+          for (int c = 0; c < BN / 32; ++c) {
             tma_load_2d(dst_b + c * (BK * 128), &map_b, full(s), p.b_n_offset + n0 + 32 * c, kbcol);
+            if (C::B_PRE)
+              tma_load_2d(dst_b_lo + c * (BK * 128), &map_b_lo, full(s), p.b_n_offset + n0 + 32 * c, kbcol);
+          }
         }
       }
       __syncwarp();
@@ -478,6 +490,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         RECNN_TIMED(w_acc, mbar_wait(acc_empty(buf), ((chunk >> 1) & 1) ^ 1));
       }
       RECNN_TIMED(w_split, mbar_wait(split(s), ph));
+      // B_PRE: both B slots were written by TMA (async proxy) and are read by the MMA (async proxy); observe
+      // the TMA barrier in this warp as well instead of relying on the workers' acquire/release chain
+      if (C::B_PRE) mbar_wait(full(s), ph);
       tc_fence_after();
       if (i == 0 && lane == 0) RECNN_TRACE(2);               // first stage loaded + split
       const uint32_t d_hi = tmem_base + (uint32_t)buf * BN;  // chunk accumulator (hi*hi)
@@ -600,7 +615,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             tmem_st16(ta + BK + 16 * half, lw);
           }
         }
-        for (uint32_t b = 0; b < 256u / ntg; ++b) {
+        for (uint32_t b = 0; !C::B_PRE && b < 256u / ntg; ++b) {
           float4 x[VB];
           const uint32_t v0 = (uint32_t)tg + b * (uint32_t)VB * ntg;
 #pragma unroll
@@ -614,7 +629,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           }
         }
       }
-      if (!(p.dbg & 8)) fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
+      // generic-proxy writes (B hi/lo in shared memory) -> visible to the tensor core (async proxy);
+      // with pre-split B the workers write no shared memory at all
+      if (!C::B_PRE && !(p.dbg & 8)) fence_proxy_async();
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
@@ -674,7 +691,18 @@ struct Operand {
   const float* ptr;
   long long ld;
   long long rows, cols;
+  const float* lo = nullptr;   // B only: non-null => `ptr` is the TF32 hi plane and `lo` the lo plane (same geometry)
 };
+
+// hi[i] = rna_tf32(src[i]), lo[i] = rna_tf32(src[i] - hi[i]) for up to 8 arrays in one launch
+// (count % 4 == 0, 16-byte aligned): the pre-split planes a B_PRE GEMM consumes.
+struct SplitJob {
+  const float* src;
+  float* hi;
+  float* lo;
+  long long count;
+};
+int launch_split_planes(const SplitJob* jobs, int n_jobs, cudaStream_t st);
 
 // k-blocks (of bk) per split and the effective split count for a requested split count.
 int split_plan(int K_total_blocks, int splits_req, int* k_chunk, int bk = 16);

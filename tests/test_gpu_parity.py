@@ -232,6 +232,39 @@ def test_quirks_on_device():
         assert m.training == ("target" not in name)
 
 
+@pytest.mark.parametrize("algo,form", [("ddpg", "frames"), ("ddpg", "dense"), ("td3", "frames")])
+def test_presplit_weight_planes_are_bit_identical(algo, form):
+    """The step with pre-split weight planes (option "presplit": forward / input-gradient GEMMs fetch TF32
+    hi/lo planes of the weights, split once per call and again after the critic's optimizer step) must
+    reproduce the in-kernel-split step bit for bit over 12 steps (policy steps 0 and 10, Polyak updates,
+    Adam): any stale plane would show up as a different weight."""
+    gold = load_golden("%s_canon_adam.npz" % algo)
+    runs = []
+    for v in (0, 1):
+        prev = _lib.set_option("presplit", v)
+        try:
+            runs.append(run_cuda_case("canon", algo, "adam", golden=gold, form=form))
+        finally:
+            _lib.set_option("presplit", prev)
+    a, b = runs
+    for k in a:
+        if k.startswith(("final.", "loss.", "after", "grad_")):
+            assert np.array_equal(a[k], b[k]), k
+    compare_with_golden(b, gold, check_grads=(algo == "ddpg"))
+
+
+def test_presplit_with_external_optimizer_and_split_phases():
+    """External torch optimizers cut the step into several C calls; planes are per call, so every call must
+    re-split what it uses (a stale critic plane after optimizer.step() would change the policy loss)."""
+    gold = load_golden("ddpg_canon_adam.npz")
+    prev = _lib.set_option("presplit", 1)
+    try:
+        got = run_cuda_case("canon", "ddpg", "adam", golden=gold, external=True)
+    finally:
+        _lib.set_option("presplit", prev)
+    compare_with_golden(got, gold)
+
+
 def test_graph_replay_equals_direct_launch(monkeypatch):
     from recnn_b200.nn.update import _engine
     a = run_cuda_case("canon", "ddpg", "adam", form="frames")

@@ -112,3 +112,39 @@ def test_wide_dynamic_range():
     """gradient-like operand (1e-6 scale) times activation-like operand: relative accuracy holds."""
     got, want = _run("tc", 256, 256, 4096, True, True, seed=5, scale_b=1e-6)
     assert np.abs(got - want).max() / np.abs(want).max() < 8e-6
+
+
+# ----------------------------------------------------------------------------- pre-split B (weights as hi/lo planes)
+@pytest.mark.parametrize("tile_n", [64, 128])
+@pytest.mark.parametrize("b_mn", [False, True])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 256, 1290), (4096, 256, 1290), (4096, 128, 256), (1000, 100, 77)])
+def test_presplit_b_is_bit_identical(M, N, K, b_mn, tile_n):
+    """tc::Cfg::B_PRE kernels (B fetched by TMA as TF32 hi / lo planes split once by split_planes_kernel)
+    against the in-kernel split: the MMA operands are the same bits, so the results must be too."""
+    import ctypes as C
+    rng = np.random.default_rng(M + N + K)
+    a_h, a_d, lda = _make(M, K, rng)
+    b_h, b_d, ldb = _make(K, N, rng) if b_mn else _make(N, K, rng)
+    ldc = _pad4(N)
+    L = _lib.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    want = torch.full((M, ldc), float("nan"), device=DEV)
+    _lib.check(L.recnn_gemm_tf32x3(M, N, K, a_d.data_ptr(), lda, 0, b_d.data_ptr(), ldb, int(b_mn),
+                                   want.data_ptr(), ldc, tile_n, st))
+    fn = L.recnn_debug_gemm_tf32x3_presplit
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
+                   C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    hi, lo = torch.empty_like(b_d), torch.empty_like(b_d)
+    got = torch.full((M, ldc), float("nan"), device=DEV)
+    _lib.check(fn(M, N, K, a_d.data_ptr(), lda, b_d.data_ptr(), ldb, int(b_mn), got.data_ptr(), ldc, tile_n,
+                  hi.data_ptr(), lo.data_ptr(), st))
+    torch.cuda.synchronize()
+    assert torch.isfinite(hi).all() and torch.isfinite(lo).all()
+    # planes: hi has a 10-bit mantissa, hi + lo reproduces b to 2^-22 relative
+    assert int((hi.view(torch.int32) & 0x1FFF).abs().max().item()) == 0
+    assert torch.all((hi.double() + lo.double() - b_d.double()).abs() <= b_d.double().abs() * 2.0 ** -21 + 1e-45)
+    assert torch.equal(got[:, :N].view(torch.int32), want[:, :N].view(torch.int32))
+    ref = a_h.astype(np.float64) @ (b_h.astype(np.float64) if b_mn else b_h.astype(np.float64).T)
+    err = np.abs(got[:, :N].cpu().numpy() - ref).max() / np.abs(ref).max()
+    assert err < 2e-6, err
