@@ -30,6 +30,8 @@ static void init_options() {
   const struct { Option o; const char* env; int def; } table[] = {
       {OPT_GATHER_VARIANT, "RECNN_B200_GATHER", 0},      // 0: one warp per row   1: balanced (row, slot) units
       {OPT_PRESPLIT, "RECNN_B200_PRESPLIT", 0},          // 1: weights pre-split into TF32 hi/lo planes
+      {OPT_WORKERS16, "RECNN_B200_WORKERS16", 0},        // 1: 64-wide GEMM tiles run 16 worker warps (4 groups)
+                                                         // 2: ... and every GEMM uses 64-wide tiles
   };
   for (const auto& t : table) {
     const char* e = getenv(t.env);
@@ -43,13 +45,14 @@ int option(Option o) {
 }
 }  // namespace recnn
 
-// name in {"gather_variant", "presplit"}; returns the previous value, or -1 for an unknown name
+// name in {"gather_variant", "presplit", "workers16"}; returns the previous value, or -1 for an unknown name
 extern "C" RECNN_API int recnn_debug_set_option(const char* name, int value) {
   recnn::init_options();
   if (!name) return -1;
   int idx = -1;
   if (strcmp(name, "gather_variant") == 0) idx = recnn::OPT_GATHER_VARIANT;
   else if (strcmp(name, "presplit") == 0) idx = recnn::OPT_PRESPLIT;
+  else if (strcmp(name, "workers16") == 0) idx = recnn::OPT_WORKERS16;
   if (idx < 0) return -1;
   return recnn::g_options[idx].exchange(value);
 }

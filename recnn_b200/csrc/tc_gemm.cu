@@ -106,7 +106,7 @@ static int launch_cfg(const Operand& A0, const Operand& A1, const Operand& B, co
   }
   dim3 grid((unsigned)ceil_div(p.N, C::BN), (unsigned)ceil_div(p.M, C::BM), (unsigned)splits);
   if (g_span && g_span_next < g_span_cap) {
-    g_span_meta[g_span_next][0] = C::BN | (C::A_MN << 12) | (C::B_MN << 13) | (C::B_PRE << 14) | (EPI << 16);
+    g_span_meta[g_span_next][0] = C::BN | (C::A_MN << 12) | (C::B_MN << 13) | (C::B_PRE << 14) | ((C::WORKERS == 16) << 15) | (EPI << 16);
     g_span_meta[g_span_next][1] = p.M;
     g_span_meta[g_span_next][2] = p.N;
     g_span_meta[g_span_next][3] = (long long)(p.K0 + p.K1) | ((long long)splits << 32);
@@ -148,6 +148,8 @@ int launch(const Operand& A0, const Operand& A1, const Operand& B, const Problem
     }
   }
   RECNN_REQUIRE(B.lo == nullptr, "pre-split B is not available for this GEMM form");
+  if (option(OPT_WORKERS16) != 0 && bn < 128)
+    return launch_cfg<Cfg<64, 32, 6, A_MN, B_MN, false, 16>, EPI>(A0, A1, B, p, splits, epi, st);
   if (bn >= 128) return launch_cfg<Cfg<128, 32, 4, A_MN, B_MN>, EPI>(A0, A1, B, p, splits, epi, st);
   return launch_cfg<Cfg<64, 32, 6, A_MN, B_MN>, EPI>(A0, A1, B, p, splits, epi, st);
 }
@@ -246,11 +248,13 @@ extern "C" RECNN_API int recnn_debug_gemm_tf32x3_presplit(int M, int N, int K, c
                                                           const float* B, int64_t ldb, int b_mn, float* C,
                                                           int64_t ldc, int tile_n, float* b_hi, float* b_lo,
                                                           void* stream) {
-  RECNN_REQUIRE(A && B && C && b_hi && b_lo && M > 0 && N > 0 && K > 0, "null pointer / sizes");
+  RECNN_REQUIRE(A && C && b_hi && b_lo && M > 0 && N > 0 && K > 0, "null pointer / sizes");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long b_rows = b_mn ? K : N;
-  const tc::SplitJob job = {B, b_hi, b_lo, b_rows * ldb};
-  RECNN_PROPAGATE(tc::launch_split_planes(&job, 1, st));
+  if (B) {                                       // B == NULL: the planes are already filled (timing runs)
+    const tc::SplitJob job = {B, b_hi, b_lo, b_rows * ldb};
+    RECNN_PROPAGATE(tc::launch_split_planes(&job, 1, st));
+  }
   Epilogue e;
   memset(&e, 0, sizeof(e));
   e.out = C;

@@ -142,7 +142,38 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+// acc[0..NC) += D[lane, col0 .. col0+NC) with round-to-nearest adds (NC = 16 or a multiple of 32)
+template <int NC>
+__device__ __forceinline__ void tmem_accumulate(uint32_t taddr, float (&acc)[NC]);
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+template <int NC>
+__device__ __forceinline__ void tmem_accumulate(uint32_t taddr, float (&acc)[NC]) {
+  if constexpr (NC == 16) {
+    uint32_t r[16];
+    tmem_ld16(taddr, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = __fadd_rn(acc[j], __uint_as_float(r[j]));
+  } else {
+#pragma unroll
+    for (int c0 = 0; c0 < NC; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(taddr + c0, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[c0 + j] = __fadd_rn(acc[c0 + j], __uint_as_float(r[j]));
+    }
+  }
+}
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
@@ -240,7 +271,7 @@ __device__ __forceinline__ unsigned long long gtimer() {
     if (p.trace) p.trace[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + (slot)] = gtimer(); \
   } while (0)
 
-template <int BN_, int BK_, int STAGES_, bool A_MN_, bool B_MN_, bool B_PRE_ = false>
+template <int BN_, int BK_, int STAGES_, bool A_MN_, bool B_MN_, bool B_PRE_ = false, int WORKERS_ = 8>
 struct Cfg {
   // BK = 32 (128-byte K-major rows) when A is K-major: TMA moves 64-byte rows at half the rate of
   // 128-byte rows (measured: 31 B/clk/SM with BK = 16), and the operand stream is the kernel's bottleneck.
@@ -260,29 +291,40 @@ struct Cfg {
   static constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = (A_TM ? A_BYTES : 2 * A_BYTES) + 2 * B_BYTES;   // raw A (+lo A) | raw B | lo B
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
-  static constexpr int WORKERS = 8;                                // warps: two per TMEM lane quarter
+  // Worker warps come in groups of four (one warp per TMEM lane quarter); the groups take k-blocks round
+  // robin.  One group needs ~3,000 clk per k-block (waits + TMEM store + fences + a chunk drain), whatever
+  // the tile width: measured 1,310 (BN = 64) and 1,460 (BN = 128) clk per k-block with two groups against
+  // tensor floors of 384 / 768.  WORKERS = 16 puts four groups in flight (BN = 64 only: its A ring in
+  // tensor memory has five slots; at BN = 128 there are two).
+  static constexpr int WORKERS = WORKERS_;
   static constexpr int COLS_PER_WORKER = BN / (WORKERS / 4);       // register-resident running sum per thread
   static constexpr int THREADS = 64 + 32 * WORKERS;
   static constexpr int TMEM_COLS = 512;                            // D_hi chunk x2 | D_lo | A ring
   static constexpr int A_COL0 = 3 * BN;
   static constexpr int K_SWZ = BK * 4;                             // K-major rows: 64 B (SWIZZLE_64B) or 128 B (SWIZZLE_128B)
   static_assert(BN == 64 || BN == 128, "BN");
+  static_assert(WORKERS == 8 || (WORKERS == 16 && BN == 64), "WORKERS");
+  static_assert(COLS_PER_WORKER == 16 || COLS_PER_WORKER % 32 == 0, "drain width");
+  static_assert(WORKERS / 4 < A_SLOTS || WORKERS == 8, "every group in flight needs its own A slot");
   static_assert(BK == 32, "BK: 128-byte operand rows");
   static_assert(SMEM_BYTES <= 227 * 1024, "smem");
 };
 
 // ------------------------------------------------------------------ epilogue on a register-resident row
-// acc[j] is C[m, nb + j] for j < NC.  Stores 16 bytes at a time when the destination allows it.
+// acc[j] is C[m, nb + j] for j < NC (NC = 16 or a multiple of 32), handled in blocks of W = min(NC, 32)
+// columns.  Stores 16 bytes at a time when the destination allows it.
 template <int EPI, int NC>
 __device__ __forceinline__ void epilogue_row(const Epilogue& e, const Problem& p, int m, int nb, int z,
                                              float (&acc)[NC]) {
+  constexpr int W = NC < 32 ? NC : 32;
+  static_assert(NC % W == 0 && (W == 16 || W == 32), "epilogue block width");
   const int N = p.N;
   if (m >= p.M) return;
   float* out_row;
   if (EPI == EPI_PARTIAL) out_row = e.out + ((long long)z * p.M + m) * e.ldo + p.n_out_offset;
   else out_row = e.out + (long long)m * e.ldo + p.n_out_offset;
 #pragma unroll
-  for (int j0 = 0; j0 < NC; j0 += 32) {
+  for (int j0 = 0; j0 < NC; j0 += W) {
     if (nb + j0 < N) {
       uint32_t keep_bits = 0xFFFFFFFFu;
       if (EPI == EPI_HIDDEN && e.train) {
@@ -290,17 +332,17 @@ __device__ __forceinline__ void epilogue_row(const Epilogue& e, const Problem& p
           keep_bits = 0;
           const uint8_t* mrow = e.mask + (long long)m * N + nb + j0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
+          for (int j = 0; j < W; ++j)
             if (nb + j0 + j < N && mrow[j]) keep_bits |= 1u << j;
         } else {
           // same stream as the CUDA-core path: bit (idx & 31) of word idx >> 5, idx = m*N + n
           const unsigned long long idx = (unsigned long long)m * N + nb + j0;
-          if ((idx & 31) == 0) {
-            keep_bits = philox_keep_bits32(e.seed, (unsigned long long)*e.rng_step, e.stream_id, idx >> 5);
+          if ((idx & 31) + W <= 32) {          // the block's W bits sit in one 32-bit word
+            keep_bits = philox_keep_bits32(e.seed, (unsigned long long)*e.rng_step, e.stream_id, idx >> 5) >> (idx & 31);
           } else {
             keep_bits = 0;
 #pragma unroll 1
-            for (int j = 0; j < 32; ++j) {
+            for (int j = 0; j < W; ++j) {
               const unsigned long long ij = idx + j;
               const uint32_t w = philox_keep_bits32(e.seed, (unsigned long long)*e.rng_step, e.stream_id, ij >> 5);
               keep_bits |= ((w >> (ij & 31)) & 1u) << j;
@@ -309,7 +351,7 @@ __device__ __forceinline__ void epilogue_row(const Epilogue& e, const Problem& p
         }
       }
 #pragma unroll
-      for (int j4 = 0; j4 < 32; j4 += 4) {
+      for (int j4 = 0; j4 < W; j4 += 4) {
         const int n = nb + j0 + j4;
         if (n < N) {
           float v[4];
@@ -398,6 +440,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   const int num_kb = max(kb_end - kb_begin, 0);
   const int num_chunks = (num_kb + CH - 1) / CH;
   const bool prof = (p.dbg & 16) != 0;
+  // dbg bit 32 (experiments, 8 workers only): all worker warps share every k-block instead of taking turns
+  const bool share_all = WORKERS == 8 && (p.dbg & 32) != 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a0);
@@ -408,7 +452,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full(s), 1);
-      mbar_init(split(s), (p.dbg & 32) ? WORKERS : WORKERS / 2);   // one arrive per worker warp that split the stage
+      mbar_init(split(s), share_all ? WORKERS : 4);      // one arrive per worker warp that split the stage
       mbar_init(empty(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -542,14 +586,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       RECNN_TIMED(w_drain, mbar_wait(acc_full(buf), (chunk >> 1) & 1));
       tc_fence_after();
       const long long ld0 = prof ? clock64() : 0;
-#pragma unroll
-      for (int c0 = 0; c0 < NC; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(lane_base + (uint32_t)buf * BN + c0, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) acc[c0 + j] = __fadd_rn(acc[c0 + j], __uint_as_float(r[j]));
-      }
+      tmem_accumulate<NC>(lane_base + (uint32_t)buf * BN, acc);
       if (prof) w_ld += clock64() - ld0;
       tc_fence_before();
       __syncwarp();
@@ -559,13 +596,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     // The two warp groups (one warp per TMEM lane quarter each) take alternate k-blocks, so one group's
     // publish latency (membar + proxy fence + tcgen05.wait::st) hides behind the other group's arithmetic.
     // dbg bit 32 (experiments): all 8 warps share every k-block instead (half a row / an eighth of B each).
-    const int ng = (p.dbg & 32) ? 1 : 2;
-    const int tg = ng == 2 ? (t & 127) : t;                   // index among the threads sharing one k-block
-    const uint32_t ntg = ng == 2 ? 128u : 256u;
+    const int ng = share_all ? 1 : WORKERS / 4;               // groups taking k-blocks round robin
+    const int tg = share_all ? t : (t & 127);                 // index among the threads sharing one k-block
+    const uint32_t ntg = share_all ? (uint32_t)NT : 128u;
     constexpr int VB = C::B_BYTES / 16 / NT;                  // float4s per thread per batch (all 256 threads = 1 batch)
     static_assert(C::B_BYTES / 16 % NT == 0 && VB >= 1, "B tile must split evenly over the worker threads");
     int next_drain = 0;
-    for (int i = (ng == 2 ? g : 0); i < num_kb; i += ng) {
+    for (int i = (share_all ? 0 : g); i < num_kb; i += ng) {
       const int s = i % STAGES;
       const uint32_t ph = (i / STAGES) & 1;
       RECNN_TIMED(w_full, mbar_wait(full(s), ph));
@@ -573,7 +610,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       const uint32_t lo = stage_addr(s, 3);                   // lo B
       const int slot = i % C::A_SLOTS;
       const uint32_t ta = tmem_base + (uint32_t(32 * q) << 16) + C::A_COL0 + slot * C::A_SLOT_COLS;
-      const int half0 = ng == 2 ? 0 : g, half1 = ng == 2 ? 2 : g + 1;
+      const int half0 = share_all ? g : 0, half1 = share_all ? g + 1 : 2;
       if (!(p.dbg & 1)) {
         RECNN_TIMED(w_afree, mbar_wait(a_free(slot), ((i / C::A_SLOTS) & 1) ^ 1));
         tc_fence_after();
@@ -615,7 +652,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             tmem_st16(ta + BK + 16 * half, lw);
           }
         }
-        for (uint32_t b = 0; !C::B_PRE && b < 256u / ntg; ++b) {
+        for (uint32_t b = 0; !C::B_PRE && b < (uint32_t)NT / ntg; ++b) {
           float4 x[VB];
           const uint32_t v0 = (uint32_t)tg + b * (uint32_t)VB * ntg;
 #pragma unroll
@@ -652,14 +689,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     }
     if (num_kb > 0) {
       // the commit behind the last acc_full covers every MMA issued before it, D_lo's included
-#pragma unroll
-      for (int c0 = 0; c0 < NC; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(lane_base + 2u * BN + c0, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) acc[c0 + j] = __fadd_rn(acc[c0 + j], __uint_as_float(r[j]));
-      }
+      tmem_accumulate<NC>(lane_base + 2u * BN, acc);
     }
     epilogue_row<EPI, NC>(epi, p, m0 + 32 * q + lane, n0 + g * NC, z, acc);
     if (t == 0) RECNN_TRACE(6);                               // epilogue stored

@@ -253,6 +253,53 @@ def test_presplit_weight_planes_are_bit_identical(algo, form):
     compare_with_golden(b, gold, check_grads=(algo == "ddpg"))
 
 
+@pytest.mark.parametrize("value", [1, 2])
+@pytest.mark.parametrize("algo", ["ddpg", "td3"])
+def test_sixteen_worker_gemm_in_the_step(algo, value):
+    """Option "workers16" (1: 64-wide GEMM tiles use the 16-worker kernel, 2: every GEMM uses 64-wide tiles):
+    per-element arithmetic does not depend on the tile shape, so the 12-step run (perf-relevant epilogues:
+    bias+ReLU+mask, linear, ReLU gate, split-K partials) must match the default kernels bit for bit."""
+    gold = load_golden("%s_canon_adam.npz" % algo)
+    base = run_cuda_case("canon", algo, "adam", golden=gold, form="frames")
+    prev = _lib.set_option("workers16", value)
+    try:
+        got = run_cuda_case("canon", algo, "adam", golden=gold, form="frames")
+    finally:
+        _lib.set_option("workers16", prev)
+    compare_with_golden(got, gold, check_grads=(algo == "ddpg"))
+    for k in base:
+        if k.startswith(("final.", "loss.")):
+            assert np.array_equal(base[k], got[k]), k
+
+
+def test_sixteen_worker_gemm_perf_mode_dropout_matches():
+    """Device-Philox dropout (perf mode) indexes keep-bits by element, not by tile: the 16-worker kernel's
+    16-column epilogue blocks must draw the same masks as the 32-column blocks of the default kernel."""
+    torch.manual_seed(3)
+    rng = np.random.default_rng(4)
+    table, items, ratings, sizes = O.synth_frames(rng, 512)
+    table_d = torch.from_numpy(table).to(DEV)
+    batch = {"items": torch.from_numpy(items), "ratings": torch.from_numpy(ratings),
+             "sizes": torch.from_numpy(sizes), "table": table_d}
+    outs = []
+    for value in (0, 2):
+        prev = _lib.set_option("workers16", value)
+        try:
+            torch.manual_seed(5)
+            agent = recnn_b200.nn.DDPG(recnn_b200.nn.Actor(1290, 128, 256, 6e-1),
+                                       recnn_b200.nn.Critic(1290, 128, 256, 54e-2)).to(torch.device(DEV))
+            losses = []
+            for _ in range(3):
+                losses.append(agent.update(batch, learn=True))
+                agent.step()
+            outs.append((losses, [p.detach().clone() for p in agent.nets["value_net"].parameters()]))
+        finally:
+            _lib.set_option("workers16", prev)
+    assert outs[0][0] == outs[1][0]
+    for p, q in zip(outs[0][1], outs[1][1]):
+        assert torch.equal(p, q)
+
+
 def test_presplit_with_external_optimizer_and_split_phases():
     """External torch optimizers cut the step into several C calls; planes are per call, so every call must
     re-split what it uses (a stale critic plane after optimizer.step() would change the policy loss)."""

@@ -148,3 +148,21 @@ def test_presplit_b_is_bit_identical(M, N, K, b_mn, tile_n):
     ref = a_h.astype(np.float64) @ (b_h.astype(np.float64) if b_mn else b_h.astype(np.float64).T)
     err = np.abs(got[:, :N].cpu().numpy() - ref).max() / np.abs(ref).max()
     assert err < 2e-6, err
+
+
+# ----------------------------------------------------------------------------- 16 worker warps (four split groups)
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("M,N,K", [(128, 64, 16), (128, 256, 64), (128, 256, 96), (300, 256, 1290), (4096, 256, 1290),
+                                   (4096, 128, 256), (1000, 100, 77), (256, 1290, 4096)])
+def test_sixteen_worker_kernel_is_bit_identical(M, N, K, a_mn, b_mn):
+    """Option "workers16": 64-wide tiles run four split groups (16 worker warps, 16 accumulator columns per
+    thread) instead of two.  Same MMA sequence and the same order of chunk additions per element, so the
+    result must equal the 8-worker kernel's bit for bit (K = 16 / 64 / 96 leave some groups without a k-block)."""
+    want, ref = _run("tc", M, N, K, a_mn, b_mn, seed=3, tile_n=64)
+    prev = _lib.set_option("workers16", 1)
+    try:
+        got, _ = _run("tc", M, N, K, a_mn, b_mn, seed=3, tile_n=64)
+    finally:
+        _lib.set_option("workers16", prev)
+    assert np.array_equal(got, want)
+    assert np.abs(got - ref).max() / np.abs(ref).max() < 2e-6
