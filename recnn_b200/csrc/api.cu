@@ -32,6 +32,8 @@ static void init_options() {
       {OPT_PRESPLIT, "RECNN_B200_PRESPLIT", 0},          // 1: weights pre-split into TF32 hi/lo planes
       {OPT_WORKERS16, "RECNN_B200_WORKERS16", 0},        // 1: 64-wide GEMM tiles run 16 worker warps (4 groups)
                                                          // 2: ... and every GEMM uses 64-wide tiles
+      {OPT_LO2, "RECNN_B200_LO2", 0},                    // 1: 64-wide tiles keep two cross-term accumulators
+      {OPT_BN64, "RECNN_B200_BN64", 0},                  // 1: every GEMM of the step uses 64-wide tiles
   };
   for (const auto& t : table) {
     const char* e = getenv(t.env);
@@ -53,6 +55,8 @@ extern "C" RECNN_API int recnn_debug_set_option(const char* name, int value) {
   if (strcmp(name, "gather_variant") == 0) idx = recnn::OPT_GATHER_VARIANT;
   else if (strcmp(name, "presplit") == 0) idx = recnn::OPT_PRESPLIT;
   else if (strcmp(name, "workers16") == 0) idx = recnn::OPT_WORKERS16;
+  else if (strcmp(name, "lo2") == 0) idx = recnn::OPT_LO2;
+  else if (strcmp(name, "bn64") == 0) idx = recnn::OPT_BN64;
   if (idx < 0) return -1;
   return recnn::g_options[idx].exchange(value);
 }

@@ -260,7 +260,7 @@ struct AloneScope {
 static int pick_bn(int64_t M, int N) {
   // 128-wide tiles when they still yield >= 64 CTAs; otherwise 64-wide (more CTAs, less reuse)
   const int64_t mt = ceil_div(M, 128);
-  if (option(OPT_WORKERS16) == 2) return 64;       // the 16-worker kernel exists for 64-wide tiles only
+  if (option(OPT_WORKERS16) == 2 || option(OPT_BN64) != 0) return 64;       // the 16-worker kernel exists for 64-wide tiles only
   if (t_alone && mt * ceil_div(N, 64) <= 2 * kNumSMs) return 64;
   if (N > 64 && mt * ceil_div(N, 128) >= 64) return 128;
   return 64;
@@ -364,7 +364,7 @@ static int weight_grad(const float* dZ, int C, const Seg& x0, const Seg& x1, int
       if (s->cols == 0) continue;
       tc::Operand b = {s->p, s->ld, n, s->cols};
       tc::Problem p = {C, s->cols, (int)n, 0, 0, 0, cols0[i], 0, i == 0 ? x1.lead : 0, 0, nullptr, nullptr};
-      const int bn = (s->cols > 64 && option(OPT_WORKERS16) != 2) ? 128 : 64;
+      const int bn = (s->cols > 64 && option(OPT_WORKERS16) != 2 && option(OPT_BN64) == 0) ? 128 : 64;
       const int r = tc::launch<true, true, EPI_PARTIAL>(a0, a1, b, p, req, bn, e, (i == 0 && use_side) ? side->stream : st);
       if (r < 0) return r;
       if (r != splits) {

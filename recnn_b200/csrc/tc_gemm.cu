@@ -106,7 +106,7 @@ static int launch_cfg(const Operand& A0, const Operand& A1, const Operand& B, co
   }
   dim3 grid((unsigned)ceil_div(p.N, C::BN), (unsigned)ceil_div(p.M, C::BM), (unsigned)splits);
   if (g_span && g_span_next < g_span_cap) {
-    g_span_meta[g_span_next][0] = C::BN | (C::A_MN << 12) | (C::B_MN << 13) | (C::B_PRE << 14) | ((C::WORKERS == 16) << 15) | (EPI << 16);
+    g_span_meta[g_span_next][0] = C::BN | (C::A_MN << 12) | (C::B_MN << 13) | (C::B_PRE << 14) | ((C::WORKERS == 16) << 15) | (EPI << 16) | (C::LO2 << 20);
     g_span_meta[g_span_next][1] = p.M;
     g_span_meta[g_span_next][2] = p.N;
     g_span_meta[g_span_next][3] = (long long)(p.K0 + p.K1) | ((long long)splits << 32);
@@ -148,8 +148,12 @@ int launch(const Operand& A0, const Operand& A1, const Operand& B, const Problem
     }
   }
   RECNN_REQUIRE(B.lo == nullptr, "pre-split B is not available for this GEMM form");
-  if (option(OPT_WORKERS16) != 0 && bn < 128)
-    return launch_cfg<Cfg<64, 32, 6, A_MN, B_MN, false, 16>, EPI>(A0, A1, B, p, splits, epi, st);
+  if (bn < 128) {
+    const bool w16 = option(OPT_WORKERS16) != 0, lo2 = option(OPT_LO2) != 0;
+    if (w16 && lo2) return launch_cfg<Cfg<64, 32, 6, A_MN, B_MN, false, 16, true>, EPI>(A0, A1, B, p, splits, epi, st);
+    if (lo2) return launch_cfg<Cfg<64, 32, 6, A_MN, B_MN, false, 8, true>, EPI>(A0, A1, B, p, splits, epi, st);
+    if (w16) return launch_cfg<Cfg<64, 32, 6, A_MN, B_MN, false, 16>, EPI>(A0, A1, B, p, splits, epi, st);
+  }
   if (bn >= 128) return launch_cfg<Cfg<128, 32, 4, A_MN, B_MN>, EPI>(A0, A1, B, p, splits, epi, st);
   return launch_cfg<Cfg<64, 32, 6, A_MN, B_MN>, EPI>(A0, A1, B, p, splits, epi, st);
 }

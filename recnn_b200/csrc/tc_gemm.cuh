@@ -271,7 +271,8 @@ __device__ __forceinline__ unsigned long long gtimer() {
     if (p.trace) p.trace[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + (slot)] = gtimer(); \
   } while (0)
 
-template <int BN_, int BK_, int STAGES_, bool A_MN_, bool B_MN_, bool B_PRE_ = false, int WORKERS_ = 8>
+template <int BN_, int BK_, int STAGES_, bool A_MN_, bool B_MN_, bool B_PRE_ = false, int WORKERS_ = 8,
+          bool LO2_ = false>
 struct Cfg {
   // BK = 32 (128-byte K-major rows) when A is K-major: TMA moves 64-byte rows at half the rate of
   // 128-byte rows (measured: 31 B/clk/SM with BK = 16), and the operand stream is the kernel's bottleneck.
@@ -287,7 +288,15 @@ struct Cfg {
   // The split A tile goes to TENSOR memory (tcgen05.st) and the MMA reads it from there, so A costs
   // shared memory one TMA write + one read instead of write + read + 2 writes + 6 MMA reads.
   static constexpr bool A_TM = true;
-  static constexpr int A_SLOT_COLS = 2 * BK, A_SLOTS = (512 - 3 * BN) / A_SLOT_COLS;   // TMEM ring for A (hi | lo per k-block): 2 slots at BN = 128, 5 at BN = 64
+  // LO2: the two cross terms (lo_a*hi_b, hi_a*lo_b) get an accumulator EACH, and the three MMAs of a k-slice
+  // rotate over three different accumulators (lo_A, hi, lo_B).  Back-to-back tcgen05.mma into the SAME
+  // accumulator do not overlap: measured ~83 clk per 128x64x8 tf32 MMA (issue slot of the MMA warp, stall
+  // accounting) against a 32 clk tensor-pipe floor when two of every three MMAs hit d_lo in a row.  With three
+  // accumulators in rotation every accumulator is touched every third instruction.  Needs a fourth BN-wide
+  // accumulator in tensor memory: BN = 64 only (A ring shrinks from five slots to four).
+  static constexpr bool LO2 = LO2_;
+  static constexpr int D_COLS = (LO2 ? 4 : 3) * BN;                  // D_hi x2 | D_lo (| D_lo2)
+  static constexpr int A_SLOT_COLS = 2 * BK, A_SLOTS = (512 - D_COLS) / A_SLOT_COLS;   // TMEM ring for A (hi | lo per k-block): 2 slots at BN = 128, 5 (4 with LO2) at BN = 64
   static constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = (A_TM ? A_BYTES : 2 * A_BYTES) + 2 * B_BYTES;   // raw A (+lo A) | raw B | lo B
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
@@ -300,12 +309,14 @@ struct Cfg {
   static constexpr int COLS_PER_WORKER = BN / (WORKERS / 4);       // register-resident running sum per thread
   static constexpr int THREADS = 64 + 32 * WORKERS;
   static constexpr int TMEM_COLS = 512;                            // D_hi chunk x2 | D_lo | A ring
-  static constexpr int A_COL0 = 3 * BN;
+  static constexpr int A_COL0 = D_COLS;
   static constexpr int K_SWZ = BK * 4;                             // K-major rows: 64 B (SWIZZLE_64B) or 128 B (SWIZZLE_128B)
   static_assert(BN == 64 || BN == 128, "BN");
   static_assert(WORKERS == 8 || (WORKERS == 16 && BN == 64), "WORKERS");
   static_assert(COLS_PER_WORKER == 16 || COLS_PER_WORKER % 32 == 0, "drain width");
-  static_assert(WORKERS / 4 < A_SLOTS || WORKERS == 8, "every group in flight needs its own A slot");
+  static_assert(WORKERS / 4 <= A_SLOTS, "every group in flight needs its own A slot");
+  static_assert(!LO2 || BN == 64, "a second cross-term accumulator only fits next to 64-wide tiles");
+  static_assert(A_SLOTS >= 2, "A ring");
   static_assert(BK == 32, "BK: 128-byte operand rows");
   static_assert(SMEM_BYTES <= 227 * 1024, "smem");
 };
@@ -551,9 +562,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           const uint64_t db_hi = db_hi0 + uint64_t((k * b_kstep) >> 4);
           const uint64_t db_lo = db_lo0 + uint64_t((k * b_kstep) >> 4);
           const uint32_t ta_hi = ta0 + k * 8, ta_lo = ta_hi + BK;
-          mma_tf32_ta(d_lo, ta_lo, db_hi, idesc, (i | k) != 0);
-          mma_tf32_ta(d_lo, ta_hi, db_lo, idesc, 1);
-          mma_tf32_ta(d_hi, ta_hi, db_hi, idesc, ((i % CH) | k) != 0);
+          if (C::LO2) {                      // three accumulators in rotation: no back-to-back dependent MMAs
+            mma_tf32_ta(d_lo, ta_lo, db_hi, idesc, (i | k) != 0);
+            mma_tf32_ta(d_hi, ta_hi, db_hi, idesc, ((i % CH) | k) != 0);
+            mma_tf32_ta(d_lo + BN, ta_hi, db_lo, idesc, (i | k) != 0);
+          } else {
+            mma_tf32_ta(d_lo, ta_lo, db_hi, idesc, (i | k) != 0);
+            mma_tf32_ta(d_lo, ta_hi, db_lo, idesc, 1);
+            mma_tf32_ta(d_hi, ta_hi, db_hi, idesc, ((i % CH) | k) != 0);
+          }
         }
       }
       if (leader) {
@@ -690,6 +707,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     if (num_kb > 0) {
       // the commit behind the last acc_full covers every MMA issued before it, D_lo's included
       tmem_accumulate<NC>(lane_base + 2u * BN, acc);
+      if (C::LO2) tmem_accumulate<NC>(lane_base + 3u * BN, acc);
     }
     epilogue_row<EPI, NC>(epi, p, m0 + 32 * q + lane, n0 + g * NC, z, acc);
     if (t == 0) RECNN_TRACE(6);                               // epilogue stored

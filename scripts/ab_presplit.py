@@ -65,7 +65,33 @@ for name, M, N, K, b_mn in [("L1 fwd actor  [4096x1290]x[1290x256]", 4096, 256, 
         presplit = timeit(lambda: _lib.check(pre(M, N, K, a.data_ptr(), lda, None, ldb, b_mn, c1.data_ptr(), ldc, tile,
                                                  hi.data_ptr(), lo.data_ptr(), st)))
         same = bool(torch.equal(c0[:, :N], c1[:, :N]))
-        out.append({"gemm": name, "tile_n": tile, "classic_us_median": classic[0], "classic_us_min": classic[1],
-                    "presplit_us_median": presplit[0], "presplit_us_min": presplit[1], "bit_identical": same,
-                    "tf32_tflops_presplit": 3 * 2.0 * M * N * K / (presplit[0] * 1e-6) / 1e12})
+        rec = {"gemm": name, "tile_n": tile, "classic_us_median": classic[0], "classic_us_min": classic[1],
+               "presplit_us_median": presplit[0], "presplit_us_min": presplit[1], "bit_identical": same,
+               "tf32_tflops_presplit": 3 * 2.0 * M * N * K / (presplit[0] * 1e-6) / 1e12}
+        if tile == 64:                   # four split groups (16 worker warps) instead of two
+            c2 = torch.empty(M, ldc, device=dev)
+            prev = _lib.set_option("workers16", 1)
+            try:
+                w16 = timeit(lambda: _lib.check(L.recnn_gemm_tf32x3(M, N, K, a.data_ptr(), lda, 0, b.data_ptr(), ldb,
+                                                                    b_mn, c2.data_ptr(), ldc, tile, st)))
+            finally:
+                _lib.set_option("workers16", prev)
+            rec.update({"workers16_us_median": w16[0], "workers16_us_min": w16[1],
+                        "workers16_bit_identical": bool(torch.equal(c0[:, :N], c2[:, :N])),
+                        "tf32_tflops_workers16": 3 * 2.0 * M * N * K / (w16[0] * 1e-6) / 1e12})
+        if tile == 64:                   # two cross-term accumulators (three-way accumulator rotation), 8 and 16 workers
+            for w16 in (0, 1):
+                c3 = torch.empty(M, ldc, device=dev)
+                p0, p1 = _lib.set_option("lo2", 1), _lib.set_option("workers16", w16)
+                try:
+                    t = timeit(lambda: _lib.check(L.recnn_gemm_tf32x3(M, N, K, a.data_ptr(), lda, 0, b.data_ptr(), ldb,
+                                                                      b_mn, c3.data_ptr(), ldc, tile, st)))
+                finally:
+                    _lib.set_option("lo2", p0)
+                    _lib.set_option("workers16", p1)
+                key = "lo2_w16" if w16 else "lo2"
+                rec.update({key + "_us_median": t[0], key + "_us_min": t[1],
+                            key + "_max_abs_diff": float((c3[:, :N] - c0[:, :N]).abs().max()),
+                            "tf32_tflops_" + key: 3 * 2.0 * M * N * K / (t[0] * 1e-6) / 1e12})
+        out.append(rec)
 print(json.dumps({"ab_presplit": out}))

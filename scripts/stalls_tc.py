@@ -9,7 +9,7 @@ if len(sys.argv) > 1:
     h.recnn_debug_set_trace.argtypes = [ctypes.c_void_p]
     st = torch.cuda.current_stream().cuda_stream
     names = ["wk.full", "wk.a_free", "wk.drain", "wk.loop", "mma.split", "mma.acc_empty", "tma.empty", "wk.drain_ld"]
-    for (M, N, K, tile, amn, bmn) in [(4096, 256, 1290, 128, 0, 0), (4096, 256, 1290, 64, 0, 0)]:
+    for (M, N, K, tile, amn, bmn) in [(4096, 256, 1290, 128, 0, 0), (4096, 256, 1290, 64, 0, 0), (4096, 256, 256, 64, 0, 0)]:
         if amn:
             A = torch.randn(K, M, device=DEV); B = torch.randn(K, (N + 3) // 4 * 4, device=DEV); lda, ldb = M, B.shape[1]
         else:
@@ -31,6 +31,7 @@ if len(sys.argv) > 1:
         print("dbg=%-3s M%d N%d K%d t%d mn%d%d span %.1f us | " % (os.environ.get("RECNN_TC_DBG"), M, N, K, tile, amn, bmn, span) +
               "  ".join("%s %.0f" % (n, v) for n, v in zip(names, med)))
     sys.exit(0)
-for dbg in ("16", str(16 + (4 << 8)), str(16 + (8 << 8))):
+# RECNN_B200_WORKERS16=1 in the environment profiles the 16-worker kernel at tile 64
+for dbg in (("16",) if os.environ.get("STALLS_QUICK") else ("16", str(16 + (4 << 8)), str(16 + (8 << 8)))):
     r = subprocess.run([sys.executable, __file__, "child"], env=dict(os.environ, RECNN_TC_DBG=dbg), capture_output=True, text=True, timeout=120)
     print(r.stdout.strip() or r.stderr[-600:])

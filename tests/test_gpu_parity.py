@@ -272,6 +272,24 @@ def test_sixteen_worker_gemm_in_the_step(algo, value):
             assert np.array_equal(base[k], got[k]), k
 
 
+@pytest.mark.parametrize("opts", [dict(lo2=1), dict(lo2=1, bn64=1), dict(lo2=1, bn64=1, workers16=1)],
+                         ids=["lo2", "lo2-bn64", "lo2-bn64-w16"])
+@pytest.mark.parametrize("algo", ["ddpg", "td3"])
+def test_lo2_gemm_in_the_step_meets_the_golden_bar(algo, opts):
+    """The step on the two-cross-term-accumulator kernels (optionally on 64-wide tiles everywhere and with
+    16 worker warps) against the golden vectors of the unmodified reference: the same 1e-5 bar as the default."""
+    gold = load_golden("%s_canon_adam.npz" % algo)
+    prev = {k: _lib.set_option(k, v) for k, v in opts.items()}
+    try:
+        got = run_cuda_case("canon", algo, "adam", golden=gold, form="frames")
+        got_sgd = run_cuda_case("tiny", algo, "sgd", golden=load_golden("%s_tiny_sgd.npz" % algo), form="dense")
+    finally:
+        for k, v in prev.items():
+            _lib.set_option(k, v)
+    compare_with_golden(got, gold, check_grads=(algo == "ddpg"))
+    compare_with_golden(got_sgd, load_golden("%s_tiny_sgd.npz" % algo), check_grads=(algo == "ddpg"))
+
+
 def test_sixteen_worker_gemm_perf_mode_dropout_matches():
     """Device-Philox dropout (perf mode) indexes keep-bits by element, not by tile: the 16-worker kernel's
     16-column epilogue blocks must draw the same masks as the 32-column blocks of the default kernel."""

@@ -166,3 +166,51 @@ def test_sixteen_worker_kernel_is_bit_identical(M, N, K, a_mn, b_mn):
         _lib.set_option("workers16", prev)
     assert np.array_equal(got, want)
     assert np.abs(got - ref).max() / np.abs(ref).max() < 2e-6
+
+
+# ----------------------------------------------------------------------------- two cross-term accumulators (LO2)
+class _options:
+    def __init__(self, **kw):
+        self.kw, self.prev = kw, {}
+
+    def __enter__(self):
+        for k, v in self.kw.items():
+            self.prev[k] = _lib.set_option(k, v)
+
+    def __exit__(self, *exc):
+        for k, v in self.prev.items():
+            _lib.set_option(k, v)
+
+
+@pytest.mark.parametrize("w16", [0, 1])
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("M,N,K", [(128, 64, 16), (128, 256, 64), (128, 256, 96), (300, 256, 1290), (4096, 256, 1290),
+                                   (4096, 128, 256), (1000, 100, 77), (256, 1290, 4096)])
+def test_two_cross_term_accumulators(M, N, K, a_mn, b_mn, w16):
+    """Option "lo2": lo_a*hi_b and hi_a*lo_b accumulate in separate TMEM tiles and the three MMAs of a k-slice
+    rotate over three accumulators.  Same products, one more fp32 add per element at the end: same accuracy bar
+    as the default kernel, and within 2 ulp-of-the-result-scale of it."""
+    base, want = _run("tc", M, N, K, a_mn, b_mn, seed=M + K, tile_n=64)
+    with _options(lo2=1, workers16=w16):
+        got, _ = _run("tc", M, N, K, a_mn, b_mn, seed=M + K, tile_n=64)
+    assert np.isfinite(got).all()
+    assert np.abs(got - want).max() / np.sqrt(K) < 8e-6
+    assert np.abs(got - want).max() / np.abs(want).max() < 8e-6
+    assert np.abs(got - base).max() / np.abs(want).max() < 5e-7
+
+
+def test_two_cross_term_accumulators_long_positive_k():
+    """No truncation bias with the extra accumulator either (cf. test_accumulation_is_not_truncated_over_long_k)."""
+    rng = np.random.default_rng(12)
+    M = N = 256
+    K = 4096
+    a = rng.uniform(0.5, 1.0, (M, K)).astype(np.float32)
+    b = rng.uniform(0.5, 1.0, (N, K)).astype(np.float32)
+    a_d, b_d = torch.from_numpy(a).to(DEV), torch.from_numpy(b).to(DEV)
+    c_d = torch.empty(M, N, device=DEV)
+    with _options(lo2=1):
+        _lib.check(_lib.lib().recnn_gemm_tf32x3(M, N, K, a_d.data_ptr(), K, 0, b_d.data_ptr(), K, 0, c_d.data_ptr(), N,
+                                               64, torch.cuda.current_stream().cuda_stream))
+    want = a.astype(np.float64) @ b.astype(np.float64).T
+    rel = (c_d.cpu().numpy() - want) / want
+    assert abs(rel.mean()) < 5e-7 and np.abs(rel).max() < 2e-6, (rel.mean(), np.abs(rel).max())
