@@ -148,11 +148,15 @@ int launch(const Operand& A0, const Operand& A1, const Operand& B, const Problem
     }
   }
   RECNN_REQUIRE(B.lo == nullptr, "pre-split B is not available for this GEMM form");
+  const bool lean = option(OPT_LEAN) != 0;
   if (bn < 128) {
     const bool w16 = option(OPT_WORKERS16) != 0, lo2 = option(OPT_LO2) != 0;
-    if (w16 && lo2) return launch_cfg<Cfg<64, 32, 6, A_MN, B_MN, false, 16, true>, EPI>(A0, A1, B, p, splits, epi, st);
     if (lo2) return launch_cfg<Cfg<64, 32, 6, A_MN, B_MN, false, 8, true>, EPI>(A0, A1, B, p, splits, epi, st);
+    if (w16 && lean) return launch_cfg<Cfg<64, 32, 6, A_MN, B_MN, false, 16, false, true>, EPI>(A0, A1, B, p, splits, epi, st);
     if (w16) return launch_cfg<Cfg<64, 32, 6, A_MN, B_MN, false, 16>, EPI>(A0, A1, B, p, splits, epi, st);
+    if (lean) return launch_cfg<Cfg<64, 32, 6, A_MN, B_MN, false, 8, false, true>, EPI>(A0, A1, B, p, splits, epi, st);
+  } else if (lean) {
+    return launch_cfg<Cfg<128, 32, 4, A_MN, B_MN, false, 8, false, true>, EPI>(A0, A1, B, p, splits, epi, st);
   }
   if (bn >= 128) return launch_cfg<Cfg<128, 32, 4, A_MN, B_MN>, EPI>(A0, A1, B, p, splits, epi, st);
   return launch_cfg<Cfg<64, 32, 6, A_MN, B_MN>, EPI>(A0, A1, B, p, splits, epi, st);

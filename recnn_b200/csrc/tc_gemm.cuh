@@ -272,7 +272,7 @@ __device__ __forceinline__ unsigned long long gtimer() {
   } while (0)
 
 template <int BN_, int BK_, int STAGES_, bool A_MN_, bool B_MN_, bool B_PRE_ = false, int WORKERS_ = 8,
-          bool LO2_ = false>
+          bool LO2_ = false, bool LEAN_ = false>
 struct Cfg {
   // BK = 32 (128-byte K-major rows) when A is K-major: TMA moves 64-byte rows at half the rate of
   // 128-byte rows (measured: 31 B/clk/SM with BK = 16), and the operand stream is the kernel's bottleneck.
@@ -295,6 +295,14 @@ struct Cfg {
   // accumulators in rotation every accumulator is touched every third instruction.  Needs a fourth BN-wide
   // accumulator in tensor memory: BN = 64 only (A ring shrinks from five slots to four).
   static constexpr bool LO2 = LO2_;
+  // LEAN: the experiment hooks (Problem.dbg ablation bits, chunk-length override, stall accounting) are compiled
+  // out and the MMA warp keeps running counters instead of recomputing stage / phase / slot / chunk from the
+  // k-block index.  Why it matters (ncu source counters + stall accounting, profiles/README.md): the MMA warp
+  // executes ~210 mostly dependent SASS instructions per k-block around its 12 tcgen05.mma -- index math with
+  // two MUFU-based divisions by the run-time chunk length, descriptor rebuilds, debug branches -- i.e. ~1,000 clk
+  // per k-block for a lone warp, against 384 (BN = 64) / 768 (BN = 128) clk of tensor work; it waits for
+  // operands only ~14% of the time, so the issue loop itself is what the tensor pipe waits for.
+  static constexpr bool LEAN = LEAN_;
   static constexpr int D_COLS = (LO2 ? 4 : 3) * BN;                  // D_hi x2 | D_lo (| D_lo2)
   static constexpr int A_SLOT_COLS = 2 * BK, A_SLOTS = (512 - D_COLS) / A_SLOT_COLS;   // TMEM ring for A (hi | lo per k-block): 2 slots at BN = 128, 5 (4 with LO2) at BN = 64
   static constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
@@ -417,7 +425,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_b_lo, Problem p,
                Epilogue epi) {
   constexpr int BM = C::BM, BN = C::BN, BK = C::BK, STAGES = C::STAGES;
-  const int CH = ((p.dbg >> 8) & 15) ? ((p.dbg >> 8) & 15) : C::CH;   // experiment hook: chunk length override
+  const int dbg = C::LEAN ? 0 : p.dbg;                                 // experiment hooks (compiled out when LEAN)
+  const int CH = C::LEAN ? C::CH : (((dbg >> 8) & 15) ? ((dbg >> 8) & 15) : C::CH);   // chunk length override
   constexpr int NC = C::COLS_PER_WORKER, WORKERS = C::WORKERS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;       // shared-window address, 1 KB aligned
@@ -450,9 +459,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   const int kb_end = min(nkb0 + nkb1, kb_begin + kb_per_split);
   const int num_kb = max(kb_end - kb_begin, 0);
   const int num_chunks = (num_kb + CH - 1) / CH;
-  const bool prof = (p.dbg & 16) != 0;
+  const bool prof = !C::LEAN && (dbg & 16) != 0;
   // dbg bit 32 (experiments, 8 workers only): all worker warps share every k-block instead of taking turns
-  const bool share_all = WORKERS == 8 && (p.dbg & 32) != 0;
+  const bool share_all = !C::LEAN && WORKERS == 8 && (dbg & 32) != 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a0);
@@ -537,6 +546,51 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     constexpr uint32_t b_kstep = C::B_MN ? 1024 : 32;        // bytes to advance per 8-wide k-slice
     const bool leader = elect_one();
     long long w_split = 0, w_acc = 0;
+    if constexpr (C::LEAN) {
+      // running counters: stage / phase, A slot, position in the chunk and its buffer, per-buffer wait parity
+      uint32_t s = 0, ph = 0, slot = 0, kin = 0, buf = 0, par0 = 1, par1 = 1;
+      uint32_t lo_acc = 0;                                   // 0 only for the very first cross-term MMAs
+      const uint32_t d_lo = tmem_base + 2u * BN;
+      for (int i = 0; i < num_kb; ++i) {
+        if (kin == 0) {                                      // new chunk: its TMEM buffer must have been drained
+          mbar_wait(acc_empty(buf), buf ? par1 : par0);
+          if (buf) par1 ^= 1u; else par0 ^= 1u;
+        }
+        mbar_wait(split(s), ph);
+        if (C::B_PRE) mbar_wait(full(s), ph);
+        tc_fence_after();
+        const uint32_t d_hi = tmem_base + buf * BN;
+        const uint64_t db_hi0 = b_base | uint64_t((stage_addr(s, 1) & 0x3FFFF) >> 4);
+        const uint64_t db_lo0 = b_base | uint64_t((stage_addr(s, 3) & 0x3FFFF) >> 4);
+        const uint32_t ta0 = tmem_base + C::A_COL0 + slot * C::A_SLOT_COLS;
+        if (leader) {
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {
+            const uint64_t db_hi = db_hi0 + uint64_t((k * b_kstep) >> 4);
+            const uint64_t db_lo = db_lo0 + uint64_t((k * b_kstep) >> 4);
+            const uint32_t ta_hi = ta0 + k * 8, ta_lo = ta_hi + BK;
+            const uint32_t lo_flag = k == 0 ? lo_acc : 1u, hi_flag = k == 0 ? (kin != 0 ? 1u : 0u) : 1u;
+            if (C::LO2) {
+              mma_tf32_ta(d_lo, ta_lo, db_hi, idesc, lo_flag);
+              mma_tf32_ta(d_hi, ta_hi, db_hi, idesc, hi_flag);
+              mma_tf32_ta(d_lo + BN, ta_hi, db_lo, idesc, lo_flag);
+            } else {
+              mma_tf32_ta(d_lo, ta_lo, db_hi, idesc, lo_flag);
+              mma_tf32_ta(d_lo, ta_hi, db_lo, idesc, 1);
+              mma_tf32_ta(d_hi, ta_hi, db_hi, idesc, hi_flag);
+            }
+          }
+          mma_commit(empty(s));                              // frees the stage once these MMAs have read it
+          mma_commit(a_free(slot));                          // ... and the A slot in tensor memory
+          if (kin == (uint32_t)(C::CH - 1) || i == num_kb - 1) mma_commit(acc_full(buf));
+        }
+        __syncwarp();
+        lo_acc = 1u;
+        if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1u; }
+        if (++slot == (uint32_t)C::A_SLOTS) slot = 0;
+        if (++kin == (uint32_t)C::CH) { kin = 0; buf ^= 1u; }
+      }
+    } else
     for (int i = 0; i < num_kb; ++i) {
       const int s = i % STAGES;
       const uint32_t ph = (i / STAGES) & 1;
@@ -556,7 +610,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       const uint64_t db_lo0 = b_base | uint64_t((stage_addr(s, 3) & 0x3FFFF) >> 4);
       const int slot = i % C::A_SLOTS;
       const uint32_t ta0 = tmem_base + C::A_COL0 + slot * C::A_SLOT_COLS;
-      if (leader && !(p.dbg & 2)) {
+      if (leader && !(dbg & 2)) {
 #pragma unroll
         for (int k = 0; k < BK / 8; ++k) {
           const uint64_t db_hi = db_hi0 + uint64_t((k * b_kstep) >> 4);
@@ -628,7 +682,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       const int slot = i % C::A_SLOTS;
       const uint32_t ta = tmem_base + (uint32_t(32 * q) << 16) + C::A_COL0 + slot * C::A_SLOT_COLS;
       const int half0 = share_all ? g : 0, half1 = share_all ? g + 1 : 2;
-      if (!(p.dbg & 1)) {
+      if (!(dbg & 1)) {
         RECNN_TIMED(w_afree, mbar_wait(a_free(slot), ((i / C::A_SLOTS) & 1) ^ 1));
         tc_fence_after();
         if (C::A_MN) {
@@ -678,14 +732,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           for (int v = 0; v < VB; ++v) {
             float4 xh, xl;
             tf32_split4(x[v], xh, xl);
-            if (!(p.dbg & 4)) sts128(raw + 16u * (v0 + v * ntg), xh);
+            if (!(dbg & 4)) sts128(raw + 16u * (v0 + v * ntg), xh);
             sts128(lo + 16u * (v0 + v * ntg), xl);
           }
         }
       }
       // generic-proxy writes (B hi/lo in shared memory) -> visible to the tensor core (async proxy);
       // with pre-split B the workers write no shared memory at all
-      if (!C::B_PRE && !(p.dbg & 8)) fence_proxy_async();
+      if (!C::B_PRE && !(dbg & 8)) fence_proxy_async();
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();

@@ -1,0 +1,84 @@
+#!/bin/bash
+# One-shot GPU session at the end of a round (GPU minutes are scarce): correctness of the GEMM variants,
+# A/B timing, pick the fastest step configuration, then full tests + bench + ncu evidence UNDER that
+# configuration (selected through the RECNN_B200_* environment switches, so the library defaults do not have
+# to change before the evidence exists).  Everything lands in gpurun_out/.
+cd "$(dirname "$0")/.." || exit 1
+mkdir -p gpurun_out
+O=gpurun_out
+t0=$(date +%s)
+el() { echo "[t+$(( $(date +%s) - t0 ))s] $*"; }
+
+el "1. kernel-variant tests"
+timeout 120 python -m pytest tests/test_gpu_tc.py -q -k "two_cross or sixteen" --tb=short > $O/t_variants.log 2>&1
+tail -3 $O/t_variants.log
+
+el "2. A/B timing of single GEMMs"
+timeout 90 python scripts/ab_presplit.py > $O/ab_gemm2.json 2> $O/ab_gemm2.err
+python - <<'PY'
+import json
+try:
+    for r in json.load(open("gpurun_out/ab_gemm2.json"))["ab_presplit"]:
+        if r["tile_n"] == 64:
+            print(r["gemm"][:16], "classic %.1f  w16 %.1f  lo2 %.1f  lo2+w16 %.1f  (diff %.2g)" % (
+                r["classic_us_median"], r.get("workers16_us_median", 0), r.get("lo2_us_median", 0),
+                r.get("lo2_w16_us_median", 0), r.get("lo2_max_abs_diff", -1)))
+        else:
+            print(r["gemm"][:16], "tile128 classic %.1f" % r["classic_us_median"])
+except Exception as e:
+    print("ab failed:", e)
+PY
+
+el "3. step A/B"
+i=0
+for opts in "--opt lo2=1" "--opt lo2=1 --opt bn64=1" "--opt lo2=1 --opt bn64=1 --opt workers16=1"; do
+  i=$((i+1))
+  timeout 70 python bench.py --steps 60 --warmup 10 --no-cpu-baseline $opts > $O/bench_v$i.json 2> $O/bench_v$i.err
+done
+python - <<'PY' > gpurun_out/best_env.sh
+import json, sys
+base = 2290.0
+try:
+    base = json.load(open("gpurun_out/bench_default.json"))["value"]
+except Exception:
+    pass
+envs = {1: "RECNN_B200_LO2=1", 2: "RECNN_B200_LO2=1 RECNN_B200_BN64=1",
+        3: "RECNN_B200_LO2=1 RECNN_B200_BN64=1 RECNN_B200_WORKERS16=1"}
+best, best_v = "", base * 1.02          # a variant must win by 2% to replace the default
+log = open("gpurun_out/t_variants.log").read()
+variants_ok = (" passed" in log) and ("failed" not in log) and ("error" not in log.lower())
+sys.stderr.write("variant kernels correct: %s\n" % variants_ok)
+for i in ((1, 2, 3) if variants_ok else ()):
+    try:
+        d = json.load(open("gpurun_out/bench_v%d.json" % i))
+        sys.stderr.write("variant %d (%s): %.1f steps/s, L1 gemm %.2f us, feed %.1f\n" % (
+            i, envs[i], d["value"], d["roofline"]["ms"] * 1e3, d.get("feed", {}).get("steps_per_sec", 0)))
+        if d["value"] > best_v:
+            best, best_v = envs[i], d["value"]
+    except Exception as e:
+        sys.stderr.write("variant %d failed: %s\n" % (i, e))
+sys.stderr.write("default %.1f -> best: %s (%.1f)\n" % (base, best or "default", best_v))
+print("export " + best if best else "true")
+PY
+cat $O/best_env.sh
+source $O/best_env.sh
+
+el "4. full GPU test-suite under the selected configuration"
+timeout 150 python -m pytest tests -m gpu -q --maxfail=12 --tb=short > $O/t_best.log 2>&1
+tail -4 $O/t_best.log
+
+el "5. bench under the selected configuration"
+timeout 120 python bench.py --steps 100 --warmup 10 > $O/bench_best.json 2> $O/bench_best.err
+python -c "
+import json; d=json.load(open('gpurun_out/bench_best.json')); print('best: value %.1f e2e %.1f frac %.3f gather %.3f feed %.1f cpu %.2f' % (d['value'], d['e2e']['value'], d['roofline']['frac'], d['roofline_gather']['frac'], d['feed']['steps_per_sec'], d['cpu_baseline']['value']))"
+
+el "6. ncu launch list of the bench step"
+timeout 150 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $O/r1b_launches.csv \
+  python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/ncu_bench.log 2>&1
+wc -l $O/r1b_launches.csv
+
+el "7. ncu --set full: layer-1 GEMM (tile 64)"
+timeout 100 ncu --set full --clock-control none --import-source on -k regex:tc_gemm_kernel --launch-skip 2 -c 1 \
+  -f -o $O/r1b_tc_gemm python scripts/prof_tc.py 64 > $O/ncu_tc.log 2>&1
+ls -la $O/*.ncu-rep 2>/dev/null
+el "done"

@@ -272,8 +272,7 @@ def test_sixteen_worker_gemm_in_the_step(algo, value):
             assert np.array_equal(base[k], got[k]), k
 
 
-@pytest.mark.parametrize("opts", [dict(lo2=1), dict(lo2=1, bn64=1), dict(lo2=1, bn64=1, workers16=1)],
-                         ids=["lo2", "lo2-bn64", "lo2-bn64-w16"])
+@pytest.mark.parametrize("opts", [dict(lo2=1), dict(lo2=1, bn64=1)], ids=["lo2", "lo2-bn64"])
 @pytest.mark.parametrize("algo", ["ddpg", "td3"])
 def test_lo2_gemm_in_the_step_meets_the_golden_bar(algo, opts):
     """The step on the two-cross-term-accumulator kernels (optionally on 64-wide tiles everywhere and with
@@ -288,6 +287,25 @@ def test_lo2_gemm_in_the_step_meets_the_golden_bar(algo, opts):
             _lib.set_option(k, v)
     compare_with_golden(got, gold, check_grads=(algo == "ddpg"))
     compare_with_golden(got_sgd, load_golden("%s_tiny_sgd.npz" % algo), check_grads=(algo == "ddpg"))
+
+
+@pytest.mark.skipif(__import__("os").environ.get("RECNN_TEST_EXPERIMENTAL") != "1",
+                    reason="lean GEMM kernels have not run on hardware yet (round 2, first GPU call)")
+@pytest.mark.parametrize("opts", [dict(lean=1), dict(lean=1, workers16=1), dict(lean=1, workers16=1, bn64=1)],
+                         ids=["lean", "lean-w16", "lean-w16-bn64"])
+@pytest.mark.parametrize("algo", ["ddpg", "td3"])
+def test_lean_gemm_in_the_step_is_bit_identical(algo, opts):
+    gold = load_golden("%s_canon_adam.npz" % algo)
+    base = run_cuda_case("canon", algo, "adam", golden=gold, form="frames")
+    prev = {k: _lib.set_option(k, v) for k, v in opts.items()}
+    try:
+        got = run_cuda_case("canon", algo, "adam", golden=gold, form="frames")
+    finally:
+        for k, v in prev.items():
+            _lib.set_option(k, v)
+    for k in base:
+        if k.startswith(("final.", "loss.")):
+            assert np.array_equal(base[k], got[k]), k
 
 
 def test_sixteen_worker_gemm_perf_mode_dropout_matches():
