@@ -399,7 +399,7 @@ def run_native(args):
             "roofline": {"bound": "tensor", "kernel": "layer-1 forward GEMM [4096x1290]x[1290x256] (tc_gemm_kernel, tcgen05 kind::tf32, 3 MMA passes/product)",
                          "achieved": 3.0 * l1_tflops, "algorithmic_fp32": l1_tflops, "peak": tf32_peak, "unit": "TFLOP/s",
                          "frac": 3.0 * l1_tflops / tf32_peak,
-                         "traffic": 22525184, "traffic_source": "dram__bytes_read+write per launch, profiles/README.md (ncu --set full, r1)", "peak_source": "%s bf16 %.0f TF/s / 2 (TF32 kind)" % (peaks["source"], peaks["bf16"]),
+                         "traffic": 22525184, "traffic_source": "dram__bytes_read+write per launch, profiles/r1b_ncu_tc_gemm_tile64_summary.csv (ncu --set full)", "peak_source": "%s bf16 %.0f TF/s / 2 (TF32 kind)" % (peaks["source"], peaks["bf16"]),
                          "ms": l1_ms},
             "roofline_gather": {"bound": "hbm", "kernel": "frame_gather_kernel", "achieved": gather_gbs,
                                 "peak": peaks["hbm"], "unit": "GB/s", "frac": gather_gbs / peaks["hbm"],

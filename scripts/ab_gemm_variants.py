@@ -1,7 +1,7 @@
 """A/B timing of the tcgen05 GEMM with in-kernel B split vs pre-split B planes (tc::Cfg::B_PRE), alone on
 the GPU, on the shapes of the update step.  CUDA events, L2 flushed between launches.  Prints one JSON line.
 
-    python scripts/ab_presplit.py > gpurun_out/ab_presplit.json
+    python scripts/ab_gemm_variants.py > gpurun_out/ab_presplit.json
 """
 import ctypes as C
 import json

@@ -14,7 +14,7 @@ timeout 120 python -m pytest tests/test_gpu_tc.py -q -k "two_cross or sixteen" -
 tail -3 $O/t_variants.log
 
 el "2. A/B timing of single GEMMs"
-timeout 90 python scripts/ab_presplit.py > $O/ab_gemm2.json 2> $O/ab_gemm2.err
+timeout 90 python scripts/ab_gemm_variants.py > $O/ab_gemm2.json 2> $O/ab_gemm2.err
 python - <<'PY'
 import json
 try:
