@@ -15,6 +15,9 @@ are produced here by differential execution of its own functions):
                  from batch_tensor_embeddings, for (i) all 14 synthetic users in storage order and
                  (ii) a shuffled 6-user minibatch.  Ragged lengths incl. the minimum F+1, float64
                  ratings that are not fp32-representable (pins the ``.float()`` rounding).
+* ingest.npz  -- recnn.data.dataset_functions.prepare_dataset + utils.make_items_tensor + sort_users_itemwise on a
+                 synthetic ratings table (24 users, sparse movie ids, unsorted timestamps): surviving users and
+                 their order, per-user time-ordered item rows / mapped ratings.
 * ddpg_<case>.npz / td3_<case>.npz -- recnn.nn.update.ddpg_update / td3_update,
                  12 consecutive steps (policy steps 0 and 10 included), torch.optim
                  Adam(lr=1e-5) and SGD(lr=1e-3) passed through the reference's
@@ -256,11 +259,59 @@ def run_collate_case(recnn):
     return out
 
 
+def ingest_case_frames(n_users=24, n_items=60, dim=6, seed=5):
+    """A small ML-20M-shaped ratings table (userId, movieId, rating, timestamp) and {movieId: embedding}:
+    sparse non-contiguous movie ids, half-star ratings, unique timestamps (so the time order is unambiguous),
+    users with 3..40 interactions (some at or below frame_size, which the ingest must drop)."""
+    import pandas as pd
+    rng = np.random.default_rng(seed)
+    movie_ids = np.sort(rng.choice(np.arange(1, 5000), size=n_items, replace=False))
+    emb = {int(m): torch.from_numpy(rng.standard_normal(dim).astype(np.float32)) for m in movie_ids}
+    rows = []
+    t = 1_000_000
+    for u in range(n_users):
+        uid = 10 + 13 * u
+        n = int(rng.integers(3, 41))
+        for _ in range(n):
+            t += int(rng.integers(1, 1000))
+            rows.append((uid, int(rng.choice(movie_ids)), float(rng.integers(1, 11)) / 2.0, t))
+    order = rng.permutation(len(rows))                       # the CSV is not time-sorted
+    df = pd.DataFrame([rows[i] for i in order], columns=["userId", "movieId", "rating", "timestamp"])
+    return df, emb
+
+
+def run_ingest_case(recnn):
+    """recnn.data.dataset_functions.prepare_dataset (the ingest behind Env.process_env, recnn/data/env.py:133-176)
+    on the synthetic table: which users survive, in which order, and their time-ordered item-row / rating arrays."""
+    frame = 10
+    df, emb = ingest_case_frames()
+    table, key_to_id, id_to_key = recnn.data.utils.make_items_tensor(emb)
+    base = recnn.data.env.EnvBase()
+    base.embeddings, base.key_to_id, base.id_to_key = table, key_to_id, id_to_key
+    dset = recnn.data.dataset_functions
+    args = dset.DataFuncArgsMut(df=df.copy(), base=base, users=None, user_dict=None)
+    dset.prepare_dataset(args, dset.DataFuncKwargs(frame_size=frame))
+    out = {"frame_size": np.int64(frame), "table": table.numpy(), "users": np.asarray(list(args.users), dtype=np.int64),
+           "keys": np.asarray(sorted(emb), dtype=np.int64), "all_users": np.asarray(sorted(args.user_dict), dtype=np.int64)}
+    for col in ("userId", "movieId", "rating", "timestamp"):                # the input table itself
+        out["csv." + col] = df[col].to_numpy()
+    out["emb"] = np.stack([emb[k].numpy() for k in sorted(emb)])
+    for u in args.user_dict:
+        out["u%d.items" % u] = np.asarray(args.user_dict[u]["items"])
+        out["u%d.ratings" % u] = np.asarray(args.user_dict[u]["ratings"])
+    sorted_users = recnn.data.utils.sort_users_itemwise(args.user_dict, list(args.users))
+    out["sorted_users"] = np.asarray(list(sorted_users), dtype=np.int64)
+    return out
+
+
 def main():
     torch.set_num_threads(max(1, min(8, os.cpu_count() or 1)))
     recnn = import_reference()
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     only = set(sys.argv[1:])
+    if not only or "ingest" in only:
+        np.savez_compressed(os.path.join(GOLDEN_DIR, "ingest.npz"), **run_ingest_case(recnn))
+        print("wrote ingest.npz")
     if not only or "collate" in only:
         np.savez_compressed(os.path.join(GOLDEN_DIR, "collate.npz"), **run_collate_case(recnn))
         print("wrote collate.npz")
