@@ -1,7 +1,7 @@
-"""A/B timing of the tcgen05 GEMM with in-kernel B split vs pre-split B planes (tc::Cfg::B_PRE), alone on
-the GPU, on the shapes of the update step.  CUDA events, L2 flushed between launches.  Prints one JSON line.
+"""A/B timing of the tcgen05 GEMM variants (in-kernel B split = default, pre-split B planes, 16 workers, two
+cross-term accumulators, LEAN issue loop), each alone on the GPU, on the shapes of the update step.  CUDA events, L2 flushed between launches.  Prints one JSON line.
 
-    python scripts/ab_gemm_variants.py > gpurun_out/ab_presplit.json
+    python scripts/ab_gemm_variants.py > gpurun_out/ab_gemm.json
 """
 import ctypes as C
 import json
@@ -93,5 +93,22 @@ for name, M, N, K, b_mn in [("L1 fwd actor  [4096x1290]x[1290x256]", 4096, 256, 
                 rec.update({key + "_us_median": t[0], key + "_us_min": t[1],
                             key + "_max_abs_diff": float((c3[:, :N] - c0[:, :N]).abs().max()),
                             "tf32_tflops_" + key: 3 * 2.0 * M * N * K / (t[0] * 1e-6) / 1e12})
+        # LEAN kernels (experiment hooks compiled out, running counters in the MMA warp), 8 and (tile 64) 16 workers
+        for w16 in ((0, 1) if tile == 64 else (0,)):
+            c4 = torch.empty(M, ldc, device=dev)
+            p0, p1 = _lib.set_option("lean", 1), _lib.set_option("workers16", w16)
+            try:
+                t = timeit(lambda: _lib.check(L.recnn_gemm_tf32x3(M, N, K, a.data_ptr(), lda, 0, b.data_ptr(), ldb,
+                                                                  b_mn, c4.data_ptr(), ldc, tile, st)))
+            except Exception as exc:                       # a trap in an unvalidated kernel must not lose the other rows
+                rec["lean_error"] = str(exc)[:200]
+                break
+            finally:
+                _lib.set_option("lean", p0)
+                _lib.set_option("workers16", p1)
+            key = "lean_w16" if w16 else "lean"
+            rec.update({key + "_us_median": t[0], key + "_us_min": t[1],
+                        key + "_bit_identical": bool(torch.equal(c0[:, :N], c4[:, :N])),
+                        "tf32_tflops_" + key: 3 * 2.0 * M * N * K / (t[0] * 1e-6) / 1e12})
         out.append(rec)
 print(json.dumps({"ab_presplit": out}))
