@@ -124,6 +124,7 @@ extern "C" int recnn_window_gather_users(const int64_t* hist_items, const float*
                                          int64_t* items, float* ratings, float* done, int64_t* sizes,
                                          int* err_flag, void* stream) {
   RECNN_REQUIRE(n_batch > 0 || n_rows == 0, "a non-empty minibatch needs at least one user");
+  if (n_batch == 0) return RECNN_OK;            // nothing to cut
   return recnn::launch_window_gather(false, hist_items, hist_ratings, hist_offsets, n_users, batch_users,
                                      row_offsets, n_batch, frame, n_rows, items, ratings, done, sizes, err_flag,
                                      static_cast<cudaStream_t>(stream));

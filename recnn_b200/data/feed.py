@@ -174,6 +174,8 @@ class DeviceFrameFeed:
         that order: what ``prepare_batch_static_size`` hands to ``embed_batch`` for the same users."""
         row_offsets, n_rows = self.csr.plan_users(user_positions)
         pos = np.asarray(user_positions, dtype=np.int64).reshape(-1)
+        if pos.size == 0:
+            raise ValueError("empty minibatch: need at least one user")    # np.concatenate([]) raises in the reference too
         plan = torch.from_numpy(np.concatenate([pos, row_offsets])).to(self.device)      # one small H2D
         items, ratings, done, sizes = self._gather_users(plan[:pos.size], plan[pos.size:], pos.size, n_rows)
         if check:
