@@ -143,6 +143,12 @@ int launch(const Operand& A0, const Operand& A1, const Operand& B, const Problem
   // every epilogue but the split-K partial.
   if constexpr (!A_MN && EPI != EPI_PARTIAL) {
     if (B.lo != nullptr) {
+      if (option(OPT_LEAN) != 0) {             // unvalidated combinations for the round-2 A/B (see Cfg::LEAN)
+        if (bn >= 128) return launch_cfg<Cfg<128, 32, 4, A_MN, B_MN, true, 8, false, true>, EPI>(A0, A1, B, p, splits, epi, st);
+        if (option(OPT_WORKERS16) != 0)
+          return launch_cfg<Cfg<64, 32, 6, A_MN, B_MN, true, 16, false, true>, EPI>(A0, A1, B, p, splits, epi, st);
+        return launch_cfg<Cfg<64, 32, 6, A_MN, B_MN, true, 8, false, true>, EPI>(A0, A1, B, p, splits, epi, st);
+      }
       if (bn >= 128) return launch_cfg<Cfg<128, 32, 4, A_MN, B_MN, true>, EPI>(A0, A1, B, p, splits, epi, st);
       return launch_cfg<Cfg<64, 32, 6, A_MN, B_MN, true>, EPI>(A0, A1, B, p, splits, epi, st);
     }

@@ -31,7 +31,8 @@ PY
 el "3. step A/B"
 timeout 100 python bench.py --steps 100 --warmup 10 --no-cpu-baseline > $O/bench_r2_default.json 2> $O/bench_r2_default.err
 i=0
-for opts in "--opt lean=1" "--opt lean=1 --opt workers16=1" "--opt lean=1 --opt workers16=1 --opt bn64=1"; do
+for opts in "--opt lean=1" "--opt lean=1 --opt workers16=1" "--opt lean=1 --opt workers16=1 --opt bn64=1" \
+            "--opt lean=1 --opt presplit=1" "--opt lean=1 --opt presplit=1 --opt workers16=1"; do
   i=$((i+1))
   timeout 100 python bench.py --steps 100 --warmup 10 --no-cpu-baseline $opts > $O/bench_r2_v$i.json 2> $O/bench_r2_v$i.err
 done
@@ -45,9 +46,10 @@ try:
 except Exception:
     base = 2300.0
 envs = {1: "RECNN_B200_LEAN=1", 2: "RECNN_B200_LEAN=1 RECNN_B200_WORKERS16=1",
-        3: "RECNN_B200_LEAN=1 RECNN_B200_WORKERS16=1 RECNN_B200_BN64=1"}
+        3: "RECNN_B200_LEAN=1 RECNN_B200_WORKERS16=1 RECNN_B200_BN64=1",
+        4: "RECNN_B200_LEAN=1 RECNN_B200_PRESPLIT=1", 5: "RECNN_B200_LEAN=1 RECNN_B200_PRESPLIT=1 RECNN_B200_WORKERS16=1"}
 best, best_v = "", base * 1.02
-for i in ((1, 2, 3) if ok else ()):
+for i in ((1, 2, 3, 4, 5) if ok else ()):
     try:
         d = json.load(open("gpurun_out/bench_r2_v%d.json" % i))
         sys.stderr.write("variant %d (%s): %.1f steps/s, L1 gemm %.2f us\n" % (i, envs[i], d["value"], d["roofline"]["ms"] * 1e3))
