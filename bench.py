@@ -390,6 +390,8 @@ def run_native(args):
             "optimizer_updates_per_sec": global_steps_per_sec,
             "rows_per_sec": global_steps_per_sec * rows_global,
             "update_tflops": flop_step * global_steps_per_sec / 1e12,
+            # (algorithmic FLOPs x 3 TF32 passes) / (t_step x TF32 peak x GPUs): the whole step, not one kernel
+            "step_tensor_frac": 3.0 * flop_step * global_steps_per_sec / 1e12 / (tf32_peak * world),
             "value_warm_l2": args.steps / (warm_ms / 1e3) * world,
             "wall_s": wall_s,
             "e2e": {"value": e2e_value, "unit": "steps/s",
