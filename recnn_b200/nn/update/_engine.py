@@ -29,12 +29,6 @@ TD3_NETS = ("value_net1", "target_value_net1", "value_net2", "target_value_net2"
             "target_policy_net")
 
 
-def _as_device(t, device, dtype):
-    if not torch.is_tensor(t):
-        t = torch.as_tensor(t)
-    return t.detach()
-
-
 class StepEngine:
     def __init__(self, algo, nets, device):
         self.algo = algo
