@@ -29,6 +29,7 @@ static void init_options() {
   if (g_options_init.load(std::memory_order_acquire)) return;
   const struct { Option o; const char* env; int def; } table[] = {
       {OPT_GATHER_VARIANT, "RECNN_B200_GATHER", 0},      // 0: one warp per row   1: balanced (row, slot) units
+                                                         // 2: as 0 with 16-byte stores where the pitches allow (in-step)
       {OPT_PRESPLIT, "RECNN_B200_PRESPLIT", 0},          // 1: weights pre-split into TF32 hi/lo planes
       {OPT_WORKERS16, "RECNN_B200_WORKERS16", 0},        // 1: 64-wide GEMM tiles run 16 worker warps (4 groups)
                                                          // 2: ... and every GEMM uses 64-wide tiles

@@ -19,7 +19,9 @@
 
 namespace recnn {
 
-template <bool VEC>
+// ST16: the destination pitches are multiples of 4 floats and the bases 16-byte aligned (the step's padded images,
+// pitch 1292), so a lane's 4 floats go out as ONE 16-byte store instead of two 8-byte ones.
+template <bool VEC, bool ST16 = false>
 __global__ void __launch_bounds__(256)
 frame_gather_kernel(const float* __restrict__ table, long long n_items, int dim,
                     const long long* __restrict__ items, const float* __restrict__ ratings,
@@ -67,17 +69,18 @@ frame_gather_kernel(const float* __restrict__ table, long long n_items, int dim,
               const int j = j0 + jj + u;
               const float2 lo = make_float2(v[u].x, v[u].y), hi = make_float2(v[u].z, v[u].w);
               if (j < frame && state) {
-                float2* d = reinterpret_cast<float2*>(state + n * s_dim + (long long)j * dim + c);
-                d[0] = lo; d[1] = hi;
+                float* dst = state + n * s_dim + (long long)j * dim + c;
+                if constexpr (ST16) *reinterpret_cast<float4*>(dst) = v[u];
+                else { float2* d = reinterpret_cast<float2*>(dst); d[0] = lo; d[1] = hi; }
               }
               if (j >= 1 && next_state) {
-                float2* d = reinterpret_cast<float2*>(next_state + n * s_dim + (long long)(j - 1) * dim + c);
-                d[0] = lo; d[1] = hi;
+                float* dst = next_state + n * s_dim + (long long)(j - 1) * dim + c;
+                if constexpr (ST16) *reinterpret_cast<float4*>(dst) = v[u];
+                else { float2* d = reinterpret_cast<float2*>(dst); d[0] = lo; d[1] = hi; }
               }
-              if (j == frame && action)
-                {
-                float2* d = reinterpret_cast<float2*>(action + n * a_ld + c);
-                d[0] = lo; d[1] = hi;
+              if (j == frame && action) {
+                float* dst = action + n * a_ld + c;     // lead-padded action rows start 8 bytes into a 16-byte unit
+                float2* d = reinterpret_cast<float2*>(dst); d[0] = lo; d[1] = hi;
               }
             }
           }
@@ -250,7 +253,13 @@ int launch_frame_gather(const float* table, int64_t n_items, int dim, const int6
     RECNN_CHECK_LAUNCH("frame_gather_units_kernel");
     return RECNN_OK;
   }
-  if (vec)
+  const bool st16 = vec && option(OPT_GATHER_VARIANT) == 2 && s_ld % 4 == 0 && (((long long)frame * dim) % 4 == 0) &&
+                    (!state || reinterpret_cast<uintptr_t>(state) % 16 == 0) &&
+                    (!next_state || reinterpret_cast<uintptr_t>(next_state) % 16 == 0);
+  if (st16)
+    frame_gather_kernel<true, true><<<grid, 256, 0, st>>>(table, n_items, dim, (const long long*)items, ratings,
+                                                          n_rows, frame, s_ld, a_ld, state, next_state, action, reward, oob_flag);
+  else if (vec)
     frame_gather_kernel<true><<<grid, 256, 0, st>>>(table, n_items, dim, (const long long*)items, ratings,
                                                     n_rows, frame, s_ld, a_ld, state, next_state, action, reward, oob_flag);
   else

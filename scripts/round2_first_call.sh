@@ -14,6 +14,8 @@ el() { echo "[t+$(( $(date +%s) - t0 ))s] $*"; }
 el "1. experimental kernel tests"
 RECNN_TEST_EXPERIMENTAL=1 timeout 240 python -m pytest tests/test_gpu_tc.py tests/test_gpu_parity.py -q -k "lean" \
   --maxfail=5 --tb=short > $O/t_lean.log 2>&1
+RECNN_TEST_EXPERIMENTAL=1 timeout 120 python -m pytest tests/test_gpu_parity.py -q -k "sixteen_byte" --tb=short > $O/t_gather16.log 2>&1
+tail -2 $O/t_gather16.log
 tail -5 $O/t_lean.log
 
 el "2. A/B timing of single GEMMs"
@@ -30,6 +32,11 @@ PY
 
 el "3. step A/B"
 timeout 100 python bench.py --steps 100 --warmup 10 --no-cpu-baseline > $O/bench_r2_default.json 2> $O/bench_r2_default.err
+timeout 100 python bench.py --steps 100 --warmup 10 --no-cpu-baseline --opt gather_variant=2 > $O/bench_r2_gather16.json 2> $O/bench_r2_gather16.err
+python -c "
+import json
+for f in ('default','gather16'):
+    d=json.load(open('gpurun_out/bench_r2_%s.json'%f)); print(f, round(d['value'],1))"
 i=0
 for opts in "--opt lean=1" "--opt lean=1 --opt workers16=1" "--opt lean=1 --opt workers16=1 --opt bn64=1" \
             "--opt lean=1 --opt presplit=1" "--opt lean=1 --opt presplit=1 --opt workers16=1"; do

@@ -309,6 +309,26 @@ def test_lean_gemm_in_the_step_is_bit_identical(algo, opts):
             assert np.array_equal(base[k], got[k]), k
 
 
+@pytest.mark.skipif(__import__("os").environ.get("RECNN_TEST_EXPERIMENTAL") != "1",
+                    reason="16-byte-store gather written after this round's GPU budget was spent (round 2, first GPU call)")
+@pytest.mark.parametrize("algo", ["ddpg", "td3"])
+def test_sixteen_byte_store_gather_in_the_step_is_bit_identical(algo):
+    """gather_variant=2: inside the step the state images have a 16-byte-multiple pitch (1292 floats), so the gather
+    can store 16 bytes per lane; it copies the same bits, so the whole run must be unchanged."""
+    gold = load_golden("%s_canon_adam.npz" % algo)
+    base = run_cuda_case("canon", algo, "adam", golden=gold, form="frames")
+    prev = _lib.set_option("gather_variant", 2)
+    try:
+        got = run_cuda_case("canon", algo, "adam", golden=gold, form="frames")
+        tiny = run_cuda_case("tiny", algo, "adam", golden=load_golden("%s_tiny_adam.npz" % algo), form="frames")
+    finally:
+        _lib.set_option("gather_variant", prev)
+    for k in base:
+        if k.startswith(("final.", "loss.")):
+            assert np.array_equal(base[k], got[k]), k
+    compare_with_golden(tiny, load_golden("%s_tiny_adam.npz" % algo), check_grads=(algo == "ddpg"))
+
+
 def test_sixteen_worker_gemm_perf_mode_dropout_matches():
     """Device-Philox dropout (perf mode) indexes keep-bits by element, not by tile: the 16-worker kernel's
     16-column epilogue blocks must draw the same masks as the 32-column blocks of the default kernel."""
