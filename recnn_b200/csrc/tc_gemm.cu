@@ -121,7 +121,22 @@ static int launch_cfg(const Operand& A0, const Operand& A1, const Operand& B, co
             C::BN, (int)C::A_MN, (int)C::B_MN, EPI, p.M, p.N, p.K0, p.K1, p.k_chunk, p.b_k1_offset, p.n_out_offset,
             p.b_n_offset, grid.x, grid.y, grid.z, (const void*)A0.ptr, A0.ld, (const void*)A1.ptr, A1.ld,
             (const void*)B.ptr, B.ld, B.rows, B.cols, (void*)epi.out, epi.ldo);
-  tc_gemm_kernel<C, EPI><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(ma0, ma1, mb, mb_lo, p, epi);
+  if (C::LEAN && option(OPT_PDL) != 0) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(C::THREADS, 1, 1);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    RECNN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<C, EPI>, ma0, ma1, mb, mb_lo, p, epi));
+  } else {
+    tc_gemm_kernel<C, EPI><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(ma0, ma1, mb, mb_lo, p, epi);
+  }
   RECNN_CHECK_LAUNCH("tc_gemm_kernel");
   if (debug) {
     const cudaError_t e = cudaStreamSynchronize(st);

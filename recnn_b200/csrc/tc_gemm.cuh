@@ -193,6 +193,12 @@ __device__ __forceinline__ void mma_tf32_ta(uint32_t d_tmem, uint32_t a_tmem, ui
       ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Programmatic dependent launch (LEAN kernels, `pdl` option): launch_dependents lets the next kernel of the stream
+// be scheduled onto idle SMs while this one still runs; its threads park at griddep_wait() -- after their prologue,
+// before any global-memory access -- until this grid has completed and its writes are visible.  Both are no-ops for
+// a launch without the programmatic-serialization attribute.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
@@ -450,6 +456,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM, z = blockIdx.z;
+  if constexpr (C::LEAN) griddep_launch_dependents();
   if (threadIdx.x == 0) RECNN_TRACE(0);                       // kernel entry
   if (threadIdx.x == 0 && p.span) atomicMin(p.span, gtimer());
   // k-blocks: segment 0 then segment 1, each padded up to a multiple of BK (TMA zero-fills the tail)
@@ -490,6 +497,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  if constexpr (C::LEAN) griddep_wait();                      // everything below may touch global memory
   if (threadIdx.x == 0) RECNN_TRACE(1);                       // prologue done
 
   if (warp == 0) {

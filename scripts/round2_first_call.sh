@@ -39,7 +39,8 @@ for f in ('default','gather16'):
     d=json.load(open('gpurun_out/bench_r2_%s.json'%f)); print(f, round(d['value'],1))"
 i=0
 for opts in "--opt lean=1" "--opt lean=1 --opt workers16=1" "--opt lean=1 --opt workers16=1 --opt bn64=1" \
-            "--opt lean=1 --opt presplit=1" "--opt lean=1 --opt presplit=1 --opt workers16=1"; do
+            "--opt lean=1 --opt presplit=1" "--opt lean=1 --opt presplit=1 --opt workers16=1" \
+            "--opt lean=1 --opt pdl=1" "--opt lean=1 --opt pdl=1 --opt workers16=1"; do
   i=$((i+1))
   timeout 100 python bench.py --steps 100 --warmup 10 --no-cpu-baseline $opts > $O/bench_r2_v$i.json 2> $O/bench_r2_v$i.err
 done
@@ -54,9 +55,10 @@ except Exception:
     base = 2300.0
 envs = {1: "RECNN_B200_LEAN=1", 2: "RECNN_B200_LEAN=1 RECNN_B200_WORKERS16=1",
         3: "RECNN_B200_LEAN=1 RECNN_B200_WORKERS16=1 RECNN_B200_BN64=1",
-        4: "RECNN_B200_LEAN=1 RECNN_B200_PRESPLIT=1", 5: "RECNN_B200_LEAN=1 RECNN_B200_PRESPLIT=1 RECNN_B200_WORKERS16=1"}
+        4: "RECNN_B200_LEAN=1 RECNN_B200_PRESPLIT=1", 5: "RECNN_B200_LEAN=1 RECNN_B200_PRESPLIT=1 RECNN_B200_WORKERS16=1",
+        6: "RECNN_B200_LEAN=1 RECNN_B200_PDL=1", 7: "RECNN_B200_LEAN=1 RECNN_B200_PDL=1 RECNN_B200_WORKERS16=1"}
 best, best_v = "", base * 1.02
-for i in ((1, 2, 3, 4, 5) if ok else ()):
+for i in ((1, 2, 3, 4, 5, 6, 7) if ok else ()):
     try:
         d = json.load(open("gpurun_out/bench_r2_v%d.json" % i))
         sys.stderr.write("variant %d (%s): %.1f steps/s, L1 gemm %.2f us\n" % (i, envs[i], d["value"], d["roofline"]["ms"] * 1e3))

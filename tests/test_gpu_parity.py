@@ -292,8 +292,10 @@ def test_lo2_gemm_in_the_step_meets_the_golden_bar(algo, opts):
 @pytest.mark.skipif(__import__("os").environ.get("RECNN_TEST_EXPERIMENTAL") != "1",
                     reason="lean GEMM kernels have not run on hardware yet (round 2, first GPU call)")
 @pytest.mark.parametrize("opts", [dict(lean=1), dict(lean=1, workers16=1), dict(lean=1, workers16=1, bn64=1),
-                                  dict(lean=1, presplit=1), dict(lean=1, presplit=1, workers16=1)],
-                         ids=["lean", "lean-w16", "lean-w16-bn64", "lean-presplit", "lean-presplit-w16"])
+                                  dict(lean=1, presplit=1), dict(lean=1, presplit=1, workers16=1),
+                                  dict(lean=1, pdl=1), dict(lean=1, pdl=1, workers16=1)],
+                         ids=["lean", "lean-w16", "lean-w16-bn64", "lean-presplit", "lean-presplit-w16", "lean-pdl",
+                              "lean-pdl-w16"])
 @pytest.mark.parametrize("algo", ["ddpg", "td3"])
 def test_lean_gemm_in_the_step_is_bit_identical(algo, opts):
     gold = load_golden("%s_canon_adam.npz" % algo)
