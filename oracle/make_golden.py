@@ -130,7 +130,7 @@ def ref_batch(recnn, inp, spec):
 
 
 def run_update_case(recnn, case, algo, opt_kind):
-    spec = C.CASES[case]
+    spec = C.CASES[case] if isinstance(case, str) else case      # a case name or a spec dict
     inp = C.make_inputs(spec, algo)
     nets = build_ref_nets(recnn, spec, inp, algo)
     opts = make_optimizers(opt_kind, nets, algo)
