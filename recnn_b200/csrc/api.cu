@@ -37,6 +37,7 @@ static void init_options() {
       {OPT_BN64, "RECNN_B200_BN64", 0},                  // 1: every GEMM of the step uses 64-wide tiles
       {OPT_LEAN, "RECNN_B200_LEAN", 0},                  // 1: GEMM kernels without experiment hooks, running counters
                                                          //    in the MMA warp (unvalidated on hardware: round 2)
+      {OPT_TAIL, "RECNN_B200_TAIL", 0},                  // 1: dZ column sums run on the side stream beside the dW GEMMs
       {OPT_PDL, "RECNN_B200_PDL", 0},                    // 1: LEAN GEMMs are launched with programmatic stream
                                                          //    serialization (prologue overlaps the predecessor's tail)
   };
@@ -64,6 +65,7 @@ extern "C" RECNN_API int recnn_debug_set_option(const char* name, int value) {
   else if (strcmp(name, "bn64") == 0) idx = recnn::OPT_BN64;
   else if (strcmp(name, "lean") == 0) idx = recnn::OPT_LEAN;
   else if (strcmp(name, "pdl") == 0) idx = recnn::OPT_PDL;
+  else if (strcmp(name, "tail") == 0) idx = recnn::OPT_TAIL;
   if (idx < 0) return -1;
   return recnn::g_options[idx].exchange(value);
 }

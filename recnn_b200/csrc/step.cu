@@ -372,11 +372,15 @@ static int weight_grad(const float* dZ, int C, const Seg& x0, const Seg& x1, int
         return RECNN_E_INVALID;
       }
     }
+    // the bias column of the partials (column sums of dZ) only reads dZ: with a side stream it runs there, behind the
+    // short action-segment GEMM and beside the long state-segment GEMM, instead of after both (`tail` option)
+    const bool colsum_on_side = use_side && option(OPT_TAIL) != 0;
+    if (colsum_on_side) RECNN_PROPAGATE(launch_colsum_partials(dZ, n, C, k_chunk, splits, partial, K1, side->stream));
     if (use_side) {
       RECNN_CHECK_CUDA(cudaEventRecord(side->join, side->stream));
       RECNN_CHECK_CUDA(cudaStreamWaitEvent(st, side->join, 0));
     }
-    RECNN_PROPAGATE(launch_colsum_partials(dZ, n, C, k_chunk, splits, partial, K1, st));
+    if (!colsum_on_side) RECNN_PROPAGATE(launch_colsum_partials(dZ, n, C, k_chunk, splits, partial, K1, st));
     return launch_reduce_partials(partial, splits, C, K1, dW, ldw, db, st);
   }
   MatView X = x1.cols ? mat_cat(x0.p + x0.lead, x0.ld, x0.cols - x0.lead, x1.p + x1.lead, x1.ld)
