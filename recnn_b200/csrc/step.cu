@@ -148,10 +148,14 @@ static int split_planes(PlaneTable& t, const int* which, int n, cudaStream_t st)
 
 // split count of a weight-gradient GEMM dW[C, K] = dZ^T X over n_rows (the contraction dim).
 // Must be a pure function of the shapes: the workspace size depends on it.
-static int dw_splits(int C, int K, int64_t n_rows, bool tc_path) {
+// policy 0 (default): aim at ~192 CTAs.  policy 1 (`dwsplit` option): the tensor-core kernel holds one CTA per SM and
+// has a ~10 us fixed cost, so more CTAs than SMs means a second wave of the whole fixed cost (measured: the critic's
+// dW1, 22+4 tiles x 8 splits = 208 CTAs, takes 48 us = two waves); aim at one wave of ~132 CTAs instead, leaving
+// room for the GEMM that runs beside it.  Fewer splits never need more workspace, so carve() sizes for policy 0.
+static int dw_splits(int C, int K, int64_t n_rows, bool tc_path, int policy = 0) {
   if (tc_path) {
     const int64_t tiles = ceil_div(C, 128) * ceil_div(K, 128);
-    int64_t s = ceil_div(192, tiles);
+    int64_t s = policy == 1 ? (132 / tiles > 0 ? 132 / tiles : 1) : ceil_div(192, tiles);
     const int64_t max_s = ceil_div(n_rows, 32) / 4 > 0 ? ceil_div(n_rows, 32) / 4 : 1;   // >= 4 k-blocks (128 rows) per split
     if (s > max_s) s = max_s;
     return (int)(s < 1 ? 1 : s);
@@ -346,7 +350,7 @@ static int weight_grad(const float* dZ, int C, const Seg& x0, const Seg& x1, int
   const bool tc_ok = math_tc() && C % 4 == 0 && C >= 32 && aligned16(dZ) && aligned16(x0.p) && x0.ld % 4 == 0 &&
                      x0.lead == 0 && (x1.cols == 0 || (aligned16(x1.p) && x1.ld % 4 == 0));
   if (tc_ok) {
-    const int req = dw_splits(C, K, n, true);
+    const int req = dw_splits(C, K, n, true, option(OPT_DWSPLIT) != 0 ? 1 : 0);
     int k_chunk = 0;
     const int splits = tc::split_plan((int)ceil_div(n, 32), req, &k_chunk, 32);
     tc::Operand a0 = {dZ, C, 0, 0}, a1 = {nullptr, 0, 0, 0};

@@ -14,7 +14,7 @@ el() { echo "[t+$(( $(date +%s) - t0 ))s] $*"; }
 el "1. experimental kernel tests"
 RECNN_TEST_EXPERIMENTAL=1 timeout 240 python -m pytest tests/test_gpu_tc.py tests/test_gpu_parity.py -q -k "lean" \
   --maxfail=5 --tb=short > $O/t_lean.log 2>&1
-RECNN_TEST_EXPERIMENTAL=1 timeout 120 python -m pytest tests/test_gpu_parity.py -q -k "sixteen_byte or column_sums" --tb=short > $O/t_gather16.log 2>&1
+RECNN_TEST_EXPERIMENTAL=1 timeout 120 python -m pytest tests/test_gpu_parity.py -q -k "sixteen_byte or column_sums or one_wave" --tb=short > $O/t_gather16.log 2>&1
 tail -2 $O/t_gather16.log
 tail -5 $O/t_lean.log
 
@@ -34,9 +34,10 @@ el "3. step A/B"
 timeout 100 python bench.py --steps 100 --warmup 10 --no-cpu-baseline > $O/bench_r2_default.json 2> $O/bench_r2_default.err
 timeout 100 python bench.py --steps 100 --warmup 10 --no-cpu-baseline --opt gather_variant=2 > $O/bench_r2_gather16.json 2> $O/bench_r2_gather16.err
 timeout 100 python bench.py --steps 100 --warmup 10 --no-cpu-baseline --opt tail=1 > $O/bench_r2_tail.json 2> $O/bench_r2_tail.err
+timeout 100 python bench.py --steps 100 --warmup 10 --no-cpu-baseline --opt dwsplit=1 > $O/bench_r2_dwsplit.json 2> $O/bench_r2_dwsplit.err
 python -c "
 import json
-for f in ('default','gather16','tail'):
+for f in ('default','gather16','tail','dwsplit'):
     d=json.load(open('gpurun_out/bench_r2_%s.json'%f)); print(f, round(d['value'],1))"
 i=0
 for opts in "--opt lean=1" "--opt lean=1 --opt workers16=1" "--opt lean=1 --opt workers16=1 --opt bn64=1" \
