@@ -142,7 +142,7 @@ def lib():
 
 
 def set_option(name: str, value: int) -> int:
-    """Runtime A/B switch of the library (``recnn_debug_set_option``: "gather_variant", "presplit", "workers16", "lo2", "bn64", "lean", "pdl", "tail", "dwsplit").
+    """Runtime A/B switch of the library (``recnn_debug_set_option``: "gather_variant", "presplit", "workers16", "lo2", "bn64", "lean", "pdl", "tail", "dwsplit", "padzero").
     Returns the previous value.  Not part of the product ABI: used by bench.py's A/B legs and by tests
     that check the kernel variants against each other."""
     h = lib()

@@ -39,6 +39,7 @@ static void init_options() {
                                                          //    in the MMA warp (unvalidated on hardware: round 2)
       {OPT_TAIL, "RECNN_B200_TAIL", 0},                  // 1: dZ column sums run on the side stream beside the dW GEMMs
       {OPT_DWSPLIT, "RECNN_B200_DWSPLIT", 0},            // 1: split-K of the weight gradients sized for ONE wave of CTAs
+      {OPT_PADZERO, "RECNN_B200_PADZERO", 0},            // 1: zero only the pad columns of the action images (one kernel)
       {OPT_PDL, "RECNN_B200_PDL", 0},                    // 1: LEAN GEMMs are launched with programmatic stream
                                                          //    serialization (prologue overlaps the predecessor's tail)
   };
@@ -68,6 +69,7 @@ extern "C" RECNN_API int recnn_debug_set_option(const char* name, int value) {
   else if (strcmp(name, "pdl") == 0) idx = recnn::OPT_PDL;
   else if (strcmp(name, "tail") == 0) idx = recnn::OPT_TAIL;
   else if (strcmp(name, "dwsplit") == 0) idx = recnn::OPT_DWSPLIT;
+  else if (strcmp(name, "padzero") == 0) idx = recnn::OPT_PADZERO;
   if (idx < 0) return -1;
   return recnn::g_options[idx].exchange(value);
 }

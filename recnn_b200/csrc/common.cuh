@@ -48,7 +48,7 @@ void count_launch();   // every kernel launch of this library bumps a process-wi
   } while (0)
 
 // ---- runtime switches (A/B experiments and regression fallbacks; recnn_debug_set_option) --------
-enum Option { OPT_GATHER_VARIANT = 0, OPT_PRESPLIT = 1, OPT_WORKERS16 = 2, OPT_LO2 = 3, OPT_BN64 = 4, OPT_LEAN = 5, OPT_PDL = 6, OPT_TAIL = 7, OPT_DWSPLIT = 8, OPT_COUNT = 9 };
+enum Option { OPT_GATHER_VARIANT = 0, OPT_PRESPLIT = 1, OPT_WORKERS16 = 2, OPT_LO2 = 3, OPT_BN64 = 4, OPT_LEAN = 5, OPT_PDL = 6, OPT_TAIL = 7, OPT_DWSPLIT = 8, OPT_PADZERO = 9, OPT_COUNT = 10 };
 int option(Option o);          // current value (initialised from RECNN_B200_GATHER / _PRESPLIT / _WORKERS16)
 
 constexpr int kNumSMs = 148;   // B200

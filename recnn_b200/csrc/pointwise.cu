@@ -294,6 +294,34 @@ int launch_colsum_partials(const float* dz, int64_t n_rows, int C, int64_t rows_
   return RECNN_OK;
 }
 
+// ---------------------------------------------------------------- pad columns of the action images
+__global__ void __launch_bounds__(256)
+zero_pad_columns_kernel(float* b0, float* b1, float* b2, long long n_rows, int ld, int lead, int cols) {
+  const int pads = ld - cols;                         // lead + trailing pad columns per row
+  float* const bufs[3] = {b0, b1, b2};
+  float* const buf = bufs[blockIdx.y];
+  if (!buf) return;
+  const long long total = n_rows * pads;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / pads;
+    const int k = (int)(i - r * pads);
+    const int col = k < lead ? k : lead + cols + (k - lead);     // lead pads, then the pads behind the data
+    buf[r * ld + col] = 0.f;
+  }
+}
+
+int launch_zero_pad_columns(float* b0, float* b1, float* b2, int64_t n_rows, int ld, int lead, int cols, cudaStream_t st) {
+  RECNN_REQUIRE(ld >= lead + cols && lead >= 0 && cols > 0, "pad geometry");
+  if (ld == lead + cols && lead == 0) return RECNN_OK;
+  if (n_rows <= 0) return RECNN_OK;
+  const int64_t total = n_rows * (ld - cols);
+  const int64_t blocks = ceil_div(total, 256);
+  dim3 grid((unsigned)(blocks < 148 ? blocks : 148), 3);
+  zero_pad_columns_kernel<<<grid, 256, 0, st>>>(b0, b1, b2, n_rows, ld, lead, cols);
+  RECNN_CHECK_LAUNCH("zero_pad_columns_kernel");
+  return RECNN_OK;
+}
+
 // ---------------------------------------------------------------- L1 clip quirk
 __global__ void __launch_bounds__(256)
 l1_clip_coef_kernel(const float* __restrict__ g, long long count, float max_norm, float* coef, float* l1_out,

@@ -80,6 +80,9 @@ int launch_l1_clip_coef(const float* grads, int64_t count, float max_norm, float
 int launch_comm_allreduce(const recnn_comm* comm, float* buf, int64_t n, float max_norm, float* coef, float* l1_out,
                           float* block_partials, cudaStream_t st);
 
+// zero the `lead` leading and the trailing pad columns of up to three [n_rows, ld] buffers whose data columns are
+// [lead, lead + cols) (the lead-padded action images of the step); one launch instead of three full memsets
+int launch_zero_pad_columns(float* b0, float* b1, float* b2, int64_t n_rows, int ld, int lead, int cols, cudaStream_t st);
 int launch_scale_inplace(float* x, int64_t count, const float* scale, cudaStream_t st);
 
 // ticket: zero-initialised self-resetting counter; when given, the kernel itself increments *net.opt_t

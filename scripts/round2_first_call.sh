@@ -35,9 +35,10 @@ timeout 100 python bench.py --steps 100 --warmup 10 --no-cpu-baseline > $O/bench
 timeout 100 python bench.py --steps 100 --warmup 10 --no-cpu-baseline --opt gather_variant=2 > $O/bench_r2_gather16.json 2> $O/bench_r2_gather16.err
 timeout 100 python bench.py --steps 100 --warmup 10 --no-cpu-baseline --opt tail=1 > $O/bench_r2_tail.json 2> $O/bench_r2_tail.err
 timeout 100 python bench.py --steps 100 --warmup 10 --no-cpu-baseline --opt dwsplit=1 > $O/bench_r2_dwsplit.json 2> $O/bench_r2_dwsplit.err
+timeout 100 python bench.py --steps 100 --warmup 10 --no-cpu-baseline --opt padzero=1 > $O/bench_r2_padzero.json 2> $O/bench_r2_padzero.err
 python -c "
 import json
-for f in ('default','gather16','tail','dwsplit'):
+for f in ('default','gather16','tail','dwsplit','padzero'):
     d=json.load(open('gpurun_out/bench_r2_%s.json'%f)); print(f, round(d['value'],1))"
 i=0
 for opts in "--opt lean=1" "--opt lean=1 --opt workers16=1" "--opt lean=1 --opt workers16=1 --opt bn64=1" \

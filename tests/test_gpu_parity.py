@@ -333,17 +333,20 @@ def test_sixteen_byte_store_gather_in_the_step_is_bit_identical(algo):
 
 @pytest.mark.skipif(__import__("os").environ.get("RECNN_TEST_EXPERIMENTAL") != "1",
                     reason="launch-order change written after this round's GPU budget was spent (round 2, first GPU call)")
-@pytest.mark.parametrize("algo", ["ddpg", "td3"])
-def test_column_sums_on_the_side_stream_are_bit_identical(algo):
+@pytest.mark.parametrize("opts", [dict(tail=1), dict(padzero=1), dict(tail=1, padzero=1)], ids=["tail", "padzero", "both"])
+@pytest.mark.parametrize("algo,form", [("ddpg", "frames"), ("td3", "frames"), ("ddpg", "dense")])
+def test_column_sums_on_the_side_stream_are_bit_identical(algo, form, opts):
     """`tail` option: the dZ column sums (bias gradients) run on the side stream beside the weight-gradient GEMMs.
-    Same kernels, same data, different launch order: results must not change."""
+    `padzero` option: one kernel zeroes the pad columns of the action images instead of three full memsets.
+    Same arithmetic on the same data: results must not change."""
     gold = load_golden("%s_canon_adam.npz" % algo)
-    base = run_cuda_case("canon", algo, "adam", golden=gold, form="frames")
-    prev = _lib.set_option("tail", 1)
+    base = run_cuda_case("canon", algo, "adam", golden=gold, form=form)
+    prev = {k: _lib.set_option(k, v) for k, v in opts.items()}
     try:
-        got = run_cuda_case("canon", algo, "adam", golden=gold, form="frames")
+        got = run_cuda_case("canon", algo, "adam", golden=gold, form=form)
     finally:
-        _lib.set_option("tail", prev)
+        for k, v in prev.items():
+            _lib.set_option(k, v)
     for k in base:
         if k.startswith(("final.", "loss.", "grad_")):
             assert np.array_equal(base[k], got[k]), k
