@@ -43,7 +43,9 @@ for f in ('default','gather16','tail','dwsplit','padzero'):
 i=0
 for opts in "--opt lean=1" "--opt lean=1 --opt workers16=1" "--opt lean=1 --opt workers16=1 --opt bn64=1" \
             "--opt lean=1 --opt presplit=1" "--opt lean=1 --opt presplit=1 --opt workers16=1" \
-            "--opt lean=1 --opt pdl=1" "--opt lean=1 --opt pdl=1 --opt workers16=1"; do
+            "--opt lean=1 --opt pdl=1" "--opt lean=1 --opt pdl=1 --opt workers16=1" \
+            "--opt lean=1 --opt presplit=1 --opt pdl=1 --opt tail=1 --opt dwsplit=1 --opt padzero=1 --opt gather_variant=2" \
+            "--opt lean=1 --opt presplit=1 --opt pdl=1 --opt tail=1 --opt dwsplit=1 --opt padzero=1 --opt gather_variant=2 --opt workers16=1"; do
   i=$((i+1))
   timeout 100 python bench.py --steps 100 --warmup 10 --no-cpu-baseline $opts > $O/bench_r2_v$i.json 2> $O/bench_r2_v$i.err
 done
@@ -51,7 +53,9 @@ python - <<'PY' > gpurun_out/best_env_r2.sh
 import json, sys
 log = open("gpurun_out/t_lean.log").read()
 ok = (" passed" in log) and ("failed" not in log) and ("error" not in log.lower())
-sys.stderr.write("lean kernels correct: %s\n" % ok)
+log2 = open("gpurun_out/t_gather16.log").read()
+ok2 = (" passed" in log2) and ("failed" not in log2) and ("error" not in log2.lower())
+sys.stderr.write("lean kernels correct: %s; gather16 / tail / dwsplit / padzero correct: %s (variants 8, 9 need both)\n" % (ok, ok2))
 try:
     base = json.load(open("gpurun_out/bench_r2_default.json"))["value"]
 except Exception:
@@ -59,9 +63,13 @@ except Exception:
 envs = {1: "RECNN_B200_LEAN=1", 2: "RECNN_B200_LEAN=1 RECNN_B200_WORKERS16=1",
         3: "RECNN_B200_LEAN=1 RECNN_B200_WORKERS16=1 RECNN_B200_BN64=1",
         4: "RECNN_B200_LEAN=1 RECNN_B200_PRESPLIT=1", 5: "RECNN_B200_LEAN=1 RECNN_B200_PRESPLIT=1 RECNN_B200_WORKERS16=1",
-        6: "RECNN_B200_LEAN=1 RECNN_B200_PDL=1", 7: "RECNN_B200_LEAN=1 RECNN_B200_PDL=1 RECNN_B200_WORKERS16=1"}
+        6: "RECNN_B200_LEAN=1 RECNN_B200_PDL=1", 7: "RECNN_B200_LEAN=1 RECNN_B200_PDL=1 RECNN_B200_WORKERS16=1",
+        8: "RECNN_B200_LEAN=1 RECNN_B200_PRESPLIT=1 RECNN_B200_PDL=1 RECNN_B200_TAIL=1 RECNN_B200_DWSPLIT=1 RECNN_B200_PADZERO=1 RECNN_B200_GATHER=2",
+        9: "RECNN_B200_LEAN=1 RECNN_B200_PRESPLIT=1 RECNN_B200_PDL=1 RECNN_B200_TAIL=1 RECNN_B200_DWSPLIT=1 RECNN_B200_PADZERO=1 RECNN_B200_GATHER=2 RECNN_B200_WORKERS16=1"}
 best, best_v = "", base * 1.02
-for i in ((1, 2, 3, 4, 5, 6, 7) if ok else ()):
+for i in ((1, 2, 3, 4, 5, 6, 7, 8, 9) if ok else ()):
+    if i >= 8 and not ok2:
+        continue
     try:
         d = json.load(open("gpurun_out/bench_r2_v%d.json" % i))
         sys.stderr.write("variant %d (%s): %.1f steps/s, L1 gemm %.2f us\n" % (i, envs[i], d["value"], d["roofline"]["ms"] * 1e3))
