@@ -68,12 +68,22 @@ class StepEngine:
         self.last_call_kernels = 0
 
     # ------------------------------------------------------------------ staging
+    def _invalidate(self):
+        """Drop everything that baked device addresses in: captured graphs (whole-step and per-segment),
+        the fast-path table of (tokens -> graph / cached StepArgs) and the first-sight bookkeeping.  Called
+        whenever a staging buffer or the workspace is (re)allocated, the batch shape changes, or data
+        parallelism is (re)configured -- a stale graph would run against freed memory."""
+        self.graphs.clear()
+        self.seg_graphs.clear()
+        self._fast.clear()
+        self.eager_runs.clear()
+
     def _buffer(self, name, shape, dtype):
         b = self.buf.get(name)
         if b is None or tuple(b.shape) != tuple(shape) or b.dtype != dtype:
             b = torch.empty(shape, dtype=dtype, device=self.device)
             self.buf[name] = b
-            self.graphs.clear()
+            self._invalidate()
         return b
 
     def _stage(self, name, src, dtype, shape=None):
@@ -137,9 +147,15 @@ class StepEngine:
             st["masks"] = None
         noise = batch.get(NOISE_KEY) if self.algo == _lib.ALGO_TD3 else None
         st["noise"] = self._stage("noise", noise, torch.float32, (n, d.action_dim)) if noise is not None else None
+        # data parallel: the loss means and gradient scales use the GLOBAL row count.  Equal shards are
+        # assumed (n * world) unless the caller says otherwise (uneven shards, e.g. dist.shard_rows of a batch
+        # that does not divide by the world size, must pass batch["n_rows_global"]).
+        st["n_global"] = int(batch["n_rows_global"]) if batch.get("n_rows_global") is not None else n * self.world
+        if st["n_global"] < n:
+            raise ValueError("batch['n_rows_global'] (%d) is smaller than this rank's row count (%d)" % (st["n_global"], n))
         if n != self.n_rows or form != self.form:
             self.n_rows, self.form = n, form
-            self.graphs.clear()
+            self._invalidate()
         return st
 
     # ------------------------------------------------------------------ arenas / args
@@ -170,7 +186,7 @@ class StepEngine:
         a.do_policy_step = int(bool(do_policy))
         a.dims = self.dims
         a.n_rows = st["n"]
-        a.n_rows_global = st["n"] * self.world
+        a.n_rows_global = st["n_global"]
         if st["form"] == "frames":
             a.table = st["table"].data_ptr()
             a.n_items = int(st["table"].shape[0])
@@ -225,7 +241,7 @@ class StepEngine:
         if ws is None or ws.numel() < nbytes:
             ws = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
             self.buf["workspace"] = ws
-            self.graphs.clear()
+            self._invalidate()
         a.workspace = ws.data_ptr()
         a.workspace_bytes = ws.numel()
         return a, pol_opt, val_opts
@@ -290,9 +306,7 @@ class StepEngine:
             self._body(a, nets, do_policy)
             return None
         if len(self.graphs) > 16:
-            self.graphs.clear()
-            self.eager_runs.clear()
-            self._fast.clear()
+            self._invalidate()
         try:
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
@@ -374,7 +388,8 @@ class StepEngine:
             o = optimizer[k]
             if isinstance(o, _optim._ArenaOptimizer):
                 g = o.param_groups[0]
-                tok.append((id(o), g["lr"], g.get("betas"), g.get("eps"), g["weight_decay"], g.get("momentum")))
+                tok.append((id(o), g["lr"], g.get("betas"), g.get("eps"), g["weight_decay"], g.get("momentum"),
+                            0 if o._m is None else o._m.data_ptr(), 0 if o._t is None else o._t.data_ptr()))
             else:
                 tok.append((id(o),))
         tok.append(tuple(sorted(params.items())) if len(params) < 16 else id(params))
@@ -383,6 +398,9 @@ class StepEngine:
             tok.append(0 if t is None else t.data_ptr())
         if st["masks"] is not None:
             tok.append(tuple(m.data_ptr() for m in st["masks"]))
+        ws = self.buf.get("workspace")
+        tok.append((0 if ws is None else ws.data_ptr(), self.losses.data_ptr(), self.rng_step.data_ptr(),
+                    st["n_global"], self.world, 0 if self.comm is None else self.comm.ptr))
         return tok
 
     def _step(self, batch, params, nets, optimizer, learn, step, debug, policy_every_key):
@@ -434,7 +452,9 @@ class StepEngine:
                 if self.world > 1:
                     for vn in value_nets:
                         self._allreduce(grad_arena(vn))
-                if builtin:
+                # Each optimizer is stepped exactly once, by whoever owns it: the C side runs the fused
+                # SGD/Adam of a built-in optimizer (a.value_optim.kind != EXTERNAL), Python steps anything else.
+                if a.value_optim.kind != P.OPT_EXTERNAL:
                     self._launch(a, P.PH_VALUE_OPT, want_debug)
                 else:
                     for vn, vo in zip(value_nets, val_opts):
@@ -445,8 +465,10 @@ class StepEngine:
                 self._launch(a, P.PH_POLICY_GRAD, want_debug)
                 if self.world > 1:
                     self._allreduce(grad_arena(nets["policy_net"]))
+                # clip coefficient (+ the fused optimizer when the policy optimizer is built in; for an
+                # external one the C side only scales the gradient in place)
                 self._launch(a, P.PH_POLICY_OPT, want_debug)
-                if not builtin:
+                if a.policy_optim.kind == P.OPT_EXTERNAL:
                     grad_arena(nets["policy_net"])
                     pol_opt.step()
                 self._launch(a, P.PH_SOFT_UPDATE, want_debug)

@@ -5,8 +5,8 @@ single-tensor semantics: lerp_ for exp_avg, bias corrections formed in double,
 L2-style weight_decay) but keep their state as flat arenas next to the net's
 parameter arena, so the update functions can run the optimizer as part of the
 same CUDA graph.  They are torch.optim.Optimizer subclasses: ``zero_grad``,
-``param_groups`` (lr can be edited between steps) and ``state_dict`` behave as
-usual, and ``step()`` may also be called on its own.
+``param_groups`` (lr can be edited between steps) behave as usual, ``state_dict`` /
+``load_state_dict`` carry the flat moment arenas and the step count (``recnn_arenas``), and ``step()`` may also be called on its own.
 
 Any other torch optimizer passed through the reference's ``optimizer`` dict is
 honoured too (the step is then split at the points where gradients are
@@ -42,11 +42,42 @@ class _ArenaOptimizer(torch.optim.Optimizer):
         return self
 
     def _state_arenas(self, flat):
-        if self._t is None or self._t.device != flat.device:
+        if self._t is None:
             self._t = torch.zeros(1, dtype=torch.int32, device=flat.device)
             self._m = torch.zeros_like(flat)
             self._v = torch.zeros_like(flat) if self._recnn_kind == _lib.OPT_ADAM else None
+        elif self._t.device != flat.device or self._m.numel() != flat.numel():
+            if self._m.numel() != flat.numel():
+                raise _lib.RecnnError("optimizer state (%d elements) does not match the net's arena (%d)"
+                                      % (self._m.numel(), flat.numel()))
+            # the net moved (Algo.to(device)): the moments and the step count move with it
+            self._t = self._t.to(flat.device)
+            self._m = self._m.to(flat.device)
+            self._v = None if self._v is None else self._v.to(flat.device)
         return self._m, self._v, self._t
+
+    # -- checkpointing: the moments / step count live in flat arenas, not in self.state -----------
+    def state_dict(self):
+        """torch's layout plus ``recnn_arenas``: the flat moment arenas (geometry of the net's parameter
+        arena, pads included) and the step count, so a resumed run continues the bias correction."""
+        sd = super().state_dict()
+        if self._t is not None:
+            sd["recnn_arenas"] = {"m": self._m.detach().cpu().clone(),
+                                  "v": None if self._v is None else self._v.detach().cpu().clone(),
+                                  "t": int(self._t.item())}
+        return sd
+
+    def load_state_dict(self, state_dict):
+        state_dict = dict(state_dict)
+        arenas = state_dict.pop("recnn_arenas", None)
+        super().load_state_dict(state_dict)
+        if arenas is None:
+            self._m = self._v = self._t = None
+            return
+        dev = self.param_groups[0]["params"][0].device
+        self._m = arenas["m"].to(dev).clone()
+        self._v = None if arenas["v"] is None else arenas["v"].to(dev).clone()
+        self._t = torch.full((1,), int(arenas["t"]), dtype=torch.int32, device=dev)
 
     def c_optim(self) -> _lib.Optim:
         raise NotImplementedError
