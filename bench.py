@@ -1,15 +1,22 @@
 #!/usr/bin/env python
-"""Benchmark of the DDPG update hot path (BASELINE.json metric:
-"DDPG update-steps/sec @ batch 4096 ...; embed-gather HBM GB/s").
+"""Benchmark of the DDPG / TD3 update hot path (BASELINE.json metric:
+"DDPG update-steps/sec @ batch 4096, 1/2/4/8xB200; embed-gather HBM GB/s").
 
-  python bench.py --gpus N --steps K --warmup W            # this framework (CUDA path)
+  python bench.py --gpus N --steps K --warmup W            # this framework (CUDA path), DDPG (BASELINE configs[1])
+  python bench.py --algo td3 ...                           # the same line for TD3 (BASELINE configs[2])
   python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores
                                                            # (numpy port in oracle/; /root/reference is Python
                                                            # and does not exist on the GPU box)
 
-One "step" = one DDPG update (ddpg_update) over one synthetic ML-20M-shaped minibatch:
+One "step" = one update (ddpg_update / td3_update) over one synthetic ML-20M-shaped minibatch:
 26,744 items x 128-d table, frame_size 10, 4096 sample rows per GPU, policy step every 10th
 step, Adam(lr=1e-5), dropout active (perf mode: on-device Philox).  Prints ONE JSON line.
+
+Timing protocol: both CUDA-graph variants of the step (policy / non-policy) are primed before any timed
+region whatever --warmup is; W untimed warm-up steps; then R repeats (R >= 3) of EXACTLY K steps, each
+repeat bracketed by barrier + synchronize, every step timed on the device with CUDA events (L2 flushed by
+a 256 MB write between steps, outside the events), max over ranks; `value` is the median repeat and
+`spread` gives min / max.
 """
 from __future__ import annotations
 
@@ -30,10 +37,12 @@ if ROOT not in sys.path:
 N_ITEMS, DIM, FRAME, HIDDEN = 26744, 128, 10, 256
 S_DIM = DIM * FRAME + FRAME
 ROWS_PER_GPU = 4096
+STRONG_ROWS = 8192                    # BASELINE configs[3]: 8192 rows sharded over the GPUs (strong scaling)
 POLICY_STEP = 10
 # algorithmic work per sample row
 GATHER_BYTES_PER_ROW = 16604
-DDPG_FLOP_NONPOLICY, DDPG_FLOP_POLICY = 5276160, 6526976
+GATHER_READ_BYTES_PER_ROW = 5764
+FLOP = {"ddpg": (5276160, 6526976), "td3": (7980544, 9231360)}      # (non-policy step, policy step)
 L1_FWD_FLOP_PER_ROW = 2 * S_DIM * HIDDEN           # the dominant kernel: layer-1 forward GEMM
 
 
@@ -107,69 +116,48 @@ def synth_step_inputs(seed, n_rows, n_steps):
     return items, ratings, done
 
 
+def workload_name(algo, n_rows=ROWS_PER_GPU, per_gpu=True):
+    cfg = "configs[1]" if algo == "ddpg" else "configs[2]"
+    return "%s batch %d rows%s, 128-d embeddings, 26744 items, frame 10 (BASELINE %s)" % (
+        algo.upper(), n_rows, "/GPU" if per_gpu else "", cfg)
+
+
 # =============================================================================== reference arm
-def run_reference(args):
-    """`--impl reference`: the reference algorithm on the host CPU (numpy port in oracle/; /root/reference is
-    Python and is not on the GPU box).  Rank 0 only."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    n_rows = ROWS_PER_GPU * args.gpus
-    stepper = _OracleStepper(n_rows)
-    limiter, threads = pick_blas_threads(stepper)
-    ctx = limiter(limits=threads) if limiter is not None else None
-    if ctx is not None:
-        ctx.__enter__()
-    try:
-        for _ in range(args.warmup):
-            stepper.run()
-        t_total = sum(stepper.run() for _ in range(args.steps))
-    finally:
-        if ctx is not None:
-            ctx.__exit__(None, None, None)
-    value = args.steps / t_total
-    line = {
-        "impl": "reference", "metric": "ddpg_update_steps_per_sec", "value": value, "unit": "steps/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "DDPG batch %d rows, 128-d embeddings, 26744 items, frame 10" % n_rows,
-                   "rows_per_step": n_rows, "optimizer": "adam lr=1e-5", "policy_step": POLICY_STEP},
-        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": threads, "host_cpus": os.cpu_count() or 1,
-                         "kind": "port",
-                         "sample": "%d full steps (gather + ddpg_update, numpy/OpenBLAS fp32, best-of thread count)" % args.steps},
-        "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
-    print(json.dumps(line))
-
-
 class _OracleStepper:
-    """Reference algorithm (gather + ddpg_update) on the host: numpy port in oracle/."""
+    """Reference algorithm (gather + ddpg_update / td3_update) on the host: numpy port in oracle/."""
 
-    def __init__(self, n_rows):
+    def __init__(self, n_rows, algo="ddpg"):
         from oracle import recnn_oracle as O
         from oracle import cases as C
-        self.O, self.C, self.n = O, C, n_rows
+        self.O, self.C, self.n, self.algo = O, C, n_rows, algo
         rng = np.random.default_rng(0)
         self.rng = rng
         self.table = rng.standard_normal((N_ITEMS, DIM), dtype=np.float32)
-        self.nets = {"policy_net": O.make_actor(rng, S_DIM, DIM, HIDDEN, 6e-1),
-                     "value_net": O.make_critic(rng, S_DIM, DIM, HIDDEN, 54e-2)}
+        self.nets = {"policy_net": O.make_actor(rng, S_DIM, DIM, HIDDEN, 6e-1)}
         self.nets["target_policy_net"] = O.copy_net(self.nets["policy_net"])
-        self.nets["target_value_net"] = O.copy_net(self.nets["value_net"])
-        self.opts = {"policy_optimizer": O.make_optimizer("adam", lr=1e-5),
-                     "value_optimizer": O.make_optimizer("adam", lr=1e-5)}
+        self.opts = {"policy_optimizer": O.make_optimizer("adam", lr=1e-5)}
+        for sfx in ([""] if algo == "ddpg" else ["1", "2"]):
+            self.nets["value_net" + sfx] = O.make_critic(rng, S_DIM, DIM, HIDDEN, 54e-2)
+            self.nets["target_value_net" + sfx] = O.copy_net(self.nets["value_net" + sfx])
+            self.opts["value_optimizer" + sfx] = O.make_optimizer("adam", lr=1e-5)
         self.sizes = np.asarray([n_rows + FRAME], dtype=np.int64)
         self.items, self.ratings, _ = synth_step_inputs(1, n_rows, 4)
         self.step = 0
 
     def run(self):
-        """One step; returns its wall time (the dropout draw is not timed: RNGs differ per implementation)."""
-        masks = self.O.synth_masks(self.rng, 6, self.n, HIDDEN)
+        """One step; returns its wall time (the dropout / noise draws are not timed: RNGs differ per implementation)."""
+        O = self.O
+        masks = O.synth_masks(self.rng, 6 if self.algo == "ddpg" else 8, self.n, HIDDEN)
+        noise = None
+        if self.algo == "td3":
+            noise = (self.rng.standard_normal((self.n, DIM)) * self.C.TD3_PARAMS["noise_std"]).astype(np.float32)
         i = self.step % 4
         t0 = time.perf_counter()
-        batch = self.O.frame_gather(self.table, self.items[i], self.ratings[i], self.sizes, FRAME)
-        self.O.ddpg_update(batch, dict(self.C.DDPG_PARAMS), self.nets, self.opts, masks, self.step, learn=True)
+        batch = O.frame_gather(self.table, self.items[i], self.ratings[i], self.sizes, FRAME)
+        if self.algo == "ddpg":
+            O.ddpg_update(batch, dict(self.C.DDPG_PARAMS), self.nets, self.opts, masks, self.step, learn=True)
+        else:
+            O.td3_update(batch, dict(self.C.TD3_PARAMS), self.nets, self.opts, masks, noise, self.step, learn=True)
         dt = time.perf_counter() - t0
         self.step += 1
         return dt
@@ -193,9 +181,9 @@ def pick_blas_threads(stepper):
     return threadpool_limits, best
 
 
-def cpu_baseline_sample(seconds_budget=15.0):
-    """Oracle port on the host cores, bounded: N=4096 DDPG steps until ~budget is used."""
-    stepper = _OracleStepper(ROWS_PER_GPU)
+def cpu_sample(n_rows, algo, seconds_budget, min_steps=10, max_steps=60):
+    """Oracle port on the host cores, bounded: steps until ~budget seconds are used."""
+    stepper = _OracleStepper(n_rows, algo)
     limiter, threads = pick_blas_threads(stepper)
     ctx = limiter(limits=threads) if limiter is not None else None
     if ctx is not None:
@@ -206,17 +194,239 @@ def cpu_baseline_sample(seconds_budget=15.0):
         while True:
             t_total += stepper.run()
             timed += 1
-            if (timed >= 10 and time.perf_counter() - t_start > seconds_budget) or timed >= 60:
+            if (timed >= min_steps and time.perf_counter() - t_start > seconds_budget) or timed >= max_steps:
                 break
     finally:
         if ctx is not None:
             ctx.__exit__(None, None, None)
     return {"value": timed / t_total, "unit": "steps/s", "cores": threads, "host_cpus": os.cpu_count() or 1,
             "kind": "port",
-            "sample": "%d DDPG steps at 4096 rows (gather + update, numpy/OpenBLAS fp32, best-of thread count)" % timed}
+            "sample": "%d %s steps at %d rows (gather + update, numpy/OpenBLAS fp32, best-of thread count)"
+                      % (timed, algo.upper(), n_rows)}
+
+
+def run_reference(args):
+    """`--impl reference`: the reference algorithm on the host CPU (numpy port in oracle/; /root/reference is
+    Python and is not on the GPU box).  Rank 0 only.  Whatever --gpus is, one unit of work is ONE 4096-row
+    minibatch through the update step -- the same unit the CUDA arm's `value` counts -- so the ratio of the two
+    arms is like for like at every N."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_rows = ROWS_PER_GPU
+    stepper = _OracleStepper(n_rows, args.algo)
+    limiter, threads = pick_blas_threads(stepper)
+    ctx = limiter(limits=threads) if limiter is not None else None
+    if ctx is not None:
+        ctx.__enter__()
+    try:
+        for _ in range(args.warmup):
+            stepper.run()
+        t_total = sum(stepper.run() for _ in range(args.steps))
+    finally:
+        if ctx is not None:
+            ctx.__exit__(None, None, None)
+    value = args.steps / t_total
+    line = {
+        "impl": "reference", "metric": "%s_update_steps_per_sec" % args.algo, "value": value, "unit": "steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.algo), "rows_per_gpu": n_rows, "rows_per_step": n_rows,
+                   "unit_def": "4096-row minibatches through the update step per second (one host, all the BLAS "
+                               "threads that help; the same unit the CUDA arm counts over its N GPUs)",
+                   "optimizer": "adam lr=1e-5", "policy_step": POLICY_STEP},
+        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": threads, "host_cpus": os.cpu_count() or 1,
+                         "kind": "port",
+                         "sample": "%d full steps at %d rows (gather + %s_update, numpy/OpenBLAS fp32, best-of thread count)"
+                                   % (args.steps, n_rows, args.algo)},
+        "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
 
 
 # =============================================================================== native arm
+class Bench:
+    """One agent (DDPG or TD3) + synthetic per-step inputs on this rank's GPU."""
+
+    def __init__(self, algo, n_rows, dev, rank, world, data_parallel, n_distinct=16, seed=1234, flush=None):
+        import torch
+        import recnn_b200
+        self.torch, self.algo, self.n_rows, self.dev, self.rank, self.world = torch, algo, n_rows, dev, rank, world
+        torch.manual_seed(seed)                       # same weights on every rank
+        rng = np.random.default_rng(0)
+        self.table = torch.from_numpy(rng.standard_normal((N_ITEMS, DIM), dtype=np.float32)).to(dev)
+        actor = recnn_b200.nn.Actor(S_DIM, DIM, HIDDEN, 6e-1)
+        if algo == "ddpg":
+            agent = recnn_b200.nn.DDPG(actor, recnn_b200.nn.Critic(S_DIM, DIM, HIDDEN, 54e-2)).to(dev)
+        else:
+            agent = recnn_b200.nn.TD3(actor, recnn_b200.nn.Critic(S_DIM, DIM, HIDDEN, 54e-2),
+                                      recnn_b200.nn.Critic(S_DIM, DIM, HIDDEN, 54e-2)).to(dev)
+        for k in list(agent.optimizers):
+            net = k.replace("optimizer", "net")
+            agent.optimizers[k] = recnn_b200.optim.Adam(agent.nets[net].parameters(), lr=1e-5)
+        if data_parallel and world > 1:
+            recnn_b200.dist.enable_data_parallel(agent)
+        self.agent = agent
+        self.n_distinct = n_distinct
+        items_np, ratings_np, done_np = synth_step_inputs(100 + rank, n_rows, n_distinct)
+        self.items_h = [torch.from_numpy(items_np[i]).pin_memory() for i in range(n_distinct)]
+        self.ratings_h = [torch.from_numpy(ratings_np[i]).pin_memory() for i in range(n_distinct)]
+        self.done_h = torch.from_numpy(done_np).pin_memory()
+        self.items_d = [t.to(dev) for t in self.items_h]
+        self.ratings_d = [t.to(dev) for t in self.ratings_h]
+        self.done_d = self.done_h.to(dev)
+        self.flush = flush if flush is not None else torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    def engine(self):
+        from recnn_b200 import _lib
+        from recnn_b200.nn.update._engine import get_engine
+        return get_engine(_lib.ALGO_DDPG if self.algo == "ddpg" else _lib.ALGO_TD3, self.agent.nets, self.dev)
+
+    def batch(self, i, host):
+        return {"items": self.items_h[i] if host else self.items_d[i],
+                "ratings": self.ratings_h[i] if host else self.ratings_d[i],
+                "done": self.done_h if host else self.done_d, "table": self.table}
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def prime(self, host):
+        """Both variants of the step (policy / non-policy) seen twice: direct launch, then graph capture --
+        so no capture can land inside a timed region whatever --warmup is."""
+        for s in (0, 0, 1, 1):
+            self.agent._step = s
+            self.agent.update(self.batch(0, host), learn=True)
+        self.agent._step = 0
+
+    def run(self, host_inputs, steps, warmup, repeats, flush_l2=True, batch_fn=None):
+        """-> dict(ms = [per-repeat device ms of `steps` steps, max over ranks], kernels per repeat, last loss)."""
+        torch = self.torch
+        self.prime(host_inputs)
+        agent = self.agent
+        agent._step = 0
+        it = 0
+        loss = None
+
+        def one(timed_events=None):
+            nonlocal it, loss
+            if flush_l2:
+                self.flush.zero_()
+            b = batch_fn() if batch_fn is not None else self.batch(it % self.n_distinct, host_inputs)
+            if timed_events is not None:
+                timed_events[0].record()
+            loss = agent.update(b, learn=True)          # H2D (if host) + fused step + D2H of the losses
+            agent.step()
+            if timed_events is not None:
+                timed_events[1].record()
+            it += 1
+
+        for _ in range(warmup):
+            one()
+        rep_ms, kernels = [], 0
+        wall = 0.0
+        for _ in range(repeats):
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+            self.barrier()
+            k0 = self.engine().kernels
+            t0 = time.perf_counter()
+            for s in range(steps):
+                one(ev[s])
+            self.barrier()
+            wall += time.perf_counter() - t0
+            kernels = self.engine().kernels - k0
+            ms = sum(a.elapsed_time(b) for a, b in ev)
+            t = torch.tensor([ms], dtype=torch.float64, device=self.dev)
+            if self.world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            rep_ms.append(float(t.item()))
+        return {"ms": rep_ms, "kernels": int(kernels), "loss": loss, "wall_s": wall}
+
+
+def summarize(rep_ms, steps, world):
+    """steps/s per repeat -> median (whole job: x world 4096-row minibatches), min, max."""
+    v = sorted(steps / (m / 1e3) * world for m in rep_ms)
+    med = float(np.median(v))
+    return med, {"repeats": len(v), "min": v[0], "max": v[-1], "rel": (v[-1] - v[0]) / med if med else None}
+
+
+def dp_check(dev, rank, world):
+    """N > 1 only (the driver's GPU test box has one GPU): three parity-mode DDPG steps (SGD, replayed dropout
+    masks) on a small canonical-shape case, rows sharded over the ranks with the peer-memory all-reduce, checked
+    (1) replicas bit-identical after the steps and (2) equal to the SAME steps run unsharded on one GPU
+    (losses 1e-5 relative; every weight within 2e-3 of the largest weight change + 1e-5 relative).  Raises on failure."""
+    import torch
+    import torch.distributed as dist
+    import recnn_b200
+    from recnn_b200.nn.arena import param_arena
+    S, A, H, n, n_items, steps = S_DIM, DIM, HIDDEN, 64 * world, 2000, 3
+    g = torch.Generator().manual_seed(4242)
+    table = torch.randn(n_items, DIM, generator=g)
+    items = torch.randint(0, n_items, (n, FRAME + 1), generator=g)
+    ratings = torch.randint(-4, 6, (n, FRAME + 1), generator=g).float()
+    done = torch.zeros(n)
+    done[n // 3] = 1.0
+    done[-1] = 1.0
+    masks = [[(torch.rand(n, H, generator=g) < 0.5).to(torch.uint8) for _ in range(6)] for _ in range(steps)]
+
+    def make():
+        torch.manual_seed(99)
+        agent = recnn_b200.nn.DDPG(recnn_b200.nn.Actor(S, A, H, 6e-1), recnn_b200.nn.Critic(S, A, H, 54e-2)).to(dev)
+        for k in list(agent.optimizers):
+            agent.optimizers[k] = recnn_b200.optim.SGD(agent.nets[k.replace("optimizer", "net")].parameters(), lr=1e-3)
+        return agent
+
+    def run(agent, lo, hi, n_global):
+        losses = []
+        tab = table.to(dev)
+        init = {k: param_arena(m).clone() for k, m in agent.nets.items()}
+        for s in range(steps):
+            agent._step = s * POLICY_STEP          # every step is a policy step: actor all-reduce + Polyak covered
+            b = {"items": items[lo:hi], "ratings": ratings[lo:hi], "done": done[lo:hi], "table": tab,
+                 "dropout_masks": [m[lo:hi].contiguous() for m in masks[s]], "n_rows_global": n_global}
+            losses.append(agent.update(b, learn=True))
+        return losses, init
+
+    dp = make()
+    recnn_b200.dist.enable_data_parallel(dp)
+    lo, hi = recnn_b200.dist.shard_rows(n, rank, world)
+    dp_losses, _ = run(dp, lo, hi, n)
+    torch.cuda.synchronize(dev)
+    # (1) replicas bit-identical
+    for name in sorted(dp.nets):
+        a = param_arena(dp.nets[name])
+        ref = a.clone()
+        dist.broadcast(ref, src=0)
+        if not torch.equal(a, ref):
+            raise AssertionError("dp_check: replica %d of %s differs from rank 0 after %d steps" % (rank, name, steps))
+    # (2) equal to the unsharded run (every rank runs it: cheap, and keeps the ranks in lock step)
+    single = make()
+    s_losses, init = run(single, 0, n, n)
+    worst = 0.0
+    for a, b in zip(dp_losses, s_losses):
+        for k in ("value", "policy"):
+            err = abs(a[k] - b[k]) / (abs(b[k]) + 0.1)
+            worst = max(worst, err)
+            if err > 1e-5:
+                raise AssertionError("dp_check: %s loss %r (sharded) vs %r (one GPU)" % (k, a[k], b[k]))
+    wdiff = 0.0
+    for name in sorted(dp.nets):
+        a, b = param_arena(dp.nets[name]), param_arena(single.nets[name])
+        change = (b - init[name]).abs().max().item()
+        d = (a - b).abs().max().item()
+        tol = 2e-3 * change + 1e-5 * b.abs().max().item()
+        wdiff = max(wdiff, d / (change + 1e-30))
+        if d > tol:
+            raise AssertionError("dp_check: %s differs from the one-GPU run by %.3e (largest change %.3e)" % (name, d, change))
+    return {"status": "ok", "ranks": world, "rows": n, "steps": steps, "replicas_bit_identical": True,
+            "max_loss_rel_err_vs_one_gpu": worst, "max_weight_diff_over_largest_change": wdiff,
+            "transport": "peer" if getattr(dp.nets["policy_net"], "_recnn_dp", (0, 0, None))[2] is not None else "nccl"}
+
+
 def run_native(args):
     import torch
     import torch.distributed as dist
@@ -232,94 +442,44 @@ def run_native(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
+    algo = args.algo
+    steps, warmup = args.steps, max(args.warmup, 3)
+    repeats = args.repeats if args.repeats > 0 else (5 if steps <= 100 else 3)
 
-    opts = {}
-    for kv in args.opt:
-        name, _, val = kv.partition("=")
-        _lib.set_option(name, int(val))
-        opts[name] = int(val)
+    check = dp_check(dev, rank, world) if world > 1 else None
 
-    torch.manual_seed(1234)                       # same weights on every rank
-    rng = np.random.default_rng(0)
-    table = torch.from_numpy(rng.standard_normal((N_ITEMS, DIM), dtype=np.float32)).to(dev)
-    actor = recnn_b200.nn.Actor(S_DIM, DIM, HIDDEN, 6e-1)
-    critic = recnn_b200.nn.Critic(S_DIM, DIM, HIDDEN, 54e-2)
-    agent = recnn_b200.nn.DDPG(actor, critic).to(dev)
-    for k, net in (("policy_optimizer", "policy_net"), ("value_optimizer", "value_net")):
-        agent.optimizers[k] = recnn_b200.optim.Adam(agent.nets[net].parameters(), lr=1e-5)
-    if world > 1:
-        recnn_b200.dist.enable_data_parallel(agent)
-
-    n_rows = ROWS_PER_GPU
-    total = args.steps + args.warmup
-    n_distinct = min(total, 16)
-    items_np, ratings_np, done_np = synth_step_inputs(100 + rank, n_rows, n_distinct)
-    items_h = [torch.from_numpy(items_np[i]).pin_memory() for i in range(n_distinct)]
-    ratings_h = [torch.from_numpy(ratings_np[i]).pin_memory() for i in range(n_distinct)]
-    done_h = torch.from_numpy(done_np).pin_memory()
-    items_d = [t.to(dev) for t in items_h]
-    ratings_d = [t.to(dev) for t in ratings_h]
-    done_d = done_h.to(dev)
-    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)    # 256 MB > 126 MB L2
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    def run_loop(host_inputs, steps, warmup, flush_l2=True):
-        agent._step = 0
-        eng_kernels0 = None
-        times = []
-        ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
-        ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
-        for it in range(warmup + steps):
-            i = it % n_distinct
-            if it == warmup:
-                barrier()
-                from recnn_b200.nn.update._engine import get_engine
-                eng = get_engine(_lib.ALGO_DDPG, agent.nets, dev)
-                eng_kernels0 = eng.kernels
-                t_wall0 = time.perf_counter()
-            if flush_l2:
-                flush.zero_()
-            batch = {"items": items_h[i] if host_inputs else items_d[i],
-                     "ratings": ratings_h[i] if host_inputs else ratings_d[i],
-                     "done": done_h if host_inputs else done_d, "table": table}
-            if it >= warmup:
-                ev0[it - warmup].record()
-            loss = agent.update(batch, learn=True)          # H2D (if host) + fused step + D2H of the losses
-            agent.step()
-            if it >= warmup:
-                ev1[it - warmup].record()
-        barrier()
-        wall = time.perf_counter() - t_wall0
-        dev_ms = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
-        t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        eng = get_engine(_lib.ALGO_DDPG, agent.nets, dev)
-        return float(t.item()), wall, eng.kernels - eng_kernels0, loss
-
+    main = Bench(algo, ROWS_PER_GPU, dev, rank, world, data_parallel=True)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    dev_ms, wall_s, kernels, last_loss = run_loop(False, args.steps, args.warmup)
+    r_dev = main.run(False, steps, warmup, repeats)
     clocks = sampler.stop() if rank == 0 else {}
-    e2e_ms, e2e_wall, _, _ = run_loop(True, args.steps, max(3, args.warmup // 2))
-    warm_ms, _, _, _ = run_loop(False, args.steps, 3, flush_l2=False)
+    r_e2e = main.run(True, steps, 3, repeats)
+    r_warm = main.run(False, steps, 3, 1, flush_l2=False)
+    value, spread = summarize(r_dev["ms"], steps, world)
+    e2e_value, e2e_spread = summarize(r_e2e["ms"], steps, world)
+    warm_value, _ = summarize(r_warm["ms"], steps, world)
+    ms_per_step = float(np.median(r_dev["ms"])) / steps
 
-    rows_global = n_rows * world
-    # One unit = one 4096-row minibatch through the update step.  Data parallel is weak scaling: every rank
-    # takes its own 4096 rows per step and the gradients are all-reduced, so a global step consumes `world`
-    # units; `value` counts units/s over the whole job (= optimizer updates/s * n_gpus).
-    global_steps_per_sec = args.steps / (dev_ms / 1e3)
-    value = global_steps_per_sec * world
-    e2e_value = args.steps / (e2e_ms / 1e3) * world
+    # strong scaling (BASELINE configs[3]): 8192 global rows sharded over the GPUs, optimizer updates/s
+    strong = None
+    if STRONG_ROWS % world == 0:
+        sb = Bench("ddpg", STRONG_ROWS // world, dev, rank, world, data_parallel=True, flush=main.flush)
+        k = min(steps, 50)
+        r = sb.run(False, k, 3, 3)
+        sv, ss = summarize(r["ms"], k, 1)
+        strong = {"workload": "DDPG batch %d rows sharded over %d GPU(s) (BASELINE configs[3])" % (STRONG_ROWS, world),
+                  "global_rows": STRONG_ROWS, "rows_per_gpu": STRONG_ROWS // world, "updates_per_sec": sv,
+                  "ms_per_step": 1e3 / sv, "spread": ss, "steps": k}
+        del sb
+
     line = None
     if rank == 0:
         L = _lib.lib()
         st = torch.cuda.current_stream(dev).cuda_stream
+        flush = main.flush
+        n_rows = ROWS_PER_GPU
+        agent, table = main.agent, main.table
 
         def time_kernel(fn, iters=20):
             for _ in range(3):
@@ -336,6 +496,7 @@ def run_native(args):
             return float(np.mean(ts))
 
         # (1) the materialising gather kernel  (HBM bound)
+        items_d, ratings_d = main.items_d, main.ratings_d
         g_state = torch.empty(n_rows, S_DIM, device=dev)
         g_next = torch.empty(n_rows, S_DIM, device=dev)
         g_act = torch.empty(n_rows, DIM, device=dev)
@@ -368,36 +529,61 @@ def run_native(args):
             h1.data_ptr(), HIDDEN, 64, st)))
         l1_tflops = n_rows * L1_FWD_FLOP_PER_ROW / (l1_ms * 1e-3) / 1e12
         tf32_peak = peaks["bf16"] / 2.0           # dense TF32 = half the dense bf16 rate
-        flop_step = rows_global * (DDPG_FLOP_POLICY + (POLICY_STEP - 1) * DDPG_FLOP_NONPOLICY) / POLICY_STEP
-        feed_info = bench_device_feed(agent, table, dev, flush, time_kernel, args) if world == 1 else None
-        cpu = cpu_baseline_sample() if (world == 1 and not args.no_cpu_baseline) else None
+        rows_global = n_rows * world
+        updates_per_sec = value / world
+
+        def flop_per_step(a, rows):
+            return rows * (FLOP[a][1] + (POLICY_STEP - 1) * FLOP[a][0]) / POLICY_STEP
+
+        feed_info = bench_device_feed(main, time_kernel, steps) if (world == 1 and algo == "ddpg") else None
+        # (3) the other algorithm (BASELINE configs[2] next to configs[1]) on one GPU, shorter run
+        other = None
+        if world == 1 and not args.no_other_algo:
+            oa = "td3" if algo == "ddpg" else "ddpg"
+            ob = Bench(oa, n_rows, dev, rank, 1, data_parallel=False, flush=flush)
+            k = min(steps, 100)
+            ro = ob.run(False, k, 3, 3)
+            ro_e2e = ob.run(True, k, 3, 3)
+            ov, osp = summarize(ro["ms"], k, 1)
+            oe, _ = summarize(ro_e2e["ms"], k, 1)
+            other = {"workload": workload_name(oa), "steps_per_sec": ov, "ms_per_step": 1e3 / ov, "spread": osp,
+                     "e2e_steps_per_sec": oe, "steps": k, "gpu_launches": ro["kernels"],
+                     "update_tflops": flop_per_step(oa, n_rows) * ov / 1e12,
+                     "step_tensor_frac": 3.0 * flop_per_step(oa, n_rows) * ov / 1e12 / tf32_peak}
+            if not args.no_cpu_baseline:
+                other["cpu_baseline"] = cpu_sample(n_rows, oa, 8.0, min_steps=6, max_steps=30)
+            del ob
+        cpu = cpu_sample(n_rows, algo, 15.0) if (world == 1 and not args.no_cpu_baseline) else None
+        cpu256 = cpu_sample(256, "ddpg", 4.0, min_steps=20, max_steps=400) if (world == 1 and not args.no_cpu_baseline) else None
+        comm = getattr(agent.nets["policy_net"], "_recnn_dp", (0, 0, None))[2]
         line = {
-            "metric": "ddpg_update_steps_per_sec", "value": value, "unit": "steps/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+            "metric": "%s_update_steps_per_sec" % algo, "value": value, "unit": "steps/s", "n_gpus": world,
+            "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "DDPG batch 4096 rows/GPU, 128-d embeddings, 26744 items, frame 10 (BASELINE configs[1])",
+            "config": {"workload": workload_name(algo),
                        "rows_per_gpu": n_rows, "global_rows": rows_global, "parallelism": "dp%d" % world,
                        "unit_def": "4096-row minibatches through the update step per second, whole job "
                                    "(each data-parallel step consumes n_gpus of them; optimizer updates/s = value / n_gpus)",
                        "grad_allreduce": ("none" if world == 1 else
-                                          "in-graph NVLink peer-memory kernels (recnn_comm_*)" if getattr(
-                                              agent.nets["policy_net"], "_recnn_dp", (0, 0, None))[2] is not None
+                                          "in-graph NVLink peer-memory kernels (recnn_comm_*)" if comm is not None
                                           else "NCCL between the step's phases"),
                        "optimizer": "adam lr=1e-5 (fused)", "policy_step": POLICY_STEP,
                        "dropout": "on (device Philox)", "l2": "flushed between timed steps (256 MB write)",
+                       "timing": "both graph variants primed before the timed region; %d repeats of %d steps, median" % (repeats, steps),
                        "inputs": "items/ratings/done resident in HBM; frames gathered on device inside the step",
                        "matmul": "tcgen05 3xTF32 (error-compensated, fp32-grade) with fp32 CUDA-core fallbacks for the 256->1 head"},
-            "optimizer_updates_per_sec": global_steps_per_sec,
-            "rows_per_sec": global_steps_per_sec * rows_global,
-            "update_tflops": flop_step * global_steps_per_sec / 1e12,
+            "spread": spread,
+            "optimizer_updates_per_sec": updates_per_sec,
+            "rows_per_sec": updates_per_sec * rows_global,
+            "update_tflops": flop_per_step(algo, rows_global) * updates_per_sec / 1e12,
             # (algorithmic FLOPs x 3 TF32 passes) / (t_step x TF32 peak x GPUs): the whole step, not one kernel
-            "step_tensor_frac": 3.0 * flop_step * global_steps_per_sec / 1e12 / (tf32_peak * world),
-            "value_warm_l2": args.steps / (warm_ms / 1e3) * world,
-            "wall_s": wall_s,
-            "e2e": {"value": e2e_value, "unit": "steps/s",
+            "step_tensor_frac": 3.0 * flop_per_step(algo, rows_global) * updates_per_sec / 1e12 / (tf32_peak * world),
+            "value_warm_l2": warm_value,
+            "wall_s": r_dev["wall_s"],
+            "e2e": {"value": e2e_value, "unit": "steps/s", "spread": e2e_spread,
                     "h2d_bytes_per_step": int(n_rows * ((FRAME + 1) * 12 + 4)), "d2h_bytes_per_step": 16,
-                    "what": "ddpg_update(batch of pinned host items/ratings/done) -> dict of python floats"},
-            "gpu_launches": int(kernels),
+                    "what": "%s_update(batch of pinned host items/ratings/done) -> dict of python floats" % algo},
+            "gpu_launches": int(r_dev["kernels"]),
             "roofline": {"bound": "tensor", "kernel": "layer-1 forward GEMM [4096x1290]x[1290x256] (tc_gemm_kernel, tcgen05 kind::tf32, 3 MMA passes/product)",
                          "achieved": 3.0 * l1_tflops, "algorithmic_fp32": l1_tflops, "peak": tf32_peak, "unit": "TFLOP/s",
                          "frac": 3.0 * l1_tflops / tf32_peak,
@@ -414,12 +600,21 @@ def run_native(args):
                                                 "note": "same kernel, 16x the rows: the 710 MB of output no longer fits in L2 and goes to HBM, "
                                                         "the 13.7 MB table is still served by L2, so DRAM traffic ~ output + table once"}},
             "clocks": clocks,
-            "last_loss": last_loss,
+            "last_loss": r_dev["loss"],
         }
-        if opts:
-            line["config"]["options"] = opts
+        if args.opt:
+            line["config"]["options"] = {kv.partition("=")[0]: int(kv.partition("=")[2]) for kv in args.opt}
+        if strong is not None:
+            line["strong"] = strong
+        if check is not None:
+            line["dp_check"] = check
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if cpu256 is not None:
+            cpu256["what"] = "BASELINE configs[0]: DDPG batch 256 on the CPU path"
+            line["cpu_baseline_n256"] = cpu256
+        if other is not None:
+            line["td3" if algo == "ddpg" else "ddpg"] = other
         if feed_info is not None:
             line["feed"] = feed_info
     if world > 1:
@@ -432,39 +627,30 @@ def run_native(args):
 FEED_BYTES_PER_ROW = (FRAME + 1) * 12 * 2 + 4          # read ids+ratings, write ids+ratings, write done
 
 
-def bench_device_feed(agent, table, dev, flush, time_kernel, args):
+def bench_device_feed(main, time_kernel, steps):
     """minibatches cut on the device out of resident user histories
     (recnn_b200.data.DeviceFrameFeed) instead of a DataLoader worker + H2D.  Synthetic "rolling users":
     2048 users x 138 interactions (128 windows each, 262,144 windows).  Reports the window-gather kernel
     alone and the update step fed by ``feed.sample(4096)`` (no host->device traffic at all)."""
     import torch
     from recnn_b200.data.feed import HistoryCSR, DeviceFrameFeed
+    dev = main.dev
     rng = np.random.default_rng(7)
     n_users, length = 2048, 138
     items = rng.integers(0, N_ITEMS, size=(n_users, length), dtype=np.int64)
     rates = rng.integers(-4, 6, size=(n_users, length)).astype(np.float64)
-    feed = DeviceFrameFeed(HistoryCSR(np.arange(n_users), list(items), list(rates), FRAME), table, dev)
+    feed = DeviceFrameFeed(HistoryCSR(np.arange(n_users), list(items), list(rates), FRAME), main.table, dev)
     n_rows = ROWS_PER_GPU
     w = torch.randint(0, feed.csr.n_windows, (n_rows,), device=dev)
     ids_ms = time_kernel(lambda: feed.windows(w))
     users32 = list(range(0, 32 * 8, 8))                    # 32 users x 128 windows = 4096 rows
     users_ms = time_kernel(lambda: feed.batch(users32))
-    steps, warm = args.steps, max(3, args.warmup // 2)
-    agent._step = 0
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-    for it in range(warm + steps):
-        flush.zero_()
-        if it >= warm:
-            ev[it - warm][0].record()
-        agent.update(feed.sample(n_rows), learn=True)      # randint + window gather + fused step + loss read-back
-        agent.step()
-        if it >= warm:
-            ev[it - warm][1].record()
-    torch.cuda.synchronize(dev)
-    ms = sum(a.elapsed_time(b) for a, b in ev)
+    k = min(steps, 100)
+    r = main.run(False, k, 3, 3, batch_fn=lambda: feed.sample(n_rows))   # randint + window gather + fused step + loss read-back
+    v, sp = summarize(r["ms"], k, 1)
     return {"what": "update step fed by DeviceFrameFeed.sample(4096): windows cut on the device from resident "
                     "histories (2048 users x 138 interactions), no host->device copies",
-            "steps_per_sec": steps / (ms / 1e3), "ms_per_step": ms / steps, "h2d_bytes_per_step": 0,
+            "steps_per_sec": v, "ms_per_step": 1e3 / v, "spread": sp, "h2d_bytes_per_step": 0,
             "window_gather_ids_ms": ids_ms, "window_gather_users_ms": users_ms,
             "window_gather_bytes_per_launch": n_rows * FEED_BYTES_PER_ROW,
             "note": "window_gather_*_ms include the output allocation and (users form) a 520-byte plan upload; "
@@ -476,10 +662,13 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--repeats", type=int, default=0, help="repeats of the K timed steps (default: 5 if K <= 100 else 3)")
+    ap.add_argument("--algo", default="ddpg", choices=["ddpg", "td3"])
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
-                    help="library A/B switch (recnn_debug_set_option), e.g. --opt presplit=1 --opt gather_variant=1")
-    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (A/B runs)")
+                    help="library A/B switch (recnn_debug_set_option)")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline legs (A/B runs)")
+    ap.add_argument("--no-other-algo", action="store_true", help="skip the sub-object of the other algorithm")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps > 40:          # bounded: the CPU port does ~3-10 steps/s
@@ -487,6 +676,11 @@ def main():
         args.warmup = min(args.warmup, 3)
         run_reference(args)
     else:
+        if args.opt:
+            from recnn_b200 import _lib
+            for kv in args.opt:
+                name, _, val = kv.partition("=")
+                _lib.set_option(name, int(val))
         run_native(args)
 
 
