@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define RECNN_B200_ABI_VERSION 1
+#define RECNN_B200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define RECNN_API __attribute__((visibility("default")))
@@ -201,7 +201,7 @@ enum {
   RECNN_PH_SOFT_UPDATE = 32, /* Polyak target updates (policy steps only)              */
   RECNN_PH_GATHER = 64,      /* frame form: materialise state/next_state/action into the
                               * workspace (split-phase callers pass it once per step)  */
-  RECNN_PH_FINISH = 128,     /* end of step: copy losses to losses_host (if set), ++*rng_step */
+  RECNN_PH_FINISH = 128,     /* end of step: error bits -> losses[4], copy losses to losses_host (if set), ++*rng_step */
   RECNN_PH_ALL = 255
 };
 
@@ -253,8 +253,11 @@ typedef struct recnn_step_args {
   int64_t* rng_step;         /* device int64 counter; read by every phase, incremented by RECNN_PH_FINISH */
 
   /* outputs */
-  float* losses;           /* device fp32[4]: value(1), value2, policy, ||actor grad||_1 */
-  float* losses_host;      /* optional PINNED host fp32[4]: RECNN_PH_FINISH copies `losses` here (async) */
+  float* losses;           /* device, 8 words: fp32 value(1), value2, policy, ||actor grad||_1; then one int32 of
+                            * error bits written by RECNN_PH_FINISH (1: an item id of the frame-form batch was outside
+                            * [0, n_items) -- such rows read table row 0; 2: the ranks of a data-parallel step
+                            * disagree on n_rows_global); 3 spare words */
+  float* losses_host;      /* optional PINNED host buffer of 8 words: RECNN_PH_FINISH copies `losses` here (async) */
   float* next_action_out;  /* optional fp32[n_rows,A] (debug["next_action"]) */
   float* gen_action_out;   /* optional fp32[n_rows,A] (debug["gen_action"])  */
 

@@ -4,22 +4,36 @@
 // GPUs of one box with an all-reduce of the Actor/Critic gradients over NVLink.  Calling NCCL between
 // the phases of the step costs three host-launched collectives and cuts the step's CUDA graph in three;
 // instead every rank maps its peers' staging buffers (cudaIpc, NVLink/NVSwitch peer access) and ONE
-// kernel per gradient arena does
-//     copy my gradient -> my staging slot | signal peers | wait for peers | sum all ranks' slots in
-//     rank order -> my gradient (in place)  [+ the L1 norm of the summed gradient for the reference's
-//     clip_grad_norm_(params, -1, 1) quirk]
+// kernel per gradient arena does a TWO-SHOT all-reduce with remote STORES only (posted writes: nothing
+// ever waits on an NVLink read round trip), fused with everything that used to sit around it:
+//
+//   A  reduce-scatter, push side: rank r owns slice r of the arena.  Every rank stores slice s of its local
+//      gradient into rank s's contribution buffer [my rank] (+ its few "aux" floats: loss partial sums and
+//      the global row count it assumed), fences, and raises flag A on every peer.
+//   B  owner side: wait for all W flags A, sum the W contributions of my slice IN RANK ORDER (the same
+//      bits on every rank), store the reduced slice into every peer's result buffer (+ this CTA's partial
+//      L1 norm of the slice), fence, raise flag B on every peer.
+//   C  wait for all W flags B.  Every rank now holds the whole reduced gradient: sum the aux floats in rank
+//      order (-> global loss means), form the reference's clip_grad_norm_(params, -1, 1) coefficient from the
+//      L1 partials (fixed order), write the gradient back to the caller's arena (scaled by the coefficient when
+//      there is one) and -- when the caller passes a built-in optimizer -- apply SGD/Adam in the same pass.
+//
+// Bytes on NVLink per rank and arena: 2 (W-1)/W x 1.72 MB (3.0 MB at W = 8) instead of the (W-1) x 1.72 MB of
+// remote READS (12 MB at W = 8) of the one-shot version of round 1; two flag hops instead of one.
 // It is an ordinary kernel on the step's stream, so the whole data-parallel step is captured in one
-// CUDA graph exactly like the single-GPU step.  The sum is taken in rank order 0..W-1 on every rank,
+// CUDA graph exactly like the single-GPU step.  All sums are taken in rank order 0..W-1 on every rank,
 // so all replicas hold bit-identical gradients (and therefore weights) after every step.
 //
 // Protocol (epoch e = number of collectives issued so far on this communicator + 1; all on one stream):
-//   * staging is double buffered by e & 1.  A rank may overwrite slot e & 1 only when every peer has
-//     finished reading the data of epoch e-2; a peer signals epoch e-1 only after its epoch e-2 kernel
-//     has completed (stream order), and this rank waited for all epoch e-1 signals before finishing e-1.
-//   * signal: after all CTAs copied (fence + counter), the last CTA stores e into flags[my_rank] in
-//     EVERY peer's memory (remote store), so the waiting side polls its own HBM.
+//   * contribution / result / aux buffers are double buffered by e & 1.  A rank can only be one epoch ahead
+//     of any peer (it needs every peer's flags of epoch e to finish e), so when it writes buffers (e+2) & 1
+//     = e & 1 during epoch e+2 every peer has completed its epoch-e kernel and no longer reads them.
+//   * flags hold epochs and are compared as signed distances (a 32-bit wrap is harmless).
 //   * waits are bounded (~20 s of %globaltimer): a lost peer makes the kernel trap instead of hanging the GPU.
+//   * ranks that disagree on n_rows_global (uneven shards without batch["n_rows_global"]) raise *err_flag.
 #include <string.h>
+
+#include <type_traits>
 
 #include "common.cuh"
 #include "pointwise.cuh"
@@ -28,21 +42,32 @@ namespace recnn {
 
 constexpr int kMaxRanks = 8;
 constexpr int kCommThreads = 512;
+constexpr int kMaxAux = 8;
 
 struct CommDev {                       // lives at the head of every rank's shared allocation
-  unsigned flags[kMaxRanks];           // flags[src] = last epoch src has published  (written by peers)
+  unsigned flag_a[kMaxRanks];          // flag_a[src] = last epoch whose contributions src has published here
+  unsigned flag_b[kMaxRanks];          // flag_b[src] = last epoch whose reduced slice src has published here
   unsigned epoch;                      // collectives completed by this rank           (local)
-  unsigned arrive;                     // CTAs that finished copying (wraps to 0)        (local)
-  unsigned done;                       // CTAs that finished reducing (wraps to 0)       (local)
-  unsigned pad[32 - kMaxRanks - 3];
+  unsigned arrive_a, arrive_b, done;   // CTA counters (wrap to 0)                     (local)
+  unsigned pad[12];
+  float aux[2][kMaxRanks][kMaxAux + 1];           // [e & 1][src]: aux floats, then the row count src assumed
+  float l1[2][kMaxRanks][kNumSMs];                // [e & 1][src][cta]: partial L1 norms of src's reduced slice
 };
-static_assert(sizeof(CommDev) == 128, "CommDev");
 
 struct CommPeers {                     // kernel parameter
   CommDev* ctrl[kMaxRanks];
-  float* stage[kMaxRanks];             // 2 slots of `capacity` floats each
-  long long capacity;
+  float* contrib[kMaxRanks];           // [2][W][slice_cap] floats: contributions to THAT rank's slice
+  float* result[kMaxRanks];            // [2][capacity] floats: the reduced gradient, assembled by the owners
+  long long capacity, slice_cap;
   int rank, world;
+};
+
+struct CommOpt {                       // optional fused optimizer (kind == RECNN_OPT_EXTERNAL: none)
+  int kind;
+  OptConsts k;
+  double beta1, beta2, lr;
+  float *p, *m, *v;
+  int* t;
 };
 
 }  // namespace recnn
@@ -70,104 +95,193 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-
-// grid <= number of SMs (all CTAs must be co-resident: they wait for each other's peers)
-__global__ void __launch_bounds__(kCommThreads, 1)
-allreduce_kernel(CommPeers c, float* __restrict__ buf, long long n, float max_norm, float* coef, float* l1_out,
-                 float* block_partials) {
-  __shared__ float red[32];
-  __shared__ unsigned s_epoch;
-  CommDev* me = c.ctrl[c.rank];
-  if (threadIdx.x == 0) s_epoch = *((volatile unsigned*)&me->epoch) + 1;
-  __syncthreads();
-  const unsigned e = s_epoch;
-  const long long slot = (long long)(e & 1u) * c.capacity;
-  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
-  const bool vec = (n & 3) == 0 && ((reinterpret_cast<uintptr_t>(buf) & 15) == 0);
-
-  // ---- A: publish my contribution
-  float* mine = c.stage[c.rank] + slot;
-  if (vec) {
-    const float4* src = reinterpret_cast<const float4*>(buf);
-    float4* dst = reinterpret_cast<float4*>(mine);
-    for (long long i = tid; i < n / 4; i += nth) dst[i] = src[i];
-  } else {
-    for (long long i = tid; i < n; i += nth) mine[i] = buf[i];
-  }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned t = atomicInc(&me->arrive, gridDim.x - 1);
-    if (t == gridDim.x - 1) {                       // every CTA's slice is visible system-wide
-      __threadfence_system();
-      for (int p = 0; p < c.world; ++p) st_release_sys(&c.ctrl[p]->flags[c.rank], e);
-    }
-  }
-  // ---- B: wait for every rank's contribution
-  if (threadIdx.x < c.world) {
+// threads [0, world) poll one peer's flag each; bounded
+__device__ __forceinline__ void wait_flags(const unsigned* flags, unsigned e, int world, int rank, const char* what) {
+  if ((int)threadIdx.x < world) {
     const unsigned long long t0 = comm_gtimer();
-    // epochs only grow; compare as a signed distance so that a 32-bit wrap is harmless
-    while ((int)(ld_acquire_sys(&me->flags[threadIdx.x]) - e) < 0) {
+    while ((int)(ld_acquire_sys(&flags[threadIdx.x]) - e) < 0) {
       if (comm_gtimer() - t0 > 20000000000ull) {
-        printf("recnn_b200 allreduce: rank %d timed out waiting for rank %d (epoch %u)\n", c.rank, (int)threadIdx.x, e);
+        printf("recnn_b200 allreduce: rank %d timed out waiting for %s of rank %d (epoch %u)\n", rank, what,
+               (int)threadIdx.x, e);
         __trap();
       }
     }
   }
   __syncthreads();
-  // ---- C: sum in rank order (bit-identical on every rank), in place
-  float l1 = 0.f;
-  if (vec) {
-    float4* out = reinterpret_cast<float4*>(buf);
-    for (long long i = tid; i < n / 4; i += nth) {
-      float4 s = __ldcg(reinterpret_cast<const float4*>(c.stage[0] + slot) + i);
-      for (int p = 1; p < c.world; ++p) {
-        const float4 v = __ldcg(reinterpret_cast<const float4*>(c.stage[p] + slot) + i);
-        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+}
+
+// grid <= number of SMs (all CTAs must be co-resident: they wait for each other's peers).
+// VEC = 4: n % 4 == 0 and buf 16-byte aligned (the arenas); VEC = 1: anything.
+template <int VEC>
+__global__ void __launch_bounds__(kCommThreads, 1)
+allreduce_kernel(CommPeers c, float* __restrict__ buf, long long n, float max_norm, float* coef_out, float* l1_out,
+                 const float* aux_in, float* aux_out, int n_aux, float check_val, int* err_flag, CommOpt opt) {
+  __shared__ float red[32];
+  __shared__ unsigned s_epoch;
+  __shared__ bool s_last;
+  __shared__ float s_coef, s_step_size, s_bc2_sqrt;
+  CommDev* me = c.ctrl[c.rank];
+  if (threadIdx.x == 0) s_epoch = *((volatile unsigned*)&me->epoch) + 1;
+  __syncthreads();
+  const unsigned e = s_epoch;
+  const int par = (int)(e & 1u);
+  const int W = c.world;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  using V = typename std::conditional<VEC == 4, float4, float>::type;
+  const long long units = n / VEC;                               // VEC == 4 => n % 4 == 0
+  const long long slice = (units + W - 1) / W;                   // units per owner (the last slice may be short)
+
+  // ---- A: push slice s of my gradient to owner s (remote stores), aux floats to everyone
+  for (long long i = tid; i < units; i += nth) {
+    const int s = (int)(i / slice);
+    V* dst = reinterpret_cast<V*>(c.contrib[s] + ((long long)par * W + c.rank) * c.slice_cap);
+    dst[i - (long long)s * slice] = reinterpret_cast<const V*>(buf)[i];
+  }
+  if (blockIdx.x == 0 && (int)threadIdx.x < W) {
+    float* dst = c.ctrl[threadIdx.x]->aux[par][c.rank];
+    for (int j = 0; j < n_aux; ++j) dst[j] = aux_in[j];
+    dst[kMaxAux] = check_val;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicInc(&me->arrive_a, gridDim.x - 1);
+    if (t == gridDim.x - 1) {                       // every CTA's stores are visible system-wide
+      __threadfence_system();
+      for (int p = 0; p < W; ++p) st_release_sys(&c.ctrl[p]->flag_a[c.rank], e);
+    }
+  }
+  // ---- B: owner: wait for all contributions, reduce my slice in rank order, push it to everyone
+  wait_flags(me->flag_a, e, W, c.rank, "the contribution");
+  {
+    const long long lo = (long long)c.rank * slice;
+    const long long cnt = units - lo < slice ? (units - lo > 0 ? units - lo : 0) : slice;
+    const float* mine = c.contrib[c.rank] + (long long)par * W * c.slice_cap;
+    float l1 = 0.f;
+    for (long long i = tid; i < cnt; i += nth) {
+      V s = __ldcg(reinterpret_cast<const V*>(mine) + i);
+      for (int p = 1; p < W; ++p) {
+        const V v = __ldcg(reinterpret_cast<const V*>(mine + (long long)p * c.slice_cap) + i);
+        if constexpr (VEC == 4) { s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
+        else s += v;
       }
-      out[i] = s;
-      l1 += fabsf(s.x) + fabsf(s.y) + fabsf(s.z) + fabsf(s.w);
+      if constexpr (VEC == 4) l1 += fabsf(s.x) + fabsf(s.y) + fabsf(s.z) + fabsf(s.w);
+      else l1 += fabsf(s);
+      for (int p = 0; p < W; ++p)
+        reinterpret_cast<V*>(c.result[p] + (long long)par * c.capacity)[lo + i] = s;
     }
-  } else {
-    for (long long i = tid; i < n; i += nth) {
-      float s = __ldcg(c.stage[0] + slot + i);
-      for (int p = 1; p < c.world; ++p) s += __ldcg(c.stage[p] + slot + i);
-      buf[i] = s;
-      l1 += fabsf(s);
+    if (coef_out) {
+      l1 = block_sum(l1, red);
+      if ((int)threadIdx.x < W) c.ctrl[threadIdx.x]->l1[par][c.rank][blockIdx.x] = l1;
     }
   }
-  if (coef) {
-    l1 = block_sum(l1, red);
-    if (threadIdx.x == 0) block_partials[blockIdx.x] = l1;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicInc(&me->arrive_b, gridDim.x - 1);
+    if (t == gridDim.x - 1) {
+      __threadfence_system();
+      for (int p = 0; p < W; ++p) st_release_sys(&c.ctrl[p]->flag_b[c.rank], e);
+    }
   }
-  // ---- D: the last CTA closes the epoch (and finishes the norm)
-  __shared__ bool is_last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) is_last = atomicInc(&me->done, gridDim.x - 1) == gridDim.x - 1;
-  __syncthreads();
-  if (is_last) {
-    if (coef) {
+  // ---- C: everyone: the reduced gradient is complete here
+  wait_flags(me->flag_b, e, W, c.rank, "the reduced slice");
+  if (threadIdx.x < 32) {
+    float coef = 1.0f;
+    if (coef_out) {
+      // ||g||_1 from the owners' per-CTA partials: lane l takes entries l, l+32, ... of the (rank-major, CTA-minor)
+      // list, then a shuffle tree -- the same order on every rank and CTA, so every replica gets the same bits
+      const int total = W * (int)gridDim.x;
       float t = 0.f;
-      for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) t += block_partials[b];
-      t = block_sum(t, red);
-      if (threadIdx.x == 0) {
-        *coef = fminf(max_norm / (t + 1e-6f), 1.0f);     // clip_grad_norm_: max_norm / (total_norm + 1e-6), <= 1
+      for (int k = (int)threadIdx.x; k < total; k += 32) t += __ldcg(&me->l1[par][k / (int)gridDim.x][k % (int)gridDim.x]);
+      t = warp_sum(t);
+      coef = fminf(max_norm / (t + 1e-6f), 1.0f);     // clip_grad_norm_: max_norm / (total_norm + 1e-6), <= 1
+      if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *coef_out = coef;
         if (l1_out) *l1_out = t;
       }
     }
-    if (threadIdx.x == 0) *((volatile unsigned*)&me->epoch) = e;
+    if (threadIdx.x == 0) {
+      s_coef = coef;
+      if (opt.kind != RECNN_OPT_EXTERNAL)
+        opt_scalars(opt.kind, opt.beta1, opt.beta2, opt.lr, *opt.t + 1, &s_step_size, &s_bc2_sqrt);
+      if (blockIdx.x == 0) {
+        bool bad = false;
+        for (int p = 0; p < W; ++p) bad = bad || __ldcg(&me->aux[par][p][kMaxAux]) != check_val;
+        if (bad && err_flag) *err_flag = 1;
+        for (int j = 0; j < n_aux; ++j) {
+          float t = 0.f;
+          for (int p = 0; p < W; ++p) t += __ldcg(&me->aux[par][p][j]);
+          aux_out[j] = t;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  {
+    const float coef = s_coef;
+    const bool scale = coef_out != nullptr;
+    const int t_next = opt.kind != RECNN_OPT_EXTERNAL ? *opt.t + 1 : 0;
+    const float* res = c.result[c.rank] + (long long)par * c.capacity;
+    for (long long i = tid; i < units; i += nth) {
+      V g = __ldcg(reinterpret_cast<const V*>(res) + i);
+      if (scale) {
+        if constexpr (VEC == 4) { g.x = __fmul_rn(g.x, coef); g.y = __fmul_rn(g.y, coef); g.z = __fmul_rn(g.z, coef); g.w = __fmul_rn(g.w, coef); }
+        else g = __fmul_rn(g, coef);
+      }
+      reinterpret_cast<V*>(buf)[i] = g;              // the caller-visible .grad (scaled, as the reference leaves it)
+      if (opt.kind != RECNN_OPT_EXTERNAL) {
+        if constexpr (VEC == 4) {
+          opt_apply(opt.kind, opt.k, s_step_size, s_bc2_sqrt, t_next, opt.p, opt.m, opt.v, 4 * i + 0, g.x);
+          opt_apply(opt.kind, opt.k, s_step_size, s_bc2_sqrt, t_next, opt.p, opt.m, opt.v, 4 * i + 1, g.y);
+          opt_apply(opt.kind, opt.k, s_step_size, s_bc2_sqrt, t_next, opt.p, opt.m, opt.v, 4 * i + 2, g.z);
+          opt_apply(opt.kind, opt.k, s_step_size, s_bc2_sqrt, t_next, opt.p, opt.m, opt.v, 4 * i + 3, g.w);
+        } else {
+          opt_apply(opt.kind, opt.k, s_step_size, s_bc2_sqrt, t_next, opt.p, opt.m, opt.v, i, g);
+        }
+      }
+    }
+  }
+  // ---- D: the last CTA closes the epoch (and advances the optimizer's step count)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicInc(&me->done, gridDim.x - 1) == gridDim.x - 1;
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    if (opt.kind != RECNN_OPT_EXTERNAL) *opt.t = *opt.t + 1;
+    *((volatile unsigned*)&me->epoch) = e;
   }
 }
 
-int launch_comm_allreduce(const recnn_comm* comm, float* buf, int64_t n, float max_norm, float* coef, float* l1_out,
-                          float* block_partials, cudaStream_t st) {
+int launch_comm_allreduce(const recnn_comm* comm, float* buf, int64_t n, const CommReduce& r, cudaStream_t st) {
   RECNN_REQUIRE(comm != nullptr && comm->connected, "communicator is not connected");
-  RECNN_REQUIRE(n > 0 && n <= comm->peers.capacity, "all-reduce larger than the communicator's staging capacity");
+  RECNN_REQUIRE(n >= 0 && n <= comm->peers.capacity, "all-reduce larger than the communicator's staging capacity");
+  RECNN_REQUIRE(n == 0 || buf != nullptr, "buf");
+  RECNN_REQUIRE(r.n_aux >= 0 && r.n_aux <= kMaxAux && (r.n_aux == 0 || (r.aux_in && r.aux_out)), "aux floats");
+  CommOpt opt;
+  memset(&opt, 0, sizeof(opt));
+  opt.kind = RECNN_OPT_EXTERNAL;
+  if (r.optim && r.optim->kind != RECNN_OPT_EXTERNAL) {
+    RECNN_REQUIRE(r.net && r.net->params && r.net->opt_t, "fused optimizer needs params and the step counter");
+    RECNN_REQUIRE(r.optim->kind == RECNN_OPT_SGD || r.optim->kind == RECNN_OPT_ADAM, "built-in optimizer kind must be SGD or ADAM");
+    if (r.optim->kind == RECNN_OPT_ADAM) RECNN_REQUIRE(r.net->opt_m && r.net->opt_v, "Adam needs exp_avg / exp_avg_sq arenas");
+    if (r.optim->kind == RECNN_OPT_SGD && r.optim->momentum != 0.f) RECNN_REQUIRE(r.net->opt_m, "SGD momentum needs a buffer arena");
+    opt.kind = r.optim->kind;
+    opt.k = opt_consts(*r.optim);
+    opt.beta1 = r.optim->beta1; opt.beta2 = r.optim->beta2; opt.lr = r.optim->lr;
+    opt.p = r.net->params; opt.m = r.net->opt_m; opt.v = r.net->opt_v; opt.t = r.net->opt_t;
+  }
   const int64_t per = (int64_t)kCommThreads * 4 * 2;              // two float4 per thread
   int64_t blocks = ceil_div(n, per);
   const int grid = (int)(blocks < 1 ? 1 : (blocks > kNumSMs ? kNumSMs : blocks));
-  allreduce_kernel<<<grid, kCommThreads, 0, st>>>(comm->peers, buf, n, max_norm, coef, l1_out, block_partials);
+  const bool vec = (n & 3) == 0 && ((reinterpret_cast<uintptr_t>(buf) & 15) == 0) &&
+                   (opt.kind == RECNN_OPT_EXTERNAL || (reinterpret_cast<uintptr_t>(opt.p) & 15) == 0);
+  if (vec)
+    allreduce_kernel<4><<<grid, kCommThreads, 0, st>>>(comm->peers, buf, n, r.max_norm, r.coef, r.l1_out, r.aux_in,
+                                                        r.aux_out, r.n_aux, r.check_val, r.err_flag, opt);
+  else
+    allreduce_kernel<1><<<grid, kCommThreads, 0, st>>>(comm->peers, buf, n, r.max_norm, r.coef, r.l1_out, r.aux_in,
+                                                        r.aux_out, r.n_aux, r.check_val, r.err_flag, opt);
   RECNN_CHECK_LAUNCH("allreduce_kernel");
   return RECNN_OK;
 }
@@ -176,6 +290,15 @@ int launch_comm_allreduce(const recnn_comm* comm, float* buf, int64_t n, float m
 
 using namespace recnn;
 
+// staging layout of one rank: CommDev | contrib [2][W][slice_cap] | result [2][capacity]   (floats)
+static size_t comm_ctrl_bytes() { return (size_t)round_up((int64_t)sizeof(CommDev), 256); }
+static void comm_carve(recnn_comm* c, int p, void* base) {
+  char* b = static_cast<char*>(base);
+  c->peers.ctrl[p] = reinterpret_cast<CommDev*>(b);
+  c->peers.contrib[p] = reinterpret_cast<float*>(b + comm_ctrl_bytes());
+  c->peers.result[p] = c->peers.contrib[p] + 2ll * c->peers.world * c->peers.slice_cap;
+}
+
 extern "C" int recnn_comm_create(int32_t rank, int32_t world, int64_t capacity_floats, recnn_comm** out) {
   RECNN_REQUIRE(out != nullptr, "out");
   RECNN_REQUIRE(world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world, "rank/world (at most 8 ranks)");
@@ -183,8 +306,15 @@ extern "C" int recnn_comm_create(int32_t rank, int32_t world, int64_t capacity_f
   capacity_floats = round_up(capacity_floats, 4);
   recnn_comm* c = new recnn_comm();
   c->connected = false;
-  for (int i = 0; i < kMaxRanks; ++i) { c->opened[i] = nullptr; c->peers.ctrl[i] = nullptr; c->peers.stage[i] = nullptr; }
-  const size_t bytes = sizeof(CommDev) + 2 * sizeof(float) * (size_t)capacity_floats;
+  for (int i = 0; i < kMaxRanks; ++i) {
+    c->opened[i] = nullptr; c->peers.ctrl[i] = nullptr; c->peers.contrib[i] = nullptr; c->peers.result[i] = nullptr;
+  }
+  c->peers.capacity = capacity_floats;
+  c->peers.slice_cap = round_up(ceil_div(capacity_floats, world), 4);
+  c->peers.rank = rank;
+  c->peers.world = world;
+  const size_t bytes = comm_ctrl_bytes() +
+                       sizeof(float) * (size_t)(2 * world * c->peers.slice_cap + 2 * capacity_floats);
   cudaError_t e = cudaMalloc(&c->local_base, bytes);
   if (e != cudaSuccess) {
     delete c;
@@ -192,9 +322,6 @@ extern "C" int recnn_comm_create(int32_t rank, int32_t world, int64_t capacity_f
     return RECNN_E_CUDA;
   }
   cudaMemset(c->local_base, 0, bytes);
-  c->peers.capacity = capacity_floats;
-  c->peers.rank = rank;
-  c->peers.world = world;
   e = cudaIpcGetMemHandle(&c->handle, c->local_base);
   if (e != cudaSuccess) {
     cudaFree(c->local_base);
@@ -235,15 +362,14 @@ extern "C" int recnn_comm_connect(recnn_comm* c, const void* all_handles) {
       }
       c->opened[p] = base;
     }
-    c->peers.ctrl[p] = static_cast<CommDev*>(base);
-    c->peers.stage[p] = reinterpret_cast<float*>(static_cast<char*>(base) + sizeof(CommDev));
+    comm_carve(c, p, base);
   }
   c->connected = true;
   return RECNN_OK;
 }
 
 extern "C" int recnn_comm_allreduce(const recnn_comm* c, float* buf, int64_t n, void* stream) {
-  return launch_comm_allreduce(c, buf, n, 0.f, nullptr, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+  return launch_comm_allreduce(c, buf, n, CommReduce(), static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int recnn_comm_destroy(recnn_comm* c) {

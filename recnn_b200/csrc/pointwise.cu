@@ -371,24 +371,15 @@ int launch_scale_inplace(float* x, int64_t count, const float* scale, cudaStream
 }
 
 // ---------------------------------------------------------------- optimizers
-// torch.optim.Adam / SGD (single-tensor CPU path of torch 2.11), one flat arena.
-struct OptConsts {
-  float lr, one_minus_b1, b2, one_minus_b2, eps, wd, momentum;
-};
-
+// torch.optim.Adam / SGD (single-tensor CPU path of torch 2.11), one flat arena.  The per-element math lives in
+// pointwise.cuh (opt_apply) so that the all-reduce kernel of the data-parallel step can apply the very same update.
 __global__ void __launch_bounds__(256)
 optimizer_kernel(int kind, OptConsts k, double beta1, double beta2, double lr, float* __restrict__ p,
                  float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                  int* __restrict__ t_ptr, const float* __restrict__ grad_scale, long long count, unsigned* ticket) {
   __shared__ float s_step_size, s_bc2_sqrt;
   const int t = *t_ptr + 1;
-  if (threadIdx.x == 0 && kind == RECNN_OPT_ADAM) {
-    // python-float (double) scalars, cast where torch casts them
-    const double bc1 = 1.0 - pow(beta1, (double)t);
-    const double bc2 = 1.0 - pow(beta2, (double)t);
-    s_step_size = (float)(lr / bc1);
-    s_bc2_sqrt = (float)sqrt(bc2);
-  }
+  if (threadIdx.x == 0) opt_scalars(kind, beta1, beta2, lr, t, &s_step_size, &s_bc2_sqrt);
   __syncthreads();
   const float gs = grad_scale ? *grad_scale : 1.0f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count;
@@ -398,24 +389,7 @@ optimizer_kernel(int kind, OptConsts k, double beta1, double beta2, double lr, f
       grad = __fmul_rn(grad, gs);
       g[i] = grad;                      // the reference leaves the scaled grad in .grad
     }
-    float w = p[i];
-    if (k.wd != 0.f) grad = __fadd_rn(grad, __fmul_rn(k.wd, w));
-    if (kind == RECNN_OPT_SGD) {
-      if (k.momentum != 0.f) {
-        const float buf = (t == 1) ? grad : __fadd_rn(__fmul_rn(k.momentum, m[i]), grad);
-        m[i] = buf;
-        grad = buf;
-      }
-      p[i] = __fsub_rn(w, __fmul_rn(k.lr, grad));
-    } else {
-      float mi = m[i], vi = v[i];
-      mi = __fadd_rn(mi, __fmul_rn(k.one_minus_b1, __fsub_rn(grad, mi)));       // lerp_
-      vi = __fadd_rn(__fmul_rn(vi, k.b2), __fmul_rn(__fmul_rn(k.one_minus_b2, grad), grad));
-      m[i] = mi;
-      v[i] = vi;
-      const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vi), s_bc2_sqrt), k.eps);
-      p[i] = __fsub_rn(w, __fmul_rn(s_step_size, __fdiv_rn(mi, denom)));
-    }
+    opt_apply(kind, k, s_step_size, s_bc2_sqrt, t, p, m, v, i, grad);
   }
   // ++t by the block that finishes last (every block has read t by then); without a ticket the
   // launcher appends a one-thread kernel instead
@@ -426,6 +400,19 @@ optimizer_kernel(int kind, OptConsts k, double beta1, double beta2, double lr, f
 
 __global__ void bump_counter_kernel(int* t) { *t += 1; }
 __global__ void bump_counter64_kernel(long long* t) { *t += 1; }
+
+// end of a step: ++*rng_step (if any) and the step's error words -> one int in the caller's loss block
+__global__ void finish_kernel(long long* rng_step, const unsigned* oob, const unsigned* dp_mismatch, float* flags_out) {
+  if (rng_step) *rng_step += 1;
+  const int bits = (*oob ? 1 : 0) | (*dp_mismatch ? 2 : 0);
+  *reinterpret_cast<int*>(flags_out) = bits;
+}
+int launch_finish(long long* rng_step, const unsigned* oob, const unsigned* dp_mismatch, float* flags_out,
+                  cudaStream_t st) {
+  finish_kernel<<<1, 1, 0, st>>>(rng_step, oob, dp_mismatch, flags_out);
+  RECNN_CHECK_LAUNCH("finish_kernel");
+  return RECNN_OK;
+}
 
 int launch_bump64(long long* t, cudaStream_t st) {
   bump_counter64_kernel<<<1, 1, 0, st>>>(t);
@@ -439,14 +426,7 @@ int launch_optimizer(const recnn_optim& o, const recnn_net& net, int64_t count, 
   RECNN_REQUIRE(net.params && net.grads && net.opt_t, "optimizer needs params, grads and the step counter");
   if (o.kind == RECNN_OPT_ADAM) RECNN_REQUIRE(net.opt_m && net.opt_v, "Adam needs exp_avg / exp_avg_sq arenas");
   if (o.kind == RECNN_OPT_SGD && o.momentum != 0.f) RECNN_REQUIRE(net.opt_m, "SGD momentum needs a buffer arena");
-  OptConsts k;
-  k.lr = (float)o.lr;
-  k.one_minus_b1 = (float)(1.0 - o.beta1);
-  k.b2 = (float)o.beta2;
-  k.one_minus_b2 = (float)(1.0 - o.beta2);
-  k.eps = (float)o.eps;
-  k.wd = (float)o.weight_decay;
-  k.momentum = (float)o.momentum;
+  const OptConsts k = opt_consts(o);
   const int64_t blocks = ceil_div(count, 256 * 4);
   const int grid = (int)(blocks < 4 * kNumSMs ? (blocks > 0 ? blocks : 1) : 4 * kNumSMs);
   optimizer_kernel<<<grid, 256, 0, st>>>(o.kind, k, o.beta1, o.beta2, o.lr, net.params,

@@ -75,21 +75,91 @@ int launch_colsum_partials(const float* dz, int64_t n_rows, int C, int64_t rows_
 int launch_l1_clip_coef(const float* grads, int64_t count, float max_norm, float* coef, float* l1_out,
                         float* block_partials, unsigned* ticket, cudaStream_t st);
 
-// comm.cu: buf <- sum over the communicator's ranks (in place, rank order).  With coef != nullptr also the
-// L1 norm of the summed gradient and its clip coefficient, as launch_l1_clip_coef would give them.
-int launch_comm_allreduce(const recnn_comm* comm, float* buf, int64_t n, float max_norm, float* coef, float* l1_out,
-                          float* block_partials, cudaStream_t st);
+// comm.cu: buf <- sum over the communicator's ranks (in place, rank order), two-shot over NVLink peer memory.
+// Optional riders of the same kernel: the L1 norm of the summed gradient and its clip coefficient (as
+// launch_l1_clip_coef would give them; the gradient is then left scaled by the coefficient), up to 8 "aux" floats
+// summed over the ranks (loss partial sums), a consistency check of a value every rank must agree on (the
+// global row count), and the built-in optimizer's update of `net` with the reduced gradient (step count included).
+struct CommReduce {
+  float max_norm = 0.f;
+  float* coef = nullptr;
+  float* l1_out = nullptr;
+  const float* aux_in = nullptr;
+  float* aux_out = nullptr;
+  int n_aux = 0;
+  float check_val = 0.f;
+  int* err_flag = nullptr;
+  const recnn_optim* optim = nullptr;
+  const recnn_net* net = nullptr;
+};
+int launch_comm_allreduce(const recnn_comm* comm, float* buf, int64_t n, const CommReduce& r, cudaStream_t st);
 
 // zero the `lead` leading and the trailing pad columns of up to three [n_rows, ld] buffers whose data columns are
 // [lead, lead + cols) (the lead-padded action images of the step); one launch instead of three full memsets
 int launch_zero_pad_columns(float* b0, float* b1, float* b2, int64_t n_rows, int ld, int lead, int cols, cudaStream_t st);
 int launch_scale_inplace(float* x, int64_t count, const float* scale, cudaStream_t st);
 
+// ---- fused optimizers: per-element update shared by optimizer_kernel and the all-reduce kernel (comm.cu) ----
+struct OptConsts {
+  float lr, one_minus_b1, b2, one_minus_b2, eps, wd, momentum;
+};
+static inline OptConsts opt_consts(const recnn_optim& o) {
+  OptConsts k;
+  k.lr = (float)o.lr;
+  k.one_minus_b1 = (float)(1.0 - o.beta1);
+  k.b2 = (float)o.beta2;
+  k.one_minus_b2 = (float)(1.0 - o.beta2);
+  k.eps = (float)o.eps;
+  k.wd = (float)o.weight_decay;
+  k.momentum = (float)o.momentum;
+  return k;
+}
+#ifdef __CUDACC__
+// Adam's step-dependent scalars: python-float (double) arithmetic, cast where torch casts them
+__device__ __forceinline__ void opt_scalars(int kind, double beta1, double beta2, double lr, int t, float* step_size,
+                                            float* bc2_sqrt) {
+  if (kind == RECNN_OPT_ADAM) {
+    const double bc1 = 1.0 - pow(beta1, (double)t);
+    const double bc2 = 1.0 - pow(beta2, (double)t);
+    *step_size = (float)(lr / bc1);
+    *bc2_sqrt = (float)sqrt(bc2);
+  } else {
+    *step_size = 0.f;
+    *bc2_sqrt = 1.f;
+  }
+}
+// one element of torch.optim.SGD / Adam (torch 2.11 single-tensor op order); `grad` already carries any clip scale
+__device__ __forceinline__ void opt_apply(int kind, const OptConsts& k, float step_size, float bc2_sqrt, int t,
+                                          float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                                          long long i, float grad) {
+  const float w = p[i];
+  if (k.wd != 0.f) grad = __fadd_rn(grad, __fmul_rn(k.wd, w));
+  if (kind == RECNN_OPT_SGD) {
+    if (k.momentum != 0.f) {
+      const float buf = (t == 1) ? grad : __fadd_rn(__fmul_rn(k.momentum, m[i]), grad);
+      m[i] = buf;
+      grad = buf;
+    }
+    p[i] = __fsub_rn(w, __fmul_rn(k.lr, grad));
+  } else {
+    float mi = m[i], vi = v[i];
+    mi = __fadd_rn(mi, __fmul_rn(k.one_minus_b1, __fsub_rn(grad, mi)));       // lerp_
+    vi = __fadd_rn(__fmul_rn(vi, k.b2), __fmul_rn(__fmul_rn(k.one_minus_b2, grad), grad));
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vi), bc2_sqrt), k.eps);
+    p[i] = __fsub_rn(w, __fmul_rn(step_size, __fdiv_rn(mi, denom)));
+  }
+}
+#endif
+
 // ticket: zero-initialised self-resetting counter; when given, the kernel itself increments *net.opt_t
 int launch_optimizer(const recnn_optim& o, const recnn_net& net, int64_t count, const float* grad_scale,
                      cudaStream_t st, unsigned* ticket = nullptr);
 
 int launch_bump64(long long* t, cudaStream_t st);
+int launch_finish(long long* rng_step, const unsigned* oob, const unsigned* dp_mismatch, float* flags_out,
+                  cudaStream_t st);
 int launch_polyak(float* target, const float* net, int64_t count, double tau, cudaStream_t st);
 
 }  // namespace recnn

@@ -415,6 +415,9 @@ struct Ctx {
   bool v_prefetched, p_prefetched, p_deferred;
   PlaneTable planes;     // pre-split weight planes of this call (indices as in Workspace::plane_hi)
 };
+// words of Workspace::tickets: 0..3 two-level reductions / optimizer step count, 6..7 error bits of the step
+// (zeroed with the tickets at the head of every call that includes RECNN_PH_GATHER or RECNN_PH_VALUE_GRAD)
+enum { kTicketDpMismatch = 6, kTicketOob = 7 };
 enum { PL_POLICY = 0, PL_TARGET_POLICY = 1, PL_VALUE0 = 2, PL_VALUE1 = 3, PL_TVALUE0 = 4, PL_TVALUE1 = 5 };
 
 // Critic hidden layers on (s, act):  h1 -> out1, h2 -> out2
@@ -558,9 +561,17 @@ static int phase_value_opt(Ctx& c) {
   if (!a.learn || a.value_optim.kind == RECNN_OPT_EXTERNAL) return RECNN_OK;
   const int n_critics = a.algo == RECNN_ALGO_TD3 ? 2 : 1;
   for (int i = 0; i < n_critics; ++i) {
-    if (a.comm)     // data parallel: every rank's shard gradient -> the global-batch gradient, over NVLink
-      RECNN_PROPAGATE(launch_comm_allreduce(a.comm, a.value[i].grads, c.lc.count, 0.f, nullptr, nullptr, nullptr, c.st));
-    RECNN_PROPAGATE(launch_optimizer(a.value_optim, a.value[i], c.lc.count, nullptr, c.st, c.ws.tickets + 3));
+    if (a.comm) {
+      // data parallel: every rank's shard gradient -> the global-batch gradient over NVLink, the optimizer update
+      // of the reduced gradient and the sum of the ranks' value-loss partial sums, all in ONE kernel
+      CommReduce r;
+      r.aux_in = a.losses + i; r.aux_out = a.losses + i; r.n_aux = 1;
+      r.check_val = (float)a.n_rows_global; r.err_flag = reinterpret_cast<int*>(c.ws.tickets + kTicketDpMismatch);
+      r.optim = &a.value_optim; r.net = &a.value[i];
+      RECNN_PROPAGATE(launch_comm_allreduce(a.comm, a.value[i].grads, c.lc.count, r, c.st));
+    } else {
+      RECNN_PROPAGATE(launch_optimizer(a.value_optim, a.value[i], c.lc.count, nullptr, c.st, c.ws.tickets + 3));
+    }
     c.planes.e[PL_VALUE0 + i].valid = false;       // weights changed: the planes are stale
   }
   return RECNN_OK;
@@ -642,13 +653,19 @@ static int phase_policy_opt(Ctx& c) {
   if (!a.do_policy_step) return RECNN_OK;
   float* coef = c.ws.scalars;
   // clip_grad_norm_(policy params, max_norm=-1, norm_type=1)   (ddpg.py:92, td3.py:133)
-  if (a.comm)       // all-reduce fused with the L1 norm of the summed gradient
-    RECNN_PROPAGATE(launch_comm_allreduce(a.comm, a.policy.grads, c.la.count, -1.0f, coef, a.losses + 3,
-                                          c.ws.block_partials, c.st));
-  else
-    RECNN_PROPAGATE(launch_l1_clip_coef(a.policy.grads, c.la.count, -1.0f, coef, a.losses + 3,
-                                        c.ws.block_partials, c.ws.tickets + 1, c.st));
   c.planes.e[PL_POLICY].valid = false;
+  if (a.comm) {
+    // one kernel: all-reduce of the actor gradient, L1 norm of the SUMMED gradient -> clip coefficient, scaled
+    // gradient written back, the built-in optimizer's update, and the sum of the ranks' policy-loss partial sums
+    CommReduce r;
+    r.max_norm = -1.0f; r.coef = coef; r.l1_out = a.losses + 3;
+    r.aux_in = a.losses + 2; r.aux_out = a.losses + 2; r.n_aux = 1;
+    r.check_val = (float)a.n_rows_global; r.err_flag = reinterpret_cast<int*>(c.ws.tickets + kTicketDpMismatch);
+    r.optim = &a.policy_optim; r.net = &a.policy;
+    return launch_comm_allreduce(a.comm, a.policy.grads, c.la.count, r, c.st);
+  }
+  RECNN_PROPAGATE(launch_l1_clip_coef(a.policy.grads, c.la.count, -1.0f, coef, a.losses + 3,
+                                      c.ws.block_partials, c.ws.tickets + 1, c.st));
   if (a.policy_optim.kind == RECNN_OPT_EXTERNAL)
     return launch_scale_inplace(a.policy.grads, c.la.count, coef, c.st);
   return launch_optimizer(a.policy_optim, a.policy, c.la.count, coef, c.st, c.ws.tickets + 3);
@@ -710,8 +727,10 @@ static int run_step(const recnn_step_args* a, int algo, void* stream) {
   c.lead = c.d.state_dim % 4;
   c.ldA = pad4(c.d.action_dim + c.lead);
   const int S = c.d.state_dim, A = c.d.action_dim;
-  // tickets of the deterministic two-level reductions start at zero
-  RECNN_CHECK_CUDA(cudaMemsetAsync(c.ws.tickets, 0, 8 * sizeof(unsigned), c.st));
+  // Head of a step: the tickets of the deterministic two-level reductions (self-resetting, but an aborted launch must
+  // not poison the next step) and the step's error words start at zero.  Later calls of a split step keep them.
+  if (a->phases & RECNN_PH_GATHER)
+    RECNN_CHECK_CUDA(cudaMemsetAsync(c.ws.tickets, 0, 8 * sizeof(unsigned), c.st));
   // The step works on state / next_state images with a 16-byte-multiple row pitch (TMA); they are
   // materialised into the workspace once per step (RECNN_PH_GATHER) from the frames or the dense batch.
   c.S = c.ws.S;
@@ -732,7 +751,8 @@ static int run_step(const recnn_step_args* a, int algo, void* stream) {
   if (frames) {
     if (a->phases & RECNN_PH_GATHER)
       RECNN_PROPAGATE(launch_frame_gather(a->table, a->n_items, a->emb_dim, a->items, a->ratings, c.n, a->frame,
-                                          c.ldS, c.ldA, c.ws.S, c.ws.S2, c.ws.ACT + c.lead, c.ws.REW, nullptr, c.st));
+                                          c.ldS, c.ldA, c.ws.S, c.ws.S2, c.ws.ACT + c.lead, c.ws.REW,
+                                          reinterpret_cast<int*>(c.ws.tickets + kTicketOob), c.st));
     c.REW = a->reward ? a->reward : c.ws.REW;
   } else {
     if (a->phases & RECNN_PH_GATHER) {
@@ -780,11 +800,21 @@ static int run_step(const recnn_step_args* a, int algo, void* stream) {
   if (a->phases & RECNN_PH_POLICY_OPT) RECNN_PROPAGATE(phase_policy_opt(c));
   if (a->phases & RECNN_PH_SOFT_UPDATE) RECNN_PROPAGATE(phase_soft_update(c));
   if (a->phases & RECNN_PH_FINISH) {
-    if (a->comm)      // losses are shard sums / n_rows_global: the sum over ranks is the global mean
-      RECNN_PROPAGATE(launch_comm_allreduce(a->comm, a->losses, 3, 0.f, nullptr, nullptr, nullptr, c.st));
-    if (a->rng_step) RECNN_PROPAGATE(launch_bump64((long long*)a->rng_step, c.st));
+    // losses are shard sums / n_rows_global: the sum over ranks is the global mean.  The value losses rode on the
+    // critics' all-reduces and, on a policy step, the policy loss on the actor's; only a non-policy step needs this
+    // scalar-only exchange (one CTA, one NVLink flag hop).
+    if (a->comm && !(a->do_policy_step && (a->phases & RECNN_PH_POLICY_OPT))) {
+      CommReduce r;
+      r.aux_in = a->losses + 2; r.aux_out = a->losses + 2; r.n_aux = 1;
+      r.check_val = (float)a->n_rows_global; r.err_flag = reinterpret_cast<int*>(c.ws.tickets + kTicketDpMismatch);
+      RECNN_PROPAGATE(launch_comm_allreduce(a->comm, nullptr, 0, r, c.st));
+    }
+    // ++rng_step; losses[4] <- error bits of this step (1: item id out of range in the gather, 2: the ranks disagree
+    // on n_rows_global)
+    RECNN_PROPAGATE(launch_finish((long long*)a->rng_step, c.ws.tickets + kTicketOob, c.ws.tickets + kTicketDpMismatch,
+                                  a->losses + 4, c.st));
     if (a->losses_host)
-      RECNN_CHECK_CUDA(cudaMemcpyAsync(a->losses_host, a->losses, 4 * sizeof(float), cudaMemcpyDeviceToHost, c.st));
+      RECNN_CHECK_CUDA(cudaMemcpyAsync(a->losses_host, a->losses, 8 * sizeof(float), cudaMemcpyDeviceToHost, c.st));
   }
   return RECNN_OK;
 }

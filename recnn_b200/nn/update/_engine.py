@@ -60,8 +60,10 @@ class StepEngine:
         self.world = 1
         self.comm = None             # recnn_b200.dist.PeerComm: in-kernel all-reduce over NVLink peer memory
         self.seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
-        self.losses = torch.zeros(4, dtype=torch.float32, device=self.device)
-        self.losses_host = torch.zeros(4, dtype=torch.float32).pin_memory()
+        # value(1), value2, policy, ||actor grad||_1, error bits (int32), 3 spare  (include/recnn_b200.h: losses)
+        self.losses = torch.zeros(8, dtype=torch.float32, device=self.device)
+        self.losses_host = torch.zeros(8, dtype=torch.float32).pin_memory()
+        self._flags_host = self.losses_host.view(torch.int32)
         self.rng_step = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.buf = {}
         self.kernels = 0             # kernels of this library launched by this engine (graph replays included)
@@ -227,6 +229,10 @@ class StepEngine:
             a.noise_std = float(params["noise_std"])
             a.noise_clip = float(params["noise_clip"])
         a.soft_tau = float(params["soft_tau"])
+        online = [nets[k] for k in self.names if not k.startswith("target")]
+        if len({bool(m.training) for m in online}) != 1:
+            raise ValueError("the online nets must all be in the same mode (train() / eval()): dropout is applied "
+                             "to every online net or to none; the target nets always run in eval mode")
         a.dropout = int(bool(nets["policy_net"].training))
         if st["masks"] is not None:
             for i, m in enumerate(st["masks"]):
@@ -365,6 +371,17 @@ class StepEngine:
         self._allreduce(self.losses[:3])
         run(2)
 
+    def _read_losses(self):
+        """After the stream synchronisation of a step: the loss scalars, or the step's error."""
+        bits = int(self._flags_host[4])
+        if bits & 1:
+            raise IndexError("batch['items'] holds an item id outside [0, n_items) (the update was applied with the "
+                             "offending rows reading table row 0)")
+        if bits & 2:
+            raise _lib.RecnnError("data parallel: the ranks disagree on the global row count; pass "
+                                  "batch['n_rows_global'] when the shards are uneven")
+        return self.losses_host[:4].tolist()
+
     # ------------------------------------------------------------------ the step
     def step(self, batch, params, nets, optimizer, learn, step, debug, policy_every_key):
         with torch.cuda.device(self.device):
@@ -419,7 +436,7 @@ class StepEngine:
                 else:
                     self._run_segments(ent[1], nets, do_policy, None)      # cached StepArgs
                 torch.cuda.current_stream(self.device).synchronize()
-                return self.losses_host.tolist()
+                return self._read_losses()
         a, pol_opt, val_opts = self._build_args(st, nets, optimizer, params, learn, do_policy)
         builtin = (not learn) or (isinstance(pol_opt, _optim._ArenaOptimizer)
                                   and all(isinstance(v, _optim._ArenaOptimizer) for v in val_opts))
@@ -436,14 +453,14 @@ class StepEngine:
             if _USE_GRAPHS:
                 self._fast[(do_policy, st["form"], st["n"])] = (self._tokens(nets, optimizer, params, st), a, 0)
             torch.cuda.current_stream(self.device).synchronize()
-            return self.losses_host.tolist()
+            return self._read_losses()
         if fused:
             g = self._run_fused(a, nets, do_policy)
             if g is not None:
                 # arenas may have been (re)built by _build_args: fingerprint after the fact
                 self._fast[(do_policy, st["form"], st["n"])] = (self._tokens(nets, optimizer, params, st), g[0], g[1])
             torch.cuda.current_stream(self.device).synchronize()
-            return self.losses_host.tolist()
+            return self._read_losses()
         else:
             P = _lib
             value_nets = [nets["value_net" + (str(i + 1) if td3 else "")] for i in range(2 if td3 else 1)]
@@ -476,7 +493,7 @@ class StepEngine:
                 self._allreduce(self.losses[:3])
             self._launch(a, P.PH_FINISH, want_debug)     # ++rng_step, losses -> pinned host
         torch.cuda.current_stream(self.device).synchronize()
-        vals = self.losses_host.tolist()
+        vals = self._read_losses()
         if want_debug is not None:
             debug["next_action"] = want_debug["next_action"]
             debug["gen_action"] = want_debug["gen_action"]
@@ -505,7 +522,7 @@ def _value_only(self, batch, params, nets, optimizer, learn, debug):
         torch.cuda.current_stream(self.device).synchronize()
         if want_debug is not None:
             debug["next_action"] = want_debug["next_action"]
-        return self.losses_host.tolist()
+        return self._read_losses()
 
 
 StepEngine.value_only = _value_only
