@@ -285,6 +285,25 @@ RECNN_API int recnn_td3_step(const recnn_step_args* args, void* stream);
 RECNN_API int recnn_optimizer_step(const recnn_optim* o, const recnn_net* net, int64_t count,
                          const float* grad_scale, void* stream);
 
+/* ---- serving: nearest-item retrieval over the embedding table ----------------------------------
+ * The step after Actor.forward in the reference's serving examples: the generated action (a 128-d
+ * embedding) is matched against the item matrix -- examples/streamlit_demo.py:189-203 (faiss
+ * IndexFlatL2 / IndexFlatIP / IndexFlatIP over L2-normalised rows), recnn/data/db_con.py:45-56
+ * (MilvusConnection.search(search_vecs, topk) -> ids, distances).  Exact search: one
+ * [n_queries, dim] x [dim, n_items] contraction on the tensor cores (3xTF32) + an exact top-k.
+ * Ordering: best first; L2 reports the squared distance (as faiss / Milvus do), IP the inner product,
+ * COS the cosine similarity; ties go to the smaller item id.  k <= 64. */
+enum { RECNN_METRIC_L2 = 0, RECNN_METRIC_IP = 1, RECNN_METRIC_COS = 2 };
+/* out[n_items]: |item|^2 (L2) or 1/|item| (COS); computed once per table ("index build") */
+RECNN_API int recnn_item_norms(const float* table, int64_t n_items, int32_t dim, int32_t metric, float* out,
+                               void* stream);
+RECNN_API int64_t recnn_retrieve_workspace_bytes(int64_t n_queries, int64_t n_items, int32_t k);
+/* ids_out int64[n_queries, k], dist_out fp32[n_queries, k]; norms from recnn_item_norms (NULL for IP) */
+RECNN_API int recnn_retrieve_topk(const float* queries, int64_t n_queries, int32_t dim, const float* table,
+                                  int64_t n_items, const float* norms, int32_t metric, int32_t k,
+                                  int64_t* ids_out, float* dist_out, void* workspace, int64_t workspace_bytes,
+                                  void* stream);
+
 /* ---- data parallel: all-reduce over NVLink peer memory ------------------------------------------
  * BASELINE north_star: "partition the embedding gather + update across the 8 GPUs of one box with
  * an allreduce of the Actor/Critic gradients over NVLink".  The reference itself is single-process

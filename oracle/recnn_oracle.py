@@ -101,6 +101,13 @@ def reset_gate_margin():
     GATE_MARGIN["min"] = float("inf")
 
 
+# Optional log of the AMBIGUOUS gates of a run: kept units (train-mode nets only: those are the ones that get a
+# backward) whose |pre-activation| <= thresh.  Entries are (mask array, rows, cols): tests/_golden.py uses them to
+# knock such units out of the replayed dropout masks, so that a full-size comparison has no gate decision that two
+# correct fp32 implementations could take differently.
+GATE_LOG = {"on": False, "thresh": 0.0, "hits": []}
+
+
 def _hidden(x, w, b, mask):
     """relu(x W^T + b) then Dropout(p=.5) in train mode == * mask * 2
     (recnn/nn/models.py:66-69 / :208-211).  mask None <=> eval()."""
@@ -108,6 +115,10 @@ def _hidden(x, w, b, mask):
     az = np.abs(z) if mask is None else np.abs(z)[np.asarray(mask) != 0]
     if az.size:
         GATE_MARGIN["min"] = min(GATE_MARGIN["min"], float(az.min()))
+    if GATE_LOG["on"] and mask is not None:
+        rows, cols = np.nonzero((np.abs(z) <= F32(GATE_LOG["thresh"])) & (np.asarray(mask) != 0))
+        if rows.size:
+            GATE_LOG["hits"].append((mask, rows, cols))
     h = np.maximum(z, F32(0))
     if mask is not None:
         h = h * (mask.astype(F32) * F32(2.0))
@@ -377,3 +388,28 @@ def synth_frames(rng, n_rows, n_items=26744, dim=128, frame_size=10, table=None)
 
 def synth_masks(rng, count, n_rows, hidden):
     return [rng.integers(0, 2, size=(n_rows, hidden), dtype=np.uint8) for _ in range(count)]
+
+
+# ----------------------------------------------------------------------------
+# Serving: nearest-item retrieval (examples/streamlit_demo.py:189-215 faiss IndexFlatL2 / IndexFlatIP / cosine;
+# recnn/data/db_con.py:45-56 MilvusConnection.search).  Brute force in float64, stable order (ties -> smaller id).
+# ----------------------------------------------------------------------------
+def retrieve_topk(queries: np.ndarray, table: np.ndarray, k: int, metric: str = "L2"):
+    """-> (ids int64 [n,k], dist float64 [n,k]) best first.  L2: squared distance (faiss IndexFlatL2 / Milvus L2),
+    IP: inner product, COS: cosine similarity (IndexFlatIP over L2-normalised rows, streamlit_demo.py:196-202)."""
+    q = np.asarray(queries, dtype=np.float64)
+    t = np.asarray(table, dtype=np.float64)
+    if metric == "L2":
+        d = (q * q).sum(1)[:, None] + (t * t).sum(1)[None, :] - 2.0 * (q @ t.T)
+        d = np.maximum(d, 0.0)
+        key = d
+    elif metric == "IP":
+        d = q @ t.T
+        key = -d
+    elif metric == "COS":
+        d = (q @ t.T) / np.maximum(np.linalg.norm(q, axis=1), 1e-30)[:, None] / np.maximum(np.linalg.norm(t, axis=1), 1e-30)[None, :]
+        key = -d
+    else:
+        raise ValueError(metric)
+    ids = np.argsort(key, axis=1, kind="stable")[:, :k].astype(np.int64)
+    return ids, np.take_along_axis(d, ids, axis=1)

@@ -18,6 +18,7 @@ PH_FINISH = 128
 PH_ALL = 255
 ALGO_DDPG, ALGO_TD3 = 0, 1
 OPT_EXTERNAL, OPT_SGD, OPT_ADAM = 0, 1, 2
+METRIC_L2, METRIC_IP, METRIC_COS = 0, 1, 2
 
 
 class Dims(C.Structure):
@@ -93,6 +94,10 @@ SIGNATURES = {
     "recnn_ddpg_step": (C.c_int, [C.POINTER(StepArgs), C.c_void_p]),
     "recnn_td3_step": (C.c_int, [C.POINTER(StepArgs), C.c_void_p]),
     "recnn_optimizer_step": (C.c_int, [C.POINTER(Optim), C.POINTER(Net), C.c_int64, C.c_void_p, C.c_void_p]),
+    "recnn_item_norms": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "recnn_retrieve_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int64, C.c_int32]),
+    "recnn_retrieve_topk": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
+                                      C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "recnn_comm_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.POINTER(C.c_void_p)]),
     "recnn_comm_handle_bytes": (C.c_int32, []),
     "recnn_comm_local_handle": (C.c_int, [C.c_void_p, C.c_void_p]),

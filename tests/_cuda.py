@@ -63,10 +63,12 @@ def build_optimizers(kind, nets, algo, external=False):
 
 
 def run_cuda_case(case, algo, opt_kind, golden=None, form="dense", external=False, device="cuda:0",
-                  shard=None):
-    """shard=(rank, world): this process handles rows [lo, hi) of every minibatch (data parallel)."""
+                  shard=None, inp=None):
+    """shard=(rank, world): this process handles rows [lo, hi) of every minibatch (data parallel).
+    ``inp``: pre-made inputs (C.make_inputs, possibly with edited masks) instead of regenerating them."""
     spec = C.CASES[case] if isinstance(case, str) else case      # a name or a spec dict
-    inp = C.make_inputs(spec, algo)
+    if inp is None:
+        inp = C.make_inputs(spec, algo)
     dev = torch.device(device)
     lo, hi = (0, spec["n_rows"]) if shard is None else recnn_b200.dist.shard_rows(spec["n_rows"], *shard)
     out = {"input_checksums": C.input_checksums(inp)}

@@ -602,3 +602,199 @@ def test_two_rank_equals_reference(algo, transport):
     for k in res[0]:
         if k.startswith("final."):
             assert np.array_equal(res[0][k], res[1][k]), "replicas diverged: " + k
+
+
+# ----------------------------------------------------------------------------- full size, tight bar
+@pytest.mark.parametrize("algo", ["ddpg", "td3"])
+def test_full_size_tight_parity_without_ambiguous_gates(algo):
+    """BASELINE configs[1] / [2] at FULL size (4096 rows, 26,744 x 128 table) held to the GOLDEN bar on EVERY weight.
+
+    test_full_size_parity_vs_live_oracle has to tolerate the few ReLU gates per step that land within fp32
+    rounding error of zero.  Here those gates are removed from the problem instead of from the bar: the oracle
+    logs every kept unit with |pre-activation| <= 2e-5 (20x the difference between fp32 GEMM implementations),
+    the replayed dropout masks drop exactly those units (tests/_golden.py:neutralise_ambiguous_gates), and the
+    same masks go to the CUDA path.  With no ambiguous gate left, the north-star bar must hold for 100% of the
+    elements: losses 1e-5; every weight 1e-5 relative (floor: 1e-7 of the tensor's largest weight); every weight
+    CHANGE within 2e-3 of the tensor's largest change.  The number of units dropped (a few hundred out of
+    ~19 million gates) is asserted to be small, which is the 'handful of flips' claim made measurable."""
+    from tests._golden import neutralise_ambiguous_gates
+    spec = C.FULL_SPEC
+    inp, dropped, rounds = neutralise_ambiguous_gates(spec, algo, "sgd")
+    gates = spec["n_rows"] * spec["hidden"] * 2 * (3 if algo == "ddpg" else 4) * spec["steps"]
+    assert dropped <= 2e-4 * gates, (dropped, gates, rounds)
+    want = run_oracle_case(spec, algo, "sgd", inp=inp)
+    got = run_cuda_case(spec, algo, "sgd", form="frames", inp=inp)
+    for k in (k for k in want if k.startswith("loss.")):
+        err = np.max(np.abs(got[k] - want[k]) / (np.abs(want[k]) + 0.1))
+        assert err <= 1e-5, (k, err, got[k], want[k])
+    checked = 0
+    for k in (k for k in want if k.startswith("final.")):
+        _, name, tensor = k.split(".")
+        init = inp["nets"][name][tensor].astype(np.float64)
+        w_want, w_got = want[k].astype(np.float64), got[k].astype(np.float64)
+        wmax = np.max(np.abs(w_want))
+        rel = np.max(np.abs(w_got - w_want) / (np.abs(w_want) + 1e-2 * wmax))
+        assert rel <= 1e-5, (k, rel)
+        d_want, d_got = w_want - init, w_got - init
+        scale = np.max(np.abs(d_want))
+        if scale == 0.0:
+            assert np.array_equal(got[k], want[k]), k
+            continue
+        ulp2 = 2.0 * 1.1920929e-07 * wmax
+        excess = np.maximum(np.abs(d_got - d_want) - ulp2, 0.0)
+        assert np.max(excess) <= 2e-3 * scale, (k, float(np.max(excess) / scale), dropped)
+        checked += 1
+    assert checked >= 12
+
+
+# ----------------------------------------------------------------------------- value_update on its own
+@pytest.mark.parametrize("case", ["tiny", "canon"])
+@pytest.mark.parametrize("opt_kind", ["sgd", "adam"])
+def test_value_update_standalone_vs_oracle(case, opt_kind):
+    """recnn.nn.update.value_update (misc.py:10-55) as a public entry point: three critic-only steps against
+    O.value_update on the same inputs -- loss tensor, the critic's weights, and nothing else moves."""
+    spec = C.CASES[case]
+    inp = C.make_inputs(spec, "ddpg")
+    dev = torch.device(DEV)
+    from tests._cuda import build_nets, build_optimizers, dump_net
+    nets = build_nets(spec, inp, dev)
+    opts = build_optimizers(opt_kind, nets, "ddpg")
+    o_nets = {k: O.copy_net(v) for k, v in inp["nets"].items()}
+    from tests._golden import oracle_optimizers
+    o_opts = oracle_optimizers(opt_kind, "ddpg")
+    ref = O.frame_gather(inp["table"], inp["items"], inp["ratings"], inp["sizes"], spec["frame"])
+    params = dict(C.DDPG_PARAMS)
+    before = {k: dump_net(m) for k, m in nets.items()}
+    for step in range(3):
+        masks = inp["masks"][step]
+        want_loss, _ = O.value_update(ref, params, o_nets, o_opts, masks[0:2], learn=True)
+        batch = {k: torch.from_numpy(v) for k, v in ref.items()}
+        batch["dropout_masks"] = [torch.from_numpy(m) for m in masks]
+        got_loss = recnn_b200.nn.update.value_update(batch, params, nets, opts, dev, {}, learn=True, step=step)
+        assert torch.is_tensor(got_loss) and got_loss.dim() == 0
+        assert abs(float(got_loss) - float(want_loss)) <= 1e-5 * (abs(float(want_loss)) + 0.1)
+    for name, m in nets.items():
+        after = dump_net(m)
+        for t in O.PARAM_ORDER:
+            if name != "value_net":
+                assert np.array_equal(after[t], before[name][t]), (name, t)      # only the critic is stepped
+                continue
+            w = o_nets[name][t].astype(np.float64)
+            wmax = np.max(np.abs(w))
+            assert np.max(np.abs(after[t] - w) / (np.abs(w) + 1e-2 * wmax)) <= 1e-5, t
+            d_want = w - before[name][t]
+            scale = np.max(np.abs(d_want))
+            assert scale > 0
+            ulp2 = 2.0 * 1.1920929e-07 * wmax
+            assert np.max(np.maximum(np.abs((after[t] - before[name][t]) - d_want) - ulp2, 0)) <= 2e-3 * scale, t
+
+
+def test_value_update_learn_false_fills_debug():
+    spec = C.CASES["tiny"]
+    inp = C.make_inputs(spec, "ddpg")
+    from tests._cuda import build_nets
+    nets = build_nets(spec, inp, torch.device(DEV))
+    ref = O.frame_gather(inp["table"], inp["items"], inp["ratings"], inp["sizes"], spec["frame"])
+    batch = {k: torch.from_numpy(v) for k, v in ref.items()}
+    debug = {}
+    loss = recnn_b200.nn.update.value_update(batch, dict(C.DDPG_PARAMS), nets, {"value_optimizer": None},
+                                             torch.device(DEV), debug, learn=False)
+    want, dbg = O.value_update(ref, dict(C.DDPG_PARAMS), {k: O.copy_net(v) for k, v in inp["nets"].items()},
+                               {}, None, learn=False)
+    # eval-mode target nets; the online critic is in train mode but learn=False gives it no masks here:
+    assert np.isfinite(float(loss))
+    np.testing.assert_allclose(debug["next_action"].cpu().numpy(), dbg["next_action"], rtol=1e-5, atol=1e-6)
+
+
+# ----------------------------------------------------------------------------- error reporting / optimizer plumbing
+def test_in_step_gather_reports_out_of_range_ids():
+    """an item id outside [0, n_items) raises IndexError like batch_tensor_embeddings does
+    (the in-step gather used to clamp silently)."""
+    torch.manual_seed(0)
+    agent = recnn_b200.nn.DDPG(recnn_b200.nn.Actor(1290, 128, 256, 6e-1),
+                               recnn_b200.nn.Critic(1290, 128, 256, 54e-2)).to(torch.device(DEV))
+    rng = np.random.default_rng(1)
+    table, items, ratings, sizes = O.synth_frames(rng, 64, 300)
+    batch = {"items": torch.from_numpy(items), "ratings": torch.from_numpy(ratings),
+             "sizes": torch.from_numpy(sizes), "table": torch.from_numpy(table).to(DEV)}
+    agent.update(batch, learn=True)                      # fine
+    bad = items.copy()
+    bad[5, 3] = 300                                      # == n_items
+    batch["items"] = torch.from_numpy(bad)
+    with pytest.raises(IndexError):
+        agent.update(batch, learn=True)
+    bad[5, 3] = -1
+    batch["items"] = torch.from_numpy(bad)
+    with pytest.raises(IndexError):
+        agent.update(batch, learn=True)
+    batch["items"] = torch.from_numpy(items)
+    assert np.isfinite(agent.update(batch, learn=True)["value"])      # the flag does not stick
+
+
+def test_online_nets_must_share_train_mode():
+    agent = recnn_b200.nn.DDPG(recnn_b200.nn.Actor(1290, 128, 256), recnn_b200.nn.Critic(1290, 128, 256)).to(torch.device(DEV))
+    rng = np.random.default_rng(1)
+    table, items, ratings, sizes = O.synth_frames(rng, 16, 300)
+    batch = {"items": torch.from_numpy(items), "ratings": torch.from_numpy(ratings),
+             "sizes": torch.from_numpy(sizes), "table": torch.from_numpy(table).to(DEV)}
+    agent.nets["value_net"].eval()
+    with pytest.raises(ValueError):
+        agent.update(batch, learn=True)
+
+
+def test_builtin_policy_with_external_value_optimizer_steps_each_once():
+    """replacing only value_optimizer by a torch optimizer used to step the policy twice."""
+    spec = C.CASES["tiny"]
+    inp = C.make_inputs(spec, "ddpg")
+    from tests._cuda import build_nets
+    dev = torch.device(DEV)
+    ref = O.frame_gather(inp["table"], inp["items"], inp["ratings"], inp["sizes"], spec["frame"])
+    results = []
+    for mixed in (False, True):
+        nets = build_nets(spec, inp, dev)
+        opts = {"policy_optimizer": recnn_b200.optim.SGD(nets["policy_net"].parameters(), lr=1e-3),
+                "value_optimizer": (torch.optim.SGD(nets["value_net"].parameters(), lr=1e-3) if mixed else
+                                    recnn_b200.optim.SGD(nets["value_net"].parameters(), lr=1e-3))}
+        for step in range(2):
+            batch = {k: torch.from_numpy(v) for k, v in ref.items()}
+            batch["dropout_masks"] = [torch.from_numpy(m) for m in inp["masks"][step]]
+            recnn_b200.nn.ddpg_update(batch, dict(C.DDPG_PARAMS), nets, opts, dev, {}, learn=True, step=step * 10)
+        assert opts["policy_optimizer"].steps_taken() == 2
+        results.append([p.detach().cpu().clone() for p in nets["policy_net"].parameters()])
+    for p, q in zip(*results):
+        assert torch.allclose(p, q, rtol=1e-6, atol=1e-8)
+
+
+def test_optimizer_state_dict_round_trip_continues_bias_correction():
+    spec = C.CASES["tiny"]
+    inp = C.make_inputs(spec, "ddpg")
+    from tests._cuda import build_nets, build_optimizers
+    dev = torch.device(DEV)
+    ref = O.frame_gather(inp["table"], inp["items"], inp["ratings"], inp["sizes"], spec["frame"])
+
+    def run(steps, nets, opts, first=0):
+        for step in range(first, first + steps):
+            batch = {k: torch.from_numpy(v) for k, v in ref.items()}
+            batch["dropout_masks"] = [torch.from_numpy(m) for m in inp["masks"][step]]
+            recnn_b200.nn.ddpg_update(batch, dict(C.DDPG_PARAMS), nets, opts, dev, {}, learn=True, step=step)
+
+    nets_a = build_nets(spec, inp, dev)
+    opts_a = build_optimizers("adam", nets_a, "ddpg")
+    run(4, nets_a, opts_a)
+    # checkpoint after 2 steps, resume in fresh objects
+    nets_b = build_nets(spec, inp, dev)
+    opts_b = build_optimizers("adam", nets_b, "ddpg")
+    run(2, nets_b, opts_b)
+    sd_nets = {k: m.state_dict() for k, m in nets_b.items()}
+    sd_opts = {k: o.state_dict() for k, o in opts_b.items()}
+    assert sd_opts["value_optimizer"]["recnn_arenas"]["t"] == 2
+    nets_c = build_nets(spec, inp, dev)
+    for k, m in nets_c.items():
+        m.load_state_dict(sd_nets[k])
+    opts_c = build_optimizers("adam", nets_c, "ddpg")
+    for k, o in opts_c.items():
+        o.load_state_dict(sd_opts[k])
+    run(2, nets_c, opts_c, first=2)
+    for k in nets_a:
+        for p, q in zip(nets_a[k].parameters(), nets_c[k].parameters()):
+            assert torch.equal(p, q), k
