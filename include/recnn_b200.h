@@ -177,16 +177,24 @@ typedef struct recnn_net {
   float* opt_m;       /* Adam exp_avg / SGD momentum buffer (built-in optimizers), else NULL */
   float* opt_v;       /* Adam exp_avg_sq, else NULL */
   int32_t* opt_t;     /* device int32: number of optimizer steps taken so far */
+  float* opt_slow;    /* Ranger: Lookahead slow weights (arena), else NULL */
 } recnn_net;
 
-enum { RECNN_OPT_EXTERNAL = 0, RECNN_OPT_SGD = 1, RECNN_OPT_ADAM = 2 };
+/* RANGER = RAdam + Lookahead as in torch_optimizer.Ranger, the optimizer recnn.nn.DDPG/TD3 construct by default
+ * (recnn/nn/algo.py:84-89, :139-147).  torch_optimizer is an un-vendored third-party dependency of the reference
+ * (requirements.txt:7, unpinned) and absent from this environment: the restatement follows the published algorithm
+ * (Liu et al. 2019 rectified Adam with the N_sma_threshhold switch; Zhang et al. 2019 Lookahead every k steps) and
+ * its parity with the package is UNPINNED. */
+enum { RECNN_OPT_EXTERNAL = 0, RECNN_OPT_SGD = 1, RECNN_OPT_ADAM = 2, RECNN_OPT_RANGER = 3 };
 
-typedef struct recnn_optim {   /* torch.optim.SGD / torch.optim.Adam semantics */
+typedef struct recnn_optim {   /* torch.optim.SGD / torch.optim.Adam / torch_optimizer.Ranger semantics */
   int32_t kind;
-  int32_t reserved;
+  int32_t k;          /* Ranger: Lookahead period (6) */
   /* doubles: torch keeps these as python floats and rounds to fp32 only where the
    * tensor op consumes them (e.g. step_size = lr / (1 - beta1**t) is formed in double) */
   double lr, beta1, beta2, eps, weight_decay, momentum;
+  double alpha;            /* Ranger: Lookahead interpolation (0.5) */
+  double n_sma_threshold;  /* Ranger: rectification switch (5) */
 } recnn_optim;
 
 /* what one call executes; OR them.  A drop-in single-GPU step passes RECNN_PH_ALL.

@@ -186,15 +186,59 @@ def make_optimizer(kind: str, **kw):
     elif kind == "adam":
         o.update(lr=kw.get("lr", 1e-3), betas=kw.get("betas", (0.9, 0.999)),
                  eps=kw.get("eps", 1e-8), weight_decay=kw.get("weight_decay", 0.0))
+    elif kind == "ranger":
+        # torch_optimizer.Ranger defaults (the reference's default optimizer, recnn/nn/algo.py:84-89).  The package is
+        # not vendored / installed: PARITY UNPINNED, restated from the published algorithm (RAdam + Lookahead).
+        o.update(lr=kw.get("lr", 1e-3), alpha=kw.get("alpha", 0.5), k=kw.get("k", 6),
+                 n_sma_threshold=kw.get("N_sma_threshhold", 5), betas=kw.get("betas", (0.95, 0.999)),
+                 eps=kw.get("eps", 1e-5), weight_decay=kw.get("weight_decay", 0.0))
     else:
         raise ValueError(kind)
     return o
 
 
+def _ranger_step(o: dict, p: dict, g: dict, t: int):
+    """One torch_optimizer.Ranger step (RAdam with the N_sma threshold, then Lookahead every k steps)."""
+    import math
+    b1, b2 = o["betas"]
+    beta2_t = b2 ** t
+    n_sma_max = 2.0 / (1.0 - b2) - 1.0
+    n_sma = n_sma_max - 2.0 * t * beta2_t / (1.0 - beta2_t)
+    adaptive = n_sma > o["n_sma_threshold"]
+    if adaptive:
+        step_size = math.sqrt((1.0 - beta2_t) * (n_sma - 4.0) / (n_sma_max - 4.0) * (n_sma - 2.0) / n_sma
+                              * n_sma_max / (n_sma_max - 2.0)) / (1.0 - b1 ** t)
+    else:
+        step_size = 1.0 / (1.0 - b1 ** t)
+    for k in PARAM_ORDER:
+        grad = g[k].astype(F32)
+        st = o["state"].get(k)
+        if st is None:
+            st = {"m": np.zeros_like(p[k]), "v": np.zeros_like(p[k]), "slow": p[k].copy()}
+            o["state"][k] = st
+        st["v"] = (st["v"] * F32(b2) + (F32(1.0 - b2) * grad) * grad).astype(F32)
+        st["m"] = (st["m"] * F32(b1) + F32(1.0 - b1) * grad).astype(F32)
+        x = p[k]
+        if o["weight_decay"] != 0.0:
+            x = (x + F32(-o["weight_decay"] * o["lr"]) * x).astype(F32)
+        if adaptive:
+            denom = (np.sqrt(st["v"]) + F32(o["eps"])).astype(F32)
+            x = (x + (F32(-step_size * o["lr"]) * st["m"]) / denom).astype(F32)
+        else:
+            x = (x + F32(-step_size * o["lr"]) * st["m"]).astype(F32)
+        if t % o["k"] == 0:
+            st["slow"] = (st["slow"] + F32(o["alpha"]) * (x - st["slow"])).astype(F32)
+            x = st["slow"].copy()
+        p[k] = x
+
+
 def optimizer_step(o: dict, p: dict, g: dict):
-    """torch.optim.SGD / torch.optim.Adam .step() on every tensor of a net."""
+    """torch.optim.SGD / torch.optim.Adam .step() (or torch_optimizer.Ranger) on every tensor of a net."""
     o["t"] += 1
     t = o["t"]
+    if o["kind"] == "ranger":
+        _ranger_step(o, p, g, t)
+        return
     for k in PARAM_ORDER:
         grad = g[k].astype(F32)
         if o["weight_decay"] != 0.0:

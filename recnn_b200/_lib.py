@@ -17,7 +17,7 @@ PH_VALUE_GRAD, PH_VALUE_OPT, PH_POLICY_LOSS, PH_POLICY_GRAD, PH_POLICY_OPT, PH_S
 PH_FINISH = 128
 PH_ALL = 255
 ALGO_DDPG, ALGO_TD3 = 0, 1
-OPT_EXTERNAL, OPT_SGD, OPT_ADAM = 0, 1, 2
+OPT_EXTERNAL, OPT_SGD, OPT_ADAM, OPT_RANGER = 0, 1, 2, 3
 METRIC_L2, METRIC_IP, METRIC_COS = 0, 1, 2
 
 
@@ -28,13 +28,13 @@ class Dims(C.Structure):
 
 class Net(C.Structure):
     _fields_ = [("params", C.c_void_p), ("grads", C.c_void_p), ("opt_m", C.c_void_p),
-                ("opt_v", C.c_void_p), ("opt_t", C.c_void_p)]
+                ("opt_v", C.c_void_p), ("opt_t", C.c_void_p), ("opt_slow", C.c_void_p)]
 
 
 class Optim(C.Structure):
-    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("lr", C.c_double), ("beta1", C.c_double),
+    _fields_ = [("kind", C.c_int32), ("k", C.c_int32), ("lr", C.c_double), ("beta1", C.c_double),
                 ("beta2", C.c_double), ("eps", C.c_double), ("weight_decay", C.c_double),
-                ("momentum", C.c_double)]
+                ("momentum", C.c_double), ("alpha", C.c_double), ("n_sma_threshold", C.c_double)]
 
 
 class StepArgs(C.Structure):

@@ -65,8 +65,9 @@ struct CommPeers {                     // kernel parameter
 struct CommOpt {                       // optional fused optimizer (kind == RECNN_OPT_EXTERNAL: none)
   int kind;
   OptConsts k;
-  double beta1, beta2, lr;
-  float *p, *m, *v;
+  double beta1, beta2, lr, wd, n_sma_threshold;
+  int k_look;
+  float *p, *m, *v, *slow;
   int* t;
 };
 
@@ -119,7 +120,8 @@ allreduce_kernel(CommPeers c, float* __restrict__ buf, long long n, float max_no
   __shared__ float red[32];
   __shared__ unsigned s_epoch;
   __shared__ bool s_last;
-  __shared__ float s_coef, s_step_size, s_bc2_sqrt;
+  __shared__ float s_coef;
+  __shared__ OptStep s_st;
   CommDev* me = c.ctrl[c.rank];
   if (threadIdx.x == 0) s_epoch = *((volatile unsigned*)&me->epoch) + 1;
   __syncthreads();
@@ -204,7 +206,7 @@ allreduce_kernel(CommPeers c, float* __restrict__ buf, long long n, float max_no
     if (threadIdx.x == 0) {
       s_coef = coef;
       if (opt.kind != RECNN_OPT_EXTERNAL)
-        opt_scalars(opt.kind, opt.beta1, opt.beta2, opt.lr, *opt.t + 1, &s_step_size, &s_bc2_sqrt);
+        s_st = opt_step_scalars(opt.kind, opt.beta1, opt.beta2, opt.lr, opt.wd, opt.n_sma_threshold, opt.k_look, *opt.t + 1);
       if (blockIdx.x == 0) {
         bool bad = false;
         for (int p = 0; p < W; ++p) bad = bad || __ldcg(&me->aux[par][p][kMaxAux]) != check_val;
@@ -222,6 +224,7 @@ allreduce_kernel(CommPeers c, float* __restrict__ buf, long long n, float max_no
     const float coef = s_coef;
     const bool scale = coef_out != nullptr;
     const int t_next = opt.kind != RECNN_OPT_EXTERNAL ? *opt.t + 1 : 0;
+    const OptStep ost = s_st;
     const float* res = c.result[c.rank] + (long long)par * c.capacity;
     for (long long i = tid; i < units; i += nth) {
       V g = __ldcg(reinterpret_cast<const V*>(res) + i);
@@ -232,12 +235,12 @@ allreduce_kernel(CommPeers c, float* __restrict__ buf, long long n, float max_no
       reinterpret_cast<V*>(buf)[i] = g;              // the caller-visible .grad (scaled, as the reference leaves it)
       if (opt.kind != RECNN_OPT_EXTERNAL) {
         if constexpr (VEC == 4) {
-          opt_apply(opt.kind, opt.k, s_step_size, s_bc2_sqrt, t_next, opt.p, opt.m, opt.v, 4 * i + 0, g.x);
-          opt_apply(opt.kind, opt.k, s_step_size, s_bc2_sqrt, t_next, opt.p, opt.m, opt.v, 4 * i + 1, g.y);
-          opt_apply(opt.kind, opt.k, s_step_size, s_bc2_sqrt, t_next, opt.p, opt.m, opt.v, 4 * i + 2, g.z);
-          opt_apply(opt.kind, opt.k, s_step_size, s_bc2_sqrt, t_next, opt.p, opt.m, opt.v, 4 * i + 3, g.w);
+          opt_apply(opt.kind, opt.k, ost, t_next, opt.p, opt.m, opt.v, opt.slow, 4 * i + 0, g.x);
+          opt_apply(opt.kind, opt.k, ost, t_next, opt.p, opt.m, opt.v, opt.slow, 4 * i + 1, g.y);
+          opt_apply(opt.kind, opt.k, ost, t_next, opt.p, opt.m, opt.v, opt.slow, 4 * i + 2, g.z);
+          opt_apply(opt.kind, opt.k, ost, t_next, opt.p, opt.m, opt.v, opt.slow, 4 * i + 3, g.w);
         } else {
-          opt_apply(opt.kind, opt.k, s_step_size, s_bc2_sqrt, t_next, opt.p, opt.m, opt.v, i, g);
+          opt_apply(opt.kind, opt.k, ost, t_next, opt.p, opt.m, opt.v, opt.slow, i, g);
         }
       }
     }
@@ -263,13 +266,16 @@ int launch_comm_allreduce(const recnn_comm* comm, float* buf, int64_t n, const C
   opt.kind = RECNN_OPT_EXTERNAL;
   if (r.optim && r.optim->kind != RECNN_OPT_EXTERNAL) {
     RECNN_REQUIRE(r.net && r.net->params && r.net->opt_t, "fused optimizer needs params and the step counter");
-    RECNN_REQUIRE(r.optim->kind == RECNN_OPT_SGD || r.optim->kind == RECNN_OPT_ADAM, "built-in optimizer kind must be SGD or ADAM");
+    RECNN_REQUIRE(r.optim->kind == RECNN_OPT_SGD || r.optim->kind == RECNN_OPT_ADAM || r.optim->kind == RECNN_OPT_RANGER,
+                  "built-in optimizer kind must be SGD, ADAM or RANGER");
     if (r.optim->kind == RECNN_OPT_ADAM) RECNN_REQUIRE(r.net->opt_m && r.net->opt_v, "Adam needs exp_avg / exp_avg_sq arenas");
+    if (r.optim->kind == RECNN_OPT_RANGER) RECNN_REQUIRE(r.net->opt_m && r.net->opt_v && r.net->opt_slow, "Ranger needs exp_avg / exp_avg_sq / slow arenas");
     if (r.optim->kind == RECNN_OPT_SGD && r.optim->momentum != 0.f) RECNN_REQUIRE(r.net->opt_m, "SGD momentum needs a buffer arena");
     opt.kind = r.optim->kind;
     opt.k = opt_consts(*r.optim);
     opt.beta1 = r.optim->beta1; opt.beta2 = r.optim->beta2; opt.lr = r.optim->lr;
-    opt.p = r.net->params; opt.m = r.net->opt_m; opt.v = r.net->opt_v; opt.t = r.net->opt_t;
+    opt.wd = r.optim->weight_decay; opt.n_sma_threshold = r.optim->n_sma_threshold; opt.k_look = r.optim->k;
+    opt.p = r.net->params; opt.m = r.net->opt_m; opt.v = r.net->opt_v; opt.slow = r.net->opt_slow; opt.t = r.net->opt_t;
   }
   const int64_t per = (int64_t)kCommThreads * 4 * 2;              // two float4 per thread
   int64_t blocks = ceil_div(n, per);

@@ -374,13 +374,15 @@ int launch_scale_inplace(float* x, int64_t count, const float* scale, cudaStream
 // torch.optim.Adam / SGD (single-tensor CPU path of torch 2.11), one flat arena.  The per-element math lives in
 // pointwise.cuh (opt_apply) so that the all-reduce kernel of the data-parallel step can apply the very same update.
 __global__ void __launch_bounds__(256)
-optimizer_kernel(int kind, OptConsts k, double beta1, double beta2, double lr, float* __restrict__ p,
-                 float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                 int* __restrict__ t_ptr, const float* __restrict__ grad_scale, long long count, unsigned* ticket) {
-  __shared__ float s_step_size, s_bc2_sqrt;
+optimizer_kernel(int kind, OptConsts k, double beta1, double beta2, double lr, double wd, double n_sma_threshold,
+                 int k_look, float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                 float* __restrict__ v, float* __restrict__ slow, int* __restrict__ t_ptr,
+                 const float* __restrict__ grad_scale, long long count, unsigned* ticket) {
+  __shared__ OptStep s_st;
   const int t = *t_ptr + 1;
-  if (threadIdx.x == 0) opt_scalars(kind, beta1, beta2, lr, t, &s_step_size, &s_bc2_sqrt);
+  if (threadIdx.x == 0) s_st = opt_step_scalars(kind, beta1, beta2, lr, wd, n_sma_threshold, k_look, t);
   __syncthreads();
+  const OptStep st = s_st;
   const float gs = grad_scale ? *grad_scale : 1.0f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count;
        i += (long long)gridDim.x * blockDim.x) {
@@ -389,7 +391,7 @@ optimizer_kernel(int kind, OptConsts k, double beta1, double beta2, double lr, f
       grad = __fmul_rn(grad, gs);
       g[i] = grad;                      // the reference leaves the scaled grad in .grad
     }
-    opt_apply(kind, k, s_step_size, s_bc2_sqrt, t, p, m, v, i, grad);
+    opt_apply(kind, k, st, t, p, m, v, slow, i, grad);
   }
   // ++t by the block that finishes last (every block has read t by then); without a ticket the
   // launcher appends a one-thread kernel instead
@@ -422,15 +424,18 @@ int launch_bump64(long long* t, cudaStream_t st) {
 
 int launch_optimizer(const recnn_optim& o, const recnn_net& net, int64_t count, const float* grad_scale,
                      cudaStream_t st, unsigned* ticket) {
-  RECNN_REQUIRE(o.kind == RECNN_OPT_SGD || o.kind == RECNN_OPT_ADAM, "built-in optimizer kind must be SGD or ADAM");
+  RECNN_REQUIRE(o.kind == RECNN_OPT_SGD || o.kind == RECNN_OPT_ADAM || o.kind == RECNN_OPT_RANGER,
+                "built-in optimizer kind must be SGD, ADAM or RANGER");
   RECNN_REQUIRE(net.params && net.grads && net.opt_t, "optimizer needs params, grads and the step counter");
   if (o.kind == RECNN_OPT_ADAM) RECNN_REQUIRE(net.opt_m && net.opt_v, "Adam needs exp_avg / exp_avg_sq arenas");
+  if (o.kind == RECNN_OPT_RANGER) RECNN_REQUIRE(net.opt_m && net.opt_v && net.opt_slow, "Ranger needs exp_avg / exp_avg_sq / slow arenas");
   if (o.kind == RECNN_OPT_SGD && o.momentum != 0.f) RECNN_REQUIRE(net.opt_m, "SGD momentum needs a buffer arena");
   const OptConsts k = opt_consts(o);
   const int64_t blocks = ceil_div(count, 256 * 4);
   const int grid = (int)(blocks < 4 * kNumSMs ? (blocks > 0 ? blocks : 1) : 4 * kNumSMs);
-  optimizer_kernel<<<grid, 256, 0, st>>>(o.kind, k, o.beta1, o.beta2, o.lr, net.params,
-                                         net.grads, net.opt_m, net.opt_v, net.opt_t, grad_scale, count, ticket);
+  optimizer_kernel<<<grid, 256, 0, st>>>(o.kind, k, o.beta1, o.beta2, o.lr, o.weight_decay, o.n_sma_threshold, o.k,
+                                         net.params, net.grads, net.opt_m, net.opt_v, net.opt_slow, net.opt_t,
+                                         grad_scale, count, ticket);
   RECNN_CHECK_LAUNCH("optimizer_kernel");
   if (!ticket) {
     bump_counter_kernel<<<1, 1, 0, st>>>(net.opt_t);

@@ -101,38 +101,89 @@ int launch_scale_inplace(float* x, int64_t count, const float* scale, cudaStream
 
 // ---- fused optimizers: per-element update shared by optimizer_kernel and the all-reduce kernel (comm.cu) ----
 struct OptConsts {
-  float lr, one_minus_b1, b2, one_minus_b2, eps, wd, momentum;
+  float lr, one_minus_b1, b1, b2, one_minus_b2, eps, wd, momentum, alpha;
 };
 static inline OptConsts opt_consts(const recnn_optim& o) {
   OptConsts k;
   k.lr = (float)o.lr;
   k.one_minus_b1 = (float)(1.0 - o.beta1);
+  k.b1 = (float)o.beta1;
   k.b2 = (float)o.beta2;
   k.one_minus_b2 = (float)(1.0 - o.beta2);
   k.eps = (float)o.eps;
   k.wd = (float)o.weight_decay;
   k.momentum = (float)o.momentum;
+  k.alpha = (float)o.alpha;
   return k;
 }
+// the step-dependent scalars of one optimizer step (python-float arithmetic in double, cast where torch casts)
+struct OptStep {
+  float step_size;     // Adam: lr / (1 - beta1^t); Ranger: -(rectified step size) * lr as torch_optimizer forms it
+  float bc2_sqrt;      // Adam: sqrt(1 - beta2^t)
+  float wd_lr;         // Ranger: -weight_decay * lr
+  int adaptive;        // Ranger: N_sma > threshold (use the variance term)
+  int lookahead;       // Ranger: t % k == 0 (interpolate towards / reset to the slow weights)
+  int first;           // Ranger: first step (slow weights start as a copy of the parameters)
+};
 #ifdef __CUDACC__
-// Adam's step-dependent scalars: python-float (double) arithmetic, cast where torch casts them
-__device__ __forceinline__ void opt_scalars(int kind, double beta1, double beta2, double lr, int t, float* step_size,
-                                            float* bc2_sqrt) {
+__device__ __forceinline__ OptStep opt_step_scalars(int kind, double beta1, double beta2, double lr, double wd,
+                                                    double n_sma_threshold, int k_look, int t) {
+  OptStep s;
+  s.step_size = 0.f; s.bc2_sqrt = 1.f; s.wd_lr = 0.f; s.adaptive = 0; s.lookahead = 0; s.first = (t == 1);
   if (kind == RECNN_OPT_ADAM) {
     const double bc1 = 1.0 - pow(beta1, (double)t);
     const double bc2 = 1.0 - pow(beta2, (double)t);
-    *step_size = (float)(lr / bc1);
-    *bc2_sqrt = (float)sqrt(bc2);
-  } else {
-    *step_size = 0.f;
-    *bc2_sqrt = 1.f;
+    s.step_size = (float)(lr / bc1);
+    s.bc2_sqrt = (float)sqrt(bc2);
+  } else if (kind == RECNN_OPT_RANGER) {
+    const double beta2_t = pow(beta2, (double)t);
+    const double n_sma_max = 2.0 / (1.0 - beta2) - 1.0;
+    const double n_sma = n_sma_max - 2.0 * t * beta2_t / (1.0 - beta2_t);
+    double step_size;
+    if (n_sma > n_sma_threshold) {
+      step_size = sqrt((1.0 - beta2_t) * (n_sma - 4.0) / (n_sma_max - 4.0) * (n_sma - 2.0) / n_sma * n_sma_max /
+                       (n_sma_max - 2.0)) / (1.0 - pow(beta1, (double)t));
+      s.adaptive = 1;
+    } else {
+      step_size = 1.0 / (1.0 - pow(beta1, (double)t));
+    }
+    s.step_size = (float)(-step_size * lr);
+    s.wd_lr = (float)(-wd * lr);
+    s.lookahead = (k_look > 0 && t % k_look == 0) ? 1 : 0;
   }
+  return s;
 }
-// one element of torch.optim.SGD / Adam (torch 2.11 single-tensor op order); `grad` already carries any clip scale
-__device__ __forceinline__ void opt_apply(int kind, const OptConsts& k, float step_size, float bc2_sqrt, int t,
+// one element of torch.optim.SGD / Adam (torch 2.11 single-tensor op order) or torch_optimizer.Ranger;
+// `grad` already carries any clip scale
+__device__ __forceinline__ void opt_apply(int kind, const OptConsts& k, const OptStep& st, int t,
                                           float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
-                                          long long i, float grad) {
+                                          float* __restrict__ slow, long long i, float grad) {
   const float w = p[i];
+  if (kind == RECNN_OPT_RANGER) {
+    // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1-beta2); exp_avg.mul_(beta1).add_(grad, alpha=1-beta1)
+    float vi = __fmul_rn(v[i], k.b2);
+    vi = __fadd_rn(vi, __fmul_rn(__fmul_rn(k.one_minus_b2, grad), grad));
+    float mi = __fmul_rn(m[i], k.b1);
+    mi = __fadd_rn(mi, __fmul_rn(k.one_minus_b1, grad));
+    v[i] = vi;
+    m[i] = mi;
+    float sl = st.first ? w : slow[i];                 // slow_buffer starts as a copy of the (un-stepped) weights
+    float x = w;
+    if (k.wd != 0.f) x = __fadd_rn(x, __fmul_rn(st.wd_lr, x));             // p.add_(p, alpha=-wd*lr)
+    if (st.adaptive) {
+      const float denom = __fadd_rn(__fsqrt_rn(vi), k.eps);                  // exp_avg_sq.sqrt().add_(eps)
+      x = __fadd_rn(x, __fdiv_rn(__fmul_rn(st.step_size, mi), denom));       // p.addcdiv_(exp_avg, denom, value=-step_size*lr)
+    } else {
+      x = __fadd_rn(x, __fmul_rn(st.step_size, mi));                         // p.add_(exp_avg, alpha=-step_size*lr)
+    }
+    if (st.lookahead) {
+      sl = __fadd_rn(sl, __fmul_rn(k.alpha, __fsub_rn(x, sl)));              // slow.add_(p - slow, alpha=alpha); p = slow
+      x = sl;
+    }
+    if (st.lookahead || st.first) slow[i] = sl;
+    p[i] = x;
+    return;
+  }
   if (k.wd != 0.f) grad = __fadd_rn(grad, __fmul_rn(k.wd, w));
   if (kind == RECNN_OPT_SGD) {
     if (k.momentum != 0.f) {
@@ -147,8 +198,8 @@ __device__ __forceinline__ void opt_apply(int kind, const OptConsts& k, float st
     vi = __fadd_rn(__fmul_rn(vi, k.b2), __fmul_rn(__fmul_rn(k.one_minus_b2, grad), grad));
     m[i] = mi;
     v[i] = vi;
-    const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vi), bc2_sqrt), k.eps);
-    p[i] = __fsub_rn(w, __fmul_rn(step_size, __fdiv_rn(mi, denom)));
+    const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vi), st.bc2_sqrt), k.eps);
+    p[i] = __fsub_rn(w, __fmul_rn(st.step_size, __fdiv_rn(mi, denom)));
   }
 }
 #endif

@@ -1,11 +1,12 @@
 """Algo / DDPG / TD3 wrappers with the reference's wiring (recnn/nn/algo.py:15-179).
 
 These are the dispatchers the update functions plug into (``Algo.algorithm``);
-they only hold state.  One deliberate difference: the reference builds
-``torch_optimizer.Ranger(lr=1e-5, weight_decay=1e-2)`` optimizers
-(algo.py:84-89), a third-party package that is not available here (SURVEY.md
-fact 4); the default is recnn_b200.optim.Adam with the same lr / weight_decay,
-and any optimizer can be supplied through ``self.optimizers`` as in the reference.
+they only hold state.  The reference builds ``torch_optimizer.Ranger(lr=1e-5,
+weight_decay=1e-2)`` optimizers (algo.py:84-89), a third-party package that is not
+available here; the default is recnn_b200.optim.Ranger -- the
+same algorithm (RAdam + Lookahead) with the package's defaults, fused into the device
+step, parity with the package unpinned -- and any optimizer can be supplied
+through ``self.optimizers`` as in the reference.
 """
 from __future__ import annotations
 
@@ -59,8 +60,8 @@ class DDPG(Algo):
         self.nets = {"value_net": value_net, "target_value_net": target_value_net,
                      "policy_net": policy_net, "target_policy_net": target_policy_net}
         self.optimizers = {
-            "policy_optimizer": optim.Adam(policy_net.parameters(), lr=1e-5, weight_decay=1e-2),
-            "value_optimizer": optim.Adam(value_net.parameters(), lr=1e-5, weight_decay=1e-2),
+            "policy_optimizer": optim.Ranger(policy_net.parameters(), lr=1e-5, weight_decay=1e-2),
+            "value_optimizer": optim.Ranger(value_net.parameters(), lr=1e-5, weight_decay=1e-2),
         }
         self.params = {"gamma": 0.99, "min_value": -10, "max_value": 10, "policy_step": 10, "soft_tau": 0.001}
         self.loss_layout = {"test": {"value": [], "policy": [], "step": []},
@@ -77,9 +78,9 @@ class TD3(Algo):
             "policy_net": policy_net, "target_policy_net": _target_of(policy_net),
         }
         self.optimizers = {
-            "policy_optimizer": optim.Adam(policy_net.parameters(), lr=1e-5, weight_decay=1e-2),
-            "value_optimizer1": optim.Adam(value_net1.parameters(), lr=1e-5, weight_decay=1e-2),
-            "value_optimizer2": optim.Adam(value_net2.parameters(), lr=1e-5, weight_decay=1e-2),
+            "policy_optimizer": optim.Ranger(policy_net.parameters(), lr=1e-5, weight_decay=1e-2),
+            "value_optimizer1": optim.Ranger(value_net1.parameters(), lr=1e-5, weight_decay=1e-2),
+            "value_optimizer2": optim.Ranger(value_net2.parameters(), lr=1e-5, weight_decay=1e-2),
         }
         self.params = {"gamma": 0.99, "noise_std": 0.5, "noise_clip": 3, "soft_tau": 0.001, "policy_update": 10,
                        "policy_lr": 1e-5, "value_lr": 1e-5, "actor_weight_init": 25e-2, "critic_weight_init": 6e-1}

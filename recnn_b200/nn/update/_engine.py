@@ -167,19 +167,19 @@ class StepEngine:
             raise _lib.RecnnError("net is on %s but the update runs on %s (call Algo.to(device) / net.cuda())"
                                   % (flat.device, self.device))
         if not with_grads:
-            return _lib.Net(flat.data_ptr(), None, None, None, None)
+            return _lib.Net(flat.data_ptr(), None, None, None, None, None)
         if isinstance(opt, _optim._ArenaOptimizer):
             if opt._module is not module:
                 opt.bind(module)
             return opt.c_net(module)
         g = grad_arena(module)
-        return _lib.Net(flat.data_ptr(), g.data_ptr(), None, None, None)
+        return _lib.Net(flat.data_ptr(), g.data_ptr(), None, None, None, None)
 
     @staticmethod
     def _c_optim(opt):
         if isinstance(opt, _optim._ArenaOptimizer):
             return opt.c_optim()
-        return _lib.Optim(_lib.OPT_EXTERNAL, 0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0)
+        return _lib.Optim(_lib.OPT_EXTERNAL, 0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0)
 
     def _build_args(self, st, nets, optimizer, params, learn, do_policy):
         a = _lib.StepArgs()
@@ -406,6 +406,7 @@ class StepEngine:
             if isinstance(o, _optim._ArenaOptimizer):
                 g = o.param_groups[0]
                 tok.append((id(o), g["lr"], g.get("betas"), g.get("eps"), g["weight_decay"], g.get("momentum"),
+                            g.get("alpha"), g.get("k"), g.get("N_sma_threshhold"),
                             0 if o._m is None else o._m.data_ptr(), 0 if o._t is None else o._t.data_ptr()))
             else:
                 tok.append((id(o),))

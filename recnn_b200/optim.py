@@ -27,7 +27,7 @@ class _ArenaOptimizer(torch.optim.Optimizer):
         super().__init__(params, defaults)
         if len(self.param_groups) != 1:
             raise ValueError("recnn_b200 optimizers take a single parameter group (one net)")
-        self._m = self._v = self._t = None
+        self._m = self._v = self._t = self._slow = None
         self._module = None
 
     # -- binding to a net -------------------------------------------------------
@@ -45,7 +45,8 @@ class _ArenaOptimizer(torch.optim.Optimizer):
         if self._t is None:
             self._t = torch.zeros(1, dtype=torch.int32, device=flat.device)
             self._m = torch.zeros_like(flat)
-            self._v = torch.zeros_like(flat) if self._recnn_kind == _lib.OPT_ADAM else None
+            self._v = torch.zeros_like(flat) if self._recnn_kind in (_lib.OPT_ADAM, _lib.OPT_RANGER) else None
+            self._slow = torch.zeros_like(flat) if self._recnn_kind == _lib.OPT_RANGER else None
         elif self._t.device != flat.device or self._m.numel() != flat.numel():
             if self._m.numel() != flat.numel():
                 raise _lib.RecnnError("optimizer state (%d elements) does not match the net's arena (%d)"
@@ -54,6 +55,7 @@ class _ArenaOptimizer(torch.optim.Optimizer):
             self._t = self._t.to(flat.device)
             self._m = self._m.to(flat.device)
             self._v = None if self._v is None else self._v.to(flat.device)
+            self._slow = None if self._slow is None else self._slow.to(flat.device)
         return self._m, self._v, self._t
 
     # -- checkpointing: the moments / step count live in flat arenas, not in self.state -----------
@@ -64,6 +66,7 @@ class _ArenaOptimizer(torch.optim.Optimizer):
         if self._t is not None:
             sd["recnn_arenas"] = {"m": self._m.detach().cpu().clone(),
                                   "v": None if self._v is None else self._v.detach().cpu().clone(),
+                                  "slow": None if self._slow is None else self._slow.detach().cpu().clone(),
                                   "t": int(self._t.item())}
         return sd
 
@@ -72,11 +75,12 @@ class _ArenaOptimizer(torch.optim.Optimizer):
         arenas = state_dict.pop("recnn_arenas", None)
         super().load_state_dict(state_dict)
         if arenas is None:
-            self._m = self._v = self._t = None
+            self._m = self._v = self._t = self._slow = None
             return
         dev = self.param_groups[0]["params"][0].device
         self._m = arenas["m"].to(dev).clone()
         self._v = None if arenas["v"] is None else arenas["v"].to(dev).clone()
+        self._slow = None if arenas.get("slow") is None else arenas["slow"].to(dev).clone()
         self._t = torch.full((1,), int(arenas["t"]), dtype=torch.int32, device=dev)
 
     def c_optim(self) -> _lib.Optim:
@@ -90,7 +94,7 @@ class _ArenaOptimizer(torch.optim.Optimizer):
         flat = param_arena(module)
         g = grad_arena(module)
         m, v, t = self._state_arenas(flat)
-        return _lib.Net(flat.data_ptr(), g.data_ptr(), _lib.ptr(m), _lib.ptr(v), t.data_ptr())
+        return _lib.Net(flat.data_ptr(), g.data_ptr(), _lib.ptr(m), _lib.ptr(v), t.data_ptr(), _lib.ptr(self._slow))
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -118,7 +122,7 @@ class Adam(_ArenaOptimizer):
     def c_optim(self):
         g = self.param_groups[0]
         return _lib.Optim(_lib.OPT_ADAM, 0, float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]),
-                          float(g["eps"]), float(g["weight_decay"]), 0.0)
+                          float(g["eps"]), float(g["weight_decay"]), 0.0, 0.0, 0.0)
 
 
 class SGD(_ArenaOptimizer):
@@ -130,4 +134,28 @@ class SGD(_ArenaOptimizer):
     def c_optim(self):
         g = self.param_groups[0]
         return _lib.Optim(_lib.OPT_SGD, 0, float(g["lr"]), 0.0, 0.0, 0.0, float(g["weight_decay"]),
-                          float(g["momentum"]))
+                          float(g["momentum"]), 0.0, 0.0)
+
+
+class Ranger(_ArenaOptimizer):
+    """torch_optimizer.Ranger (RAdam + Lookahead), the optimizer recnn.nn.DDPG / TD3 build by default
+    (recnn/nn/algo.py:84-89: ``Ranger(params, lr=..., weight_decay=...)``), with the package's signature and
+    defaults.  torch_optimizer is not vendored in the reference and not installed here; this follows the published
+    algorithm (rectified Adam with the N_sma_threshhold switch, Lookahead with slow weights every k steps) and its
+    bit-level parity with the package is UNPINNED -- see DESIGN.md section 2."""
+    _recnn_kind = _lib.OPT_RANGER
+
+    def __init__(self, params, lr=1e-3, alpha=0.5, k=6, N_sma_threshhold=5, betas=(0.95, 0.999), eps=1e-5,
+                 weight_decay=0):
+        if not 0.0 <= alpha <= 1.0:
+            raise ValueError("Invalid slow update rate: %r" % alpha)
+        if not 1 <= k:
+            raise ValueError("Invalid lookahead steps: %r" % k)
+        super().__init__(params, dict(lr=lr, alpha=alpha, k=k, N_sma_threshhold=N_sma_threshhold, betas=betas,
+                                      eps=eps, weight_decay=weight_decay))
+
+    def c_optim(self):
+        g = self.param_groups[0]
+        return _lib.Optim(_lib.OPT_RANGER, int(g["k"]), float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]),
+                          float(g["eps"]), float(g["weight_decay"]), 0.0, float(g["alpha"]),
+                          float(g["N_sma_threshhold"]))

@@ -51,6 +51,8 @@ def build_optimizers(kind, nets, algo, external=False):
         if external:
             return torch.optim.Adam(net.parameters(), lr=1e-5) if kind == "adam" else \
                 torch.optim.SGD(net.parameters(), lr=1e-3)
+        if kind == "ranger":
+            return recnn_b200.optim.Ranger(net.parameters(), lr=1e-4, weight_decay=1e-2)
         return recnn_b200.optim.Adam(net.parameters(), lr=1e-5) if kind == "adam" else \
             recnn_b200.optim.SGD(net.parameters(), lr=1e-3)
     names = {"policy_optimizer": "policy_net"}

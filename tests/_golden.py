@@ -20,6 +20,7 @@ def load_golden(name):
 
 def oracle_optimizers(kind, algo):
     mk = (lambda: O.make_optimizer("adam", lr=1e-5)) if kind == "adam" else \
+         (lambda: O.make_optimizer("ranger", lr=1e-4, weight_decay=1e-2)) if kind == "ranger" else \
          (lambda: O.make_optimizer("sgd", lr=1e-3))
     names = ("policy_optimizer", "value_optimizer") if algo == "ddpg" else \
             ("policy_optimizer", "value_optimizer1", "value_optimizer2")

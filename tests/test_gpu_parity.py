@@ -798,3 +798,39 @@ def test_optimizer_state_dict_round_trip_continues_bias_correction():
     for k in nets_a:
         for p, q in zip(nets_a[k].parameters(), nets_c[k].parameters()):
             assert torch.equal(p, q), k
+
+
+# ----------------------------------------------------------------------------- Ranger (the reference's default optimizer)
+@pytest.mark.parametrize("algo", ["ddpg", "td3"])
+@pytest.mark.parametrize("case", ["tiny", "canon"])
+def test_ranger_step_vs_oracle(case, algo):
+    """recnn.nn.DDPG / TD3 build torch_optimizer.Ranger by default (algo.py:84-89).  The fused RANGER kind against
+    the oracle's restatement (whose RAdam half is pinned against torch.optim.RAdam and whose Lookahead half against
+    its definition, tests/test_oracle_golden.py) over 12 steps: rectification switch at step 6, Lookahead at 6 / 12."""
+    want = run_oracle_case(case, algo, "ranger")
+    got = run_cuda_case(case, algo, "ranger", form="frames")
+    inp = C.make_inputs(C.CASES[case], algo)
+    for k in (k for k in want if k.startswith("loss.")):
+        err = np.max(np.abs(got[k] - want[k]) / (np.abs(want[k]) + 0.1))
+        assert err <= 1e-5, (k, err)
+    for k in (k for k in want if k.startswith("final.")):
+        _, name, tensor = k.split(".")
+        w = want[k].astype(np.float64)
+        wmax = np.max(np.abs(w))
+        assert np.max(np.abs(got[k] - w) / (np.abs(w) + 1e-2 * wmax)) <= 1e-5, k
+        d_want = w - inp["nets"][name][tensor]
+        scale = np.max(np.abs(d_want))
+        if scale == 0:
+            assert np.array_equal(got[k], want[k]), k
+            continue
+        ulp2 = 2.0 * 1.1920929e-07 * wmax
+        excess = np.maximum(np.abs((got[k] - inp["nets"][name][tensor]) - d_want) - ulp2, 0)
+        assert np.max(excess) <= 2e-3 * scale, (k, float(np.max(excess) / scale))
+
+
+def test_default_optimizers_are_ranger_like_the_reference():
+    agent = recnn_b200.nn.DDPG(recnn_b200.nn.Actor(44, 8, 32), recnn_b200.nn.Critic(44, 8, 32))
+    for o in agent.optimizers.values():
+        assert isinstance(o, recnn_b200.optim.Ranger)
+        g = o.param_groups[0]
+        assert (g["lr"], g["weight_decay"], g["k"], g["alpha"], g["betas"], g["eps"]) == (1e-5, 1e-2, 6, 0.5, (0.95, 0.999), 1e-5)

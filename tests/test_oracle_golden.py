@@ -54,3 +54,43 @@ def test_quirks():
     for k in g:                                       # sign flipped
         assert np.all(np.sign(g[k]) == -np.sign(before[k]))
     assert total > 0
+
+
+def test_oracle_ranger_radam_half_matches_torch_radam():
+    """torch_optimizer.Ranger is absent (parity unpinned); its RAdam half is the same update as
+    torch.optim.RAdam(decoupled_weight_decay=True), which IS available: with Lookahead disabled (k beyond the run)
+    the oracle's Ranger must track it over the rectification switch (steps 1..5 un-rectified, then rectified)."""
+    import torch
+    from oracle import recnn_oracle as O
+    rng = np.random.default_rng(0)
+    p0 = {k: rng.standard_normal(s).astype(np.float32) for k, s in
+          zip(O.PARAM_ORDER, [(8, 5), (8,), (8, 8), (8,), (3, 8), (3,)])}
+    p = {k: v.copy() for k, v in p0.items()}
+    tp = [torch.nn.Parameter(torch.from_numpy(p0[k].copy())) for k in O.PARAM_ORDER]
+    topt = torch.optim.RAdam(tp, lr=1e-2, betas=(0.95, 0.999), eps=1e-5, weight_decay=1e-2, decoupled_weight_decay=True)
+    o = O.make_optimizer("ranger", lr=1e-2, weight_decay=1e-2, k=10 ** 9)
+    for step in range(12):
+        g = {k: rng.standard_normal(p0[k].shape).astype(np.float32) for k in O.PARAM_ORDER}
+        for q, k in zip(tp, O.PARAM_ORDER):
+            q.grad = torch.from_numpy(g[k].copy())
+        topt.step()
+        O.optimizer_step(o, p, g)
+        for q, k in zip(tp, O.PARAM_ORDER):
+            np.testing.assert_allclose(p[k], q.detach().numpy(), rtol=2e-5, atol=2e-6, err_msg="%s step %d" % (k, step))
+
+
+def test_oracle_ranger_lookahead_half():
+    """Every k-th step the weights are pulled half way (alpha) back to the slow copy, which starts at the initial weights."""
+    from oracle import recnn_oracle as O
+    rng = np.random.default_rng(1)
+    p = {k: rng.standard_normal((4, 4) if k.startswith("w") else (4,)).astype(np.float32) for k in O.PARAM_ORDER}
+    init = {k: v.copy() for k, v in p.items()}
+    fast = {k: v.copy() for k, v in p.items()}
+    o = O.make_optimizer("ranger", lr=1e-2, k=3, alpha=0.5)
+    o_fast = O.make_optimizer("ranger", lr=1e-2, k=10 ** 9)
+    for step in range(3):
+        g = {k: rng.standard_normal(p[k].shape).astype(np.float32) for k in O.PARAM_ORDER}
+        O.optimizer_step(o, p, g)
+        O.optimizer_step(o_fast, fast, g)
+    for k in O.PARAM_ORDER:
+        np.testing.assert_allclose(p[k], init[k] + 0.5 * (fast[k] - init[k]), rtol=1e-6, atol=1e-7)
