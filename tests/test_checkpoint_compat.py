@@ -46,15 +46,22 @@ def test_saved_state_dict_loads_into_the_reference_classes():
     from oracle.ref_import import reference_available, import_reference
     if not reference_available():
         pytest.skip("reference tree not present (GPU box)")
-    recnn = import_reference()
-    ck = _load()
-    S, A, H = ck["dims"]
-    ours = recnn_b200.nn.Actor(S, A, H)
-    ours.load_state_dict(ck["actor"])
-    theirs = recnn.nn.models.Actor(S, A, H).eval()
-    theirs.load_state_dict(ours.state_dict(), strict=True)
-    with torch.no_grad():
-        assert torch.equal(theirs(ck["state"]), ck["out"]["actor"])
+    import sys
+    before = set(sys.modules)
+    try:
+        recnn = import_reference()
+        ck = _load()
+        S, A, H = ck["dims"]
+        ours = recnn_b200.nn.Actor(S, A, H)
+        ours.load_state_dict(ck["actor"])
+        theirs = recnn.nn.models.Actor(S, A, H).eval()
+        theirs.load_state_dict(ours.state_dict(), strict=True)
+        with torch.no_grad():
+            assert torch.equal(theirs(ck["state"]), ck["out"]["actor"])
+    finally:          # leave no 'recnn' behind: tests/test_host.py registers recnn_b200 under that name
+        for name in set(sys.modules) - before:
+            if name == "recnn" or name.startswith("recnn."):
+                del sys.modules[name]
 
 
 @pytest.mark.gpu
