@@ -495,6 +495,32 @@ def run_native(args):
                 ts.append(a.elapsed_time(b))
             return float(np.mean(ts))
 
+        def graph_time(fns, reps=10):
+            """Average DEVICE time of one launch: the launches `fns` (each on its own operands, together larger than
+            the 126 MB L2, so no launch finds its streamed operand cached) are captured into one CUDA graph and the
+            graph is replayed `reps` times between two events.  Unlike an event pair around a single host launch this
+            contains no host-side launch preparation (tensor-map encoding) and is not limited by the ~2 us event
+            resolution; it does contain the inter-kernel gaps, as the step's own graph does."""
+            for f in fns:
+                f()
+            torch.cuda.synchronize(dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for f in fns:
+                    f()
+            g.replay()
+            torch.cuda.synchronize(dev)
+            ts = []
+            for _ in range(reps):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                g.replay()
+                b.record()
+                torch.cuda.synchronize(dev)
+                ts.append(a.elapsed_time(b) / len(fns))
+            return float(np.median(ts)), float(min(ts)), float(max(ts))
+
         # (1) the materialising gather kernel  (HBM bound)
         items_d, ratings_d = main.items_d, main.ratings_d
         g_state = torch.empty(n_rows, S_DIM, device=dev)
@@ -519,15 +545,28 @@ def run_native(args):
         gather_big_gbs = big * GATHER_BYTES_PER_ROW / (gather_big_ms * 1e-3) / 1e9
         del gb_state, gb_next, gb_act, gb_rew, gb_items, gb_ratings
         # (2) the dominant kernel of the step: layer-1 forward GEMM [4096,1290] x [1290,256]
-        #     (same tcgen05 3xTF32 kernel and operand pitches as inside the step; plain-store epilogue)
+        #     (same tcgen05 3xTF32 kernel and operand pitches as inside the step; plain-store epilogue).
+        #     Eight launches on eight different state images (8 x 21 MB > L2) in one graph: average device time.
         ld_s = (S_DIM + 3) // 4 * 4
-        x_img = torch.randn(n_rows, ld_s, device=dev)
+        x_imgs = [torch.randn(n_rows, ld_s, device=dev) for _ in range(8)]
         w1 = agent.nets["policy_net"].linear1.weight            # strided view into the arena, pitch 1292
-        h1 = torch.empty(n_rows, HIDDEN, device=dev)
-        l1_ms = time_kernel(lambda: _lib.check(L.recnn_gemm_tf32x3(
-            n_rows, HIDDEN, S_DIM, x_img.data_ptr(), ld_s, 0, w1.data_ptr(), w1.stride(0), 0,
-            h1.data_ptr(), HIDDEN, 64, st)))
+        h1s = [torch.empty(n_rows, HIDDEN, device=dev) for _ in range(8)]
+
+        def l1_launch(i, tile):
+            return lambda: _lib.check(L.recnn_gemm_tf32x3(
+                n_rows, HIDDEN, S_DIM, x_imgs[i].data_ptr(), ld_s, 0, w1.data_ptr(), w1.stride(0), 0,
+                h1s[i].data_ptr(), HIDDEN, tile, st))
+
+        l1 = {}
+        for tile in (64, 128):
+            med, lo, hi = graph_time([l1_launch(i, tile) for i in range(8)])
+            l1[tile] = {"ms": med, "ms_min": lo, "ms_max": hi,
+                        "tf32_tflops": 3.0 * n_rows * L1_FWD_FLOP_PER_ROW / (med * 1e-3) / 1e12}
+        l1_single_ms = time_kernel(l1_launch(0, 64))                # round-1 method (one host launch between events)
+        best_tile = min(l1, key=lambda t: l1[t]["ms"])
+        l1_ms = l1[best_tile]["ms"]
         l1_tflops = n_rows * L1_FWD_FLOP_PER_ROW / (l1_ms * 1e-3) / 1e12
+        del x_imgs, h1s
         tf32_peak = peaks["bf16"] / 2.0           # dense TF32 = half the dense bf16 rate
         rows_global = n_rows * world
         updates_per_sec = value / world
@@ -588,7 +627,10 @@ def run_native(args):
                          "achieved": 3.0 * l1_tflops, "algorithmic_fp32": l1_tflops, "peak": tf32_peak, "unit": "TFLOP/s",
                          "frac": 3.0 * l1_tflops / tf32_peak,
                          "traffic": 22525184, "traffic_source": "dram__bytes_read+write per launch, profiles/r1b_ncu_tc_gemm_tile64_summary.csv (ncu --set full)", "peak_source": "%s bf16 %.0f TF/s / 2 (TF32 kind)" % (peaks["source"], peaks["bf16"]),
-                         "ms": l1_ms},
+                         "ms": l1_ms, "tile_n": best_tile, "per_tile": {str(k): v for k, v in l1.items()},
+                         "timing": "8 launches on 8 distinct state images (8 x 21 MB > L2) captured in one CUDA graph, "
+                                   "replayed 10x between CUDA events, L2 flushed between replays; median per launch",
+                         "ms_single_launch_between_events": l1_single_ms},
             "roofline_gather": {"bound": "hbm", "kernel": "frame_gather_kernel", "achieved": gather_gbs,
                                 "peak": peaks["hbm"], "unit": "GB/s", "frac": gather_gbs / peaks["hbm"],
                                 "traffic": 12083712, "traffic_source": "dram__bytes_read+write per launch, profiles/README.md: the 44 MB of "

@@ -137,12 +137,16 @@ RECNN_API int recnn_net_layout(const recnn_dims* d, int is_critic, int64_t* out)
 
 /* recnn/nn/models.py:59-73 Actor.forward.  masks: two uint8[n_rows,H] arrays
  * (train mode: h = relu(z) * mask * 2) or NULL,NULL for eval().  apply_tanh as
- * the reference's `tanh` argument.  scratch: fp32[2*n_rows*H]. */
+ * the reference's `tanh` argument.  scratch: fp32[recnn_forward_scratch_floats(d, n_rows, 0)]
+ * (two hidden activations + a 16-byte-pitch image of `state` when its row pitch is not a 16-byte multiple,
+ * so that every layer runs on the tensor cores). */
+RECNN_API int64_t recnn_forward_scratch_floats(const recnn_dims* d, int64_t n_rows, int is_critic);
 RECNN_API int recnn_actor_forward(const recnn_dims* d, const float* params, const float* state,
                         int64_t n_rows, const uint8_t* mask1, const uint8_t* mask2,
                         int apply_tanh, float* action_out, float* scratch, void* stream);
 
-/* recnn/nn/models.py:205-213 Critic.forward (concat is virtual).  value_out fp32[n_rows]. */
+/* recnn/nn/models.py:205-213 Critic.forward (concat is virtual).  value_out fp32[n_rows];
+ * scratch: fp32[recnn_forward_scratch_floats(d, n_rows, 1)]. */
 RECNN_API int recnn_critic_forward(const recnn_dims* d, const float* params, const float* state,
                          const float* action, int64_t n_rows,
                          const uint8_t* mask1, const uint8_t* mask2,

@@ -79,6 +79,7 @@ SIGNATURES = {
     "recnn_actor_param_count": (C.c_int64, [C.POINTER(Dims)]),
     "recnn_critic_param_count": (C.c_int64, [C.POINTER(Dims)]),
     "recnn_net_layout": (C.c_int, [C.POINTER(Dims), C.c_int, C.POINTER(C.c_int64)]),
+    "recnn_forward_scratch_floats": (C.c_int64, [C.POINTER(Dims), C.c_int64, C.c_int]),
     "recnn_actor_forward": (C.c_int, [C.POINTER(Dims), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                       C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "recnn_critic_forward": (C.c_int, [C.POINTER(Dims), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
@@ -147,9 +148,8 @@ def lib():
 
 
 def set_option(name: str, value: int) -> int:
-    """Runtime A/B switch of the library (``recnn_debug_set_option``: "gather_variant", "presplit", "workers16", "lo2", "bn64", "lean", "pdl", "tail", "dwsplit", "padzero").
-    Returns the previous value.  Not part of the product ABI: used by bench.py's A/B legs and by tests
-    that check the kernel variants against each other."""
+    """Runtime A/B switch of the library (``recnn_debug_set_option``); returns the previous value.  Not part of the
+    product ABI.  Only the knobs of experiments still in flight exist (currently: "experiment")."""
     h = lib()
     fn = h.recnn_debug_set_option
     fn.restype, fn.argtypes = C.c_int, [C.c_char_p, C.c_int]

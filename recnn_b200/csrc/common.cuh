@@ -47,9 +47,9 @@ void count_launch();   // every kernel launch of this library bumps a process-wi
     if (_s != RECNN_OK) return _s;                                                    \
   } while (0)
 
-// ---- runtime switches (A/B experiments and regression fallbacks; recnn_debug_set_option) --------
-enum Option { OPT_GATHER_VARIANT = 0, OPT_PRESPLIT = 1, OPT_WORKERS16 = 2, OPT_LO2 = 3, OPT_BN64 = 4, OPT_LEAN = 5, OPT_PDL = 6, OPT_TAIL = 7, OPT_DWSPLIT = 8, OPT_PADZERO = 9, OPT_COUNT = 10 };
-int option(Option o);          // current value (initialised from RECNN_B200_GATHER / _PRESPLIT / _WORKERS16)
+// ---- runtime switches (A/B experiments still in flight; recnn_debug_set_option) --------
+enum Option { OPT_EXPERIMENT = 0, OPT_COUNT = 1 };
+int option(Option o);
 
 constexpr int kNumSMs = 148;   // B200
 

@@ -102,100 +102,6 @@ frame_gather_kernel(const float* __restrict__ table, long long n_items, int dim,
   }
 }
 
-// Variant 1 ("units"): the work item is one (row, slot) pair = one table row copied to up to three
-// destinations.  The grid is exactly one resident wave (148 SMs x CTAs that fit per SM) and every
-// warp takes a CONTIGUOUS, equally sized range of units (+-1), so there is no partial second wave:
-// at 4096 rows the one-warp-per-row kernel launches 512 CTAs of which 444 are resident, and the
-// 68-CTA tail runs at a fraction of the machine.  Four units are in flight per lane, as above.
-template <bool VEC>
-__global__ void __launch_bounds__(256, 3)
-frame_gather_units_kernel(const float* __restrict__ table, long long n_items, int dim,
-                          const long long* __restrict__ items, const float* __restrict__ ratings,
-                          long long n_rows, int frame, long long s_ld, long long a_ld,
-                          float* __restrict__ state, float* __restrict__ next_state,
-                          float* __restrict__ action, float* __restrict__ reward, int* __restrict__ oob) {
-  const int lane = threadIdx.x & 31;
-  const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
-  const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int f1 = frame + 1;
-  const long long total = n_rows * f1;
-  const long long per = total / n_warps, rem = total % n_warps;      // first `rem` warps take one more
-  const long long u_begin = gw * per + (gw < rem ? gw : rem);
-  const long long u_end = u_begin + per + (gw < rem ? 1 : 0);
-  const long long tail = (long long)frame * dim;                      // column of the first rating
-
-  for (long long u0 = u_begin; u0 < u_end; u0 += 4) {
-    long long row[4], id[4];
-    int slot[4];
-    const int cnt = (int)((u_end - u0) < 4 ? (u_end - u0) : 4);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const long long u = u0 + (k < cnt ? k : cnt - 1);
-      row[k] = u / f1;
-      slot[k] = (int)(u - row[k] * f1);
-      long long v = __ldg(items + u);                                  // items is [n_rows, f1] dense: index == u
-      if (v < 0 || v >= n_items) {
-        if (oob && lane == 0) atomicOr(oob, 1);
-        v = 0;
-      }
-      id[k] = v;
-    }
-    // ratings tail + reward: done by the warp that owns the row's slot-0 unit
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (k < cnt && slot[k] == 0) {
-        const long long n = row[k];
-        for (int t = lane; t < f1; t += 32) {
-          const float r = ratings[n * f1 + t];
-          if (t < frame && state) state[n * s_ld + tail + t] = r;
-          if (t >= 1 && next_state) next_state[n * s_ld + tail + (t - 1)] = r;
-          if (t == frame && reward) reward[n] = r;
-        }
-      }
-    }
-    if (VEC) {
-      for (int c = lane * 4; c < dim; c += 128) {
-        float4 v[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (k < cnt) v[k] = __ldg(reinterpret_cast<const float4*>(table + id[k] * dim + c));
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (k >= cnt) break;
-          const int j = slot[k];
-          const long long n = row[k];
-          const float2 lo = make_float2(v[k].x, v[k].y), hi = make_float2(v[k].z, v[k].w);
-          if (j < frame && state) {
-            float2* d = reinterpret_cast<float2*>(state + n * s_ld + (long long)j * dim + c);
-            d[0] = lo; d[1] = hi;
-          }
-          if (j >= 1 && next_state) {
-            float2* d = reinterpret_cast<float2*>(next_state + n * s_ld + (long long)(j - 1) * dim + c);
-            d[0] = lo; d[1] = hi;
-          }
-          if (j == frame && action) {
-            float2* d = reinterpret_cast<float2*>(action + n * a_ld + c);
-            d[0] = lo; d[1] = hi;
-          }
-        }
-      }
-    } else {
-      for (int c = lane; c < dim; c += 32) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (k >= cnt) break;
-          const int j = slot[k];
-          const long long n = row[k];
-          const float v = __ldg(table + id[k] * dim + c);
-          if (j < frame && state) state[n * s_ld + (long long)j * dim + c] = v;
-          if (j >= 1 && next_state) next_state[n * s_ld + (long long)(j - 1) * dim + c] = v;
-          if (j == frame && action) action[n * a_ld + c] = v;
-        }
-      }
-    }
-  }
-}
-
 __global__ void done_from_sizes_kernel(const long long* __restrict__ sizes, long long n_users, int frame,
                                        float* __restrict__ done, long long n_rows) {
   // done[cumsum(sizes - frame) - 1] = 1.  n_users is small (25 in the reference's
@@ -232,28 +138,9 @@ int launch_frame_gather(const float* table, int64_t n_items, int dim, const int6
   const int warps_per_block = 8;
   const int64_t blocks = ceil_div(n_rows, warps_per_block);
   const int grid = (int)(blocks < (int64_t)kNumSMs * 8 ? blocks : (int64_t)kNumSMs * 8);
-  if (option(OPT_GATHER_VARIANT) == 1) {
-    // one resident wave: 148 x (CTAs of this kernel that fit on an SM), never more warps than units
-    static int per_sm[2] = {0, 0};
-    if (per_sm[vec] == 0) {
-      int b = 0;
-      const cudaError_t e = vec ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, frame_gather_units_kernel<true>, 256, 0)
-                                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, frame_gather_units_kernel<false>, 256, 0);
-      per_sm[vec] = (e == cudaSuccess && b > 0) ? b : 2;
-    }
-    const int64_t units = n_rows * (frame + 1);
-    int64_t g = (int64_t)kNumSMs * per_sm[vec];
-    if (g * warps_per_block > units) g = ceil_div(units, warps_per_block);
-    if (vec)
-      frame_gather_units_kernel<true><<<(int)g, 256, 0, st>>>(table, n_items, dim, (const long long*)items, ratings,
-                                                              n_rows, frame, s_ld, a_ld, state, next_state, action, reward, oob_flag);
-    else
-      frame_gather_units_kernel<false><<<(int)g, 256, 0, st>>>(table, n_items, dim, (const long long*)items, ratings,
-                                                               n_rows, frame, s_ld, a_ld, state, next_state, action, reward, oob_flag);
-    RECNN_CHECK_LAUNCH("frame_gather_units_kernel");
-    return RECNN_OK;
-  }
-  const bool st16 = vec && option(OPT_GATHER_VARIANT) == 2 && s_ld % 4 == 0 && (((long long)frame * dim) % 4 == 0) &&
+  // 16-byte stores whenever the destination pitches allow it (the step's state images have a 16-byte-multiple
+  // pitch; the public API's dense 1290-float rows are only 8-byte aligned)
+  const bool st16 = vec && s_ld % 4 == 0 && (((long long)frame * dim) % 4 == 0) &&
                     (!state || reinterpret_cast<uintptr_t>(state) % 16 == 0) &&
                     (!next_state || reinterpret_cast<uintptr_t>(next_state) % 16 == 0);
   if (st16)

@@ -85,77 +85,18 @@ struct Workspace {
   float* block_partials;  // [1024]
   float* scalars;         // [8]: 0 = clip coef
   unsigned* tickets;      // [8]
-  // TF32 hi / lo planes of the six nets' arenas (pre-split weights for the B_PRE GEMMs), same geometry
-  // as the arenas: 0 policy, 1 target policy (actor layout); 2,3 value[0..1]; 4,5 target value[0..1]
-  float* plane_hi[6];
-  float* plane_lo[6];
   int64_t bytes;
 };
 
-// ---------------------------------------------------------------- pre-split weight planes
-// Forward and input-gradient GEMMs take a WEIGHT matrix as their B operand.  Splitting it into TF32
-// hi/lo inside every GEMM costs the split warps a shared-memory read + two writes of the B tile and a
-// proxy fence per k-block -- for a matrix that only changes at an optimizer / Polyak step.  Instead one
-// small kernel splits the nets' whole arenas at the start of the call (and the online critic again after
-// its optimizer step), and the GEMMs fetch hi and lo straight from those planes (tc::Cfg::B_PRE).
-// A plane is only used while `valid`: any path that changes an arena inside the call clears the flag,
-// and a GEMM whose weights have no valid plane silently uses the in-kernel split (identical results).
-struct PlaneEntry {
-  const float* base;       // arena
-  float* hi;
-  float* lo;
-  int64_t count;
-  bool valid;
-};
-struct PlaneTable {
-  PlaneEntry e[6];
-  bool enabled;
-};
-static thread_local PlaneTable* t_planes = nullptr;
-struct PlaneScope {
-  PlaneTable* prev;
-  explicit PlaneScope(PlaneTable* t) : prev(t_planes) { t_planes = t; }
-  ~PlaneScope() { t_planes = prev; }
-};
-// hi/lo plane addresses of the weight matrix at `W` (inside one of the registered arenas), or false
-static bool planes_for(const float* W, const float** hi, const float** lo) {
-  const PlaneTable* t = t_planes;
-  if (!t || !t->enabled) return false;
-  for (const PlaneEntry& e : t->e) {
-    if (e.valid && e.base && W >= e.base && W < e.base + e.count) {
-      *hi = e.hi + (W - e.base);
-      *lo = e.lo + (W - e.base);
-      return true;
-    }
-  }
-  return false;
-}
-// (re)split the listed entries that are not valid; one launch
-static int split_planes(PlaneTable& t, const int* which, int n, cudaStream_t st) {
-  if (!t.enabled) return RECNN_OK;
-  tc::SplitJob jobs[6];
-  int nj = 0;
-  for (int i = 0; i < n; ++i) {
-    PlaneEntry& e = t.e[which[i]];
-    if (!e.base || e.valid) continue;
-    bool dup = false;                       // the same arena registered twice (a net used in two roles)
-    for (int k = 0; k < nj; ++k) dup = dup || jobs[k].src == e.base;
-    if (!dup) jobs[nj++] = tc::SplitJob{e.base, e.hi, e.lo, (long long)e.count};
-    e.valid = true;
-  }
-  return tc::launch_split_planes(jobs, nj, st);
-}
-
 // split count of a weight-gradient GEMM dW[C, K] = dZ^T X over n_rows (the contraction dim).
 // Must be a pure function of the shapes: the workspace size depends on it.
-// policy 0 (default): aim at ~192 CTAs.  policy 1 (`dwsplit` option): the tensor-core kernel holds one CTA per SM and
-// has a ~10 us fixed cost, so more CTAs than SMs means a second wave of the whole fixed cost (measured: the critic's
-// dW1, 22+4 tiles x 8 splits = 208 CTAs, takes 48 us = two waves); aim at one wave of ~132 CTAs instead, leaving
-// room for the GEMM that runs beside it.  Fewer splits never need more workspace, so carve() sizes for policy 0.
-static int dw_splits(int C, int K, int64_t n_rows, bool tc_path, int policy = 0) {
+// The tensor-core kernel holds one CTA per SM and has a fixed cost of several microseconds, so more CTAs than SMs
+// means a second wave of the whole fixed cost (measured in round 1: the critic's dW1 as 22+4 tiles x 8 splits = 208
+// CTAs took 48 us = two waves); aim at ONE wave of ~132 CTAs, leaving room for the GEMM that runs beside it.
+static int dw_splits(int C, int K, int64_t n_rows, bool tc_path) {
   if (tc_path) {
     const int64_t tiles = ceil_div(C, 128) * ceil_div(K, 128);
-    int64_t s = policy == 1 ? (132 / tiles > 0 ? 132 / tiles : 1) : ceil_div(192, tiles);
+    int64_t s = 132 / tiles > 0 ? 132 / tiles : 1;
     const int64_t max_s = ceil_div(n_rows, 32) / 4 > 0 ? ceil_div(n_rows, 32) / 4 : 1;   // >= 4 k-blocks (128 rows) per split
     if (s > max_s) s = max_s;
     return (int)(s < 1 ? 1 : s);
@@ -215,13 +156,6 @@ static Workspace carve(const recnn_dims& d, int64_t n, void* base) {
   w.block_partials = take(1024);
   w.scalars = take(8);
   w.tickets = reinterpret_cast<unsigned*>(take(8));
-  {
-    const int64_t ca = actor_layout(d).count, cc = critic_layout(d).count;
-    for (int i = 0; i < 6; ++i) {
-      w.plane_hi[i] = take(i < 2 ? ca : cc);
-      w.plane_lo[i] = take(i < 2 ? ca : cc);
-    }
-  }
   w.bytes = off;
   return w;
 }
@@ -264,7 +198,6 @@ struct AloneScope {
 static int pick_bn(int64_t M, int N) {
   // 128-wide tiles when they still yield >= 64 CTAs; otherwise 64-wide (more CTAs, less reuse)
   const int64_t mt = ceil_div(M, 128);
-  if (option(OPT_WORKERS16) == 2 || option(OPT_BN64) != 0) return 64;       // the 16-worker kernel exists for 64-wide tiles only
   if (t_alone && mt * ceil_div(N, 64) <= 2 * kNumSMs) return 64;
   if (N > 64 && mt * ceil_div(N, 128) >= 64) return 128;
   return 64;
@@ -280,9 +213,9 @@ static int gemm_nt(const Seg& x0, const Seg& x1, const float* W, long long ldw, 
                      (x1.cols == 0 || (x0.cols - x1.lead) % 4 == 0);
   if (tc_ok) {
     tc::Operand a0 = {x0.p, x0.ld, 0, 0}, a1 = {x1.p, x1.ld, 0, 0}, b = {W, ldw, N, K};
-    const float *whi, *wlo;
-    if (planes_for(W, &whi, &wlo)) { b.ptr = whi; b.lo = wlo; }
-    tc::Problem p = {(int)n, N, x0.cols, x1.cols, 0, x0.cols - x1.lead, 0, 0, 0, 0, nullptr, nullptr};
+    tc::Problem p;
+    memset(&p, 0, sizeof(p));
+    p.M = (int)n; p.N = N; p.K0 = x0.cols; p.K1 = x1.cols; p.b_k1_offset = x0.cols - x1.lead;
     const int r = tc::launch<false, false, EPI>(a0, a1, b, p, 1, pick_bn(n, N), e, st);
     return r < 0 ? r : RECNN_OK;
   }
@@ -324,9 +257,9 @@ static int backprop_hidden(const float* dZ, int C, const float* W, long long ldw
   const bool tc_ok = math_tc() && aligned16(dZ) && aligned16(W) && C % 4 == 0 && ldw % 4 == 0 && col0 % 4 == 0;
   if (tc_ok) {
     tc::Operand a0 = {dZ, C, 0, 0}, a1 = {nullptr, 0, 0, 0}, b = {W, ldw, C, w_cols};
-    const float *whi, *wlo;
-    if (planes_for(W, &whi, &wlo)) { b.ptr = whi; b.lo = wlo; }
-    tc::Problem p = {(int)n, K, C, 0, 0, C, 0, col0, 0, 0, nullptr, nullptr};
+    tc::Problem p;
+    memset(&p, 0, sizeof(p));
+    p.M = (int)n; p.N = K; p.K0 = C; p.b_k1_offset = C; p.b_n_offset = col0;
     const int bn = pick_bn(n, K);
     const int r = h ? tc::launch<false, true, EPI_GATE>(a0, a1, b, p, 1, bn, e, st)
                     : tc::launch<false, true, EPI_STORE>(a0, a1, b, p, 1, bn, e, st);
@@ -350,7 +283,7 @@ static int weight_grad(const float* dZ, int C, const Seg& x0, const Seg& x1, int
   const bool tc_ok = math_tc() && C % 4 == 0 && C >= 32 && aligned16(dZ) && aligned16(x0.p) && x0.ld % 4 == 0 &&
                      x0.lead == 0 && (x1.cols == 0 || (aligned16(x1.p) && x1.ld % 4 == 0));
   if (tc_ok) {
-    const int req = dw_splits(C, K, n, true, option(OPT_DWSPLIT) != 0 ? 1 : 0);
+    const int req = dw_splits(C, K, n, true);
     int k_chunk = 0;
     const int splits = tc::split_plan((int)ceil_div(n, 32), req, &k_chunk, 32);
     tc::Operand a0 = {dZ, C, 0, 0}, a1 = {nullptr, 0, 0, 0};
@@ -367,8 +300,10 @@ static int weight_grad(const float* dZ, int C, const Seg& x0, const Seg& x1, int
       const Seg* s = segs[i];
       if (s->cols == 0) continue;
       tc::Operand b = {s->p, s->ld, n, s->cols};
-      tc::Problem p = {C, s->cols, (int)n, 0, 0, 0, cols0[i], 0, i == 0 ? x1.lead : 0, 0, nullptr, nullptr};
-      const int bn = (s->cols > 64 && option(OPT_WORKERS16) != 2 && option(OPT_BN64) == 0) ? 128 : 64;
+      tc::Problem p;
+      memset(&p, 0, sizeof(p));
+      p.M = C; p.N = s->cols; p.K0 = (int)n; p.n_out_offset = cols0[i]; p.n_skip = i == 0 ? x1.lead : 0;
+      const int bn = s->cols > 64 ? 128 : 64;
       const int r = tc::launch<true, true, EPI_PARTIAL>(a0, a1, b, p, req, bn, e, (i == 0 && use_side) ? side->stream : st);
       if (r < 0) return r;
       if (r != splits) {
@@ -377,8 +312,8 @@ static int weight_grad(const float* dZ, int C, const Seg& x0, const Seg& x1, int
       }
     }
     // the bias column of the partials (column sums of dZ) only reads dZ: with a side stream it runs there, behind the
-    // short action-segment GEMM and beside the long state-segment GEMM, instead of after both (`tail` option)
-    const bool colsum_on_side = use_side && option(OPT_TAIL) != 0;
+    // short action-segment GEMM and beside the long state-segment GEMM, instead of after both
+    const bool colsum_on_side = use_side;
     if (colsum_on_side) RECNN_PROPAGATE(launch_colsum_partials(dZ, n, C, k_chunk, splits, partial, K1, side->stream));
     if (use_side) {
       RECNN_CHECK_CUDA(cudaEventRecord(side->join, side->stream));
@@ -413,12 +348,10 @@ struct Ctx {
   float gate;
   AuxStreams* aux;       // non-null: chains V and P run on side streams
   bool v_prefetched, p_prefetched, p_deferred;
-  PlaneTable planes;     // pre-split weight planes of this call (indices as in Workspace::plane_hi)
 };
 // words of Workspace::tickets: 0..3 two-level reductions / optimizer step count, 6..7 error bits of the step
 // (zeroed with the tickets at the head of every call that includes RECNN_PH_GATHER or RECNN_PH_VALUE_GRAD)
 enum { kTicketDpMismatch = 6, kTicketOob = 7 };
-enum { PL_POLICY = 0, PL_TARGET_POLICY = 1, PL_VALUE0 = 2, PL_VALUE1 = 3, PL_TVALUE0 = 4, PL_TVALUE1 = 5 };
 
 // Critic hidden layers on (s, act):  h1 -> out1, h2 -> out2
 static int critic_hidden(const Ctx& c, const float* params, const float* s, const float* act, bool train,
@@ -572,7 +505,6 @@ static int phase_value_opt(Ctx& c) {
     } else {
       RECNN_PROPAGATE(launch_optimizer(a.value_optim, a.value[i], c.lc.count, nullptr, c.st, c.ws.tickets + 3));
     }
-    c.planes.e[PL_VALUE0 + i].valid = false;       // weights changed: the planes are stale
   }
   return RECNN_OK;
 }
@@ -597,14 +529,6 @@ static int phase_policy_loss(Ctx& c) {
   const int vm = td3 ? 6 : 4;                       // mask slots (header: call order)
   float *v1 = c.ws.hb[0], *v2 = c.ws.hb[1];
   float* gen = c.ws.ab[1];
-  {
-    // the critic was stepped since the value phase (built-in optimizer above, or an external optimizer /
-    // all-reduce between two calls): its planes are re-split here; the actor's only if this call did not
-    // already split them for the prefetched chain P
-    if (!(a.phases & RECNN_PH_VALUE_OPT) || a.value_optim.kind == RECNN_OPT_EXTERNAL) c.planes.e[PL_VALUE0].valid = false;
-    const int need[2] = {PL_VALUE0, PL_POLICY};
-    RECNN_PROPAGATE(split_planes(c.planes, need, 2, c.st));
-  }
   // gen_action = policy_net(state); policy_loss = -value_net(state, gen_action)  (ddpg.py:78-79, td3.py:116-118)
   if (c.p_prefetched) RECNN_CHECK_CUDA(cudaStreamWaitEvent(c.st, c.aux->p_done, 0));
   else RECNN_PROPAGATE(policy_actor_forward(c, c.st));
@@ -653,7 +577,6 @@ static int phase_policy_opt(Ctx& c) {
   if (!a.do_policy_step) return RECNN_OK;
   float* coef = c.ws.scalars;
   // clip_grad_norm_(policy params, max_norm=-1, norm_type=1)   (ddpg.py:92, td3.py:133)
-  c.planes.e[PL_POLICY].valid = false;
   if (a.comm) {
     // one kernel: all-reduce of the actor gradient, L1 norm of the SUMMED gradient -> clip coefficient, scaled
     // gradient written back, the built-in optimizer's update, and the sum of the ranks' policy-loss partial sums
@@ -738,15 +661,9 @@ static int run_step(const recnn_step_args* a, int algo, void* stream) {
   c.ACT = c.ws.ACT;
   if (a->phases & RECNN_PH_GATHER) {
     // action buffers carry `lead` zero columns (and pitch padding) that the kernels never write
-    if (c.ldA != A) {
-      if (option(OPT_PADZERO) != 0) {        // only the pad columns need to be zero: one small kernel, 1/30 of the bytes
-        RECNN_PROPAGATE(launch_zero_pad_columns(c.ws.ACT, c.ws.ab[0], c.ws.ab[1], c.n, (int)c.ldA, c.lead, A, c.st));
-      } else {
-        RECNN_CHECK_CUDA(cudaMemsetAsync(c.ws.ACT, 0, sizeof(float) * c.n * c.ldA, c.st));
-        RECNN_CHECK_CUDA(cudaMemsetAsync(c.ws.ab[0], 0, sizeof(float) * c.n * c.ldA, c.st));
-        RECNN_CHECK_CUDA(cudaMemsetAsync(c.ws.ab[1], 0, sizeof(float) * c.n * c.ldA, c.st));
-      }
-    }
+    // (only the pad columns: one small kernel touching 1/30 of the bytes of three memsets)
+    if (c.ldA != A)
+      RECNN_PROPAGATE(launch_zero_pad_columns(c.ws.ACT, c.ws.ab[0], c.ws.ab[1], c.n, (int)c.ldA, c.lead, A, c.st));
   }
   if (frames) {
     if (a->phases & RECNN_PH_GATHER)
@@ -764,21 +681,6 @@ static int run_step(const recnn_step_args* a, int algo, void* stream) {
                                          cudaMemcpyDeviceToDevice, c.st));
     }
     c.REW = a->reward;
-  }
-  // pre-split weight planes (see PlaneTable): registered for the whole call, filled before the fork so that
-  // the side-stream chains see them through the fork event
-  {
-    const float* bases[6] = {a->policy.params, a->target_policy.params, a->value[0].params,
-                             n_critics > 1 ? a->value[1].params : nullptr, a->target_value[0].params,
-                             n_critics > 1 ? a->target_value[1].params : nullptr};
-    for (int i = 0; i < 6; ++i)
-      c.planes.e[i] = PlaneEntry{bases[i], c.ws.plane_hi[i], c.ws.plane_lo[i], i < 2 ? c.la.count : c.lc.count, false};
-    c.planes.enabled = math_tc() && option(OPT_PRESPLIT) != 0;
-  }
-  PlaneScope plane_scope(&c.planes);
-  if (a->phases & RECNN_PH_VALUE_GRAD) {
-    const int all[6] = {PL_POLICY, PL_TARGET_POLICY, PL_VALUE0, PL_VALUE1, PL_TVALUE0, PL_TVALUE1};
-    RECNN_PROPAGATE(split_planes(c.planes, all, 6, c.st));
   }
   // fork: chain V (online critic forward) and chain P (online policy forward) on side streams
   c.aux = nullptr;
@@ -848,8 +750,30 @@ extern "C" int recnn_net_layout(const recnn_dims* d, int is_critic, int64_t* out
   return RECNN_OK;
 }
 
-// Inference entry points take densely packed inputs ([n, S] / [n, A]); a row pitch that is not a
-// 16-byte multiple (S = 1290) sends layer 1 to the CUDA-core kernel, everything else to tcgen05.
+// Inference entry points take densely packed inputs ([n, S] / [n, A]).  A row pitch that is not a 16-byte
+// multiple (S = 1290) cannot be a TMA tensor, so the inputs are first re-pitched into scratch images (one 2-D
+// device copy each, 21 MB at 4096 rows) and every layer runs on the tcgen05 path -- the CUDA-core kernel took
+// 62 us per layer-1 launch at this shape, 30x a tensor-core launch.
+extern "C" int64_t recnn_forward_scratch_floats(const recnn_dims* d, int64_t n_rows, int is_critic) {
+  if (!d || n_rows <= 0) return 0;
+  const int64_t ldS = pad4(d->state_dim), ldA = pad4(d->action_dim + d->state_dim % 4);
+  return 2 * n_rows * d->hidden + n_rows * ldS + (is_critic ? n_rows * ldA : 0) + 64;
+}
+
+// state [n, S] (pitch S) -> a pitch-ldS image when needed; returns the Seg to read
+static int repitch_state(const recnn_dims& d, const float* state, int64_t n, float* img, Seg* out, cudaStream_t st) {
+  const int S = d.state_dim;
+  if (S % 4 == 0 && aligned16(state)) {
+    *out = Seg{state, S, S, 0};
+    return RECNN_OK;
+  }
+  const int ldS = pad4(S);
+  RECNN_CHECK_CUDA(cudaMemcpy2DAsync(img, (size_t)ldS * 4, state, (size_t)S * 4, (size_t)S * 4, n,
+                                     cudaMemcpyDeviceToDevice, st));
+  *out = Seg{img, S, ldS, 0};
+  return RECNN_OK;
+}
+
 extern "C" int recnn_actor_forward(const recnn_dims* d, const float* params, const float* state, int64_t n_rows,
                                    const uint8_t* mask1, const uint8_t* mask2, int apply_tanh, float* action_out,
                                    float* scratch, void* stream) {
@@ -861,9 +785,12 @@ extern "C" int recnn_actor_forward(const recnn_dims* d, const float* params, con
   const int H = d->hidden;
   float* h1 = scratch;
   float* h2 = scratch + n_rows * H;
+  float* img = reinterpret_cast<float*>(round_up(reinterpret_cast<int64_t>(h2 + n_rows * H), 16));
   Rng rng = {nullptr, 0, nullptr};
   const bool train = mask1 != nullptr;
-  const Seg xs = {state, d->state_dim, d->state_dim, 0}, s1 = {h1, H, H, 0}, s2 = {h2, H, H, 0};
+  Seg xs;
+  RECNN_PROPAGATE(repitch_state(*d, state, n_rows, img, &xs, st));
+  const Seg s1 = {h1, H, H, 0}, s2 = {h2, H, H, 0};
   RECNN_PROPAGATE(hidden_layer(xs, kNoSeg, params + l.w1, l.ld1, params + l.b1, H, n_rows, train, mask1, rng, 0, h1, st));
   RECNN_PROPAGATE(hidden_layer(s1, kNoSeg, params + l.w2, l.ld2, params + l.b2, H, n_rows, train, mask2, rng, 1, h2, st));
   return linear_out(s2, params + l.w3, l.ld3, params + l.b3, d->action_dim, n_rows, apply_tanh, nullptr, action_out,
@@ -881,9 +808,22 @@ extern "C" int recnn_critic_forward(const recnn_dims* d, const float* params, co
   const int H = d->hidden, S = d->state_dim, A = d->action_dim;
   float* h1 = scratch;
   float* h2 = scratch + n_rows * H;
+  float* img = reinterpret_cast<float*>(round_up(reinterpret_cast<int64_t>(h2 + n_rows * H), 16));
   Rng rng = {nullptr, 0, nullptr};
   const bool train = mask1 != nullptr;
-  const Seg xs = {state, S, S, 0}, xa = {action, A, A, 0}, s1 = {h1, H, H, 0};
+  Seg xs;
+  RECNN_PROPAGATE(repitch_state(*d, state, n_rows, img, &xs, st));
+  // the action block starts at weight column S: with S % 4 != 0 it needs `lead` zero columns in front (see Seg)
+  const int lead = S % 4, ldA = pad4(A + lead);
+  Seg xa = {action, A, A, 0};
+  if (lead != 0 || A % 4 != 0 || !aligned16(action)) {
+    float* aimg = img + n_rows * (int64_t)pad4(S);
+    RECNN_CHECK_CUDA(cudaMemsetAsync(aimg, 0, sizeof(float) * n_rows * ldA, st));
+    RECNN_CHECK_CUDA(cudaMemcpy2DAsync(aimg + lead, (size_t)ldA * 4, action, (size_t)A * 4, (size_t)A * 4, n_rows,
+                                       cudaMemcpyDeviceToDevice, st));
+    xa = Seg{aimg, A + lead, ldA, lead};
+  }
+  const Seg s1 = {h1, H, H, 0};
   RECNN_PROPAGATE(hidden_layer(xs, xa, params + l.w1, l.ld1, params + l.b1, H, n_rows, train, mask1, rng, 0, h1, st));
   RECNN_PROPAGATE(hidden_layer(s1, kNoSeg, params + l.w2, l.ld2, params + l.b2, H, n_rows, train, mask2, rng, 1, h2, st));
   HeadArgs h;

@@ -22,14 +22,20 @@
 // hi is rounded to nearest (not truncated), so |lo| <= 2^-12 |x| is symmetric and the dropped
 // lo*lo term is unbiased.  Measured result: ~3e-7 worst-case systematic error, independent of K.
 //
-// Warp roles (one 128 x BN output tile per CTA, BN in {64,128}; 10 warps):
+// Warp roles (one 128 x BN output tile per CTA; BN = 128 with 8 worker warps, BN = 64 with 16):
 //   warp 0        TMA producer: raw fp32 tiles of A and B -> smem stage s             (full[s])
-//   warp 1        MMA issuer (one lane): per stage 3 x BK/8 tcgen05.mma, commit -> empty[s];
-//                 per chunk commit -> acc_full[buf]
-//   workers       8 warps.  (1) splitter: read the raw stage with ld.shared, write `hi` back in
-//                 place and the `lo` tile next to it                                   (split[s])
+//   warp 1        MMA issuer (one elected lane): per stage 3 x BK/8 tcgen05.mma, commit -> empty[s];
+//                 per chunk commit -> acc_full[buf].  Running counters only (stage / phase / A slot / position
+//                 in the chunk): the issue loop must not be the limiter (round 1: ~210 instructions per k-block
+//                 around 12 MMAs made it so; ~95 now).
+//   workers       groups of four warps taking k-blocks round robin.  (1) splitter: read the raw stage with
+//                 ld.shared, A -> hi/lo into TENSOR memory (tcgen05.st), B -> `hi` back in place and the `lo`
+//                 tile next to it                                                      (split[s])
 //                 (2) drain: TMEM chunk -> registers, running sum += chunk             (acc_empty[buf])
 //                 (3) epilogue on the register-resident row (bias/relu/dropout/...), store.
+// Programmatic dependent launch: every kernel calls griddepcontrol.launch_dependents at entry and
+// griddepcontrol.wait after its prologue (barrier init, TMEM allocation, tensor-map prefetch), and is launched
+// with programmatic stream serialization, so the next GEMM's prologue overlaps this one's drain / epilogue.
 // Operand tiles in smem are the canonical UMMA layouts written by TMA with hardware
 // swizzle, so the splitter is swizzle-agnostic (same offset in the `lo` buffer) and the
 // same smem descriptors serve hi and lo.
@@ -106,15 +112,6 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                         uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 // arrives on `bar` once every tcgen05.mma issued so far by this thread has completed
 // One lane of a fully converged warp (elect.sync); the compiler then knows the guarded tcgen05/TMA
 // instructions run in a single thread and emits them without a per-lane serialisation loop.
@@ -193,7 +190,7 @@ __device__ __forceinline__ void mma_tf32_ta(uint32_t d_tmem, uint32_t a_tmem, ui
       ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// Programmatic dependent launch (LEAN kernels, `pdl` option): launch_dependents lets the next kernel of the stream
+// Programmatic dependent launch: launch_dependents lets the next kernel of the stream
 // be scheduled onto idle SMs while this one still runs; its threads park at griddep_wait() -- after their prologue,
 // before any global-memory access -- until this grid has completed and its writes are visible.  Both are no-ops for
 // a launch without the programmatic-serialization attribute.
@@ -216,15 +213,17 @@ __device__ __forceinline__ float tf32_rna(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 // x = hi + lo (+ <= 2^-24 |x|): hi = rna_tf32(x), lo = rna_tf32(x - hi)
+template <bool LO_RAW = false>
 __device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) {
   hi = tf32_rna(x);
-  lo = tf32_rna(x - hi);
+  lo = LO_RAW ? x - hi : tf32_rna(x - hi);
 }
+template <bool LO_RAW = false>
 __device__ __forceinline__ void tf32_split4(const float4& x, float4& hi, float4& lo) {
-  tf32_split(x.x, hi.x, lo.x);
-  tf32_split(x.y, hi.y, lo.y);
-  tf32_split(x.z, hi.z, lo.z);
-  tf32_split(x.w, hi.w, lo.w);
+  tf32_split<LO_RAW>(x.x, hi.x, lo.x);
+  tf32_split<LO_RAW>(x.y, hi.y, lo.y);
+  tf32_split<LO_RAW>(x.z, hi.z, lo.z);
+  tf32_split<LO_RAW>(x.w, hi.w, lo.w);
 }
 
 // ------------------------------------------------------------------ descriptors
@@ -246,92 +245,50 @@ struct Problem {
   int n_out_offset;      // column offset added when storing (C window)
   int b_n_offset;        // B's n coordinate of output column 0 (window into a wider B, e.g. W1[:, S:S+A])
   int n_skip;            // the first n_skip output columns are computed but not stored (operand lead pads)
-  int dbg;               // timing experiments only (results become wrong): 1 no split, 2 no MMA, 4 no hi store, 8 no fence
-  unsigned long long* trace;   // optional: per-CTA %globaltimer stamps (8 per CTA) for pipeline analysis
-  unsigned long long* span;    // optional: {min entry, max exit} of this launch (timeline of a whole step)
+#ifdef RECNN_TC_INSTRUMENT
+  unsigned long long* trace;   // per-CTA %globaltimer stamps (8 per CTA): instrumented builds only
+#endif
 };
 
+#ifdef RECNN_TC_INSTRUMENT
 __device__ __forceinline__ unsigned long long gtimer() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-// stall accounting (dbg bit 16): cycles spent inside a wait, written behind the stamps of all CTAs
-#define RECNN_TIMED(counter, stmt)                         \
-  do {                                                     \
-    if (prof) {                                            \
-      const long long c0__ = clock64();                    \
-      stmt;                                                \
-      counter += clock64() - c0__;                         \
-    } else {                                               \
-      stmt;                                                \
-    }                                                      \
-  } while (0)
-#define RECNN_PROF_OUT(slot, v)                                                                    \
-  do {                                                                                             \
-    if (prof && p.trace)                                                                           \
-      p.trace[((gridDim.z * gridDim.y * gridDim.x) + (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + (slot)] = (unsigned long long)(v); \
-  } while (0)
 #define RECNN_TRACE(slot)                                                                          \
   do {                                                                                             \
     if (p.trace) p.trace[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + (slot)] = gtimer(); \
   } while (0)
+#else
+#define RECNN_TRACE(slot) do { } while (0)
+#endif
 
-template <int BN_, int BK_, int STAGES_, bool A_MN_, bool B_MN_, bool B_PRE_ = false, int WORKERS_ = 8,
-          bool LO2_ = false, bool LEAN_ = false>
+template <int BN_, int STAGES_, bool A_MN_, bool B_MN_>
 struct Cfg {
-  // BK = 32 (128-byte K-major rows) when A is K-major: TMA moves 64-byte rows at half the rate of
-  // 128-byte rows (measured: 31 B/clk/SM with BK = 16), and the operand stream is the kernel's bottleneck.
-  static constexpr int BM = 128, BN = BN_, BK = BK_, STAGES = STAGES_;
+  // BK = 32 (128-byte K-major rows): TMA moves 64-byte rows at half the rate of 128-byte rows (measured:
+  // 31 B/clk/SM with BK = 16), and the operand stream is one of the kernel's bottlenecks.
+  static constexpr int BM = 128, BN = BN_, BK = 32, STAGES = STAGES_;
   static constexpr int CH = 64 / BK;                               // k-blocks per TMEM accumulation chunk (K = 64)
   static constexpr bool A_MN = A_MN_, B_MN = B_MN_;
-  // B_PRE: B arrives already split into TF32 hi / lo planes in global memory (weights: split once per
-  // optimizer step by split_planes_kernel).  TMA then fills both B slots of the stage and the worker
-  // warps never touch B: per k-block that removes a 128*BN-byte shared-memory read, a 256*BN-byte write
-  // and the generic->async proxy fence from the split warps' critical path, at the price of fetching
-  // B twice from L2.  Same hi/lo values as the in-kernel split => bit-identical results.
-  static constexpr bool B_PRE = B_PRE_;
-  // The split A tile goes to TENSOR memory (tcgen05.st) and the MMA reads it from there, so A costs
-  // shared memory one TMA write + one read instead of write + read + 2 writes + 6 MMA reads.
-  static constexpr bool A_TM = true;
-  // LO2: the two cross terms (lo_a*hi_b, hi_a*lo_b) get an accumulator EACH, and the three MMAs of a k-slice
-  // rotate over three different accumulators (lo_A, hi, lo_B).  Back-to-back tcgen05.mma into the SAME
-  // accumulator do not overlap: measured ~83 clk per 128x64x8 tf32 MMA (issue slot of the MMA warp, stall
-  // accounting) against a 32 clk tensor-pipe floor when two of every three MMAs hit d_lo in a row.  With three
-  // accumulators in rotation every accumulator is touched every third instruction.  Needs a fourth BN-wide
-  // accumulator in tensor memory: BN = 64 only (A ring shrinks from five slots to four).
-  static constexpr bool LO2 = LO2_;
-  // LEAN: the experiment hooks (Problem.dbg ablation bits, chunk-length override, stall accounting) are compiled
-  // out and the MMA warp keeps running counters instead of recomputing stage / phase / slot / chunk from the
-  // k-block index.  Why it matters (ncu source counters + stall accounting, profiles/README.md): the MMA warp
-  // executes ~210 mostly dependent SASS instructions per k-block around its 12 tcgen05.mma -- index math with
-  // two MUFU-based divisions by the run-time chunk length, descriptor rebuilds, debug branches -- i.e. ~1,000 clk
-  // per k-block for a lone warp, against 384 (BN = 64) / 768 (BN = 128) clk of tensor work; it waits for
-  // operands only ~14% of the time, so the issue loop itself is what the tensor pipe waits for.
-  static constexpr bool LEAN = LEAN_;
-  static constexpr int D_COLS = (LO2 ? 4 : 3) * BN;                  // D_hi x2 | D_lo (| D_lo2)
-  static constexpr int A_SLOT_COLS = 2 * BK, A_SLOTS = (512 - D_COLS) / A_SLOT_COLS;   // TMEM ring for A (hi | lo per k-block): 2 slots at BN = 128, 5 (4 with LO2) at BN = 64
+  static constexpr int D_COLS = 3 * BN;                            // D_hi chunk x2 | D_lo
+  // The split A tile goes to TENSOR memory (tcgen05.st) and the MMA reads it from there, so A costs shared
+  // memory one TMA write + one read instead of write + read + 2 writes + 6 MMA reads.
+  static constexpr int A_SLOT_COLS = 2 * BK, A_SLOTS = (512 - D_COLS) / A_SLOT_COLS;   // hi | lo per k-block: 2 slots at BN = 128, 5 at BN = 64
   static constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
-  static constexpr int STAGE_BYTES = (A_TM ? A_BYTES : 2 * A_BYTES) + 2 * B_BYTES;   // raw A (+lo A) | raw B | lo B
+  static constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;        // raw A | raw B (split in place into hi) | lo B
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
-  // Worker warps come in groups of four (one warp per TMEM lane quarter); the groups take k-blocks round
-  // robin.  One group needs ~3,000 clk per k-block (waits + TMEM store + fences + a chunk drain), whatever
-  // the tile width: measured 1,310 (BN = 64) and 1,460 (BN = 128) clk per k-block with two groups against
-  // tensor floors of 384 / 768.  WORKERS = 16 puts four groups in flight (BN = 64 only: its A ring in
-  // tensor memory has five slots; at BN = 128 there are two).
-  static constexpr int WORKERS = WORKERS_;
+  // Worker warps come in groups of four (one warp per TMEM lane quarter); the groups take k-blocks round robin.
+  // 64-wide tiles run four groups (their A ring in tensor memory has five slots), 128-wide tiles two.
+  static constexpr int WORKERS = BN == 64 ? 16 : 8;
   static constexpr int COLS_PER_WORKER = BN / (WORKERS / 4);       // register-resident running sum per thread
   static constexpr int THREADS = 64 + 32 * WORKERS;
   static constexpr int TMEM_COLS = 512;                            // D_hi chunk x2 | D_lo | A ring
   static constexpr int A_COL0 = D_COLS;
-  static constexpr int K_SWZ = BK * 4;                             // K-major rows: 64 B (SWIZZLE_64B) or 128 B (SWIZZLE_128B)
+  static constexpr int K_SWZ = BK * 4;                             // K-major rows: 128 B (SWIZZLE_128B)
   static_assert(BN == 64 || BN == 128, "BN");
-  static_assert(WORKERS == 8 || (WORKERS == 16 && BN == 64), "WORKERS");
   static_assert(COLS_PER_WORKER == 16 || COLS_PER_WORKER % 32 == 0, "drain width");
   static_assert(WORKERS / 4 <= A_SLOTS, "every group in flight needs its own A slot");
-  static_assert(!LO2 || BN == 64, "a second cross-term accumulator only fits next to 64-wide tiles");
-  static_assert(A_SLOTS >= 2, "A ring");
-  static_assert(BK == 32, "BK: 128-byte operand rows");
   static_assert(SMEM_BYTES <= 227 * 1024, "smem");
 };
 
@@ -425,23 +382,21 @@ __device__ __forceinline__ void epilogue_row(const Epilogue& e, const Problem& p
 }
 
 // ------------------------------------------------------------------ the kernel
-template <class C, int EPI>
+// LO_RAW (experiment, `experiment` option bit 0): lo = x - hi is handed to the tensor core as is (the kind::tf32
+// datapath ignores its low 13 bits, i.e. truncates it) instead of being rounded to TF32 first: two integer
+// instructions fewer per operand element in the split warps, at the price of up to 2^-22 |x| (instead of 2^-23)
+// in the cross terms.
+template <class C, int EPI, bool LO_RAW>
 __global__ void __launch_bounds__(C::THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
-               const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_b_lo, Problem p,
-               Epilogue epi) {
-  constexpr int BM = C::BM, BN = C::BN, BK = C::BK, STAGES = C::STAGES;
-  const int dbg = C::LEAN ? 0 : p.dbg;                                 // experiment hooks (compiled out when LEAN)
-  const int CH = C::LEAN ? C::CH : (((dbg >> 8) & 15) ? ((dbg >> 8) & 15) : C::CH);   // chunk length override
-  constexpr int NC = C::COLS_PER_WORKER, WORKERS = C::WORKERS;
+               const __grid_constant__ CUtensorMap map_b, Problem p, Epilogue epi) {
+  constexpr int BM = C::BM, BN = C::BN, BK = C::BK, STAGES = C::STAGES, CH = C::CH;
+  constexpr int NC = C::COLS_PER_WORKER, WORKERS = C::WORKERS, NG = WORKERS / 4;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;       // shared-window address, 1 KB aligned
-  auto stage_addr = [&](int s, int which) -> uint32_t {              // 0 rawA, 1 rawB, 2 loA, 3 loB
+  auto stage_addr = [&](int s, int which) -> uint32_t {              // 0 raw A, 1 raw B (-> hi B), 2 lo B
     const uint32_t base = smem + (uint32_t)s * C::STAGE_BYTES;
-    return which == 0 ? base
-         : which == 1 ? base + C::A_BYTES
-         : which == 2 ? base + C::A_BYTES + C::B_BYTES
-                      : base + (C::A_TM ? C::A_BYTES : 2 * C::A_BYTES) + C::B_BYTES;
+    return which == 0 ? base : which == 1 ? base + C::A_BYTES : base + C::A_BYTES + C::B_BYTES;
   };
   const uint32_t bars = smem + (uint32_t)STAGES * C::STAGE_BYTES;
   auto full = [&](int s) { return bars + 8u * s; };                   // TMA -> workers
@@ -456,9 +411,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM, z = blockIdx.z;
-  if constexpr (C::LEAN) griddep_launch_dependents();
+  griddep_launch_dependents();                                // the next kernel of the stream may start its prologue
   if (threadIdx.x == 0) RECNN_TRACE(0);                       // kernel entry
-  if (threadIdx.x == 0 && p.span) atomicMin(p.span, gtimer());
   // k-blocks: segment 0 then segment 1, each padded up to a multiple of BK (TMA zero-fills the tail)
   const int nkb0 = (p.K0 + BK - 1) / BK, nkb1 = (p.K1 + BK - 1) / BK;
   const int kb_per_split = p.k_chunk / BK;
@@ -466,20 +420,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   const int kb_end = min(nkb0 + nkb1, kb_begin + kb_per_split);
   const int num_kb = max(kb_end - kb_begin, 0);
   const int num_chunks = (num_kb + CH - 1) / CH;
-  const bool prof = !C::LEAN && (dbg & 16) != 0;
-  // dbg bit 32 (experiments, 8 workers only): all worker warps share every k-block instead of taking turns
-  const bool share_all = !C::LEAN && WORKERS == 8 && (dbg & 32) != 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a0);
     tma_prefetch_desc(&map_b);
     if (p.K1 > 0) tma_prefetch_desc(&map_a1);
-    if (C::B_PRE) tma_prefetch_desc(&map_b_lo);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full(s), 1);
-      mbar_init(split(s), share_all ? WORKERS : 4);      // one arrive per worker warp that split the stage
+      mbar_init(split(s), 4);                            // one arrive per warp of the group that split the stage
       mbar_init(empty(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -497,25 +447,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
-  if constexpr (C::LEAN) griddep_wait();                      // everything below may touch global memory
+  griddep_wait();                                             // everything below may touch global memory
   if (threadIdx.x == 0) RECNN_TRACE(1);                       // prologue done
 
   if (warp == 0) {
     // ===================================================== TMA producer (whole warp walks, one elected lane issues)
     const bool leader = elect_one();
-    long long w0 = 0;
+    uint32_t s = 0, ph = 0;
     for (int i = 0; i < num_kb; ++i) {
-      const int s = i % STAGES;
-      const uint32_t ph = (i / STAGES) & 1;
-      RECNN_TIMED(w0, mbar_wait(empty(s), ph ^ 1));
+      mbar_wait(empty(s), ph ^ 1u);
       const int kb = kb_begin + i;
       const bool seg1 = kb >= nkb0;
       const int ka = seg1 ? (kb - nkb0) * BK : kb * BK;                     // k coordinate inside A's segment
       const int kbcol = seg1 ? p.b_k1_offset + (kb - nkb0) * BK : kb * BK;  // k coordinate in B
       const CUtensorMap* ma = seg1 ? &map_a1 : &map_a0;
-      const uint32_t dst_a = stage_addr(s, 0), dst_b = stage_addr(s, 1), dst_b_lo = stage_addr(s, 3);
+      const uint32_t dst_a = stage_addr(s, 0), dst_b = stage_addr(s, 1);
       if (leader) {
-        mbar_expect_tx(full(s), C::A_BYTES + (C::B_PRE ? 2 : 1) * C::B_BYTES);
+        mbar_expect_tx(full(s), C::A_BYTES + C::B_BYTES);
         if (!C::A_MN) {
           tma_load_2d(dst_a, ma, full(s), ka, m0);                            // box {BK, 128}
         } else {
@@ -525,19 +473,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         }
         if (!C::B_MN) {
           tma_load_2d(dst_b, &map_b, full(s), kbcol, p.b_n_offset + n0);      // box {BK, BN}
-          if (C::B_PRE) tma_load_2d(dst_b_lo, &map_b_lo, full(s), kbcol, p.b_n_offset + n0);
         } else {
 #pragma unroll
-          for (int c = 0; c < BN / 32; ++c) {
+          for (int c = 0; c < BN / 32; ++c)
             tma_load_2d(dst_b + c * (BK * 128), &map_b, full(s), p.b_n_offset + n0 + 32 * c, kbcol);
-            if (C::B_PRE)
-              tma_load_2d(dst_b_lo + c * (BK * 128), &map_b_lo, full(s), p.b_n_offset + n0 + 32 * c, kbcol);
-          }
         }
       }
       __syncwarp();
+      if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1u; }
     }
-    if (lane == 0) RECNN_PROF_OUT(6, w0);
   } else if (warp == 1) {
     // ===================================================== MMA issuer
     // The whole warp walks the pipeline (so every value below is warp-uniform and lives in uniform
@@ -553,232 +497,153 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     constexpr uint64_t b_base = C::B_MN ? smem_desc_base(BK * 128, 512, 1) : smem_desc_base(16, 8 * C::K_SWZ, 2);
     constexpr uint32_t b_kstep = C::B_MN ? 1024 : 32;        // bytes to advance per 8-wide k-slice
     const bool leader = elect_one();
-    long long w_split = 0, w_acc = 0;
-    if constexpr (C::LEAN) {
-      // running counters: stage / phase, A slot, position in the chunk and its buffer, per-buffer wait parity
-      uint32_t s = 0, ph = 0, slot = 0, kin = 0, buf = 0, par0 = 1, par1 = 1;
-      uint32_t lo_acc = 0;                                   // 0 only for the very first cross-term MMAs
-      const uint32_t d_lo = tmem_base + 2u * BN;
-      for (int i = 0; i < num_kb; ++i) {
-        if (kin == 0) {                                      // new chunk: its TMEM buffer must have been drained
-          mbar_wait(acc_empty(buf), buf ? par1 : par0);
-          if (buf) par1 ^= 1u; else par0 ^= 1u;
-        }
-        mbar_wait(split(s), ph);
-        if (C::B_PRE) mbar_wait(full(s), ph);
-        tc_fence_after();
-        const uint32_t d_hi = tmem_base + buf * BN;
-        const uint64_t db_hi0 = b_base | uint64_t((stage_addr(s, 1) & 0x3FFFF) >> 4);
-        const uint64_t db_lo0 = b_base | uint64_t((stage_addr(s, 3) & 0x3FFFF) >> 4);
-        const uint32_t ta0 = tmem_base + C::A_COL0 + slot * C::A_SLOT_COLS;
-        if (leader) {
-#pragma unroll
-          for (int k = 0; k < BK / 8; ++k) {
-            const uint64_t db_hi = db_hi0 + uint64_t((k * b_kstep) >> 4);
-            const uint64_t db_lo = db_lo0 + uint64_t((k * b_kstep) >> 4);
-            const uint32_t ta_hi = ta0 + k * 8, ta_lo = ta_hi + BK;
-            const uint32_t lo_flag = k == 0 ? lo_acc : 1u, hi_flag = k == 0 ? (kin != 0 ? 1u : 0u) : 1u;
-            if (C::LO2) {
-              mma_tf32_ta(d_lo, ta_lo, db_hi, idesc, lo_flag);
-              mma_tf32_ta(d_hi, ta_hi, db_hi, idesc, hi_flag);
-              mma_tf32_ta(d_lo + BN, ta_hi, db_lo, idesc, lo_flag);
-            } else {
-              mma_tf32_ta(d_lo, ta_lo, db_hi, idesc, lo_flag);
-              mma_tf32_ta(d_lo, ta_hi, db_lo, idesc, 1);
-              mma_tf32_ta(d_hi, ta_hi, db_hi, idesc, hi_flag);
-            }
-          }
-          mma_commit(empty(s));                              // frees the stage once these MMAs have read it
-          mma_commit(a_free(slot));                          // ... and the A slot in tensor memory
-          if (kin == (uint32_t)(C::CH - 1) || i == num_kb - 1) mma_commit(acc_full(buf));
-        }
-        __syncwarp();
-        lo_acc = 1u;
-        if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1u; }
-        if (++slot == (uint32_t)C::A_SLOTS) slot = 0;
-        if (++kin == (uint32_t)C::CH) { kin = 0; buf ^= 1u; }
-      }
-    } else
+    // running counters: stage / phase, A slot, position in the chunk and its buffer, per-buffer wait parity
+    uint32_t s = 0, ph = 0, slot = 0, kin = 0, buf = 0, par0 = 1, par1 = 1;
+    uint32_t lo_acc = 0;                                     // 0 only for the very first cross-term MMAs
+    const uint32_t d_lo = tmem_base + 2u * BN;               // tile-lifetime accumulator (cross terms)
     for (int i = 0; i < num_kb; ++i) {
-      const int s = i % STAGES;
-      const uint32_t ph = (i / STAGES) & 1;
-      const int chunk = i / CH, buf = chunk & 1;
-      if (i % CH == 0) {                                     // new chunk: its TMEM buffer must have been drained
-        RECNN_TIMED(w_acc, mbar_wait(acc_empty(buf), ((chunk >> 1) & 1) ^ 1));
+      if (kin == 0) {                                        // new chunk: its TMEM buffer must have been drained
+        mbar_wait(acc_empty(buf), buf ? par1 : par0);
+        if (buf) par1 ^= 1u; else par0 ^= 1u;
       }
-      RECNN_TIMED(w_split, mbar_wait(split(s), ph));
-      // B_PRE: both B slots were written by TMA (async proxy) and are read by the MMA (async proxy); observe
-      // the TMA barrier in this warp as well instead of relying on the workers' acquire/release chain
-      if (C::B_PRE) mbar_wait(full(s), ph);
+      mbar_wait(split(s), ph);
       tc_fence_after();
       if (i == 0 && lane == 0) RECNN_TRACE(2);               // first stage loaded + split
-      const uint32_t d_hi = tmem_base + (uint32_t)buf * BN;  // chunk accumulator (hi*hi)
-      const uint32_t d_lo = tmem_base + 2u * BN;             // tile-lifetime accumulator (cross terms)
+      const uint32_t d_hi = tmem_base + buf * BN;            // chunk accumulator (hi*hi)
       const uint64_t db_hi0 = b_base | uint64_t((stage_addr(s, 1) & 0x3FFFF) >> 4);
-      const uint64_t db_lo0 = b_base | uint64_t((stage_addr(s, 3) & 0x3FFFF) >> 4);
-      const int slot = i % C::A_SLOTS;
+      const uint64_t db_lo0 = b_base | uint64_t((stage_addr(s, 2) & 0x3FFFF) >> 4);
       const uint32_t ta0 = tmem_base + C::A_COL0 + slot * C::A_SLOT_COLS;
-      if (leader && !(dbg & 2)) {
+      if (leader) {
 #pragma unroll
         for (int k = 0; k < BK / 8; ++k) {
           const uint64_t db_hi = db_hi0 + uint64_t((k * b_kstep) >> 4);
           const uint64_t db_lo = db_lo0 + uint64_t((k * b_kstep) >> 4);
           const uint32_t ta_hi = ta0 + k * 8, ta_lo = ta_hi + BK;
-          if (C::LO2) {                      // three accumulators in rotation: no back-to-back dependent MMAs
-            mma_tf32_ta(d_lo, ta_lo, db_hi, idesc, (i | k) != 0);
-            mma_tf32_ta(d_hi, ta_hi, db_hi, idesc, ((i % CH) | k) != 0);
-            mma_tf32_ta(d_lo + BN, ta_hi, db_lo, idesc, (i | k) != 0);
-          } else {
-            mma_tf32_ta(d_lo, ta_lo, db_hi, idesc, (i | k) != 0);
-            mma_tf32_ta(d_lo, ta_hi, db_lo, idesc, 1);
-            mma_tf32_ta(d_hi, ta_hi, db_hi, idesc, ((i % CH) | k) != 0);
-          }
+          const uint32_t lo_flag = k == 0 ? lo_acc : 1u, hi_flag = k == 0 ? (kin != 0 ? 1u : 0u) : 1u;
+          mma_tf32_ta(d_lo, ta_lo, db_hi, idesc, lo_flag);
+          mma_tf32_ta(d_lo, ta_hi, db_lo, idesc, 1);
+          mma_tf32_ta(d_hi, ta_hi, db_hi, idesc, hi_flag);
         }
-      }
-      if (leader) {
         mma_commit(empty(s));                                // frees the stage once these MMAs have read it
         mma_commit(a_free(slot));                            // ... and the A slot in tensor memory
-        if (i % CH == CH - 1 || i == num_kb - 1) mma_commit(acc_full(buf));
+        if (kin == (uint32_t)(CH - 1) || i == num_kb - 1) mma_commit(acc_full(buf));
       }
       __syncwarp();
+      lo_acc = 1u;
+      if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1u; }
+      if (++slot == (uint32_t)C::A_SLOTS) slot = 0;
+      if (++kin == (uint32_t)CH) { kin = 0; buf ^= 1u; }
     }
-    if (lane == 0) {
-      RECNN_TRACE(3);                                         // last MMA issued
-      RECNN_PROF_OUT(4, w_split);
-      RECNN_PROF_OUT(5, w_acc);
-    }
+    if (lane == 0) RECNN_TRACE(3);                            // last MMA issued
   } else {
     // ===================================================== workers: split, drain, epilogue
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
-    const int g = (warp - 2) >> 2;           // which column slab (drain/epilogue) / k-half (A split) it owns
-    const int t = threadIdx.x - 64;
-    constexpr int NT = 32 * WORKERS;
+    const int g = (warp - 2) >> 2;           // worker group: k-blocks g, g + NG, ...; column slab g of the drain / epilogue
+    const int tg = (threadIdx.x - 64) & 127; // index among the 128 threads of the group
     float acc[NC];
 #pragma unroll
     for (int j = 0; j < NC; ++j) acc[j] = 0.f;
     const uint32_t lane_base = tmem_base + (uint32_t(32 * q) << 16) + (uint32_t)g * NC;
-    long long w_full = 0, w_afree = 0, w_drain = 0, w_ld = 0;
-    const long long loop0 = clock64();
 
     auto drain = [&](int chunk) {
       const int buf = chunk & 1;
-      RECNN_TIMED(w_drain, mbar_wait(acc_full(buf), (chunk >> 1) & 1));
+      mbar_wait(acc_full(buf), (chunk >> 1) & 1);
       tc_fence_after();
-      const long long ld0 = prof ? clock64() : 0;
       tmem_accumulate<NC>(lane_base + (uint32_t)buf * BN, acc);
-      if (prof) w_ld += clock64() - ld0;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty(buf));
     };
 
-    // The two warp groups (one warp per TMEM lane quarter each) take alternate k-blocks, so one group's
-    // publish latency (membar + proxy fence + tcgen05.wait::st) hides behind the other group's arithmetic.
-    // dbg bit 32 (experiments): all 8 warps share every k-block instead (half a row / an eighth of B each).
-    const int ng = share_all ? 1 : WORKERS / 4;               // groups taking k-blocks round robin
-    const int tg = share_all ? t : (t & 127);                 // index among the threads sharing one k-block
-    const uint32_t ntg = share_all ? (uint32_t)NT : 128u;
-    constexpr int VB = C::B_BYTES / 16 / NT;                  // float4s per thread per batch (all 256 threads = 1 batch)
-    static_assert(C::B_BYTES / 16 % NT == 0 && VB >= 1, "B tile must split evenly over the worker threads");
+    // The groups take k-blocks round robin, so one group's publish latency (membar + proxy fence +
+    // tcgen05.wait::st) hides behind the other groups' arithmetic.
+    constexpr int VB = C::B_BYTES / 16 / 128;                 // float4s of the B tile per thread of the group
+    static_assert(C::B_BYTES / 16 % 128 == 0 && VB >= 1, "B tile must split evenly over a worker group");
     int next_drain = 0;
-    for (int i = (share_all ? 0 : g); i < num_kb; i += ng) {
+    for (int i = g; i < num_kb; i += NG) {
       const int s = i % STAGES;
       const uint32_t ph = (i / STAGES) & 1;
-      RECNN_TIMED(w_full, mbar_wait(full(s), ph));
+      mbar_wait(full(s), ph);
       const uint32_t raw = stage_addr(s, 1);                  // raw B, split in place into hi
-      const uint32_t lo = stage_addr(s, 3);                   // lo B
+      const uint32_t lo = stage_addr(s, 2);                   // lo B
       const int slot = i % C::A_SLOTS;
       const uint32_t ta = tmem_base + (uint32_t(32 * q) << 16) + C::A_COL0 + slot * C::A_SLOT_COLS;
-      const int half0 = share_all ? g : 0, half1 = share_all ? g + 1 : 2;
-      if (!(dbg & 1)) {
-        RECNN_TIMED(w_afree, mbar_wait(a_free(slot), ((i / C::A_SLOTS) & 1) ^ 1));
-        tc_fence_after();
-        if (C::A_MN) {
-          // MN-major A tile: 4 chunks (32 rows of M each) x BK k-rows of 128 bytes; TMA's 128B_ATOM_32B swizzle
-          // XORs the 32-byte unit index with (k & 3).  My TMEM lane is row m = 32*q + lane: chunk q, element `lane`
-          // of every k-row -> one conflict-free 128-byte wavefront per k for the warp.
-          const uint32_t cbase = stage_addr(s, 0) + (uint32_t)q * (BK * 128u) + (((uint32_t)lane & 7u) << 2);
-          const uint32_t unit = (uint32_t)lane >> 3;
-          for (int half = half0; half < half1; ++half) {
-            float hi[16], lw[16];
+      mbar_wait(a_free(slot), ((i / C::A_SLOTS) & 1) ^ 1);
+      tc_fence_after();
+      if (C::A_MN) {
+        // MN-major A tile: 4 chunks (32 rows of M each) x BK k-rows of 128 bytes; TMA's 128B_ATOM_32B swizzle
+        // XORs the 32-byte unit index with (k & 3).  My TMEM lane is row m = 32*q + lane: chunk q, element `lane`
+        // of every k-row -> one conflict-free 128-byte wavefront per k for the warp.
+        const uint32_t cbase = stage_addr(s, 0) + (uint32_t)q * (BK * 128u) + (((uint32_t)lane & 7u) << 2);
+        const uint32_t unit = (uint32_t)lane >> 3;
 #pragma unroll
-            for (int kk = 0; kk < 16; ++kk) {
-              const uint32_t k = 16u * half + kk;
-              float x;
-              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(cbase + k * 128u + ((unit ^ (k & 3u)) << 5)));
-              tf32_split(x, hi[kk], lw[kk]);
-            }
-            tmem_st16(ta + 16 * half, hi);
-            tmem_st16(ta + BK + 16 * half, lw);
-          }
-        } else {
-          // my row of the K-major A tile -> hi/lo in TMEM.  Rows are 128 bytes; TMA's SWIZZLE_128B XORs the
-          // 16-byte chunk index with address bits [7, 10) = row & 7.
-          const int row = 32 * q + lane;
-          const uint32_t rbase = stage_addr(s, 0) + (uint32_t)row * 128u;
-          const uint32_t sw = (uint32_t)row & 7u;
-          for (int half = half0; half < half1; ++half) {
-            float hi[16], lw[16];
+        for (int half = 0; half < 2; ++half) {
+          float hi[16], lw[16];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 x = lds128(rbase + (((4 * half + j) ^ sw) << 4));
-              tf32_split(x.x, hi[4 * j + 0], lw[4 * j + 0]);
-              tf32_split(x.y, hi[4 * j + 1], lw[4 * j + 1]);
-              tf32_split(x.z, hi[4 * j + 2], lw[4 * j + 2]);
-              tf32_split(x.w, hi[4 * j + 3], lw[4 * j + 3]);
-            }
-            tmem_st16(ta + 16 * half, hi);
-            tmem_st16(ta + BK + 16 * half, lw);
+          for (int kk = 0; kk < 16; ++kk) {
+            const uint32_t k = 16u * half + kk;
+            float x;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(cbase + k * 128u + ((unit ^ (k & 3u)) << 5)));
+            tf32_split<LO_RAW>(x, hi[kk], lw[kk]);
           }
+          tmem_st16(ta + 16 * half, hi);
+          tmem_st16(ta + BK + 16 * half, lw);
         }
-        for (uint32_t b = 0; !C::B_PRE && b < (uint32_t)NT / ntg; ++b) {
-          float4 x[VB];
-          const uint32_t v0 = (uint32_t)tg + b * (uint32_t)VB * ntg;
+      } else {
+        // my row of the K-major A tile -> hi/lo in TMEM.  Rows are 128 bytes; TMA's SWIZZLE_128B XORs the
+        // 16-byte chunk index with address bits [7, 10) = row & 7.
+        const int row = 32 * q + lane;
+        const uint32_t rbase = stage_addr(s, 0) + (uint32_t)row * 128u;
+        const uint32_t sw = (uint32_t)row & 7u;
 #pragma unroll
-          for (int v = 0; v < VB; ++v) x[v] = lds128(raw + 16u * (v0 + v * ntg));
+        for (int half = 0; half < 2; ++half) {
+          float hi[16], lw[16];
 #pragma unroll
-          for (int v = 0; v < VB; ++v) {
-            float4 xh, xl;
-            tf32_split4(x[v], xh, xl);
-            if (!(dbg & 4)) sts128(raw + 16u * (v0 + v * ntg), xh);
-            sts128(lo + 16u * (v0 + v * ntg), xl);
+          for (int j = 0; j < 4; ++j) {
+            const float4 x = lds128(rbase + (((4 * half + j) ^ sw) << 4));
+            tf32_split<LO_RAW>(x.x, hi[4 * j + 0], lw[4 * j + 0]);
+            tf32_split<LO_RAW>(x.y, hi[4 * j + 1], lw[4 * j + 1]);
+            tf32_split<LO_RAW>(x.z, hi[4 * j + 2], lw[4 * j + 2]);
+            tf32_split<LO_RAW>(x.w, hi[4 * j + 3], lw[4 * j + 3]);
           }
+          tmem_st16(ta + 16 * half, hi);
+          tmem_st16(ta + BK + 16 * half, lw);
         }
       }
-      // generic-proxy writes (B hi/lo in shared memory) -> visible to the tensor core (async proxy);
-      // with pre-split B the workers write no shared memory at all
-      if (!C::B_PRE && !(dbg & 8)) fence_proxy_async();
+      {
+        float4 x[VB];
+#pragma unroll
+        for (int v = 0; v < VB; ++v) x[v] = lds128(raw + 16u * ((uint32_t)tg + v * 128u));
+#pragma unroll
+        for (int v = 0; v < VB; ++v) {
+          float4 xh, xl;
+          tf32_split4<LO_RAW>(x[v], xh, xl);
+          sts128(raw + 16u * ((uint32_t)tg + v * 128u), xh);
+          sts128(lo + 16u * ((uint32_t)tg + v * 128u), xl);
+        }
+      }
+      // generic-proxy writes (B hi/lo in shared memory) -> visible to the tensor core (async proxy)
+      fence_proxy_async();
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(split(s));
       // after my last k-block of chunk c, chunk c-1 has long been accumulated: drain it
-      if ((i + ng) / CH != i / CH)
+      if ((i + NG) / CH != i / CH)
         while (next_drain < i / CH) drain(next_drain++);
     }
-    if (t == 0) RECNN_TRACE(4);                               // last stage split
+    if (threadIdx.x == 64) RECNN_TRACE(4);                    // last stage split
     while (next_drain < num_chunks) drain(next_drain++);      // the last full chunk (and a trailing partial one)
-    if (t == 0) RECNN_TRACE(5);                               // all chunks drained (MMAs complete)
-    if (t == 0) {
-      RECNN_PROF_OUT(0, w_full);
-      RECNN_PROF_OUT(1, w_afree);
-      RECNN_PROF_OUT(2, w_drain);
-      RECNN_PROF_OUT(3, clock64() - loop0);
-      RECNN_PROF_OUT(7, w_ld);
-    }
-    if (num_kb > 0) {
-      // the commit behind the last acc_full covers every MMA issued before it, D_lo's included
+    if (threadIdx.x == 64) RECNN_TRACE(5);                    // all chunks drained (MMAs complete)
+    if (num_kb > 0)   // the commit behind the last acc_full covers every MMA issued before it, D_lo's included
       tmem_accumulate<NC>(lane_base + 2u * BN, acc);
-      if (C::LO2) tmem_accumulate<NC>(lane_base + 3u * BN, acc);
-    }
     epilogue_row<EPI, NC>(epi, p, m0 + 32 * q + lane, n0 + g * NC, z, acc);
-    if (t == 0) RECNN_TRACE(6);                               // epilogue stored
+    if (threadIdx.x == 64) RECNN_TRACE(6);                    // epilogue stored
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
   if (threadIdx.x == 0) RECNN_TRACE(7);
-  if (threadIdx.x == 0 && p.span) atomicMax(p.span + 1, gtimer());
 }
 
 // ------------------------------------------------------------------ host side
@@ -801,18 +666,7 @@ struct Operand {
   const float* ptr;
   long long ld;
   long long rows, cols;
-  const float* lo = nullptr;   // B only: non-null => `ptr` is the TF32 hi plane and `lo` the lo plane (same geometry)
 };
-
-// hi[i] = rna_tf32(src[i]), lo[i] = rna_tf32(src[i] - hi[i]) for up to 8 arrays in one launch
-// (count % 4 == 0, 16-byte aligned): the pre-split planes a B_PRE GEMM consumes.
-struct SplitJob {
-  const float* src;
-  float* hi;
-  float* lo;
-  long long count;
-};
-int launch_split_planes(const SplitJob* jobs, int n_jobs, cudaStream_t st);
 
 // k-blocks (of bk) per split and the effective split count for a requested split count.
 int split_plan(int K_total_blocks, int splits_req, int* k_chunk, int bk = 16);

@@ -61,7 +61,7 @@ class Actor(nn.Module):
         flat = param_arena(self)
         m1, m2 = masks if masks is not None else _train_masks(self, n, d.hidden, dev)
         out = torch.empty(n, d.action_dim, device=dev, dtype=torch.float32)
-        scratch = torch.empty(2 * n * d.hidden, device=dev, dtype=torch.float32)
+        scratch = torch.empty(_lib.lib().recnn_forward_scratch_floats(d, n, 0), device=dev, dtype=torch.float32)
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().recnn_actor_forward(
                 d, flat.data_ptr(), state.data_ptr(), n, _lib.ptr(m1), _lib.ptr(m2), int(bool(tanh)),
@@ -94,7 +94,7 @@ class Critic(nn.Module):
         flat = param_arena(self)
         m1, m2 = masks if masks is not None else _train_masks(self, n, d.hidden, dev)
         out = torch.empty(n, 1, device=dev, dtype=torch.float32)
-        scratch = torch.empty(2 * n * d.hidden, device=dev, dtype=torch.float32)
+        scratch = torch.empty(_lib.lib().recnn_forward_scratch_floats(d, n, 1), device=dev, dtype=torch.float32)
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().recnn_critic_forward(
                 d, flat.data_ptr(), state.data_ptr(), action.data_ptr(), n, _lib.ptr(m1), _lib.ptr(m2),

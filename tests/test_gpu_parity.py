@@ -54,24 +54,19 @@ def test_gather_vs_oracle(n_rows, n_items, dim, frame):
         assert np.array_equal(_bits(got[k].cpu().numpy()), _bits(want[k])), k
 
 
-@pytest.mark.parametrize("variant", [0, 1])
 @pytest.mark.parametrize("n_rows,n_items,dim,frame", [
     (1, 7, 128, 10), (4096, 26744, 128, 10), (4097, 500, 128, 10), (64, 31, 7, 3), (40, 20, 8, 33), (100, 64, 256, 10)])
-def test_gather_variants_bit_exact(variant, n_rows, n_items, dim, frame):
-    """Both gather kernels (0: one warp per row, 1: balanced (row, slot) units, one resident wave)."""
+def test_gather_bit_exact_and_out_of_range_ids(n_rows, n_items, dim, frame):
+    """The gather kernel (one warp per row) on ragged shapes, and IndexError on an id == n_items."""
     rng = np.random.default_rng(n_rows + 7 * dim)
     table, items, ratings, sizes = O.synth_frames(rng, n_rows, n_items, dim, frame)
     want = O.frame_gather(table, items, ratings, sizes, frame)
     batch = {"items": torch.from_numpy(items), "ratings": torch.from_numpy(ratings),
              "sizes": torch.from_numpy(sizes), "users": torch.zeros(1, dtype=torch.int64)}
-    prev = _lib.set_option("gather_variant", variant)
-    try:
-        got = recnn_b200.data.batch_tensor_embeddings(batch, torch.from_numpy(table).to(DEV), frame)
-        bad = dict(batch, items=torch.from_numpy(np.where(items == items.max(), n_items, items)))
-        with pytest.raises(IndexError):
-            recnn_b200.data.batch_tensor_embeddings(bad, torch.from_numpy(table).to(DEV), frame)
-    finally:
-        _lib.set_option("gather_variant", prev)
+    got = recnn_b200.data.batch_tensor_embeddings(batch, torch.from_numpy(table).to(DEV), frame)
+    bad = dict(batch, items=torch.from_numpy(np.where(items == items.max(), n_items, items)))
+    with pytest.raises(IndexError):
+        recnn_b200.data.batch_tensor_embeddings(bad, torch.from_numpy(table).to(DEV), frame)
     for k in ("state", "next_state", "action", "reward", "done"):
         assert np.array_equal(_bits(got[k].cpu().numpy()), _bits(want[k])), k
 
@@ -232,185 +227,11 @@ def test_quirks_on_device():
         assert m.training == ("target" not in name)
 
 
-@pytest.mark.parametrize("algo,form", [("ddpg", "frames"), ("ddpg", "dense"), ("td3", "frames")])
-def test_presplit_weight_planes_are_bit_identical(algo, form):
-    """The step with pre-split weight planes (option "presplit": forward / input-gradient GEMMs fetch TF32
-    hi/lo planes of the weights, split once per call and again after the critic's optimizer step) must
-    reproduce the in-kernel-split step bit for bit over 12 steps (policy steps 0 and 10, Polyak updates,
-    Adam): any stale plane would show up as a different weight."""
-    gold = load_golden("%s_canon_adam.npz" % algo)
-    runs = []
-    for v in (0, 1):
-        prev = _lib.set_option("presplit", v)
-        try:
-            runs.append(run_cuda_case("canon", algo, "adam", golden=gold, form=form))
-        finally:
-            _lib.set_option("presplit", prev)
-    a, b = runs
-    for k in a:
-        if k.startswith(("final.", "loss.", "after", "grad_")):
-            assert np.array_equal(a[k], b[k]), k
-    compare_with_golden(b, gold, check_grads=(algo == "ddpg"))
-
-
-@pytest.mark.parametrize("value", [1, 2])
-@pytest.mark.parametrize("algo", ["ddpg", "td3"])
-def test_sixteen_worker_gemm_in_the_step(algo, value):
-    """Option "workers16" (1: 64-wide GEMM tiles use the 16-worker kernel, 2: every GEMM uses 64-wide tiles):
-    per-element arithmetic does not depend on the tile shape, so the 12-step run (perf-relevant epilogues:
-    bias+ReLU+mask, linear, ReLU gate, split-K partials) must match the default kernels bit for bit."""
-    gold = load_golden("%s_canon_adam.npz" % algo)
-    base = run_cuda_case("canon", algo, "adam", golden=gold, form="frames")
-    prev = _lib.set_option("workers16", value)
-    try:
-        got = run_cuda_case("canon", algo, "adam", golden=gold, form="frames")
-    finally:
-        _lib.set_option("workers16", prev)
-    compare_with_golden(got, gold, check_grads=(algo == "ddpg"))
-    for k in base:
-        if k.startswith(("final.", "loss.")):
-            assert np.array_equal(base[k], got[k]), k
-
-
-@pytest.mark.parametrize("opts", [dict(lo2=1), dict(lo2=1, bn64=1)], ids=["lo2", "lo2-bn64"])
-@pytest.mark.parametrize("algo", ["ddpg", "td3"])
-def test_lo2_gemm_in_the_step_meets_the_golden_bar(algo, opts):
-    """The step on the two-cross-term-accumulator kernels (optionally on 64-wide tiles everywhere and with
-    16 worker warps) against the golden vectors of the unmodified reference: the same 1e-5 bar as the default."""
-    gold = load_golden("%s_canon_adam.npz" % algo)
-    prev = {k: _lib.set_option(k, v) for k, v in opts.items()}
-    try:
-        got = run_cuda_case("canon", algo, "adam", golden=gold, form="frames")
-        got_sgd = run_cuda_case("tiny", algo, "sgd", golden=load_golden("%s_tiny_sgd.npz" % algo), form="dense")
-    finally:
-        for k, v in prev.items():
-            _lib.set_option(k, v)
-    compare_with_golden(got, gold, check_grads=(algo == "ddpg"))
-    compare_with_golden(got_sgd, load_golden("%s_tiny_sgd.npz" % algo), check_grads=(algo == "ddpg"))
-
-
-@pytest.mark.skipif(__import__("os").environ.get("RECNN_TEST_EXPERIMENTAL") != "1",
-                    reason="lean GEMM kernels have not run on hardware yet (round 2, first GPU call)")
-@pytest.mark.parametrize("opts", [dict(lean=1), dict(lean=1, workers16=1), dict(lean=1, workers16=1, bn64=1),
-                                  dict(lean=1, presplit=1), dict(lean=1, presplit=1, workers16=1),
-                                  dict(lean=1, pdl=1), dict(lean=1, pdl=1, workers16=1)],
-                         ids=["lean", "lean-w16", "lean-w16-bn64", "lean-presplit", "lean-presplit-w16", "lean-pdl",
-                              "lean-pdl-w16"])
-@pytest.mark.parametrize("algo", ["ddpg", "td3"])
-def test_lean_gemm_in_the_step_is_bit_identical(algo, opts):
-    gold = load_golden("%s_canon_adam.npz" % algo)
-    base = run_cuda_case("canon", algo, "adam", golden=gold, form="frames")
-    prev = {k: _lib.set_option(k, v) for k, v in opts.items()}
-    try:
-        got = run_cuda_case("canon", algo, "adam", golden=gold, form="frames")
-    finally:
-        for k, v in prev.items():
-            _lib.set_option(k, v)
-    for k in base:
-        if k.startswith(("final.", "loss.")):
-            assert np.array_equal(base[k], got[k]), k
-
-
-@pytest.mark.skipif(__import__("os").environ.get("RECNN_TEST_EXPERIMENTAL") != "1",
-                    reason="16-byte-store gather written after this round's GPU budget was spent (round 2, first GPU call)")
-@pytest.mark.parametrize("algo", ["ddpg", "td3"])
-def test_sixteen_byte_store_gather_in_the_step_is_bit_identical(algo):
-    """gather_variant=2: inside the step the state images have a 16-byte-multiple pitch (1292 floats), so the gather
-    can store 16 bytes per lane; it copies the same bits, so the whole run must be unchanged."""
-    gold = load_golden("%s_canon_adam.npz" % algo)
-    base = run_cuda_case("canon", algo, "adam", golden=gold, form="frames")
-    prev = _lib.set_option("gather_variant", 2)
-    try:
-        got = run_cuda_case("canon", algo, "adam", golden=gold, form="frames")
-        tiny = run_cuda_case("tiny", algo, "adam", golden=load_golden("%s_tiny_adam.npz" % algo), form="frames")
-    finally:
-        _lib.set_option("gather_variant", prev)
-    for k in base:
-        if k.startswith(("final.", "loss.")):
-            assert np.array_equal(base[k], got[k]), k
-    compare_with_golden(tiny, load_golden("%s_tiny_adam.npz" % algo), check_grads=(algo == "ddpg"))
-
-
-@pytest.mark.skipif(__import__("os").environ.get("RECNN_TEST_EXPERIMENTAL") != "1",
-                    reason="launch-order change written after this round's GPU budget was spent (round 2, first GPU call)")
-@pytest.mark.parametrize("opts", [dict(tail=1), dict(padzero=1), dict(tail=1, padzero=1)], ids=["tail", "padzero", "both"])
-@pytest.mark.parametrize("algo,form", [("ddpg", "frames"), ("td3", "frames"), ("ddpg", "dense")])
-def test_column_sums_on_the_side_stream_are_bit_identical(algo, form, opts):
-    """`tail` option: the dZ column sums (bias gradients) run on the side stream beside the weight-gradient GEMMs.
-    `padzero` option: one kernel zeroes the pad columns of the action images instead of three full memsets.
-    Same arithmetic on the same data: results must not change."""
-    gold = load_golden("%s_canon_adam.npz" % algo)
-    base = run_cuda_case("canon", algo, "adam", golden=gold, form=form)
-    prev = {k: _lib.set_option(k, v) for k, v in opts.items()}
-    try:
-        got = run_cuda_case("canon", algo, "adam", golden=gold, form=form)
-    finally:
-        for k, v in prev.items():
-            _lib.set_option(k, v)
-    for k in base:
-        if k.startswith(("final.", "loss.", "grad_")):
-            assert np.array_equal(base[k], got[k]), k
-
-
-@pytest.mark.skipif(__import__("os").environ.get("RECNN_TEST_EXPERIMENTAL") != "1",
-                    reason="split-K policy written after this round's GPU budget was spent (round 2, first GPU call)")
-@pytest.mark.parametrize("algo,spec", [("ddpg", "canon"), ("td3", "canon"), ("ddpg", C.FULL_SPEC)],
-                         ids=["ddpg-canon", "td3-canon", "ddpg-4096"])
-def test_one_wave_split_k_policy_meets_the_parity_bar(algo, spec):
-    """`dwsplit` option: fewer, longer split-K chunks for the weight gradients (one wave of CTAs).  The summation
-    order of the partials changes, so the result is not bit-identical; it must meet the same bars as the default."""
-    prev = _lib.set_option("dwsplit", 1)
-    try:
-        if spec == "canon":
-            gold = load_golden("%s_canon_adam.npz" % algo)
-            got = run_cuda_case("canon", algo, "adam", golden=gold, form="frames")
-            compare_with_golden(got, gold, check_grads=(algo == "ddpg"))
-        else:
-            want = run_oracle_case(spec, algo, "sgd")
-            got = run_cuda_case(spec, algo, "sgd", form="frames")
-            for k in (k for k in want if k.startswith("loss.")):
-                assert np.max(np.abs(got[k] - want[k]) / (np.abs(want[k]) + 0.1)) <= 1e-5, k
-    finally:
-        _lib.set_option("dwsplit", prev)
-
-
-def test_sixteen_worker_gemm_perf_mode_dropout_matches():
-    """Device-Philox dropout (perf mode) indexes keep-bits by element, not by tile: the 16-worker kernel's
-    16-column epilogue blocks must draw the same masks as the 32-column blocks of the default kernel."""
-    torch.manual_seed(3)
-    rng = np.random.default_rng(4)
-    table, items, ratings, sizes = O.synth_frames(rng, 512)
-    table_d = torch.from_numpy(table).to(DEV)
-    batch = {"items": torch.from_numpy(items), "ratings": torch.from_numpy(ratings),
-             "sizes": torch.from_numpy(sizes), "table": table_d}
-    outs = []
-    for value in (0, 2):
-        prev = _lib.set_option("workers16", value)
-        try:
-            torch.manual_seed(5)
-            agent = recnn_b200.nn.DDPG(recnn_b200.nn.Actor(1290, 128, 256, 6e-1),
-                                       recnn_b200.nn.Critic(1290, 128, 256, 54e-2)).to(torch.device(DEV))
-            losses = []
-            for _ in range(3):
-                losses.append(agent.update(batch, learn=True))
-                agent.step()
-            outs.append((losses, [p.detach().clone() for p in agent.nets["value_net"].parameters()]))
-        finally:
-            _lib.set_option("workers16", prev)
-    assert outs[0][0] == outs[1][0]
-    for p, q in zip(outs[0][1], outs[1][1]):
-        assert torch.equal(p, q)
-
-
-def test_presplit_with_external_optimizer_and_split_phases():
-    """External torch optimizers cut the step into several C calls; planes are per call, so every call must
-    re-split what it uses (a stale critic plane after optimizer.step() would change the policy loss)."""
+def test_external_optimizer_split_phases_meet_the_golden_bar():
+    """External torch optimizers cut the step into several C calls (gradients complete -> optimizer.step() in
+    Python -> next phase); the result must meet the same golden bar as the fused step."""
     gold = load_golden("ddpg_canon_adam.npz")
-    prev = _lib.set_option("presplit", 1)
-    try:
-        got = run_cuda_case("canon", "ddpg", "adam", golden=gold, external=True)
-    finally:
-        _lib.set_option("presplit", prev)
+    got = run_cuda_case("canon", "ddpg", "adam", golden=gold, external=True)
     compare_with_golden(got, gold)
 
 
