@@ -552,10 +552,10 @@ def run_native(args):
         w1 = agent.nets["policy_net"].linear1.weight            # strided view into the arena, pitch 1292
         h1s = [torch.empty(n_rows, HIDDEN, device=dev) for _ in range(8)]
 
-        def l1_launch(i, tile):
+        def l1_launch(i, tile):      # the stream is looked up at call time: graph capture runs on its own stream
             return lambda: _lib.check(L.recnn_gemm_tf32x3(
                 n_rows, HIDDEN, S_DIM, x_imgs[i].data_ptr(), ld_s, 0, w1.data_ptr(), w1.stride(0), 0,
-                h1s[i].data_ptr(), HIDDEN, tile, st))
+                h1s[i].data_ptr(), HIDDEN, tile, torch.cuda.current_stream(dev).cuda_stream))
 
         l1 = {}
         for tile in (64, 128):

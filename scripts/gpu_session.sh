@@ -10,7 +10,7 @@ t0=$(date +%s)
 el() { echo "[t+$(( $(date +%s) - t0 ))s] $*"; }
 
 el "1. GPU test-suite"
-timeout 900 python -m pytest tests -m gpu -q --maxfail=15 --tb=short -x -p no:cacheprovider > $O/${tag}_tests.log 2>&1
+timeout 900 python -m pytest tests -m gpu -q --maxfail=25 --tb=short -p no:cacheprovider > $O/${tag}_tests.log 2>&1
 tail -5 $O/${tag}_tests.log
 
 el "2. bench"
@@ -28,19 +28,21 @@ except Exception as e:
     print("bench failed:", e); print(open("$O/${tag}_bench.err").read()[-2000:])
 PY
 
-el "3. experiment A/B (bit 0: raw lo)"
-RECNN_B200_EXPERIMENT=1 timeout 300 python -m pytest tests/test_gpu_tc.py tests/test_gpu_parity.py -m gpu -q --tb=line -p no:cacheprovider \
-  -k "not tight and not full_size" > $O/${tag}_tests_exp1.log 2>&1
-tail -3 $O/${tag}_tests_exp1.log
-timeout 200 python bench.py --steps 100 --warmup 10 --no-cpu-baseline --no-other-algo --opt experiment=1 > $O/${tag}_bench_exp1.json 2> $O/${tag}_bench_exp1.err
-python - <<PY
+el "3. experiment A/B (bit 0: raw lo, bit 1: [hi;lo] concatenated B operand)"
+for ex in 1 2 3; do
+  RECNN_B200_EXPERIMENT=$ex timeout 400 python -m pytest tests/test_gpu_tc.py tests/test_gpu_parity.py -m gpu -q --tb=line -p no:cacheprovider \
+    -k "not tight and not full_size" > $O/${tag}_tests_exp$ex.log 2>&1
+  echo "exp$ex tests: $(tail -1 $O/${tag}_tests_exp$ex.log)"
+  timeout 200 python bench.py --steps 100 --warmup 10 --no-cpu-baseline --no-other-algo --opt experiment=$ex > $O/${tag}_bench_exp$ex.json 2> $O/${tag}_bench_exp$ex.err
+  python - <<PY
 import json
 try:
-    d = json.load(open("$O/${tag}_bench_exp1.json"))
-    print("exp1: value %.1f  L1 %s" % (d["value"], {k: round(v["ms"] * 1e3, 2) for k, v in d["roofline"]["per_tile"].items()}))
+    d = json.load(open("$O/${tag}_bench_exp$ex.json"))
+    print("exp$ex: value %.1f  L1 %s" % (d["value"], {k: round(v["ms"] * 1e3, 2) for k, v in d["roofline"]["per_tile"].items()}))
 except Exception as e:
-    print("exp1 bench failed:", e)
+    print("exp$ex bench failed:", e); print(open("$O/${tag}_bench_exp$ex.err").read()[-1500:])
 PY
+done
 
 if [ "$2" != "skip-ncu" ]; then
 el "4. ncu: launch list of the step"

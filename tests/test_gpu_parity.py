@@ -259,8 +259,9 @@ def test_full_size_perf_mode_runs_and_learns(algo):
     else:
         agent = recnn_b200.nn.TD3(actor, recnn_b200.nn.Critic(1290, 128, 256, 54e-2),
                                   recnn_b200.nn.Critic(1290, 128, 256, 54e-2)).to(torch.device(DEV))
-    for k in agent.optimizers:                    # bigger lr so 30 steps visibly reduce the loss
-        agent.optimizers[k].param_groups[0]["lr"] = 1e-3
+    for k in list(agent.optimizers):              # Adam with a bigger lr so 30 steps visibly reduce the loss
+        net = agent.nets[k.replace("optimizer", "net")]     # (the default Ranger warms up for its first steps)
+        agent.optimizers[k] = recnn_b200.optim.Adam(net.parameters(), lr=1e-3, weight_decay=1e-2)
     batch = {"items": torch.from_numpy(items), "ratings": torch.from_numpy(ratings),
              "sizes": torch.from_numpy(sizes), "table": table_d}
     key = "value" if algo == "ddpg" else "value1"
