@@ -2,8 +2,8 @@
 // Restates recnn/data/utils.py:51-71 (batch_tensor_embeddings) as one HBM-bound
 // copy kernel.  Bit-exact (no arithmetic on the payload).
 //
-// Layout: one warp per sample row.  The warp reads the row's F+1 item ids with
-// one coalesced load, then for each slot j streams the D-float table row with
+// Layout: one warp per (sample row, group of four slots).  The warp reads the unit's item ids,
+// then for each slot j streams the D-float table row with
 // 16-byte loads (table rows are D*4-byte aligned) and writes it to
 //   state[n, j*D ...]        if j <  F
 //   next_state[n, (j-1)*D..] if j >= 1
@@ -32,32 +32,42 @@ frame_gather_kernel(const float* __restrict__ table, long long n_items, int dim,
   const long long warps_per_grid = (long long)gridDim.x * (blockDim.x >> 5);
   const int f1 = frame + 1;
   const long long s_dim = s_ld;       // row pitch of state / next_state (>= frame*dim + frame)
+  // Work unit = (row, group of four slots): a warp keeps exactly one batch of four table rows in flight per unit.
+  // Units rather than whole rows because 4096 rows over the ~3,500 resident warps of the machine is 1.15 rows per
+  // warp -- i.e. TWO rounds for everybody; with three units per row it is 3.5 -> four rounds of a third the length.
+  const int groups = (f1 + 3) >> 2;
+  const long long n_units = n_rows * groups;
 
-  for (long long n = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); n < n_rows;
-       n += warps_per_grid) {
-    // ---- ratings tail + reward (tiny) --------------------------------------
-    for (int t = lane; t < f1; t += 32) {
-      const float r = ratings[n * f1 + t];
-      if (t < frame && state) state[n * s_dim + (long long)frame * dim + t] = r;
-      if (t >= 1 && next_state) next_state[n * s_dim + (long long)frame * dim + (t - 1)] = r;
-      if (t == frame && reward) reward[n] = r;
+  for (long long unit = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); unit < n_units;
+       unit += warps_per_grid) {
+    const long long n = unit / groups;
+    const int j0 = (int)(unit - n * groups) * 4;             // first slot of this unit
+    if (j0 == 0) {
+      // ---- ratings tail + reward (tiny): the row's first unit ---------------
+      for (int t = lane; t < f1; t += 32) {
+        const float r = ratings[n * f1 + t];
+        if (t < frame && state) state[n * s_dim + (long long)frame * dim + t] = r;
+        if (t >= 1 && next_state) next_state[n * s_dim + (long long)frame * dim + (t - 1)] = r;
+        if (t == frame && reward) reward[n] = r;
+      }
     }
-    // ---- item ids: one coalesced read, broadcast by shuffle ------------------
-    for (int j0 = 0; j0 < f1; j0 += 32) {
+    // ---- item ids of the unit's (up to) four slots: lanes 0..3 read, everybody gets them by shuffle --------
+    {
+      const int cnt = min(4, f1 - j0);
       long long my_id = 0;
-      if (j0 + lane < f1) {
+      if (lane < cnt) {
         my_id = items[n * f1 + j0 + lane];
         if (my_id < 0 || my_id >= n_items) {
           if (oob) atomicOr(oob, 1);
           my_id = 0;
         }
       }
-      const int cnt = min(32, f1 - j0);
-      for (int jj = 0; jj < cnt; jj += 4) {
+      {
+        const int jj = 0;
         long long id[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) id[u] = __shfl_sync(0xffffffffu, my_id, min(jj + u, cnt - 1));
-        if (VEC) {
+        for (int u = 0; u < 4; ++u) id[u] = __shfl_sync(0xffffffffu, my_id, min(u, cnt - 1));
+        if (VEC && ST16) {
           for (int c = lane * 4; c < dim; c += 128) {
             float4 v[4];
 #pragma unroll
@@ -67,20 +77,41 @@ frame_gather_kernel(const float* __restrict__ table, long long n_items, int dim,
             for (int u = 0; u < 4; ++u) {
               if (jj + u >= cnt) break;
               const int j = j0 + jj + u;
-              const float2 lo = make_float2(v[u].x, v[u].y), hi = make_float2(v[u].z, v[u].w);
-              if (j < frame && state) {
-                float* dst = state + n * s_dim + (long long)j * dim + c;
-                if constexpr (ST16) *reinterpret_cast<float4*>(dst) = v[u];
-                else { float2* d = reinterpret_cast<float2*>(dst); d[0] = lo; d[1] = hi; }
+              if (j < frame && state) *reinterpret_cast<float4*>(state + n * s_dim + (long long)j * dim + c) = v[u];
+              if (j >= 1 && next_state)
+                *reinterpret_cast<float4*>(next_state + n * s_dim + (long long)(j - 1) * dim + c) = v[u];
+              if (j == frame && action) {   // lead-padded action rows start 8 bytes into a 16-byte unit
+                float2* d = reinterpret_cast<float2*>(action + n * a_ld + c);
+                d[0] = make_float2(v[u].x, v[u].y);
+                d[1] = make_float2(v[u].z, v[u].w);
               }
-              if (j >= 1 && next_state) {
-                float* dst = next_state + n * s_dim + (long long)(j - 1) * dim + c;
-                if constexpr (ST16) *reinterpret_cast<float4*>(dst) = v[u];
-                else { float2* d = reinterpret_cast<float2*>(dst); d[0] = lo; d[1] = hi; }
+            }
+          }
+        } else if (VEC) {
+          // destinations are only 8-byte aligned (dense 1290-float rows): lane l moves the 8 bytes at column 2l of
+          // every 64-column span, so each store instruction writes 256 CONTIGUOUS bytes (full 32-byte sectors);
+          // 16-byte loads with 8-byte stores would leave every sector half written per instruction
+          for (int c = lane * 2; c < dim; c += 128) {
+            float2 v[4][2];
+            const bool second = c + 64 < dim;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (jj + u < cnt) {
+                v[u][0] = __ldg(reinterpret_cast<const float2*>(table + id[u] * dim + c));
+                if (second) v[u][1] = __ldg(reinterpret_cast<const float2*>(table + id[u] * dim + c + 64));
               }
-              if (j == frame && action) {
-                float* dst = action + n * a_ld + c;     // lead-padded action rows start 8 bytes into a 16-byte unit
-                float2* d = reinterpret_cast<float2*>(dst); d[0] = lo; d[1] = hi;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (jj + u >= cnt) break;
+              const int j = j0 + jj + u;
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                if (h == 1 && !second) break;
+                const int cc = c + 64 * h;
+                if (j < frame && state) *reinterpret_cast<float2*>(state + n * s_dim + (long long)j * dim + cc) = v[u][h];
+                if (j >= 1 && next_state)
+                  *reinterpret_cast<float2*>(next_state + n * s_dim + (long long)(j - 1) * dim + cc) = v[u][h];
+                if (j == frame && action) *reinterpret_cast<float2*>(action + n * a_ld + cc) = v[u][h];
               }
             }
           }
@@ -136,8 +167,9 @@ int launch_frame_gather(const float* table, int64_t n_items, int dim, const int6
                        (!action || reinterpret_cast<uintptr_t>(action) % 8 == 0);
   const bool vec = aligned && (dim % 4 == 0) && (s_dim % 2 == 0) && (a_ld % 2 == 0);
   const int warps_per_block = 8;
-  const int64_t blocks = ceil_div(n_rows, warps_per_block);
-  const int grid = (int)(blocks < (int64_t)kNumSMs * 8 ? blocks : (int64_t)kNumSMs * 8);
+  const int64_t units = n_rows * ((frame + 1 + 3) / 4);            // (row, four slots) work units, one per warp
+  const int64_t blocks = ceil_div(units, warps_per_block);
+  const int grid = (int)(blocks < (int64_t)kNumSMs * 16 ? blocks : (int64_t)kNumSMs * 16);
   // 16-byte stores whenever the destination pitches allow it (the step's state images have a 16-byte-multiple
   // pitch; the public API's dense 1290-float rows are only 8-byte aligned)
   const bool st16 = vec && s_ld % 4 == 0 && (((long long)frame * dim) % 4 == 0) &&

@@ -61,13 +61,11 @@ int split_plan(int K_total_blocks, int splits_req, int* k_chunk, int bk) {
 
 template <class C, int EPI>
 static int launch_cfg(const Operand& A0, const Operand& A1, const Operand& B, const Problem& p_in, int splits,
-                      const Epilogue& epi, cudaStream_t st, bool lo_raw) {
+                      const Epilogue& epi, cudaStream_t st) {
   Problem p = p_in;
   static bool attr_set = false;
   if (!attr_set) {
-    RECNN_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<C, EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          C::SMEM_BYTES));
-    RECNN_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<C, EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    RECNN_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<C, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           C::SMEM_BYTES));
     attr_set = true;
   }
@@ -107,10 +105,7 @@ static int launch_cfg(const Operand& A0, const Operand& A1, const Operand& B, co
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (lo_raw)
-    RECNN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<C, EPI, true>, ma0, ma1, mb, p, epi));
-  else
-    RECNN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<C, EPI, false>, ma0, ma1, mb, p, epi));
+  RECNN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<C, EPI>, ma0, ma1, mb, p, epi));
   RECNN_CHECK_LAUNCH("tc_gemm_kernel");
   if (debug) {
     const cudaError_t e = cudaStreamSynchronize(st);
@@ -127,14 +122,8 @@ template <bool A_MN, bool B_MN, int EPI>
 int launch(const Operand& A0, const Operand& A1, const Operand& B, const Problem& p, int splits, int bn,
            const Epilogue& epi, cudaStream_t st) {
   // stages chosen to fill ~190 KB of shared memory: stage = 16 KB (raw A) + 2 * BN/8 KB (B hi | B lo)
-  const int ex = option(OPT_EXPERIMENT);
-  const bool lo_raw = (ex & 1) != 0;
-  if (ex & 2) {          // NCAT: one more B tile per stage -> one stage less
-    if (bn >= 128) return launch_cfg<Cfg<128, 3, A_MN, B_MN, true>, EPI>(A0, A1, B, p, splits, epi, st, lo_raw);
-    return launch_cfg<Cfg<64, 5, A_MN, B_MN, true>, EPI>(A0, A1, B, p, splits, epi, st, lo_raw);
-  }
-  if (bn >= 128) return launch_cfg<Cfg<128, 4, A_MN, B_MN>, EPI>(A0, A1, B, p, splits, epi, st, lo_raw);
-  return launch_cfg<Cfg<64, 6, A_MN, B_MN>, EPI>(A0, A1, B, p, splits, epi, st, lo_raw);
+  if (bn >= 128) return launch_cfg<Cfg<128, 4, A_MN, B_MN>, EPI>(A0, A1, B, p, splits, epi, st);
+  return launch_cfg<Cfg<64, 6, A_MN, B_MN>, EPI>(A0, A1, B, p, splits, epi, st);
 }
 
 // explicit instantiations used by step.cu / the generic entry points

@@ -213,17 +213,19 @@ __device__ __forceinline__ float tf32_rna(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 // x = hi + lo (+ <= 2^-24 |x|): hi = rna_tf32(x), lo = rna_tf32(x - hi)
-template <bool LO_RAW = false>
+// lo is handed to the tensor core as is: the kind::tf32 datapath ignores an operand's low 13 bits, i.e. it truncates
+// the (at most 13-bit) remainder to 11 bits -- an error of at most 2^-22 |x| with random sign (hi is rounded to
+// nearest, so lo is symmetric), against 2^-23 |x| if lo were rounded first, for two integer instructions less per
+// operand element in the split warps (measured: -4% on the layer-1 GEMM, all accuracy bars unchanged, profiles/r2c).
 __device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) {
   hi = tf32_rna(x);
-  lo = LO_RAW ? x - hi : tf32_rna(x - hi);
+  lo = x - hi;
 }
-template <bool LO_RAW = false>
 __device__ __forceinline__ void tf32_split4(const float4& x, float4& hi, float4& lo) {
-  tf32_split<LO_RAW>(x.x, hi.x, lo.x);
-  tf32_split<LO_RAW>(x.y, hi.y, lo.y);
-  tf32_split<LO_RAW>(x.z, hi.z, lo.z);
-  tf32_split<LO_RAW>(x.w, hi.w, lo.w);
+  tf32_split(x.x, hi.x, lo.x);
+  tf32_split(x.y, hi.y, lo.y);
+  tf32_split(x.z, hi.z, lo.z);
+  tf32_split(x.w, hi.w, lo.w);
 }
 
 // ------------------------------------------------------------------ descriptors
@@ -264,19 +266,8 @@ __device__ __forceinline__ unsigned long long gtimer() {
 #define RECNN_TRACE(slot) do { } while (0)
 #endif
 
-// NCAT (experiment, `experiment` option bit 1): the hi and lo tiles of B sit next to each other in shared memory
-// and are read as ONE [hi ; lo] operand of 2*BN rows, so a k-slice takes two tcgen05.mma instead of three:
-//     [D_hi | D_lo] += A_hi x [B_hi ; B_lo]        (N = 2*BN)          D_lo += A_lo x B_hi      (N = BN)
-// Why: the MMA warp's loop overhead (~60 clk per instruction: descriptor arithmetic in the uniform datapath,
-// barrier polls) is not hidden by the tensor pipe's short queue, so the mainloop costs ~(overhead + pipe time) per
-// instruction; fewer, wider instructions do the same tensor work with a third less overhead.  TMEM layout becomes
-// D_hi0 | D_lo | D_hi1 (the concatenated result must be contiguous): even chunks read B as [hi ; lo_after] into
-// columns [0, 2BN), odd chunks as [lo_before ; hi] into [BN, 3BN) -- the splitters write lo before or after hi by
-// chunk parity.  One instruction covers both accumulators, so the "overwrite at the start of a chunk" flag cannot be
-// used for D_hi alone: every MMA accumulates, and the workers zero D_hi after draining it (and everything once at start).
-template <int BN_, int STAGES_, bool A_MN_, bool B_MN_, bool NCAT_ = false>
+template <int BN_, int STAGES_, bool A_MN_, bool B_MN_>
 struct Cfg {
-  static constexpr bool NCAT = NCAT_;
   // BK = 32 (128-byte K-major rows): TMA moves 64-byte rows at half the rate of 128-byte rows (measured:
   // 31 B/clk/SM with BK = 16), and the operand stream is one of the kernel's bottlenecks.
   static constexpr int BM = 128, BN = BN_, BK = 32, STAGES = STAGES_;
@@ -287,7 +278,7 @@ struct Cfg {
   // memory one TMA write + one read instead of write + read + 2 writes + 6 MMA reads.
   static constexpr int A_SLOT_COLS = 2 * BK, A_SLOTS = (512 - D_COLS) / A_SLOT_COLS;   // hi | lo per k-block: 2 slots at BN = 128, 5 at BN = 64
   static constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
-  static constexpr int STAGE_BYTES = A_BYTES + (NCAT ? 3 : 2) * B_BYTES;   // raw A | (lo B before) | raw B (split in place into hi) | lo B after
+  static constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;        // raw A | raw B (split in place into hi) | lo B
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
   // Worker warps come in groups of four (one warp per TMEM lane quarter); the groups take k-blocks round robin.
   // 64-wide tiles run four groups (their A ring in tensor memory has five slots), 128-wide tiles two.
@@ -393,20 +384,7 @@ __device__ __forceinline__ void epilogue_row(const Epilogue& e, const Problem& p
 }
 
 // ------------------------------------------------------------------ the kernel
-// LO_RAW (experiment, `experiment` option bit 0): lo = x - hi is handed to the tensor core as is (the kind::tf32
-// datapath ignores its low 13 bits, i.e. truncates it) instead of being rounded to TF32 first: two integer
-// instructions fewer per operand element in the split warps, at the price of up to 2^-22 |x| (instead of 2^-23)
-// in the cross terms.
-template <int NC>
-__device__ __forceinline__ void tmem_zero(uint32_t taddr) {
-  float z[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) z[j] = 0.f;
-#pragma unroll
-  for (int c0 = 0; c0 < NC; c0 += 16) tmem_st16(taddr + c0, z);
-}
-
-template <class C, int EPI, bool LO_RAW>
+template <class C, int EPI>
 __global__ void __launch_bounds__(C::THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_b, Problem p, Epilogue epi) {
@@ -414,10 +392,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   constexpr int NC = C::COLS_PER_WORKER, WORKERS = C::WORKERS, NG = WORKERS / 4;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;       // shared-window address, 1 KB aligned
-  auto stage_addr = [&](int s, int which) -> uint32_t {    // 0 raw A, 1 raw B (-> hi B), 2 lo B (after hi), 3 lo B before hi (NCAT)
+  auto stage_addr = [&](int s, int which) -> uint32_t {              // 0 raw A, 1 raw B (-> hi B), 2 lo B
     const uint32_t base = smem + (uint32_t)s * C::STAGE_BYTES;
-    const uint32_t hi = base + C::A_BYTES + (C::NCAT ? C::B_BYTES : 0);
-    return which == 0 ? base : which == 1 ? hi : which == 2 ? hi + C::B_BYTES : base + C::A_BYTES;
+    return which == 0 ? base : which == 1 ? base + C::A_BYTES : base + C::A_BYTES + C::B_BYTES;
   };
   const uint32_t bars = smem + (uint32_t)STAGES * C::STAGE_BYTES;
   auto full = [&](int s) { return bars + 8u * s; };                   // TMA -> workers
@@ -519,11 +496,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     constexpr uint32_t b_kstep = C::B_MN ? 1024 : 32;        // bytes to advance per 8-wide k-slice
     const bool leader = elect_one();
     // running counters: stage / phase, A slot, position in the chunk and its buffer, per-buffer wait parity
-    // NCAT: the first wait on each chunk buffer is a real one (the workers zero tensor memory first)
-    uint32_t s = 0, ph = 0, slot = 0, kin = 0, buf = 0, par0 = C::NCAT ? 0 : 1, par1 = C::NCAT ? 0 : 1;
+    uint32_t s = 0, ph = 0, slot = 0, kin = 0, buf = 0, par0 = 1, par1 = 1;
     uint32_t lo_acc = 0;                                     // 0 only for the very first cross-term MMAs
-    const uint32_t d_lo = tmem_base + (C::NCAT ? 1u : 2u) * BN;   // tile-lifetime accumulator (cross terms)
-    constexpr uint32_t idesc_cat = instr_desc_tf32(BM, 2 * BN, false, C::B_MN);
+    const uint32_t d_lo = tmem_base + 2u * BN;               // tile-lifetime accumulator (cross terms)
     for (int i = 0; i < num_kb; ++i) {
       if (kin == 0) {                                        // new chunk: its TMEM buffer must have been drained
         mbar_wait(acc_empty(buf), buf ? par1 : par0);
@@ -532,24 +507,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       mbar_wait(split(s), ph);
       tc_fence_after();
       if (i == 0 && lane == 0) RECNN_TRACE(2);               // first stage loaded + split
-      const uint32_t d_hi = tmem_base + buf * (C::NCAT ? 2u : 1u) * BN;   // chunk accumulator (hi*hi)
+      const uint32_t d_hi = tmem_base + buf * BN;            // chunk accumulator (hi*hi)
       const uint64_t db_hi0 = b_base | uint64_t((stage_addr(s, 1) & 0x3FFFF) >> 4);
       const uint64_t db_lo0 = b_base | uint64_t((stage_addr(s, 2) & 0x3FFFF) >> 4);
       const uint32_t ta0 = tmem_base + C::A_COL0 + slot * C::A_SLOT_COLS;
       if (leader) {
-        if constexpr (C::NCAT) {
-          // even chunk: [hi ; lo_after] -> columns [0, 2BN) = D_hi0 | D_lo;  odd: [lo_before ; hi] -> [BN, 3BN) = D_lo | D_hi1
-          const uint64_t db_cat0 = buf ? (b_base | uint64_t((stage_addr(s, 3) & 0x3FFFF) >> 4)) : db_hi0;
-          const uint32_t d_cat = tmem_base + buf * BN;
-#pragma unroll
-          for (int k = 0; k < BK / 8; ++k) {
-            const uint64_t db_hi = db_hi0 + uint64_t((k * b_kstep) >> 4);
-            const uint64_t db_cat = db_cat0 + uint64_t((k * b_kstep) >> 4);
-            const uint32_t ta_hi = ta0 + k * 8, ta_lo = ta_hi + BK;
-            mma_tf32_ta(d_cat, ta_hi, db_cat, idesc_cat, 1);
-            mma_tf32_ta(d_lo, ta_lo, db_hi, idesc, 1);
-          }
-        } else {
 #pragma unroll
         for (int k = 0; k < BK / 8; ++k) {
           const uint64_t db_hi = db_hi0 + uint64_t((k * b_kstep) >> 4);
@@ -559,7 +521,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           mma_tf32_ta(d_lo, ta_lo, db_hi, idesc, lo_flag);
           mma_tf32_ta(d_lo, ta_hi, db_lo, idesc, 1);
           mma_tf32_ta(d_hi, ta_hi, db_hi, idesc, hi_flag);
-        }
         }
         mma_commit(empty(s));                                // frees the stage once these MMAs have read it
         mma_commit(a_free(slot));                            // ... and the A slot in tensor memory
@@ -586,25 +547,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       const int buf = chunk & 1;
       mbar_wait(acc_full(buf), (chunk >> 1) & 1);
       tc_fence_after();
-      const uint32_t d_hi = lane_base + (uint32_t)buf * (C::NCAT ? 2u : 1u) * BN;
-      tmem_accumulate<NC>(d_hi, acc);
-      if constexpr (C::NCAT) {              // every MMA accumulates: hand the buffer back zeroed
-        tmem_zero<NC>(d_hi);
-        tmem_st_wait();
-      }
+      tmem_accumulate<NC>(lane_base + (uint32_t)buf * BN, acc);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty(buf));
     };
-    if constexpr (C::NCAT) {                // D_hi0 | D_lo | D_hi1 start at zero; completes phase 0 of both acc_empty barriers
-      tmem_zero<NC>(lane_base);
-      tmem_zero<NC>(lane_base + BN);
-      tmem_zero<NC>(lane_base + 2u * BN);
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) { mbar_arrive(acc_empty(0)); mbar_arrive(acc_empty(1)); }
-    }
 
     // The groups take k-blocks round robin, so one group's publish latency (membar + proxy fence +
     // tcgen05.wait::st) hides behind the other groups' arithmetic.
@@ -616,7 +563,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       const uint32_t ph = (i / STAGES) & 1;
       mbar_wait(full(s), ph);
       const uint32_t raw = stage_addr(s, 1);                  // raw B, split in place into hi
-      const uint32_t lo = stage_addr(s, (C::NCAT && ((i / CH) & 1)) ? 3 : 2);   // lo B (NCAT: before hi on odd chunks)
+      const uint32_t lo = stage_addr(s, 2);                   // lo B
       const int slot = i % C::A_SLOTS;
       const uint32_t ta = tmem_base + (uint32_t(32 * q) << 16) + C::A_COL0 + slot * C::A_SLOT_COLS;
       mbar_wait(a_free(slot), ((i / C::A_SLOTS) & 1) ^ 1);
@@ -635,7 +582,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             const uint32_t k = 16u * half + kk;
             float x;
             asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(cbase + k * 128u + ((unit ^ (k & 3u)) << 5)));
-            tf32_split<LO_RAW>(x, hi[kk], lw[kk]);
+            tf32_split(x, hi[kk], lw[kk]);
           }
           tmem_st16(ta + 16 * half, hi);
           tmem_st16(ta + BK + 16 * half, lw);
@@ -652,10 +599,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float4 x = lds128(rbase + (((4 * half + j) ^ sw) << 4));
-            tf32_split<LO_RAW>(x.x, hi[4 * j + 0], lw[4 * j + 0]);
-            tf32_split<LO_RAW>(x.y, hi[4 * j + 1], lw[4 * j + 1]);
-            tf32_split<LO_RAW>(x.z, hi[4 * j + 2], lw[4 * j + 2]);
-            tf32_split<LO_RAW>(x.w, hi[4 * j + 3], lw[4 * j + 3]);
+            tf32_split(x.x, hi[4 * j + 0], lw[4 * j + 0]);
+            tf32_split(x.y, hi[4 * j + 1], lw[4 * j + 1]);
+            tf32_split(x.z, hi[4 * j + 2], lw[4 * j + 2]);
+            tf32_split(x.w, hi[4 * j + 3], lw[4 * j + 3]);
           }
           tmem_st16(ta + 16 * half, hi);
           tmem_st16(ta + BK + 16 * half, lw);
@@ -668,7 +615,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 #pragma unroll
         for (int v = 0; v < VB; ++v) {
           float4 xh, xl;
-          tf32_split4<LO_RAW>(x[v], xh, xl);
+          tf32_split4(x[v], xh, xl);
           sts128(raw + 16u * ((uint32_t)tg + v * 128u), xh);
           sts128(lo + 16u * ((uint32_t)tg + v * 128u), xl);
         }
@@ -687,7 +634,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     while (next_drain < num_chunks) drain(next_drain++);      // the last full chunk (and a trailing partial one)
     if (threadIdx.x == 64) RECNN_TRACE(5);                    // all chunks drained (MMAs complete)
     if (num_kb > 0)   // the commit behind the last acc_full covers every MMA issued before it, D_lo's included
-      tmem_accumulate<NC>(lane_base + (C::NCAT ? 1u : 2u) * BN, acc);
+      tmem_accumulate<NC>(lane_base + 2u * BN, acc);
     epilogue_row<EPI, NC>(epi, p, m0 + 32 * q + lane, n0 + g * NC, z, acc);
     if (threadIdx.x == 64) RECNN_TRACE(6);                    // epilogue stored
   }

@@ -29,7 +29,7 @@ except Exception as e:
 PY
 
 el "3. experiment A/B (bit 0: raw lo, bit 1: [hi;lo] concatenated B operand)"
-for ex in 1 2 3; do
+for ex in ; do
   RECNN_B200_EXPERIMENT=$ex timeout 400 python -m pytest tests/test_gpu_tc.py tests/test_gpu_parity.py -m gpu -q --tb=line -p no:cacheprovider \
     -k "not tight and not full_size" > $O/${tag}_tests_exp$ex.log 2>&1
   echo "exp$ex tests: $(tail -1 $O/${tag}_tests_exp$ex.log)"
@@ -55,5 +55,8 @@ timeout 120 ncu -i $O/${tag}_tc_gemm.ncu-rep --page raw --csv > $O/${tag}_tc_gem
 timeout 300 ncu --set full --clock-control none -k regex:frame_gather -c 2 -f -o $O/${tag}_gather \
   python scripts/prof_gather.py > $O/${tag}_ncu_gather.log 2>&1
 timeout 120 ncu -i $O/${tag}_gather.ncu-rep --page raw --csv > $O/${tag}_gather_raw.csv 2>/dev/null
+timeout 300 ncu --set full --clock-control none -k regex:frame_gather -c 2 -f -o $O/${tag}_gather_big \
+  python scripts/prof_gather.py 65536 > $O/${tag}_ncu_gather_big.log 2>&1
+timeout 120 ncu -i $O/${tag}_gather_big.ncu-rep --page raw --csv > $O/${tag}_gather_big_raw.csv 2>/dev/null
 fi
 el "done"

@@ -1,0 +1,32 @@
+#!/bin/bash
+# Multi-GPU session (gpurun --gpus N): data-parallel parity tests at every world size the box offers, then the
+# bench's N-GPU legs (dp_check, weak scaling, strong scaling) for N = 2, 4, 8 as far as the box goes.
+#   usage: bash scripts/gpu_session_multi.sh <tag>
+cd "$(dirname "$0")/.." || exit 1
+tag=${1:-r2m}
+mkdir -p gpurun_out
+O=gpurun_out
+ng=$(python -c "import torch; print(torch.cuda.device_count())")
+echo "GPUs: $ng"
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q --tb=short -p no:cacheprovider -k "data_parallel" > $O/${tag}_tests.log 2>&1
+tail -4 $O/${tag}_tests.log
+timeout 200 python bench.py --steps 100 --warmup 10 --no-cpu-baseline --no-other-algo > $O/${tag}_bench_n1.json 2> $O/${tag}_bench_n1.err
+for n in 2 4 8; do
+  [ $n -le $ng ] || continue
+  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500 + n)) \
+    bench.py --gpus $n --steps 100 --warmup 10 --no-cpu-baseline > $O/${tag}_bench_n$n.json 2> $O/${tag}_bench_n$n.err
+done
+python - <<PY
+import json
+base = None
+for n in (1, 2, 4, 8):
+    try:
+        d = json.load(open("$O/${tag}_bench_n%d.json" % n))
+    except Exception as e:
+        print(n, "no result:", e); continue
+    if n == 1: base = d["value"]
+    st = d.get("strong", {})
+    print("N=%d value %.1f (eff %.3f) ms/step %.4f  strong %.1f upd/s  dp_check %s" % (
+        n, d["value"], d["value"] / (n * base) if base else 0, d["ms_per_step"], st.get("updates_per_sec", 0),
+        d.get("dp_check", {}).get("status")))
+PY
