@@ -85,6 +85,29 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
+// same, observing arrivals from the peer CTA of the cluster (acquire at cluster scope)
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) {
+      printf("recnn_b200: cluster mbarrier wait timed out (block %d,%d,%d thread %d bar %u)\n", blockIdx.x, blockIdx.y,
+             blockIdx.z, threadIdx.x, bar);
+      __trap();
+    }
+  }
+}
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -100,15 +123,42 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// PAIR = the cta_group::2 forms: two CTAs of a cluster (the two SMs of a TPC) run ONE tcgen05.mma over 256 rows;
+// allocation / free are issued by the same warp of BOTH CTAs with the same shared-memory destination offset.
+template <bool PAIR>
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
-               : "memory");
+  if constexpr (PAIR)
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  else
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
 }
+template <bool PAIR>
 __device__ __forceinline__ void tmem_relinquish() {
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if constexpr (PAIR) asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  else asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 }
+template <bool PAIR>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(rank)
+      : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -124,8 +174,15 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
+template <bool PAIR>
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  if constexpr (PAIR) {     // arrives on the barrier at this offset in BOTH CTAs of the pair
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+  } else {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  }
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -181,14 +238,23 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // A operand read from tensor memory (128 lanes = rows, 8 fp32 columns = one k-slice), B from shared memory
+template <bool PAIR>
 __device__ __forceinline__ void mma_tf32_ta(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
                                             uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
+  if constexpr (PAIR)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
 // Programmatic dependent launch: launch_dependents lets the next kernel of the stream
 // be scheduled onto idle SMs while this one still runs; its threads park at griddep_wait() -- after their prologue,
@@ -266,8 +332,18 @@ __device__ __forceinline__ unsigned long long gtimer() {
 #define RECNN_TRACE(slot) do { } while (0)
 #endif
 
-template <int BN_, int STAGES_, bool A_MN_, bool B_MN_>
+// PAIR: two CTAs of a (1,2,1) cluster -- the two SMs of a TPC -- own 256 consecutive rows of C and run ONE
+// tcgen05.mma.cta_group::2 per k-slice: each CTA keeps its own 128 rows of A in its tensor memory and only HALF of
+// the B tile in its shared memory (the tensor cores read the other half from the peer SM).  Per CTA and k-block that
+// halves the TMA write, the split warps' read + two writes and the MMA's three reads of B -- the measured limiter of
+// the single-CTA kernel is shared-memory bandwidth (profiles/README.md r2c: ~100 of 128 B/clk at both tile widths)
+// with the L2->SM fabric close behind.  Protocol: TMA, the full / empty / a_free / acc_full barriers and the drains
+// stay per CTA; the MMA is issued by CTA 0's warp 1 only, whose `split` and `acc_empty` barriers collect the arrivals
+// of BOTH CTAs' workers (the peer arrives remotely), and whose commits are multicast to both CTAs' barriers.
+template <int BN_, int STAGES_, bool A_MN_, bool B_MN_, bool PAIR_ = false>
 struct Cfg {
+  static constexpr bool PAIR = PAIR_;
+  static constexpr int NCTA = PAIR_ ? 2 : 1;
   // BK = 32 (128-byte K-major rows): TMA moves 64-byte rows at half the rate of 128-byte rows (measured:
   // 31 B/clk/SM with BK = 16), and the operand stream is one of the kernel's bottlenecks.
   static constexpr int BM = 128, BN = BN_, BK = 32, STAGES = STAGES_;
@@ -277,7 +353,8 @@ struct Cfg {
   // The split A tile goes to TENSOR memory (tcgen05.st) and the MMA reads it from there, so A costs shared
   // memory one TMA write + one read instead of write + read + 2 writes + 6 MMA reads.
   static constexpr int A_SLOT_COLS = 2 * BK, A_SLOTS = (512 - D_COLS) / A_SLOT_COLS;   // hi | lo per k-block: 2 slots at BN = 128, 5 at BN = 64
-  static constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
+  static constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4 / NCTA;   // B_BYTES: this CTA's share of the B tile
+  static constexpr int BN_LOCAL = BN / NCTA;                       // B rows (n) held by this CTA
   static constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;        // raw A | raw B (split in place into hi) | lo B
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
   // Worker warps come in groups of four (one warp per TMEM lane quarter); the groups take k-blocks round robin.
@@ -409,6 +486,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM, z = blockIdx.z;
+  const uint32_t cta_rank = C::PAIR ? cluster_ctarank() : 0u;          // 0 = the CTA whose warp 1 issues the pair's MMAs
   griddep_launch_dependents();                                // the next kernel of the stream may start its prologue
   if (threadIdx.x == 0) RECNN_TRACE(0);                       // kernel entry
   // k-blocks: segment 0 then segment 1, each padded up to a multiple of BK (TMA zero-fills the tail)
@@ -427,22 +505,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full(s), 1);
-      mbar_init(split(s), 4);                            // one arrive per warp of the group that split the stage
+      mbar_init(split(s), 4 * C::NCTA);                  // one arrive per warp of the group(s) that split the stage
       mbar_init(empty(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(acc_full(b), 1);
-      mbar_init(acc_empty(b), WORKERS);
+      mbar_init(acc_empty(b), WORKERS * C::NCTA);
     }
     for (int i = 0; i < C::A_SLOTS; ++i) mbar_init(a_free(i), 1);
     fence_barrier_init();
   }
   if (warp == 1) {                       // whole warp: TMEM allocation
-    tmem_alloc(tmem_slot, C::TMEM_COLS);
-    tmem_relinquish();
+    tmem_alloc<C::PAIR>(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish<C::PAIR>();
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (C::PAIR) cluster_sync_all();     // both CTAs' barriers are initialised before any remote arrive / multicast commit
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
   griddep_wait();                                             // everything below may touch global memory
@@ -469,25 +548,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           for (int c = 0; c < BM / 32; ++c)                                   // box {32, BK} per 32-wide M chunk
             tma_load_2d(dst_a + c * (BK * 128), ma, full(s), m0 + 32 * c, ka);
         }
+        const int nb = p.b_n_offset + n0 + (int)cta_rank * C::BN_LOCAL;      // PAIR: this CTA's half of the B tile
         if (!C::B_MN) {
-          tma_load_2d(dst_b, &map_b, full(s), kbcol, p.b_n_offset + n0);      // box {BK, BN}
+          tma_load_2d(dst_b, &map_b, full(s), kbcol, nb);                     // box {BK, BN_LOCAL}
         } else {
 #pragma unroll
-          for (int c = 0; c < BN / 32; ++c)
-            tma_load_2d(dst_b + c * (BK * 128), &map_b, full(s), p.b_n_offset + n0 + 32 * c, kbcol);
+          for (int c = 0; c < C::BN_LOCAL / 32; ++c)
+            tma_load_2d(dst_b + c * (BK * 128), &map_b, full(s), nb + 32 * c, kbcol);
         }
       }
       __syncwarp();
       if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1u; }
     }
-  } else if (warp == 1) {
-    // ===================================================== MMA issuer
+  } else if (warp == 1 && cta_rank == 0) {
+    // ===================================================== MMA issuer (PAIR: CTA 0 issues for both SMs)
     // The whole warp walks the pipeline (so every value below is warp-uniform and lives in uniform
     // registers); one elected lane issues the MMAs and commits.  Issuing under `if (lane == 0)` instead makes
     // the compiler wrap every tcgen05 instruction in an ELECT/BRA.U.ANY loop, which made the issue stream,
     // not the tensor pipe, the limiter (~130 clk per MMA against a 64 clk floor).
     // A read from tensor memory is always [M lanes, K columns] = K-major, whatever its layout in global memory.
-    constexpr uint32_t idesc = instr_desc_tf32(BM, BN, false, C::B_MN);
+    constexpr uint32_t idesc = instr_desc_tf32(BM * C::NCTA, BN, false, C::B_MN);
     // K-major B: rows of 128 bytes, LBO unused (1), SBO = 8 rows.  MN-major fp32/tf32 operands must
     // use the 128B_BASE32B layout (cute: "for mn-major tf32 operands, SW128_32B is the only available
     // smem layout"): 128-byte rows of 32 MN elements, swizzle period 4 k-rows => SBO = 512 B between
@@ -501,10 +581,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     const uint32_t d_lo = tmem_base + 2u * BN;               // tile-lifetime accumulator (cross terms)
     for (int i = 0; i < num_kb; ++i) {
       if (kin == 0) {                                        // new chunk: its TMEM buffer must have been drained
-        mbar_wait(acc_empty(buf), buf ? par1 : par0);
+        if constexpr (C::PAIR) mbar_wait_cluster(acc_empty(buf), buf ? par1 : par0);
+        else mbar_wait(acc_empty(buf), buf ? par1 : par0);
         if (buf) par1 ^= 1u; else par0 ^= 1u;
       }
-      mbar_wait(split(s), ph);
+      if constexpr (C::PAIR) mbar_wait_cluster(split(s), ph);
+      else mbar_wait(split(s), ph);
       tc_fence_after();
       if (i == 0 && lane == 0) RECNN_TRACE(2);               // first stage loaded + split
       const uint32_t d_hi = tmem_base + buf * BN;            // chunk accumulator (hi*hi)
@@ -518,13 +600,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           const uint64_t db_lo = db_lo0 + uint64_t((k * b_kstep) >> 4);
           const uint32_t ta_hi = ta0 + k * 8, ta_lo = ta_hi + BK;
           const uint32_t lo_flag = k == 0 ? lo_acc : 1u, hi_flag = k == 0 ? (kin != 0 ? 1u : 0u) : 1u;
-          mma_tf32_ta(d_lo, ta_lo, db_hi, idesc, lo_flag);
-          mma_tf32_ta(d_lo, ta_hi, db_lo, idesc, 1);
-          mma_tf32_ta(d_hi, ta_hi, db_hi, idesc, hi_flag);
+          mma_tf32_ta<C::PAIR>(d_lo, ta_lo, db_hi, idesc, lo_flag);
+          mma_tf32_ta<C::PAIR>(d_lo, ta_hi, db_lo, idesc, 1);
+          mma_tf32_ta<C::PAIR>(d_hi, ta_hi, db_hi, idesc, hi_flag);
         }
-        mma_commit(empty(s));                                // frees the stage once these MMAs have read it
-        mma_commit(a_free(slot));                            // ... and the A slot in tensor memory
-        if (kin == (uint32_t)(CH - 1) || i == num_kb - 1) mma_commit(acc_full(buf));
+        mma_commit<C::PAIR>(empty(s));                       // frees the stage once these MMAs have read it
+        mma_commit<C::PAIR>(a_free(slot));                   // ... and the A slot in tensor memory
+        if (kin == (uint32_t)(CH - 1) || i == num_kb - 1) mma_commit<C::PAIR>(acc_full(buf));
       }
       __syncwarp();
       lo_acc = 1u;
@@ -533,7 +615,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       if (++kin == (uint32_t)CH) { kin = 0; buf ^= 1u; }
     }
     if (lane == 0) RECNN_TRACE(3);                            // last MMA issued
-  } else {
+  } else if (warp >= 2) {
     // ===================================================== workers: split, drain, epilogue
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
     const int g = (warp - 2) >> 2;           // worker group: k-blocks g, g + NG, ...; column slab g of the drain / epilogue
@@ -550,7 +632,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       tmem_accumulate<NC>(lane_base + (uint32_t)buf * BN, acc);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty(buf));
+      if (lane == 0) {
+        if (C::PAIR && cta_rank != 0) mbar_arrive_remote(acc_empty(buf), 0);   // the issuing CTA's barrier
+        else mbar_arrive(acc_empty(buf));
+      }
     };
 
     // The groups take k-blocks round robin, so one group's publish latency (membar + proxy fence +
@@ -625,7 +710,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(split(s));
+      if (lane == 0) {
+        if (C::PAIR && cta_rank != 0) mbar_arrive_remote(split(s), 0);
+        else mbar_arrive(split(s));
+      }
       // after my last k-block of chunk c, chunk c-1 has long been accumulated: drain it
       if ((i + NG) / CH != i / CH)
         while (next_drain < i / CH) drain(next_drain++);
@@ -639,8 +727,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     if (threadIdx.x == 64) RECNN_TRACE(6);                    // epilogue stored
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+  if constexpr (C::PAIR) cluster_sync_all();     // the peer's shared memory / tensor memory are in use until both are done
+  else __syncthreads();
+  if (warp == 1) tmem_dealloc<C::PAIR>(tmem_base, C::TMEM_COLS);
   if (threadIdx.x == 0) RECNN_TRACE(7);
 }
 
