@@ -440,6 +440,8 @@ def run_native(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "WARN"      # NCCL would print its banner on stdout, which carries the ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
     algo = args.algo

@@ -66,6 +66,8 @@ class StepEngine:
         self._flags_host = self.losses_host.view(torch.int32)
         self.rng_step = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.buf = {}
+        self._probes = {}            # net name -> (module, first parameter, last parameter): see _tokens
+        self._params_seen, self._params_version = None, 0
         self.kernels = 0             # kernels of this library launched by this engine (graph replays included)
         self.last_call_kernels = 0
 
@@ -392,33 +394,42 @@ class StepEngine:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
 
     def _tokens(self, nets, optimizer, params, st):
-        """Cheap fingerprint of everything a cached StepArgs / CUDA graph depends on: storage
-        addresses of the nets (first and last parameter), optimizer hyper-parameters, the algorithm's
-        scalars and the staged batch buffers."""
+        """Cheap fingerprint of everything a cached StepArgs / CUDA graph depends on: storage addresses of the nets
+        (first and last parameter, gradient), optimizer hyper-parameters and state arenas, the algorithm's scalars
+        and the staged batch buffers.  This runs on every step between the batch copies and the graph launch, i.e.
+        while the GPU idles, so it avoids nn.Module attribute lookups (the Parameter objects are cached per net) and
+        compares the params dict with one C-level dict comparison."""
         tok = []
+        probes = self._probes
         for name in self.names:
             m = nets[name]
-            w, b = m.linear1.weight, m.linear3.bias
+            pr = probes.get(name)
+            if pr is None or pr[0] is not m:
+                pr = probes[name] = (m, m.linear1.weight, m.linear3.bias)
+            w, b = pr[1], pr[2]
             g = w.grad
-            tok.append((id(m), w.data_ptr(), b.data_ptr(), 0 if g is None else g.data_ptr(), m.training))
-        for k in sorted(optimizer):
+            tok.append((w.data_ptr(), b.data_ptr(), 0 if g is None else g.data_ptr(), m.training))
+        for k in optimizer:
             o = optimizer[k]
             if isinstance(o, _optim._ArenaOptimizer):
                 g = o.param_groups[0]
-                tok.append((id(o), g["lr"], g.get("betas"), g.get("eps"), g["weight_decay"], g.get("momentum"),
+                tok.append((k, id(o), g["lr"], g.get("betas"), g.get("eps"), g["weight_decay"], g.get("momentum"),
                             g.get("alpha"), g.get("k"), g.get("N_sma_threshhold"),
                             0 if o._m is None else o._m.data_ptr(), 0 if o._t is None else o._t.data_ptr()))
             else:
-                tok.append((id(o),))
-        tok.append(tuple(sorted(params.items())) if len(params) < 16 else id(params))
+                tok.append((k, id(o)))
+        if self._params_seen is None or self._params_seen != params:
+            self._params_seen = dict(params)
+            self._params_version += 1
+        tok.append(self._params_version)
         for k in ("table", "items", "ratings", "state", "next_state", "action", "reward", "done", "noise"):
             t = st.get(k)
             tok.append(0 if t is None else t.data_ptr())
         if st["masks"] is not None:
             tok.append(tuple(m.data_ptr() for m in st["masks"]))
         ws = self.buf.get("workspace")
-        tok.append((0 if ws is None else ws.data_ptr(), self.losses.data_ptr(), self.rng_step.data_ptr(),
-                    st["n_global"], self.world, 0 if self.comm is None else self.comm.ptr))
+        tok.append((0 if ws is None else ws.data_ptr(), st["n_global"], self.world,
+                    0 if self.comm is None else self.comm.ptr))
         return tok
 
     def _step(self, batch, params, nets, optimizer, learn, step, debug, policy_every_key):

@@ -16,12 +16,17 @@ for n in 2 4 8; do
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500 + n)) \
     bench.py --gpus $n --steps 100 --warmup 10 --no-cpu-baseline > $O/${tag}_bench_n$n.json 2> $O/${tag}_bench_n$n.err
 done
+for n in 2 4 8; do
+  [ $n -le $ng ] || continue
+  timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29600 + n)) \
+    scripts/bench_comm.py 2> $O/${tag}_comm_n$n.err | tail -1 | tee $O/${tag}_comm_n$n.json
+done
 python - <<PY
 import json
 base = None
 for n in (1, 2, 4, 8):
     try:
-        d = json.load(open("$O/${tag}_bench_n%d.json" % n))
+        d = json.loads(open("$O/${tag}_bench_n%d.json" % n).read().strip().splitlines()[-1])
     except Exception as e:
         print(n, "no result:", e); continue
     if n == 1: base = d["value"]
