@@ -116,7 +116,8 @@ __device__ __forceinline__ void wait_flags(const unsigned* flags, unsigned e, in
 template <int VEC>
 __global__ void __launch_bounds__(kCommThreads, 1)
 allreduce_kernel(CommPeers c, float* __restrict__ buf, long long n, float max_norm, float* coef_out, float* l1_out,
-                 const float* aux_in, float* aux_out, int n_aux, float check_val, int* err_flag, CommOpt opt) {
+                 const float* aux_in, float* aux_out, int n_aux, float check_val, int* err_flag, CommOpt opt,
+                 GradSource src) {
   __shared__ float red[32];
   __shared__ unsigned s_epoch;
   __shared__ bool s_last;
@@ -137,7 +138,15 @@ allreduce_kernel(CommPeers c, float* __restrict__ buf, long long n, float max_no
   for (long long i = tid; i < units; i += nth) {
     const int s = (int)(i / slice);
     V* dst = reinterpret_cast<V*>(c.contrib[s] + ((long long)par * W + c.rank) * c.slice_cap);
-    dst[i - (long long)s * slice] = reinterpret_cast<const V*>(buf)[i];
+    V g;
+    if (src.n_layers) {              // the local gradient is still in split-K partials: reduce them on the way out
+      if constexpr (VEC == 4) g = make_float4(grad_at(src, buf, 4 * i), grad_at(src, buf, 4 * i + 1), grad_at(src, buf, 4 * i + 2),
+                                              grad_at(src, buf, 4 * i + 3));
+      else g = grad_at(src, buf, i);
+    } else {
+      g = reinterpret_cast<const V*>(buf)[i];
+    }
+    dst[i - (long long)s * slice] = g;
   }
   if (blockIdx.x == 0 && (int)threadIdx.x < W) {
     float* dst = c.ctrl[threadIdx.x]->aux[par][c.rank];
@@ -277,6 +286,9 @@ int launch_comm_allreduce(const recnn_comm* comm, float* buf, int64_t n, const C
     opt.wd = r.optim->weight_decay; opt.n_sma_threshold = r.optim->n_sma_threshold; opt.k_look = r.optim->k;
     opt.p = r.net->params; opt.m = r.net->opt_m; opt.v = r.net->opt_v; opt.slow = r.net->opt_slow; opt.t = r.net->opt_t;
   }
+  GradSource gsrc;
+  memset(&gsrc, 0, sizeof(gsrc));
+  if (r.src) gsrc = *r.src;
   const int64_t per = (int64_t)kCommThreads * 4 * 2;              // two float4 per thread
   int64_t blocks = ceil_div(n, per);
   const int grid = (int)(blocks < 1 ? 1 : (blocks > kNumSMs ? kNumSMs : blocks));
@@ -284,10 +296,10 @@ int launch_comm_allreduce(const recnn_comm* comm, float* buf, int64_t n, const C
                    (opt.kind == RECNN_OPT_EXTERNAL || (reinterpret_cast<uintptr_t>(opt.p) & 15) == 0);
   if (vec)
     allreduce_kernel<4><<<grid, kCommThreads, 0, st>>>(comm->peers, buf, n, r.max_norm, r.coef, r.l1_out, r.aux_in,
-                                                        r.aux_out, r.n_aux, r.check_val, r.err_flag, opt);
+                                                        r.aux_out, r.n_aux, r.check_val, r.err_flag, opt, gsrc);
   else
     allreduce_kernel<1><<<grid, kCommThreads, 0, st>>>(comm->peers, buf, n, r.max_norm, r.coef, r.l1_out, r.aux_in,
-                                                        r.aux_out, r.n_aux, r.check_val, r.err_flag, opt);
+                                                        r.aux_out, r.n_aux, r.check_val, r.err_flag, opt, gsrc);
   RECNN_CHECK_LAUNCH("allreduce_kernel");
   return RECNN_OK;
 }

@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(256)
 optimizer_kernel(int kind, OptConsts k, double beta1, double beta2, double lr, double wd, double n_sma_threshold,
                  int k_look, float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
                  float* __restrict__ v, float* __restrict__ slow, int* __restrict__ t_ptr,
-                 const float* __restrict__ grad_scale, long long count, unsigned* ticket) {
+                 const float* __restrict__ grad_scale, long long count, unsigned* ticket, GradSource src) {
   __shared__ OptStep s_st;
   const int t = *t_ptr + 1;
   if (threadIdx.x == 0) s_st = opt_step_scalars(kind, beta1, beta2, lr, wd, n_sma_threshold, k_look, t);
@@ -386,11 +386,9 @@ optimizer_kernel(int kind, OptConsts k, double beta1, double beta2, double lr, d
   const float gs = grad_scale ? *grad_scale : 1.0f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count;
        i += (long long)gridDim.x * blockDim.x) {
-    float grad = g[i];
-    if (grad_scale) {
-      grad = __fmul_rn(grad, gs);
-      g[i] = grad;                      // the reference leaves the scaled grad in .grad
-    }
+    float grad = src.n_layers ? grad_at(src, g, i) : g[i];
+    if (grad_scale) grad = __fmul_rn(grad, gs);
+    if (grad_scale || src.n_layers) g[i] = grad;     // .grad holds what the optimizer consumed (scaled, as the reference leaves it)
     opt_apply(kind, k, st, t, p, m, v, slow, i, grad);
   }
   // ++t by the block that finishes last (every block has read t by then); without a ticket the
@@ -423,7 +421,7 @@ int launch_bump64(long long* t, cudaStream_t st) {
 }
 
 int launch_optimizer(const recnn_optim& o, const recnn_net& net, int64_t count, const float* grad_scale,
-                     cudaStream_t st, unsigned* ticket) {
+                     cudaStream_t st, unsigned* ticket, const GradSource* src) {
   RECNN_REQUIRE(o.kind == RECNN_OPT_SGD || o.kind == RECNN_OPT_ADAM || o.kind == RECNN_OPT_RANGER,
                 "built-in optimizer kind must be SGD, ADAM or RANGER");
   RECNN_REQUIRE(net.params && net.grads && net.opt_t, "optimizer needs params, grads and the step counter");
@@ -431,11 +429,14 @@ int launch_optimizer(const recnn_optim& o, const recnn_net& net, int64_t count, 
   if (o.kind == RECNN_OPT_RANGER) RECNN_REQUIRE(net.opt_m && net.opt_v && net.opt_slow, "Ranger needs exp_avg / exp_avg_sq / slow arenas");
   if (o.kind == RECNN_OPT_SGD && o.momentum != 0.f) RECNN_REQUIRE(net.opt_m, "SGD momentum needs a buffer arena");
   const OptConsts k = opt_consts(o);
+  GradSource gs;
+  memset(&gs, 0, sizeof(gs));
+  if (src) gs = *src;
   const int64_t blocks = ceil_div(count, 256 * 4);
   const int grid = (int)(blocks < 4 * kNumSMs ? (blocks > 0 ? blocks : 1) : 4 * kNumSMs);
   optimizer_kernel<<<grid, 256, 0, st>>>(o.kind, k, o.beta1, o.beta2, o.lr, o.weight_decay, o.n_sma_threshold, o.k,
                                          net.params, net.grads, net.opt_m, net.opt_v, net.opt_slow, net.opt_t,
-                                         grad_scale, count, ticket);
+                                         grad_scale, count, ticket, gs);
   RECNN_CHECK_LAUNCH("optimizer_kernel");
   if (!ticket) {
     bump_counter_kernel<<<1, 1, 0, st>>>(net.opt_t);

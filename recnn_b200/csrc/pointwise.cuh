@@ -4,6 +4,49 @@
 
 namespace recnn {
 
+// ---- where a gradient element comes from -------------------------------------------------------------------
+// The weight-gradient GEMMs leave split-K partials [splits][C][K1] (column K1-1 = the bias gradient, written by the
+// column-sum kernel).  Instead of a reduce kernel per layer followed by the optimizer pass, the optimizer (and the
+// data-parallel all-reduce) read the partials directly: grad_at() sums the splits of the element's layer in a fixed
+// order; elements outside the listed layers (the critic's head, written by the fused value-head kernel) come from
+// the gradient arena itself.  Two launches and one pass over the arena less on the step's serial tail.
+struct PartialLayer {
+  const float* part;       // [splits][C][K1]
+  int splits, C, K1;
+  int ld;                  // row pitch of the weight in the arena
+  long long w_off, b_off;  // arena offsets of the weight [C, ld] and of the bias [C]
+};
+struct GradSource {
+  PartialLayer l[2];
+  int n_layers;            // 0: every element comes from the gradient arena
+};
+#ifdef __CUDACC__
+__device__ __forceinline__ float grad_at(const GradSource& s, const float* __restrict__ direct, long long i) {
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    if (k >= s.n_layers) break;
+    const PartialLayer& L = s.l[k];
+    const long long tot = (long long)L.C * L.K1;
+    if (i >= L.w_off && i < L.w_off + (long long)L.C * L.ld) {
+      const long long e = i - L.w_off;
+      const int r = (int)(e / L.ld), c = (int)(e - (long long)r * L.ld);
+      if (c >= L.K1 - 1) return 0.f;                      // pitch padding
+      float g = 0.f;
+      for (int z = 0; z < L.splits; ++z) g += L.part[(long long)z * tot + (long long)r * L.K1 + c];
+      return g;
+    }
+    if (i >= L.b_off && i < L.b_off + ((L.C + 3) / 4) * 4) {
+      const int r = (int)(i - L.b_off);
+      if (r >= L.C) return 0.f;
+      float g = 0.f;
+      for (int z = 0; z < L.splits; ++z) g += L.part[(long long)z * tot + (long long)r * L.K1 + (L.K1 - 1)];
+      return g;
+    }
+  }
+  return direct[i];
+}
+#endif
+
 enum HeadMode {
   HEAD_PLAIN = 0,        // out[n] = q
   HEAD_TARGET_DDPG = 1,  // y[n] = clamp(r + (1-d)*gamma*q, min, max)            misc.py:30-35
@@ -91,6 +134,7 @@ struct CommReduce {
   int* err_flag = nullptr;
   const recnn_optim* optim = nullptr;
   const recnn_net* net = nullptr;
+  const GradSource* src = nullptr;     // local gradient = split-K partials (see GradSource) instead of `buf`
 };
 int launch_comm_allreduce(const recnn_comm* comm, float* buf, int64_t n, const CommReduce& r, cudaStream_t st);
 
@@ -206,7 +250,7 @@ __device__ __forceinline__ void opt_apply(int kind, const OptConsts& k, const Op
 
 // ticket: zero-initialised self-resetting counter; when given, the kernel itself increments *net.opt_t
 int launch_optimizer(const recnn_optim& o, const recnn_net& net, int64_t count, const float* grad_scale,
-                     cudaStream_t st, unsigned* ticket = nullptr);
+                     cudaStream_t st, unsigned* ticket = nullptr, const GradSource* src = nullptr);
 
 int launch_bump64(long long* t, cudaStream_t st);
 int launch_finish(long long* rng_step, const unsigned* oob, const unsigned* dp_mismatch, float* flags_out,

@@ -275,8 +275,11 @@ struct SideLaunch {        // run the second K-segment's GEMM on `stream`, fork/
   cudaEvent_t fork, join;
 };
 
+// `defer` (with the gradient arena's base): do not reduce the split-K partials here; describe them instead, for the
+// optimizer / all-reduce pass that consumes them directly (GradSource).
 static int weight_grad(const float* dZ, int C, const Seg& x0, const Seg& x1, int64_t n, float* dW, long long ldw,
-                       float* db, float* partial, cudaStream_t st, const SideLaunch* side = nullptr) {
+                       float* db, float* partial, cudaStream_t st, const SideLaunch* side = nullptr,
+                       PartialLayer* defer = nullptr, const float* grads_base = nullptr) {
   const int K = x0.cols + x1.cols - x1.lead, K1 = K + 1;
   Epilogue e = base_epi();
   e.out = partial; e.ldo = K1;
@@ -320,6 +323,10 @@ static int weight_grad(const float* dZ, int C, const Seg& x0, const Seg& x1, int
       RECNN_CHECK_CUDA(cudaStreamWaitEvent(st, side->join, 0));
     }
     if (!colsum_on_side) RECNN_PROPAGATE(launch_colsum_partials(dZ, n, C, k_chunk, splits, partial, K1, st));
+    if (defer) {
+      *defer = PartialLayer{partial, splits, C, K1, (int)ldw, (long long)(dW - grads_base), (long long)(db - grads_base)};
+      return RECNN_OK;
+    }
     return launch_reduce_partials(partial, splits, C, K1, dW, ldw, db, st);
   }
   MatView X = x1.cols ? mat_cat(x0.p + x0.lead, x0.ld, x0.cols - x0.lead, x1.p + x1.lead, x1.ld)
@@ -330,6 +337,10 @@ static int weight_grad(const float* dZ, int C, const Seg& x0, const Seg& x1, int
   const int k_chunk = (int)round_up(ceil_div(n, splits_req), 16);
   const int splits = (int)ceil_div(n, k_chunk);
   RECNN_PROPAGATE((launch_gemm_simt<false, false, EPI_PARTIAL>(mat(dZ, C), X, C, K1, (int)n, splits_req, e, st)));
+  if (defer) {
+    *defer = PartialLayer{partial, splits, C, K1, (int)ldw, (long long)(dW - grads_base), (long long)(db - grads_base)};
+    return RECNN_OK;
+  }
   return launch_reduce_partials(partial, splits, C, K1, dW, ldw, db, st);
 }
 
@@ -348,6 +359,7 @@ struct Ctx {
   float gate;
   AuxStreams* aux;       // non-null: chains V and P run on side streams
   bool v_prefetched, p_prefetched, p_deferred;
+  bool value_opt_done[2];   // critic i was already stepped inside the value-gradient phase (fused with the split-K reduction)
 };
 // words of Workspace::tickets: 0..3 two-level reductions / optimizer step count, 6..7 error bits of the step
 // (zeroed with the tickets at the head of every call that includes RECNN_PH_GATHER or RECNN_PH_VALUE_GRAD)
@@ -391,6 +403,7 @@ static HeadArgs head_args(const Ctx& c, const float* params, const float* h2, in
 
 // ---------------------------------------------------------------- phases
 static int policy_actor_forward(const Ctx& c, cudaStream_t st);
+static int value_opt_one(Ctx& c, int i, const GradSource* src);
 
 static int phase_value_grad(Ctx& c) {
   const recnn_step_args& a = *c.a;
@@ -469,43 +482,62 @@ static int phase_value_grad(Ctx& c) {
       RECNN_PROPAGATE(launch_critic_head_bwd(c.ws.dq, 0.f, P + c.lc.w3, c2, c.gate, dz2, c.n, H, c.st));
     }
     const Seg sc1 = {c1, H, H, 0}, ss = {c.S, S, c.ldS, 0}, sa = {c.ACT, A + c.lead, c.ldA, c.lead};
+    // When this call also runs the built-in optimizer, the split-K partials of layers 1-2 are not reduced by
+    // kernels of their own: the optimizer (or the data-parallel all-reduce) pass sums them (GradSource).
+    const bool fuse_opt = (a.phases & RECNN_PH_VALUE_OPT) && a.value_optim.kind != RECNN_OPT_EXTERNAL;
+    GradSource gs;
+    memset(&gs, 0, sizeof(gs));
+    PartialLayer* d1 = fuse_opt ? &gs.l[0] : nullptr;
+    PartialLayer* d2 = fuse_opt ? &gs.l[1] : nullptr;
     if (c.aux) {
       // dW2 (needs dz2, c1) on the side stream while the main stream back-propagates to dz1;
       // dW1's action segment on a third stream next to its state segment
       RECNN_CHECK_CUDA(cudaEventRecord(c.aux->ev[0], c.st));
       RECNN_CHECK_CUDA(cudaStreamWaitEvent(c.aux->sv, c.aux->ev[0], 0));
-      RECNN_PROPAGATE(weight_grad(dz2, H, sc1, kNoSeg, c.n, G + c.lc.w2, c.lc.ld2, G + c.lc.b2, c.ws.partial2, c.aux->sv));
+      RECNN_PROPAGATE(weight_grad(dz2, H, sc1, kNoSeg, c.n, G + c.lc.w2, c.lc.ld2, G + c.lc.b2, c.ws.partial2, c.aux->sv,
+                                  nullptr, d2, G));
       RECNN_CHECK_CUDA(cudaEventRecord(c.aux->ev[1], c.aux->sv));
       RECNN_PROPAGATE(backprop_hidden(dz2, H, P + c.lc.w2, c.lc.ld2, H, 0, H, c.n, c1, c.gate, dz1, c.st));
       const SideLaunch side = {c.aux->sw, c.aux->ev[2], c.aux->ev[3]};
-      RECNN_PROPAGATE(weight_grad(dz1, H, ss, sa, c.n, G + c.lc.w1, c.lc.ld1, G + c.lc.b1, c.ws.partial, c.st, &side));
+      RECNN_PROPAGATE(weight_grad(dz1, H, ss, sa, c.n, G + c.lc.w1, c.lc.ld1, G + c.lc.b1, c.ws.partial, c.st, &side, d1, G));
       RECNN_CHECK_CUDA(cudaStreamWaitEvent(c.st, c.aux->ev[1], 0));
     } else {
-      RECNN_PROPAGATE(weight_grad(dz2, H, sc1, kNoSeg, c.n, G + c.lc.w2, c.lc.ld2, G + c.lc.b2, c.ws.partial, c.st));
+      RECNN_PROPAGATE(weight_grad(dz2, H, sc1, kNoSeg, c.n, G + c.lc.w2, c.lc.ld2, G + c.lc.b2, c.ws.partial2, c.st,
+                                  nullptr, d2, G));
       RECNN_PROPAGATE(backprop_hidden(dz2, H, P + c.lc.w2, c.lc.ld2, H, 0, H, c.n, c1, c.gate, dz1, c.st));
-      RECNN_PROPAGATE(weight_grad(dz1, H, ss, sa, c.n, G + c.lc.w1, c.lc.ld1, G + c.lc.b1, c.ws.partial, c.st));
+      RECNN_PROPAGATE(weight_grad(dz1, H, ss, sa, c.n, G + c.lc.w1, c.lc.ld1, G + c.lc.b1, c.ws.partial, c.st, nullptr, d1, G));
+    }
+    if (fuse_opt) {
+      gs.n_layers = 2;
+      RECNN_PROPAGATE(value_opt_one(c, i, &gs));
+      c.value_opt_done[i] = true;
     }
   }
   return RECNN_OK;
+}
+
+// the critic's optimizer step (data parallel: all-reduce + optimizer + value-loss sum in one kernel).  `src`: the
+// gradient of layers 1-2 still sits in split-K partials, summed inside this pass instead of by reduce kernels.
+static int value_opt_one(Ctx& c, int i, const GradSource* src) {
+  const recnn_step_args& a = *c.a;
+  if (a.comm) {
+    // data parallel: every rank's shard gradient -> the global-batch gradient over NVLink, the optimizer update
+    // of the reduced gradient and the sum of the ranks' value-loss partial sums, all in ONE kernel
+    CommReduce r;
+    r.aux_in = a.losses + i; r.aux_out = a.losses + i; r.n_aux = 1;
+    r.check_val = (float)a.n_rows_global; r.err_flag = reinterpret_cast<int*>(c.ws.tickets + kTicketDpMismatch);
+    r.optim = &a.value_optim; r.net = &a.value[i]; r.src = src;
+    return launch_comm_allreduce(a.comm, a.value[i].grads, c.lc.count, r, c.st);
+  }
+  return launch_optimizer(a.value_optim, a.value[i], c.lc.count, nullptr, c.st, c.ws.tickets + 3, src);
 }
 
 static int phase_value_opt(Ctx& c) {
   const recnn_step_args& a = *c.a;
   if (!a.learn || a.value_optim.kind == RECNN_OPT_EXTERNAL) return RECNN_OK;
   const int n_critics = a.algo == RECNN_ALGO_TD3 ? 2 : 1;
-  for (int i = 0; i < n_critics; ++i) {
-    if (a.comm) {
-      // data parallel: every rank's shard gradient -> the global-batch gradient over NVLink, the optimizer update
-      // of the reduced gradient and the sum of the ranks' value-loss partial sums, all in ONE kernel
-      CommReduce r;
-      r.aux_in = a.losses + i; r.aux_out = a.losses + i; r.n_aux = 1;
-      r.check_val = (float)a.n_rows_global; r.err_flag = reinterpret_cast<int*>(c.ws.tickets + kTicketDpMismatch);
-      r.optim = &a.value_optim; r.net = &a.value[i];
-      RECNN_PROPAGATE(launch_comm_allreduce(a.comm, a.value[i].grads, c.lc.count, r, c.st));
-    } else {
-      RECNN_PROPAGATE(launch_optimizer(a.value_optim, a.value[i], c.lc.count, nullptr, c.st, c.ws.tickets + 3));
-    }
-  }
+  for (int i = 0; i < n_critics; ++i)
+    if (!c.value_opt_done[i]) RECNN_PROPAGATE(value_opt_one(c, i, nullptr));
   return RECNN_OK;
 }
 
@@ -685,6 +717,7 @@ static int run_step(const recnn_step_args* a, int algo, void* stream) {
   // fork: chain V (online critic forward) and chain P (online policy forward) on side streams
   c.aux = nullptr;
   c.v_prefetched = c.p_prefetched = c.p_deferred = false;
+  c.value_opt_done[0] = c.value_opt_done[1] = false;
   if ((a->phases & RECNN_PH_VALUE_GRAD) && (c.aux = aux_streams()) != nullptr) {
     RECNN_CHECK_CUDA(cudaEventRecord(c.aux->fork, c.st));
     RECNN_CHECK_CUDA(cudaStreamWaitEvent(c.aux->sv, c.aux->fork, 0));
