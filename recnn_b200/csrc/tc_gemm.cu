@@ -84,8 +84,10 @@ static int launch_cfg(const Operand& A0, const Operand& A1, const Operand& B, co
   }
   if (!C::B_MN) RECNN_PROPAGATE(make_tmap(&mb, B.ptr, B.rows, B.cols, B.ld, C::BK, C::BN_LOCAL, C::K_SWZ));
   else RECNN_PROPAGATE(make_tmap(&mb, B.ptr, B.rows, B.cols, B.ld, 32, C::BK, 1032));
-  // PAIR: CTA pairs along M (cluster 1 x 2 x 1); an odd tile count gets one idle-but-participating CTA
-  dim3 grid((unsigned)ceil_div(p.N, C::BN), (unsigned)round_up(ceil_div(p.M, C::BM), C::NCTA), (unsigned)splits);
+  // PAIR: CTA pairs along M, which then runs along grid x (cluster 2 x 1 x 1); an odd tile count gets one
+  // idle-but-participating CTA
+  dim3 grid((unsigned)ceil_div(p.N, C::BN), (unsigned)ceil_div(p.M, C::BM), (unsigned)splits);
+  if (C::PAIR) grid = dim3((unsigned)round_up(ceil_div(p.M, C::BM), 2), (unsigned)ceil_div(p.N, C::BN), (unsigned)splits);
   static const bool debug = getenv("RECNN_B200_DEBUG") != nullptr;
   if (debug)
     fprintf(stderr, "[tc_gemm] BN=%d A_MN=%d B_MN=%d EPI=%d M=%d N=%d K0=%d K1=%d k_chunk=%d bk1=%d nout=%d bn_off=%d "
@@ -108,8 +110,8 @@ static int launch_cfg(const Operand& A0, const Operand& A1, const Operand& B, co
   cfg.numAttrs = 1;
   if (C::PAIR) {
     attr[1].id = cudaLaunchAttributeClusterDimension;
-    attr[1].val.clusterDim.x = 1;
-    attr[1].val.clusterDim.y = 2;
+    attr[1].val.clusterDim.x = 2;
+    attr[1].val.clusterDim.y = 1;
     attr[1].val.clusterDim.z = 1;
     cfg.numAttrs = 2;
   }

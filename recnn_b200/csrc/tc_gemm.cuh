@@ -332,7 +332,7 @@ __device__ __forceinline__ unsigned long long gtimer() {
 #define RECNN_TRACE(slot) do { } while (0)
 #endif
 
-// PAIR: two CTAs of a (1,2,1) cluster -- the two SMs of a TPC -- own 256 consecutive rows of C and run ONE
+// PAIR: two CTAs of a (2,1,1) cluster -- the two SMs of a TPC -- own 256 consecutive rows of C and run ONE
 // tcgen05.mma.cta_group::2 per k-slice: each CTA keeps its own 128 rows of A in its tensor memory and only HALF of
 // the B tile in its shared memory (the tensor cores read the other half from the peer SM).  Per CTA and k-block that
 // halves the TMA write, the split warps' read + two writes and the MMA's three reads of B -- the measured limiter of
@@ -485,7 +485,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM, z = blockIdx.z;
+  // PAIR: the two CTAs of a pair must be neighbours along x (cluster 2 x 1 x 1: a cluster whose x extent is odd is
+  // rejected at launch for kernels that use cta_group::2), so the M tiles run along x there
+  const int n0 = (C::PAIR ? blockIdx.y : blockIdx.x) * BN, m0 = (C::PAIR ? blockIdx.x : blockIdx.y) * BM, z = blockIdx.z;
   const uint32_t cta_rank = C::PAIR ? cluster_ctarank() : 0u;          // 0 = the CTA whose warp 1 issues the pair's MMAs
   griddep_launch_dependents();                                // the next kernel of the stream may start its prologue
   if (threadIdx.x == 0) RECNN_TRACE(0);                       // kernel entry
