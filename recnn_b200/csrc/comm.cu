@@ -140,8 +140,7 @@ allreduce_kernel(CommPeers c, float* __restrict__ buf, long long n, float max_no
     V* dst = reinterpret_cast<V*>(c.contrib[s] + ((long long)par * W + c.rank) * c.slice_cap);
     V g;
     if (src.n_layers) {              // the local gradient is still in split-K partials: reduce them on the way out
-      if constexpr (VEC == 4) g = make_float4(grad_at(src, buf, 4 * i), grad_at(src, buf, 4 * i + 1), grad_at(src, buf, 4 * i + 2),
-                                              grad_at(src, buf, 4 * i + 3));
+      if constexpr (VEC == 4) g = grad4_at(src, buf, (unsigned)(4 * i));
       else g = grad_at(src, buf, i);
     } else {
       g = reinterpret_cast<const V*>(buf)[i];

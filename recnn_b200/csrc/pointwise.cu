@@ -384,12 +384,30 @@ optimizer_kernel(int kind, OptConsts k, double beta1, double beta2, double lr, d
   __syncthreads();
   const OptStep st = s_st;
   const float gs = grad_scale ? *grad_scale : 1.0f;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count;
-       i += (long long)gridDim.x * blockDim.x) {
-    float grad = src.n_layers ? grad_at(src, g, i) : g[i];
-    if (grad_scale) grad = __fmul_rn(grad, gs);
-    if (grad_scale || src.n_layers) g[i] = grad;     // .grad holds what the optimizer consumed (scaled, as the reference leaves it)
-    opt_apply(kind, k, st, t, p, m, v, slow, i, grad);
+  if (src.n_layers) {
+    // gradient still in split-K partials (arena: count % 4 == 0, 16-byte aligned): four elements per thread
+    for (long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i4 < (count >> 2);
+         i4 += (long long)gridDim.x * blockDim.x) {
+      float4 gv = grad4_at(src, g, (unsigned)(4 * i4));
+      if (grad_scale) {
+        gv.x = __fmul_rn(gv.x, gs); gv.y = __fmul_rn(gv.y, gs); gv.z = __fmul_rn(gv.z, gs); gv.w = __fmul_rn(gv.w, gs);
+      }
+      *reinterpret_cast<float4*>(g + 4 * i4) = gv;       // .grad holds what the optimizer consumed
+      opt_apply(kind, k, st, t, p, m, v, slow, 4 * i4 + 0, gv.x);
+      opt_apply(kind, k, st, t, p, m, v, slow, 4 * i4 + 1, gv.y);
+      opt_apply(kind, k, st, t, p, m, v, slow, 4 * i4 + 2, gv.z);
+      opt_apply(kind, k, st, t, p, m, v, slow, 4 * i4 + 3, gv.w);
+    }
+  } else {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+         i += (long long)gridDim.x * blockDim.x) {
+      float grad = g[i];
+      if (grad_scale) {
+        grad = __fmul_rn(grad, gs);
+        g[i] = grad;                      // the reference leaves the scaled grad in .grad
+      }
+      opt_apply(kind, k, st, t, p, m, v, slow, i, grad);
+    }
   }
   // ++t by the block that finishes last (every block has read t by then); without a ticket the
   // launcher appends a one-thread kernel instead
@@ -431,7 +449,10 @@ int launch_optimizer(const recnn_optim& o, const recnn_net& net, int64_t count, 
   const OptConsts k = opt_consts(o);
   GradSource gs;
   memset(&gs, 0, sizeof(gs));
-  if (src) gs = *src;
+  if (src) {
+    RECNN_REQUIRE(count % 4 == 0 && (reinterpret_cast<uintptr_t>(net.grads) & 15) == 0, "partial-sourced gradients need a 16-byte aligned arena");
+    gs = *src;
+  }
   const int64_t blocks = ceil_div(count, 256 * 4);
   const int grid = (int)(blocks < 4 * kNumSMs ? (blocks > 0 ? blocks : 1) : 4 * kNumSMs);
   optimizer_kernel<<<grid, 256, 0, st>>>(o.kind, k, o.beta1, o.beta2, o.lr, o.weight_decay, o.n_sma_threshold, o.k,

@@ -21,29 +21,44 @@ struct GradSource {
   int n_layers;            // 0: every element comes from the gradient arena
 };
 #ifdef __CUDACC__
-__device__ __forceinline__ float grad_at(const GradSource& s, const float* __restrict__ direct, long long i) {
+// four consecutive arena elements starting at i (i % 4 == 0; weight rows and bias segments start on multiples of 4,
+// so the four never straddle a row or a segment).  32-bit index arithmetic: an arena has far fewer than 2^31 elements.
+__device__ __forceinline__ float4 grad4_at(const GradSource& s, const float* __restrict__ direct, unsigned i) {
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
     if (k >= s.n_layers) break;
     const PartialLayer& L = s.l[k];
-    const long long tot = (long long)L.C * L.K1;
-    if (i >= L.w_off && i < L.w_off + (long long)L.C * L.ld) {
-      const long long e = i - L.w_off;
-      const int r = (int)(e / L.ld), c = (int)(e - (long long)r * L.ld);
-      if (c >= L.K1 - 1) return 0.f;                      // pitch padding
-      float g = 0.f;
-      for (int z = 0; z < L.splits; ++z) g += L.part[(long long)z * tot + (long long)r * L.K1 + c];
-      return g;
+    const unsigned tot = (unsigned)L.C * (unsigned)L.K1;
+    const unsigned ew = i - (unsigned)L.w_off, eb = i - (unsigned)L.b_off;
+    if (ew < (unsigned)L.C * (unsigned)L.ld) {
+      const unsigned r = ew / (unsigned)L.ld, c = ew - r * (unsigned)L.ld;
+      const float* p0 = L.part + (size_t)r * L.K1 + c;
+      float g[4] = {0.f, 0.f, 0.f, 0.f};
+      const int valid = (int)(L.K1 - 1) - (int)c;              // columns c .. c+3 that are real weights (the rest: pitch padding)
+      for (int z = 0; z < L.splits; ++z) {
+        const float* p = p0 + (size_t)z * tot;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j < valid) g[j] += p[j];
+      }
+      return make_float4(g[0], g[1], g[2], g[3]);
     }
-    if (i >= L.b_off && i < L.b_off + ((L.C + 3) / 4) * 4) {
-      const int r = (int)(i - L.b_off);
-      if (r >= L.C) return 0.f;
-      float g = 0.f;
-      for (int z = 0; z < L.splits; ++z) g += L.part[(long long)z * tot + (long long)r * L.K1 + (L.K1 - 1)];
-      return g;
+    if (eb < (unsigned)(((L.C + 3) / 4) * 4)) {
+      float g[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int z = 0; z < L.splits; ++z) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (eb + j < (unsigned)L.C) g[j] += L.part[(size_t)z * tot + (size_t)(eb + j) * L.K1 + (L.K1 - 1)];
+      }
+      return make_float4(g[0], g[1], g[2], g[3]);
     }
   }
-  return direct[i];
+  return *reinterpret_cast<const float4*>(direct + i);
+}
+__device__ __forceinline__ float grad_at(const GradSource& s, const float* __restrict__ direct, long long i) {
+  const float4 v = grad4_at(s, direct, (unsigned)(i & ~3ll));
+  const int j = (int)(i & 3);
+  return j == 0 ? v.x : j == 1 ? v.y : j == 2 ? v.z : v.w;
 }
 #endif
 
