@@ -63,6 +63,7 @@ template <class C, int EPI>
 static int launch_cfg(const Operand& A0, const Operand& A1, const Operand& B, const Problem& p_in, int splits,
                       const Epilogue& epi, cudaStream_t st) {
   Problem p = p_in;
+  p.flags = option(OPT_EXPERIMENT) & 3;
   static bool attr_set = false;
   if (!attr_set) {
     RECNN_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<C, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -82,12 +83,9 @@ static int launch_cfg(const Operand& A0, const Operand& A1, const Operand& B, co
     RECNN_PROPAGATE(make_tmap(&ma0, A0.ptr, p.K0, p.M, A0.ld, 32, C::BK, 1032));
     ma1 = ma0;
   }
-  if (!C::B_MN) RECNN_PROPAGATE(make_tmap(&mb, B.ptr, B.rows, B.cols, B.ld, C::BK, C::BN_LOCAL, C::K_SWZ));
+  if (!C::B_MN) RECNN_PROPAGATE(make_tmap(&mb, B.ptr, B.rows, B.cols, B.ld, C::BK, C::BN, C::K_SWZ));
   else RECNN_PROPAGATE(make_tmap(&mb, B.ptr, B.rows, B.cols, B.ld, 32, C::BK, 1032));
-  // PAIR: CTA pairs along M, which then runs along grid x (cluster 2 x 1 x 1); an odd tile count gets one
-  // idle-but-participating CTA
   dim3 grid((unsigned)ceil_div(p.N, C::BN), (unsigned)ceil_div(p.M, C::BM), (unsigned)splits);
-  if (C::PAIR) grid = dim3((unsigned)round_up(ceil_div(p.M, C::BM), 2), (unsigned)ceil_div(p.N, C::BN), (unsigned)splits);
   static const bool debug = getenv("RECNN_B200_DEBUG") != nullptr;
   if (debug)
     fprintf(stderr, "[tc_gemm] BN=%d A_MN=%d B_MN=%d EPI=%d M=%d N=%d K0=%d K1=%d k_chunk=%d bk1=%d nout=%d bn_off=%d "
@@ -103,18 +101,11 @@ static int launch_cfg(const Operand& A0, const Operand& A1, const Operand& B, co
   cfg.blockDim = dim3(C::THREADS, 1, 1);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (C::PAIR) {
-    attr[1].id = cudaLaunchAttributeClusterDimension;
-    attr[1].val.clusterDim.x = 2;
-    attr[1].val.clusterDim.y = 1;
-    attr[1].val.clusterDim.z = 1;
-    cfg.numAttrs = 2;
-  }
   RECNN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<C, EPI>, ma0, ma1, mb, p, epi));
   RECNN_CHECK_LAUNCH("tc_gemm_kernel");
   if (debug) {
@@ -132,12 +123,6 @@ template <bool A_MN, bool B_MN, int EPI>
 int launch(const Operand& A0, const Operand& A1, const Operand& B, const Problem& p, int splits, int bn,
            const Epilogue& epi, cudaStream_t st) {
   // stages chosen to fill ~190 KB of shared memory: stage = 16 KB (raw A) + 2 * BN/8 KB (B hi | B lo)
-  // CTA pairs (cta_group::2) when there are at least two M tiles; opt-in (`experiment` bit 0) until validated on hardware
-  const bool pair = (option(OPT_EXPERIMENT) & 1) != 0 && ceil_div(p.M, 128) >= 2;
-  if (pair) {            // stage = 16 KB (raw A) + 2 * BN/16 KB (this CTA's half of B: hi | lo)
-    if (bn >= 128) return launch_cfg<Cfg<128, 6, A_MN, B_MN, true>, EPI>(A0, A1, B, p, splits, epi, st);
-    return launch_cfg<Cfg<64, 8, A_MN, B_MN, true>, EPI>(A0, A1, B, p, splits, epi, st);
-  }
   if (bn >= 128) return launch_cfg<Cfg<128, 4, A_MN, B_MN>, EPI>(A0, A1, B, p, splits, epi, st);
   return launch_cfg<Cfg<64, 6, A_MN, B_MN>, EPI>(A0, A1, B, p, splits, epi, st);
 }

@@ -85,29 +85,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
-// same, observing arrivals from the peer CTA of the cluster (acquire at cluster scope)
-__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.b32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait_cluster(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait_cluster(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) {
-      printf("recnn_b200: cluster mbarrier wait timed out (block %d,%d,%d thread %d bar %u)\n", blockIdx.x, blockIdx.y,
-             blockIdx.z, threadIdx.x, bar);
-      __trap();
-    }
-  }
-}
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -123,42 +100,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
-// PAIR = the cta_group::2 forms: two CTAs of a cluster (the two SMs of a TPC) run ONE tcgen05.mma over 256 rows;
-// allocation / free are issued by the same warp of BOTH CTAs with the same shared-memory destination offset.
-template <bool PAIR>
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-  if constexpr (PAIR)
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-  else
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
+               : "memory");
 }
-template <bool PAIR>
 __device__ __forceinline__ void tmem_relinquish() {
-  if constexpr (PAIR) asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-  else asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 }
-template <bool PAIR>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-  else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
-  asm volatile(
-      "{\n\t.reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
-      ::"r"(bar), "r"(rank)
-      : "memory");
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -174,15 +124,8 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
-template <bool PAIR>
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
-  if constexpr (PAIR) {     // arrives on the barrier at this offset in BOTH CTAs of the pair
-    const uint16_t mask = 3;
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(bar), "h"(mask) : "memory");
-  } else {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-  }
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -238,23 +181,14 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // A operand read from tensor memory (128 lanes = rows, 8 fp32 columns = one k-slice), B from shared memory
-template <bool PAIR>
 __device__ __forceinline__ void mma_tf32_ta(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
                                             uint32_t accumulate) {
-  if constexpr (PAIR)
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-  else
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 // Programmatic dependent launch: launch_dependents lets the next kernel of the stream
 // be scheduled onto idle SMs while this one still runs; its threads park at griddep_wait() -- after their prologue,
@@ -313,6 +247,7 @@ struct Problem {
   int n_out_offset;      // column offset added when storing (C window)
   int b_n_offset;        // B's n coordinate of output column 0 (window into a wider B, e.g. W1[:, S:S+A])
   int n_skip;            // the first n_skip output columns are computed but not stored (operand lead pads)
+  int flags;             // experiments: bit 0 look-ahead barrier polls in the MMA warp, bit 1 two alternating MMA-issue warps
 #ifdef RECNN_TC_INSTRUMENT
   unsigned long long* trace;   // per-CTA %globaltimer stamps (8 per CTA): instrumented builds only
 #endif
@@ -332,18 +267,8 @@ __device__ __forceinline__ unsigned long long gtimer() {
 #define RECNN_TRACE(slot) do { } while (0)
 #endif
 
-// PAIR: two CTAs of a (2,1,1) cluster -- the two SMs of a TPC -- own 256 consecutive rows of C and run ONE
-// tcgen05.mma.cta_group::2 per k-slice: each CTA keeps its own 128 rows of A in its tensor memory and only HALF of
-// the B tile in its shared memory (the tensor cores read the other half from the peer SM).  Per CTA and k-block that
-// halves the TMA write, the split warps' read + two writes and the MMA's three reads of B -- the measured limiter of
-// the single-CTA kernel is shared-memory bandwidth (profiles/README.md r2c: ~100 of 128 B/clk at both tile widths)
-// with the L2->SM fabric close behind.  Protocol: TMA, the full / empty / a_free / acc_full barriers and the drains
-// stay per CTA; the MMA is issued by CTA 0's warp 1 only, whose `split` and `acc_empty` barriers collect the arrivals
-// of BOTH CTAs' workers (the peer arrives remotely), and whose commits are multicast to both CTAs' barriers.
-template <int BN_, int STAGES_, bool A_MN_, bool B_MN_, bool PAIR_ = false>
+template <int BN_, int STAGES_, bool A_MN_, bool B_MN_>
 struct Cfg {
-  static constexpr bool PAIR = PAIR_;
-  static constexpr int NCTA = PAIR_ ? 2 : 1;
   // BK = 32 (128-byte K-major rows): TMA moves 64-byte rows at half the rate of 128-byte rows (measured:
   // 31 B/clk/SM with BK = 16), and the operand stream is one of the kernel's bottlenecks.
   static constexpr int BM = 128, BN = BN_, BK = 32, STAGES = STAGES_;
@@ -353,15 +278,14 @@ struct Cfg {
   // The split A tile goes to TENSOR memory (tcgen05.st) and the MMA reads it from there, so A costs shared
   // memory one TMA write + one read instead of write + read + 2 writes + 6 MMA reads.
   static constexpr int A_SLOT_COLS = 2 * BK, A_SLOTS = (512 - D_COLS) / A_SLOT_COLS;   // hi | lo per k-block: 2 slots at BN = 128, 5 at BN = 64
-  static constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4 / NCTA;   // B_BYTES: this CTA's share of the B tile
-  static constexpr int BN_LOCAL = BN / NCTA;                       // B rows (n) held by this CTA
+  static constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;        // raw A | raw B (split in place into hi) | lo B
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
   // Worker warps come in groups of four (one warp per TMEM lane quarter); the groups take k-blocks round robin.
   // 64-wide tiles run four groups (their A ring in tensor memory has five slots), 128-wide tiles two.
   static constexpr int WORKERS = BN == 64 ? 16 : 8;
   static constexpr int COLS_PER_WORKER = BN / (WORKERS / 4);       // register-resident running sum per thread
-  static constexpr int THREADS = 64 + 32 * WORKERS;
+  static constexpr int THREADS = 96 + 32 * WORKERS;                // TMA warp, two MMA-issue warps, workers
   static constexpr int TMEM_COLS = 512;                            // D_hi chunk x2 | D_lo | A ring
   static constexpr int A_COL0 = D_COLS;
   static constexpr int K_SWZ = BK * 4;                             // K-major rows: 128 B (SWIZZLE_128B)
@@ -480,15 +404,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   auto acc_full = [&](int b) { return bars + 8u * (3 * STAGES + b); };       // MMA -> workers
   auto acc_empty = [&](int b) { return bars + 8u * (3 * STAGES + 2 + b); };  // workers -> MMA
   auto a_free = [&](int i) { return bars + 8u * (3 * STAGES + 4 + i); };    // MMA -> workers (A TMEM ring)
-  const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 4 + C::A_SLOTS);
+  auto turn = [&](int x) { return bars + 8u * (3 * STAGES + 4 + C::A_SLOTS + x); };   // MMA warp x may issue (two-issuer mode)
+  const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 6 + C::A_SLOTS);
   volatile uint32_t* tmem_slot_gen =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // PAIR: the two CTAs of a pair must be neighbours along x (cluster 2 x 1 x 1: a cluster whose x extent is odd is
-  // rejected at launch for kernels that use cta_group::2), so the M tiles run along x there
-  const int n0 = (C::PAIR ? blockIdx.y : blockIdx.x) * BN, m0 = (C::PAIR ? blockIdx.x : blockIdx.y) * BM, z = blockIdx.z;
-  const uint32_t cta_rank = C::PAIR ? cluster_ctarank() : 0u;          // 0 = the CTA whose warp 1 issues the pair's MMAs
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM, z = blockIdx.z;
   griddep_launch_dependents();                                // the next kernel of the stream may start its prologue
   if (threadIdx.x == 0) RECNN_TRACE(0);                       // kernel entry
   // k-blocks: segment 0 then segment 1, each padded up to a multiple of BK (TMA zero-fills the tail)
@@ -507,23 +429,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full(s), 1);
-      mbar_init(split(s), 4 * C::NCTA);                  // one arrive per warp of the group(s) that split the stage
+      mbar_init(split(s), 4);                            // one arrive per warp of the group that split the stage
       mbar_init(empty(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(acc_full(b), 1);
-      mbar_init(acc_empty(b), WORKERS * C::NCTA);
+      mbar_init(acc_full(b), (p.flags & 2) ? 2 : 1);        // one commit per MMA-issue warp
+      mbar_init(acc_empty(b), WORKERS);
     }
     for (int i = 0; i < C::A_SLOTS; ++i) mbar_init(a_free(i), 1);
+    mbar_init(turn(0), 1);
+    mbar_init(turn(1), 1);
     fence_barrier_init();
   }
   if (warp == 1) {                       // whole warp: TMEM allocation
-    tmem_alloc<C::PAIR>(tmem_slot, C::TMEM_COLS);
-    tmem_relinquish<C::PAIR>();
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
   }
   tc_fence_before();
-  if constexpr (C::PAIR) cluster_sync_all();     // both CTAs' barriers are initialised before any remote arrive / multicast commit
-  else __syncthreads();
+  __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
   griddep_wait();                                             // everything below may touch global memory
@@ -550,78 +473,102 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           for (int c = 0; c < BM / 32; ++c)                                   // box {32, BK} per 32-wide M chunk
             tma_load_2d(dst_a + c * (BK * 128), ma, full(s), m0 + 32 * c, ka);
         }
-        const int nb = p.b_n_offset + n0 + (int)cta_rank * C::BN_LOCAL;      // PAIR: this CTA's half of the B tile
         if (!C::B_MN) {
-          tma_load_2d(dst_b, &map_b, full(s), kbcol, nb);                     // box {BK, BN_LOCAL}
+          tma_load_2d(dst_b, &map_b, full(s), kbcol, p.b_n_offset + n0);      // box {BK, BN}
         } else {
 #pragma unroll
-          for (int c = 0; c < C::BN_LOCAL / 32; ++c)
-            tma_load_2d(dst_b + c * (BK * 128), &map_b, full(s), nb + 32 * c, kbcol);
+          for (int c = 0; c < BN / 32; ++c)
+            tma_load_2d(dst_b + c * (BK * 128), &map_b, full(s), p.b_n_offset + n0 + 32 * c, kbcol);
         }
       }
       __syncwarp();
       if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1u; }
     }
-  } else if (warp == 1 && cta_rank == 0) {
-    // ===================================================== MMA issuer (PAIR: CTA 0 issues for both SMs)
+  } else if (warp == 1 || warp == 2) {
+    // ===================================================== MMA issuer(s)
     // The whole warp walks the pipeline (so every value below is warp-uniform and lives in uniform
     // registers); one elected lane issues the MMAs and commits.  Issuing under `if (lane == 0)` instead makes
     // the compiler wrap every tcgen05 instruction in an ELECT/BRA.U.ANY loop, which made the issue stream,
     // not the tensor pipe, the limiter (~130 clk per MMA against a 64 clk floor).
     // A read from tensor memory is always [M lanes, K columns] = K-major, whatever its layout in global memory.
-    constexpr uint32_t idesc = instr_desc_tf32(BM * C::NCTA, BN, false, C::B_MN);
+    //
+    // Two-issuer mode (flags bit 1): measured on the single-issuer kernel (profiles/README.md r2b/r2c), a k-block costs
+    // ~(500 clk of loop overhead -- barrier polls at ~90 clk each, descriptor arithmetic in the uniform datapath) PLUS the
+    // pipe time of its 12 MMAs, because the tensor core's instruction queue is too shallow to keep the pipe busy across
+    // the overhead.  With two warps taking alternate k-blocks, one warp's polls and arithmetic for k-block i+1 run while
+    // the other issues k-block i; a `turn` barrier hands the issue slot over (tcgen05.fence::before_thread_sync ->
+    // arrive -> wait -> fence::after_thread_sync orders the two threads' MMAs), and both warps commit to acc_full.
+    constexpr uint32_t idesc = instr_desc_tf32(BM, BN, false, C::B_MN);
     // K-major B: rows of 128 bytes, LBO unused (1), SBO = 8 rows.  MN-major fp32/tf32 operands must
     // use the 128B_BASE32B layout (cute: "for mn-major tf32 operands, SW128_32B is the only available
     // smem layout"): 128-byte rows of 32 MN elements, swizzle period 4 k-rows => SBO = 512 B between
     // 4-row groups, LBO = pitch between 32-element MN chunks (BK rows * 128 B).
     constexpr uint64_t b_base = C::B_MN ? smem_desc_base(BK * 128, 512, 1) : smem_desc_base(16, 8 * C::K_SWZ, 2);
     constexpr uint32_t b_kstep = C::B_MN ? 1024 : 32;        // bytes to advance per 8-wide k-slice
-    const bool leader = elect_one();
-    // running counters: stage / phase, A slot, position in the chunk and its buffer, per-buffer wait parity
-    uint32_t s = 0, ph = 0, slot = 0, kin = 0, buf = 0, par0 = 1, par1 = 1;
-    uint32_t lo_acc = 0;                                     // 0 only for the very first cross-term MMAs
-    const uint32_t d_lo = tmem_base + 2u * BN;               // tile-lifetime accumulator (cross terms)
-    for (int i = 0; i < num_kb; ++i) {
-      if (kin == 0) {                                        // new chunk: its TMEM buffer must have been drained
-        if constexpr (C::PAIR) mbar_wait_cluster(acc_empty(buf), buf ? par1 : par0);
-        else mbar_wait(acc_empty(buf), buf ? par1 : par0);
-        if (buf) par1 ^= 1u; else par0 ^= 1u;
-      }
-      if constexpr (C::PAIR) mbar_wait_cluster(split(s), ph);
-      else mbar_wait(split(s), ph);
-      tc_fence_after();
-      if (i == 0 && lane == 0) RECNN_TRACE(2);               // first stage loaded + split
-      const uint32_t d_hi = tmem_base + buf * BN;            // chunk accumulator (hi*hi)
-      const uint64_t db_hi0 = b_base | uint64_t((stage_addr(s, 1) & 0x3FFFF) >> 4);
-      const uint64_t db_lo0 = b_base | uint64_t((stage_addr(s, 2) & 0x3FFFF) >> 4);
-      const uint32_t ta0 = tmem_base + C::A_COL0 + slot * C::A_SLOT_COLS;
-      if (leader) {
-#pragma unroll
-        for (int k = 0; k < BK / 8; ++k) {
-          const uint64_t db_hi = db_hi0 + uint64_t((k * b_kstep) >> 4);
-          const uint64_t db_lo = db_lo0 + uint64_t((k * b_kstep) >> 4);
-          const uint32_t ta_hi = ta0 + k * 8, ta_lo = ta_hi + BK;
-          const uint32_t lo_flag = k == 0 ? lo_acc : 1u, hi_flag = k == 0 ? (kin != 0 ? 1u : 0u) : 1u;
-          mma_tf32_ta<C::PAIR>(d_lo, ta_lo, db_hi, idesc, lo_flag);
-          mma_tf32_ta<C::PAIR>(d_lo, ta_hi, db_lo, idesc, 1);
-          mma_tf32_ta<C::PAIR>(d_hi, ta_hi, db_hi, idesc, hi_flag);
+    const bool two = (p.flags & 2) != 0, lookahead = (p.flags & 1) != 0;
+    const int me = warp - 1;                                 // issuer index
+    const int step = two ? 2 : 1;
+    if (me == 0 || two) {
+      const bool leader = elect_one();
+      const uint32_t d_lo = tmem_base + 2u * BN;             // tile-lifetime accumulator (cross terms)
+      bool ready = false;                                    // split barrier of the current k-block already seen complete
+      for (int i = me; i < num_kb; i += step) {
+        const uint32_t s = (uint32_t)i % STAGES, ph = ((uint32_t)i / STAGES) & 1u;
+        const uint32_t slot = (uint32_t)i % C::A_SLOTS;
+        const uint32_t kin = (uint32_t)i % CH, chunk = (uint32_t)i / CH, buf = chunk & 1u;
+        if (kin == 0)                                        // new chunk: its TMEM buffer must have been drained
+          mbar_wait(acc_empty(buf), ((chunk >> 1) & 1u) ^ 1u);
+        if (!ready) mbar_wait(split(s), ph);
+        // my k-block i follows the other warp's k-block i-1: its (i-1)/2-th hand-over on my turn barrier
+        if (two && i > 0) mbar_wait(turn(me), (((uint32_t)i - 1u) >> 1) & 1u);
+        tc_fence_after();
+        if (i == 0 && lane == 0) RECNN_TRACE(2);             // first stage loaded + split
+        bool ready_next = false;
+        if (lookahead && i + step < num_kb) {                // poll the next k-block's barrier now: its latency hides behind the issue below
+          const uint32_t i2 = (uint32_t)(i + step);
+          ready_next = mbar_try_wait(split(i2 % STAGES), (i2 / STAGES) & 1u);
         }
-        mma_commit<C::PAIR>(empty(s));                       // frees the stage once these MMAs have read it
-        mma_commit<C::PAIR>(a_free(slot));                   // ... and the A slot in tensor memory
-        if (kin == (uint32_t)(CH - 1) || i == num_kb - 1) mma_commit<C::PAIR>(acc_full(buf));
+        const uint32_t d_hi = tmem_base + buf * BN;          // chunk accumulator (hi*hi)
+        const uint64_t db_hi0 = b_base | uint64_t((stage_addr(s, 1) & 0x3FFFF) >> 4);
+        const uint64_t db_lo0 = b_base | uint64_t((stage_addr(s, 2) & 0x3FFFF) >> 4);
+        const uint32_t ta0 = tmem_base + C::A_COL0 + slot * C::A_SLOT_COLS;
+        if (leader) {
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {
+            const uint64_t db_hi = db_hi0 + uint64_t((k * b_kstep) >> 4);
+            const uint64_t db_lo = db_lo0 + uint64_t((k * b_kstep) >> 4);
+            const uint32_t ta_hi = ta0 + k * 8, ta_lo = ta_hi + BK;
+            const uint32_t lo_flag = (k == 0 && i == 0) ? 0u : 1u, hi_flag = (k == 0 && kin == 0) ? 0u : 1u;
+            mma_tf32_ta(d_lo, ta_lo, db_hi, idesc, lo_flag);
+            mma_tf32_ta(d_lo, ta_hi, db_lo, idesc, 1);
+            mma_tf32_ta(d_hi, ta_hi, db_hi, idesc, hi_flag);
+          }
+          mma_commit(empty(s));                              // frees the stage once these MMAs have read it
+          mma_commit(a_free(slot));                          // ... and the A slot in tensor memory
+          const bool last_of_chunk = kin == (uint32_t)(CH - 1) || i == num_kb - 1;
+          if (two) {
+            // every issuer that put MMAs into this chunk commits once; the issuer of the tile's last k-block also
+            // commits for a partner that had no k-block in the (short) last chunk
+            mma_commit(acc_full(buf));
+            if (i == num_kb - 1 && kin == 0) mma_commit(acc_full(buf));
+          } else if (last_of_chunk) {
+            mma_commit(acc_full(buf));
+          }
+        }
+        __syncwarp();
+        if (two && i + 1 < num_kb) {                         // hand the issue slot to the other warp
+          tc_fence_before();
+          if (lane == 0) mbar_arrive(turn(me ^ 1));
+        }
+        ready = ready_next;
       }
-      __syncwarp();
-      lo_acc = 1u;
-      if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1u; }
-      if (++slot == (uint32_t)C::A_SLOTS) slot = 0;
-      if (++kin == (uint32_t)CH) { kin = 0; buf ^= 1u; }
+      if (lane == 0 && me == 0) RECNN_TRACE(3);               // last MMA issued (issuer 0)
     }
-    if (lane == 0) RECNN_TRACE(3);                            // last MMA issued
-  } else if (warp >= 2) {
+  } else {
     // ===================================================== workers: split, drain, epilogue
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
-    const int g = (warp - 2) >> 2;           // worker group: k-blocks g, g + NG, ...; column slab g of the drain / epilogue
-    const int tg = (threadIdx.x - 64) & 127; // index among the 128 threads of the group
+    const int g = (warp - 3) >> 2;           // worker group: k-blocks g, g + NG, ...; column slab g of the drain / epilogue
+    const int tg = (threadIdx.x - 96) & 127; // index among the 128 threads of the group
     float acc[NC];
 #pragma unroll
     for (int j = 0; j < NC; ++j) acc[j] = 0.f;
@@ -634,10 +581,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       tmem_accumulate<NC>(lane_base + (uint32_t)buf * BN, acc);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
-        if (C::PAIR && cta_rank != 0) mbar_arrive_remote(acc_empty(buf), 0);   // the issuing CTA's barrier
-        else mbar_arrive(acc_empty(buf));
-      }
+      if (lane == 0) mbar_arrive(acc_empty(buf));
     };
 
     // The groups take k-blocks round robin, so one group's publish latency (membar + proxy fence +
@@ -712,26 +656,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
-        if (C::PAIR && cta_rank != 0) mbar_arrive_remote(split(s), 0);
-        else mbar_arrive(split(s));
-      }
+      if (lane == 0) mbar_arrive(split(s));
       // after my last k-block of chunk c, chunk c-1 has long been accumulated: drain it
       if ((i + NG) / CH != i / CH)
         while (next_drain < i / CH) drain(next_drain++);
     }
-    if (threadIdx.x == 64) RECNN_TRACE(4);                    // last stage split
+    if (threadIdx.x == 96) RECNN_TRACE(4);                    // last stage split
     while (next_drain < num_chunks) drain(next_drain++);      // the last full chunk (and a trailing partial one)
-    if (threadIdx.x == 64) RECNN_TRACE(5);                    // all chunks drained (MMAs complete)
+    if (threadIdx.x == 96) RECNN_TRACE(5);                    // all chunks drained (MMAs complete)
     if (num_kb > 0)   // the commit behind the last acc_full covers every MMA issued before it, D_lo's included
       tmem_accumulate<NC>(lane_base + 2u * BN, acc);
     epilogue_row<EPI, NC>(epi, p, m0 + 32 * q + lane, n0 + g * NC, z, acc);
-    if (threadIdx.x == 64) RECNN_TRACE(6);                    // epilogue stored
+    if (threadIdx.x == 96) RECNN_TRACE(6);                    // epilogue stored
   }
   tc_fence_before();
-  if constexpr (C::PAIR) cluster_sync_all();     // the peer's shared memory / tensor memory are in use until both are done
-  else __syncthreads();
-  if (warp == 1) tmem_dealloc<C::PAIR>(tmem_base, C::TMEM_COLS);
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
   if (threadIdx.x == 0) RECNN_TRACE(7);
 }
 
