@@ -63,7 +63,6 @@ template <class C, int EPI>
 static int launch_cfg(const Operand& A0, const Operand& A1, const Operand& B, const Problem& p_in, int splits,
                       const Epilogue& epi, cudaStream_t st) {
   Problem p = p_in;
-  p.flags = option(OPT_EXPERIMENT) & 3;
   static bool attr_set = false;
   if (!attr_set) {
     RECNN_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<C, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,

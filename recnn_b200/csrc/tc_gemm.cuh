@@ -42,6 +42,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "gemm_simt.cuh"   // Epilogue struct + EpiKind
 
@@ -247,7 +249,6 @@ struct Problem {
   int n_out_offset;      // column offset added when storing (C window)
   int b_n_offset;        // B's n coordinate of output column 0 (window into a wider B, e.g. W1[:, S:S+A])
   int n_skip;            // the first n_skip output columns are computed but not stored (operand lead pads)
-  int flags;             // experiments: bit 0 look-ahead barrier polls in the MMA warp, bit 1 two alternating MMA-issue warps
 #ifdef RECNN_TC_INSTRUMENT
   unsigned long long* trace;   // per-CTA %globaltimer stamps (8 per CTA): instrumented builds only
 #endif
@@ -433,7 +434,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       mbar_init(empty(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(acc_full(b), (p.flags & 2) ? 2 : 1);        // one commit per MMA-issue warp
+      mbar_init(acc_full(b), 2);                            // one commit per MMA-issue warp
       mbar_init(acc_empty(b), WORKERS);
     }
     for (int i = 0; i < C::A_SLOTS; ++i) mbar_init(a_free(i), 1);
@@ -492,10 +493,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     // not the tensor pipe, the limiter (~130 clk per MMA against a 64 clk floor).
     // A read from tensor memory is always [M lanes, K columns] = K-major, whatever its layout in global memory.
     //
-    // Two-issuer mode (flags bit 1): measured on the single-issuer kernel (profiles/README.md r2b/r2c), a k-block costs
+    // Two issuers: measured on the single-issuer kernel (profiles/README.md r2b/r2c), a k-block costs
     // ~(500 clk of loop overhead -- barrier polls at ~90 clk each, descriptor arithmetic in the uniform datapath) PLUS the
     // pipe time of its 12 MMAs, because the tensor core's instruction queue is too shallow to keep the pipe busy across
-    // the overhead.  With two warps taking alternate k-blocks, one warp's polls and arithmetic for k-block i+1 run while
+    // the overhead.  With two warps (1 and 2) taking alternate k-blocks, one warp's polls and arithmetic for k-block i+1 run while
     // the other issues k-block i; a `turn` barrier hands the issue slot over (tcgen05.fence::before_thread_sync ->
     // arrive -> wait -> fence::after_thread_sync orders the two threads' MMAs), and both warps commit to acc_full.
     constexpr uint32_t idesc = instr_desc_tf32(BM, BN, false, C::B_MN);
@@ -505,29 +506,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     // 4-row groups, LBO = pitch between 32-element MN chunks (BK rows * 128 B).
     constexpr uint64_t b_base = C::B_MN ? smem_desc_base(BK * 128, 512, 1) : smem_desc_base(16, 8 * C::K_SWZ, 2);
     constexpr uint32_t b_kstep = C::B_MN ? 1024 : 32;        // bytes to advance per 8-wide k-slice
-    const bool two = (p.flags & 2) != 0, lookahead = (p.flags & 1) != 0;
-    const int me = warp - 1;                                 // issuer index
-    const int step = two ? 2 : 1;
-    if (me == 0 || two) {
+    // Each of the two warps keeps running counters for ITS k-blocks (me, me + 2, ...): no division, no modulo --
+    // every instruction in this loop sits between two tensor-core instructions (with index arithmetic instead of
+    // counters the same kernel was 26% slower, profiles/r2f).  CH = 2, so issuer 0 always opens a chunk (waits for its
+    // drained buffer, overwrites with its first hi*hi MMA) and issuer 1 always closes it.
+    static_assert(CH == 2 && STAGES % 2 == 0, "the two-issuer schedule assumes two k-blocks per chunk and an even ring");
+    auto issue = [&](auto me_c) {
+      constexpr int ME = decltype(me_c)::value;
       const bool leader = elect_one();
       const uint32_t d_lo = tmem_base + 2u * BN;             // tile-lifetime accumulator (cross terms)
-      bool ready = false;                                    // split barrier of the current k-block already seen complete
-      for (int i = me; i < num_kb; i += step) {
-        const uint32_t s = (uint32_t)i % STAGES, ph = ((uint32_t)i / STAGES) & 1u;
-        const uint32_t slot = (uint32_t)i % C::A_SLOTS;
-        const uint32_t kin = (uint32_t)i % CH, chunk = (uint32_t)i / CH, buf = chunk & 1u;
-        if (kin == 0)                                        // new chunk: its TMEM buffer must have been drained
-          mbar_wait(acc_empty(buf), ((chunk >> 1) & 1u) ^ 1u);
-        if (!ready) mbar_wait(split(s), ph);
-        // my k-block i follows the other warp's k-block i-1: its (i-1)/2-th hand-over on my turn barrier
-        if (two && i > 0) mbar_wait(turn(me), (((uint32_t)i - 1u) >> 1) & 1u);
-        tc_fence_after();
-        if (i == 0 && lane == 0) RECNN_TRACE(2);             // first stage loaded + split
-        bool ready_next = false;
-        if (lookahead && i + step < num_kb) {                // poll the next k-block's barrier now: its latency hides behind the issue below
-          const uint32_t i2 = (uint32_t)(i + step);
-          ready_next = mbar_try_wait(split(i2 % STAGES), (i2 / STAGES) & 1u);
+      uint32_t s = ME, ph = 0, slot = ME, buf = 0, par0 = 1, par1 = 1, tpar = 0;
+      for (int i = ME; i < num_kb; i += 2) {
+        if (ME == 0) {                                       // new chunk: its TMEM buffer must have been drained
+          mbar_wait(acc_empty(buf), buf ? par1 : par0);
+          if (buf) par1 ^= 1u; else par0 ^= 1u;
         }
+        mbar_wait(split(s), ph);
+        if (i > 0) {                                         // my k-block follows the other warp's k-block i - 1
+          mbar_wait(turn(ME), tpar);
+          tpar ^= 1u;
+        }
+        tc_fence_after();
+        if (ME == 0 && i == 0 && lane == 0) RECNN_TRACE(2);  // first stage loaded + split
         const uint32_t d_hi = tmem_base + buf * BN;          // chunk accumulator (hi*hi)
         const uint64_t db_hi0 = b_base | uint64_t((stage_addr(s, 1) & 0x3FFFF) >> 4);
         const uint64_t db_lo0 = b_base | uint64_t((stage_addr(s, 2) & 0x3FFFF) >> 4);
@@ -538,32 +538,33 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             const uint64_t db_hi = db_hi0 + uint64_t((k * b_kstep) >> 4);
             const uint64_t db_lo = db_lo0 + uint64_t((k * b_kstep) >> 4);
             const uint32_t ta_hi = ta0 + k * 8, ta_lo = ta_hi + BK;
-            const uint32_t lo_flag = (k == 0 && i == 0) ? 0u : 1u, hi_flag = (k == 0 && kin == 0) ? 0u : 1u;
+            const uint32_t lo_flag = (ME == 0 && k == 0 && i == 0) ? 0u : 1u, hi_flag = (ME == 0 && k == 0) ? 0u : 1u;
             mma_tf32_ta(d_lo, ta_lo, db_hi, idesc, lo_flag);
             mma_tf32_ta(d_lo, ta_hi, db_lo, idesc, 1);
             mma_tf32_ta(d_hi, ta_hi, db_hi, idesc, hi_flag);
           }
           mma_commit(empty(s));                              // frees the stage once these MMAs have read it
           mma_commit(a_free(slot));                          // ... and the A slot in tensor memory
-          const bool last_of_chunk = kin == (uint32_t)(CH - 1) || i == num_kb - 1;
-          if (two) {
-            // every issuer that put MMAs into this chunk commits once; the issuer of the tile's last k-block also
-            // commits for a partner that had no k-block in the (short) last chunk
-            mma_commit(acc_full(buf));
-            if (i == num_kb - 1 && kin == 0) mma_commit(acc_full(buf));
-          } else if (last_of_chunk) {
-            mma_commit(acc_full(buf));
-          }
+          // acc_full collects one commit per issuer (a commit covers the issuing thread's MMAs only); the issuer of a
+          // tile's last k-block also commits for a partner that has no k-block in the (short) last chunk
+          mma_commit(acc_full(buf));
+          if (ME == 0 && i == num_kb - 1) mma_commit(acc_full(buf));
         }
         __syncwarp();
-        if (two && i + 1 < num_kb) {                         // hand the issue slot to the other warp
+        if (i + 1 < num_kb) {                                // hand the issue slot to the other warp
           tc_fence_before();
-          if (lane == 0) mbar_arrive(turn(me ^ 1));
+          if (lane == 0) mbar_arrive(turn(ME ^ 1));
         }
-        ready = ready_next;
+        s += 2;
+        if (s >= (uint32_t)STAGES) { s -= (uint32_t)STAGES; ph ^= 1u; }
+        slot += 2;
+        if (slot >= (uint32_t)C::A_SLOTS) slot -= (uint32_t)C::A_SLOTS;
+        buf ^= 1u;
       }
-      if (lane == 0 && me == 0) RECNN_TRACE(3);               // last MMA issued (issuer 0)
-    }
+      if (ME == 0 && lane == 0) RECNN_TRACE(3);               // last MMA issued by issuer 0
+    };
+    if (warp == 1) issue(std::integral_constant<int, 0>{});
+    else issue(std::integral_constant<int, 1>{});
   } else {
     // ===================================================== workers: split, drain, epilogue
     const int q = warp & 3;                  // TMEM lane quarter this warp may access

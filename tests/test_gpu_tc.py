@@ -126,23 +126,3 @@ def test_tile_shapes_are_bit_identical(M, N, K, a_mn, b_mn):
     got128, _ = _run("tc", M, N, K, a_mn, b_mn, seed=3, tile_n=128)
     assert np.array_equal(got64, got128)
     assert np.abs(got64 - ref).max() / np.abs(ref).max() < 2e-6
-
-
-# ----------------------------------------------------------------------------- MMA-issue experiments keep the bits
-@pytest.mark.parametrize("ex", [1, 2, 3])
-@pytest.mark.parametrize("tile_n", [64, 128])
-@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (True, True)])
-@pytest.mark.parametrize("M,N,K", [(128, 64, 32), (128, 256, 64), (128, 256, 96), (300, 256, 1290), (4096, 256, 1290),
-                                   (1000, 100, 77), (256, 1290, 4096)])
-def test_issue_experiments_are_bit_identical(M, N, K, a_mn, b_mn, tile_n, ex):
-    """`experiment` bit 0 (look-ahead barrier polls) and bit 1 (two alternating MMA-issue warps) only change WHO issues
-    the tensor-core instructions and when the barriers are polled: the products and their accumulation order are the
-    same, so the results must be bit-identical (K = 32 / 64 / 96: one, two and three k-blocks -- an idle second issuer,
-    a full chunk, a short last chunk)."""
-    base, ref = _run("tc", M, N, K, a_mn, b_mn, seed=13, tile_n=tile_n)
-    prev = _lib.set_option("experiment", ex)
-    try:
-        got, _ = _run("tc", M, N, K, a_mn, b_mn, seed=13, tile_n=tile_n)
-    finally:
-        _lib.set_option("experiment", prev)
-    assert np.array_equal(got, base)
