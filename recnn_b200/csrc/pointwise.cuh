@@ -35,11 +35,20 @@ __device__ __forceinline__ float4 grad4_at(const GradSource& s, const float* __r
       const float* p0 = L.part + (size_t)r * L.K1 + c;
       float g[4] = {0.f, 0.f, 0.f, 0.f};
       const int valid = (int)(L.K1 - 1) - (int)c;              // columns c .. c+3 that are real weights (the rest: pitch padding)
-      for (int z = 0; z < L.splits; ++z) {
-        const float* p = p0 + (size_t)z * tot;
+      // eight splits per round with all their loads issued before the first add (the serial tail of the step waits
+      // for this pass: a load-add chain per split made it latency-bound)
+      for (int z0 = 0; z0 < L.splits; z0 += 8) {
+        float v[8][4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (j < valid) g[j] += p[j];
+        for (int u = 0; u < 8; ++u) {
+          const float* p = p0 + (size_t)(z0 + u) * tot;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[u][j] = (z0 + u < L.splits && j < valid) ? p[j] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) g[j] += v[u][j];
       }
       return make_float4(g[0], g[1], g[2], g[3]);
     }

@@ -93,9 +93,9 @@ struct Workspace {
 // The tensor-core kernel holds one CTA per SM and has a fixed cost of several microseconds, so more CTAs than SMs
 // means a second wave of the whole fixed cost (measured in round 1: the critic's dW1 as 22+4 tiles x 8 splits = 208
 // CTAs took 48 us = two waves); aim at ONE wave of ~132 CTAs, leaving room for the GEMM that runs beside it.
-static int dw_splits(int C, int K, int64_t n_rows, bool tc_path) {
+static int dw_splits(int C, int K, int64_t n_rows, bool tc_path, int bn = 128) {
   if (tc_path) {
-    const int64_t tiles = ceil_div(C, 128) * ceil_div(K, 128);
+    const int64_t tiles = ceil_div(C, 128) * ceil_div(K, bn);
     int64_t s = 132 / tiles > 0 ? 132 / tiles : 1;
     const int64_t max_s = ceil_div(n_rows, 32) / 4 > 0 ? ceil_div(n_rows, 32) / 4 : 1;   // >= 4 k-blocks (128 rows) per split
     if (s > max_s) s = max_s;
@@ -286,7 +286,7 @@ static int weight_grad(const float* dZ, int C, const Seg& x0, const Seg& x1, int
   const bool tc_ok = math_tc() && C % 4 == 0 && C >= 32 && aligned16(dZ) && aligned16(x0.p) && x0.ld % 4 == 0 &&
                      x0.lead == 0 && (x1.cols == 0 || (aligned16(x1.p) && x1.ld % 4 == 0));
   if (tc_ok) {
-    const int req = dw_splits(C, K, n, true);
+    const int req = dw_splits(C, K, n, true, (option(OPT_EXPERIMENT) & 1) ? 64 : 128);
     int k_chunk = 0;
     const int splits = tc::split_plan((int)ceil_div(n, 32), req, &k_chunk, 32);
     tc::Operand a0 = {dZ, C, 0, 0}, a1 = {nullptr, 0, 0, 0};
@@ -306,7 +306,7 @@ static int weight_grad(const float* dZ, int C, const Seg& x0, const Seg& x1, int
       tc::Problem p;
       memset(&p, 0, sizeof(p));
       p.M = C; p.N = s->cols; p.K0 = (int)n; p.n_out_offset = cols0[i]; p.n_skip = i == 0 ? x1.lead : 0;
-      const int bn = s->cols > 64 ? 128 : 64;
+      const int bn = (s->cols > 64 && !(option(OPT_EXPERIMENT) & 1)) ? 128 : 64;     // experiment bit 0: 64-wide dW tiles
       const int r = tc::launch<true, true, EPI_PARTIAL>(a0, a1, b, p, req, bn, e, (i == 0 && use_side) ? side->stream : st);
       if (r < 0) return r;
       if (r != splits) {

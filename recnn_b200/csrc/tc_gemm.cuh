@@ -286,7 +286,11 @@ struct Cfg {
   // 64-wide tiles run four groups (their A ring in tensor memory has five slots), 128-wide tiles two.
   static constexpr int WORKERS = BN == 64 ? 16 : 8;
   static constexpr int COLS_PER_WORKER = BN / (WORKERS / 4);       // register-resident running sum per thread
-  static constexpr int THREADS = 96 + 32 * WORKERS;                // TMA warp, two MMA-issue warps, workers
+  // MMA-issue warps: 64-wide tiles run two that take alternate k-blocks (their MMAs are short, 32 clk of pipe each, so
+  // the issue loop's overhead is what the pipe waits for: -3% with two issuers), 128-wide tiles one (measured 4%
+  // slower with two: the hand-over costs more than the overlap gains when every MMA keeps the pipe busy for 64 clk)
+  static constexpr int ISSUERS = BN == 64 ? 2 : 1;
+  static constexpr int THREADS = 96 + 32 * WORKERS;                // TMA warp, two MMA-issue warp slots, workers
   static constexpr int TMEM_COLS = 512;                            // D_hi chunk x2 | D_lo | A ring
   static constexpr int A_COL0 = D_COLS;
   static constexpr int K_SWZ = BK * 4;                             // K-major rows: 128 B (SWIZZLE_128B)
@@ -434,7 +438,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       mbar_init(empty(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(acc_full(b), 2);                            // one commit per MMA-issue warp
+      mbar_init(acc_full(b), C::ISSUERS);                   // one commit per MMA-issue warp
       mbar_init(acc_empty(b), WORKERS);
     }
     for (int i = 0; i < C::A_SLOTS; ++i) mbar_init(a_free(i), 1);
@@ -510,19 +514,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     // every instruction in this loop sits between two tensor-core instructions (with index arithmetic instead of
     // counters the same kernel was 26% slower, profiles/r2f).  CH = 2, so issuer 0 always opens a chunk (waits for its
     // drained buffer, overwrites with its first hi*hi MMA) and issuer 1 always closes it.
-    static_assert(CH == 2 && STAGES % 2 == 0, "the two-issuer schedule assumes two k-blocks per chunk and an even ring");
+    static_assert(CH == 2 && STAGES % 2 == 0, "the issue schedules assume two k-blocks per chunk and an even ring");
+    constexpr int NI = C::ISSUERS;                           // k-blocks ME, ME + NI, ... belong to issuer ME
     auto issue = [&](auto me_c) {
       constexpr int ME = decltype(me_c)::value;
       const bool leader = elect_one();
       const uint32_t d_lo = tmem_base + 2u * BN;             // tile-lifetime accumulator (cross terms)
-      uint32_t s = ME, ph = 0, slot = ME, buf = 0, par0 = 1, par1 = 1, tpar = 0;
-      for (int i = ME; i < num_kb; i += 2) {
-        if (ME == 0) {                                       // new chunk: its TMEM buffer must have been drained
+      uint32_t s = ME, ph = 0, slot = ME, kin = ME, buf = 0, par0 = 1, par1 = 1, tpar = 0;
+      for (int i = ME; i < num_kb; i += NI) {
+        if (kin == 0) {                                      // new chunk: its TMEM buffer must have been drained
           mbar_wait(acc_empty(buf), buf ? par1 : par0);
           if (buf) par1 ^= 1u; else par0 ^= 1u;
         }
         mbar_wait(split(s), ph);
-        if (i > 0) {                                         // my k-block follows the other warp's k-block i - 1
+        if (NI == 2 && i > 0) {                              // my k-block follows the other warp's k-block i - 1
           mbar_wait(turn(ME), tpar);
           tpar ^= 1u;
         }
@@ -538,33 +543,42 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             const uint64_t db_hi = db_hi0 + uint64_t((k * b_kstep) >> 4);
             const uint64_t db_lo = db_lo0 + uint64_t((k * b_kstep) >> 4);
             const uint32_t ta_hi = ta0 + k * 8, ta_lo = ta_hi + BK;
-            const uint32_t lo_flag = (ME == 0 && k == 0 && i == 0) ? 0u : 1u, hi_flag = (ME == 0 && k == 0) ? 0u : 1u;
+            const uint32_t lo_flag = (ME == 0 && k == 0 && i == 0) ? 0u : 1u, hi_flag = (k == 0 && kin == 0) ? 0u : 1u;
             mma_tf32_ta(d_lo, ta_lo, db_hi, idesc, lo_flag);
             mma_tf32_ta(d_lo, ta_hi, db_lo, idesc, 1);
             mma_tf32_ta(d_hi, ta_hi, db_hi, idesc, hi_flag);
           }
           mma_commit(empty(s));                              // frees the stage once these MMAs have read it
           mma_commit(a_free(slot));                          // ... and the A slot in tensor memory
-          // acc_full collects one commit per issuer (a commit covers the issuing thread's MMAs only); the issuer of a
-          // tile's last k-block also commits for a partner that has no k-block in the (short) last chunk
-          mma_commit(acc_full(buf));
-          if (ME == 0 && i == num_kb - 1) mma_commit(acc_full(buf));
+          if (NI == 2) {
+            // acc_full collects one commit per issuer (a commit covers the issuing thread's MMAs only); the issuer of a
+            // tile's last k-block also commits for a partner that has no k-block in the (short) last chunk
+            mma_commit(acc_full(buf));
+            if (ME == 0 && i == num_kb - 1) mma_commit(acc_full(buf));
+          } else if (kin == (uint32_t)(CH - 1) || i == num_kb - 1) {
+            mma_commit(acc_full(buf));
+          }
         }
         __syncwarp();
-        if (i + 1 < num_kb) {                                // hand the issue slot to the other warp
+        if (NI == 2 && i + 1 < num_kb) {                     // hand the issue slot to the other warp
           tc_fence_before();
           if (lane == 0) mbar_arrive(turn(ME ^ 1));
         }
-        s += 2;
+        s += NI;
         if (s >= (uint32_t)STAGES) { s -= (uint32_t)STAGES; ph ^= 1u; }
-        slot += 2;
+        slot += NI;
         if (slot >= (uint32_t)C::A_SLOTS) slot -= (uint32_t)C::A_SLOTS;
-        buf ^= 1u;
+        if (NI == 2) {
+          buf ^= 1u;                                         // kin stays ME: issuer 0 opens every chunk, issuer 1 closes it
+        } else if (++kin == (uint32_t)CH) {
+          kin = 0;
+          buf ^= 1u;
+        }
       }
       if (ME == 0 && lane == 0) RECNN_TRACE(3);               // last MMA issued by issuer 0
     };
     if (warp == 1) issue(std::integral_constant<int, 0>{});
-    else issue(std::integral_constant<int, 1>{});
+    else if (NI == 2) issue(std::integral_constant<int, 1>{});
   } else {
     // ===================================================== workers: split, drain, epilogue
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
