@@ -286,7 +286,7 @@ static int weight_grad(const float* dZ, int C, const Seg& x0, const Seg& x1, int
   const bool tc_ok = math_tc() && C % 4 == 0 && C >= 32 && aligned16(dZ) && aligned16(x0.p) && x0.ld % 4 == 0 &&
                      x0.lead == 0 && (x1.cols == 0 || (aligned16(x1.p) && x1.ld % 4 == 0));
   if (tc_ok) {
-    const int req = dw_splits(C, K, n, true, (option(OPT_EXPERIMENT) & 1) ? 64 : 128);
+    const int req = dw_splits(C, K, n, true);
     int k_chunk = 0;
     const int splits = tc::split_plan((int)ceil_div(n, 32), req, &k_chunk, 32);
     tc::Operand a0 = {dZ, C, 0, 0}, a1 = {nullptr, 0, 0, 0};
@@ -306,7 +306,7 @@ static int weight_grad(const float* dZ, int C, const Seg& x0, const Seg& x1, int
       tc::Problem p;
       memset(&p, 0, sizeof(p));
       p.M = C; p.N = s->cols; p.K0 = (int)n; p.n_out_offset = cols0[i]; p.n_skip = i == 0 ? x1.lead : 0;
-      const int bn = (s->cols > 64 && !(option(OPT_EXPERIMENT) & 1)) ? 128 : 64;     // experiment bit 0: 64-wide dW tiles
+      const int bn = s->cols > 64 ? 128 : 64;
       const int r = tc::launch<true, true, EPI_PARTIAL>(a0, a1, b, p, req, bn, e, (i == 0 && use_side) ? side->stream : st);
       if (r < 0) return r;
       if (r != splits) {
@@ -484,7 +484,8 @@ static int phase_value_grad(Ctx& c) {
     const Seg sc1 = {c1, H, H, 0}, ss = {c.S, S, c.ldS, 0}, sa = {c.ACT, A + c.lead, c.ldA, c.lead};
     // When this call also runs the built-in optimizer, the split-K partials of layers 1-2 are not reduced by
     // kernels of their own: the optimizer (or the data-parallel all-reduce) pass sums them (GradSource).
-    const bool fuse_opt = (a.phases & RECNN_PH_VALUE_OPT) && a.value_optim.kind != RECNN_OPT_EXTERNAL;
+    const bool fuse_opt = (a.phases & RECNN_PH_VALUE_OPT) && a.value_optim.kind != RECNN_OPT_EXTERNAL &&
+                          !(option(OPT_EXPERIMENT) & 1);        // experiment bit 0: separate reduce kernels (A/B)
     GradSource gs;
     memset(&gs, 0, sizeof(gs));
     PartialLayer* d1 = fuse_opt ? &gs.l[0] : nullptr;

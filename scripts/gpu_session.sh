@@ -28,7 +28,7 @@ except Exception as e:
     print("bench failed:", e); print(open("$O/${tag}_bench.err").read()[-2000:])
 PY
 
-el "3. experiment A/B (bit 0: 64-wide tiles for the weight-gradient GEMMs)"
+el "3. experiment A/B (bit 0: separate split-K reduce kernels instead of the fused optimizer pass)"
 for ex in 1; do
   RECNN_B200_EXPERIMENT=$ex timeout 400 python -m pytest tests/test_gpu_tc.py tests/test_gpu_parity.py -m gpu -q --tb=line -p no:cacheprovider \
     -k "not tight and not full_size" > $O/${tag}_tests_exp$ex.log 2>&1
