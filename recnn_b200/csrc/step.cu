@@ -42,7 +42,7 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 struct AuxStreams {
   cudaStream_t sv, sp, sw;
   cudaEvent_t fork, v_done, p_done;
-  cudaEvent_t ev[6];       // fork/join pairs for the concurrent weight-gradient GEMMs
+  cudaEvent_t ev[9];       // fork/join pairs: 0-3 weight-gradient GEMMs, 4 chain P, 5-8 TD3's second critic
   bool ok;
 };
 static AuxStreams* aux_streams() {
@@ -75,7 +75,7 @@ struct Workspace {
   float* S2;       // [N, ldS]
   float* ACT;      // [N, ldA] batch action, stored with `lead` zero columns in front (see Seg)
   float* REW;      // [N]
-  float* hb[8];    // [N,H] activation / gradient buffers (lifetimes in DESIGN.md)
+  float* hb[12];   // [N,H] activation / gradient buffers (lifetimes in DESIGN.md); 8..11: TD3's second critic (target hidden, online hidden)
   float* ab[3];    // [N, ldA] next_action / gen_action (lead-padded) ; [N,A] d gen_action
   float* y;        // [N] TD target
   float* qtmp;     // [N]
@@ -358,7 +358,7 @@ struct Ctx {
   bool train;
   float gate;
   AuxStreams* aux;       // non-null: chains V and P run on side streams
-  bool v_prefetched, p_prefetched, p_deferred;
+  bool v_prefetched, p_prefetched, p_deferred, v1_prefetched;
   bool value_opt_done[2];   // critic i was already stepped inside the value-gradient phase (fused with the split-K reduction)
 };
 // words of Workspace::tickets: 0..3 two-level reductions / optimizer step count, 6..7 error bits of the step
@@ -433,12 +433,27 @@ static int phase_value_grad(Ctx& c) {
     RECNN_CHECK_CUDA(cudaMemcpy2DAsync(a.next_action_out, (size_t)A * 4, a2 + c.lead, c.ldA * 4, (size_t)A * 4, c.n,
                                        cudaMemcpyDeviceToDevice, c.st));
 
-  // target critic(s) -> TD target y (misc.py:29-35 / td3.py:80-86)
+  // target critic(s) -> TD target y (misc.py:29-35 / td3.py:80-86).  TD3: the second target critic's hidden layers run
+  // on a side stream into their own buffers, beside the first's; the two heads (min of the two Q's) follow in order.
+  const bool tc1_side = td3 && c.aux != nullptr;
+  float *T0 = c.ws.hb[8], *T1 = c.ws.hb[9];
+  if (tc1_side) {
+    RECNN_CHECK_CUDA(cudaEventRecord(c.aux->ev[6], c.st));              // next_action is ready
+    RECNN_CHECK_CUDA(cudaStreamWaitEvent(c.aux->sw, c.aux->ev[6], 0));
+    RECNN_PROPAGATE(critic_hidden(c, a.target_value[1].params, c.S2, a2, false, 0, T0, T1, c.aux->sw));
+    RECNN_CHECK_CUDA(cudaEventRecord(c.aux->ev[7], c.aux->sw));
+  }
   for (int i = 0; i < n_critics; ++i) {
-    AloneScope alone(c.aux != nullptr && !c.p_prefetched);   // alone unless chain P runs alongside
-    RECNN_PROPAGATE(critic_hidden(c, a.target_value[i].params, c.S2, a2, false, 0, X0, X1, c.st));
+    AloneScope alone(c.aux != nullptr && !c.p_prefetched && !tc1_side);   // alone unless another chain runs alongside
+    float* th2 = X1;
+    if (i == 1 && tc1_side) {
+      RECNN_CHECK_CUDA(cudaStreamWaitEvent(c.st, c.aux->ev[7], 0));
+      th2 = T1;
+    } else {
+      RECNN_PROPAGATE(critic_hidden(c, a.target_value[i].params, c.S2, a2, false, 0, X0, X1, c.st));
+    }
     if (fuse_head && !td3) continue;       // DDPG: the TD target is formed inside the fused value-head kernel
-    HeadArgs h = head_args(c, a.target_value[i].params, X1,
+    HeadArgs h = head_args(c, a.target_value[i].params, th2,
                            td3 ? (i == 0 ? HEAD_TARGET_TD3_A : HEAD_TARGET_TD3_B) : HEAD_TARGET_DDPG);
     RECNN_PROPAGATE(launch_critic_head(h, c.st));
   }
@@ -446,7 +461,11 @@ static int phase_value_grad(Ctx& c) {
   // online critic(s): value, loss, backward (misc.py:37-43 / td3.py:88-101)
   for (int i = 0; i < n_critics; ++i) {
     const float* P = a.value[i].params;
-    if (i == 0 && c.v_prefetched) {
+    if (i == 1 && c.v1_prefetched) {        // the second critic's forward ran on its own stream into its own buffers
+      c1 = c.ws.hb[10];
+      c2 = c.ws.hb[11];
+      RECNN_CHECK_CUDA(cudaStreamWaitEvent(c.st, c.aux->ev[5], 0));
+    } else if (i == 0 && c.v_prefetched) {
       RECNN_CHECK_CUDA(cudaStreamWaitEvent(c.st, c.aux->v_done, 0));      // chain V ran on the side stream
     } else {
       RECNN_PROPAGATE(critic_hidden(c, P, c.S, c.ACT, c.train, 2 * i, c1, c2, c.st));
@@ -717,7 +736,7 @@ static int run_step(const recnn_step_args* a, int algo, void* stream) {
   }
   // fork: chain V (online critic forward) and chain P (online policy forward) on side streams
   c.aux = nullptr;
-  c.v_prefetched = c.p_prefetched = c.p_deferred = false;
+  c.v_prefetched = c.p_prefetched = c.p_deferred = c.v1_prefetched = false;
   c.value_opt_done[0] = c.value_opt_done[1] = false;
   if ((a->phases & RECNN_PH_VALUE_GRAD) && (c.aux = aux_streams()) != nullptr) {
     RECNN_CHECK_CUDA(cudaEventRecord(c.aux->fork, c.st));
@@ -725,6 +744,13 @@ static int run_step(const recnn_step_args* a, int algo, void* stream) {
     RECNN_PROPAGATE(critic_hidden(c, a->value[0].params, c.S, c.ACT, c.train, 0, c.ws.hb[2], c.ws.hb[3], c.aux->sv));
     RECNN_CHECK_CUDA(cudaEventRecord(c.aux->v_done, c.aux->sv));
     c.v_prefetched = true;
+    if (a->algo == RECNN_ALGO_TD3) {
+      // TD3's second online critic: forward on a third stream into its own buffers (td3.py:88-89 for value_net2)
+      RECNN_CHECK_CUDA(cudaStreamWaitEvent(c.aux->sw, c.aux->fork, 0));
+      RECNN_PROPAGATE(critic_hidden(c, a->value[1].params, c.S, c.ACT, c.train, 2, c.ws.hb[10], c.ws.hb[11], c.aux->sw));
+      RECNN_CHECK_CUDA(cudaEventRecord(c.aux->ev[5], c.aux->sw));
+      c.v1_prefetched = true;
+    }
     // chain P is forked later (after the target policy's hidden layers, see phase_value_grad): three
     // concurrent layer-1 GEMMs are 192 CTAs = two waves on 148 SMs, two are one wave
     c.p_deferred = (a->phases & RECNN_PH_POLICY_LOSS) != 0;
