@@ -51,6 +51,7 @@ struct CommDev {                       // lives at the head of every rank's shar
   unsigned arrive_a, arrive_b, done;   // CTA counters (wrap to 0)                     (local)
   unsigned pad[12];
   float aux[2][kMaxRanks][kMaxAux + 1];           // [e & 1][src]: aux floats, then the row count src assumed
+  unsigned long long aux_ll[2][kMaxRanks][kMaxAux + 1];   // the same for scalar-only exchanges: {value, epoch} words
   float l1[2][kMaxRanks][kNumSMs];                // [e & 1][src][cta]: partial L1 norms of src's reduced slice
 };
 
@@ -100,15 +101,23 @@ __device__ __forceinline__ void st_relaxed_sys(unsigned* p, unsigned v) {
 // and counted by then): ONE system-scope fence, then W relaxed flag stores issued by W different threads in parallel.
 // (r2m8 measured what W sequential st.release.sys from one thread cost: each release drains the thread's outstanding
 // remote stores again -- 31 us per collective at W = 4 and 47 us at W = 8 for a 16-byte payload.)
-__device__ __forceinline__ void raise_flags(unsigned* const* flag_ptrs_unused, CommPeers& c, bool phase_b, unsigned e) {
-  (void)flag_ptrs_unused;
-  if (threadIdx.x == 0) __threadfence_system();
-  __syncthreads();
+__device__ __forceinline__ void raise_flags(CommPeers& c, bool phase_b, unsigned e) {
   if ((int)threadIdx.x < c.world) {
     __threadfence_system();
     CommDev* peer = c.ctrl[threadIdx.x];
     st_relaxed_sys(phase_b ? &peer->flag_b[c.rank] : &peer->flag_a[c.rank], e);
   }
+}
+// "LL" words of the scalar-only exchange: {value, epoch} travel in ONE 8-byte store, so the receiver polls the
+// payload itself and no fence or flag is needed (NCCL's low-latency protocol, for 36 bytes per peer)
+__device__ __forceinline__ void st_ll(unsigned long long* p, float v, unsigned e) {
+  const unsigned long long w = ((unsigned long long)e << 32) | (unsigned long long)__float_as_uint(v);
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_ll(const unsigned long long* p) {
+  unsigned long long w;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+  return w;
 }
 // threads [0, world) poll one peer's flag each; bounded
 __device__ __forceinline__ void wait_flags(const unsigned* flags, unsigned e, int world, int rank, const char* what) {
@@ -148,6 +157,39 @@ allreduce_kernel(CommPeers c, float* __restrict__ buf, long long n, float max_no
   const long long units = n / VEC;                               // VEC == 4 => n % 4 == 0
   const long long slice = (units + W - 1) / W;                   // units per owner (the last slice may be short)
 
+  if (n == 0) {
+    // ---- scalar-only exchange (one CTA): LL words to every peer, poll my own copies, sum in rank order.  One NVLink
+    // write latency end to end; no fences, no flags.
+    const int nw = n_aux + 1;
+    if ((int)threadIdx.x < W) {
+      unsigned long long* dst = c.ctrl[threadIdx.x]->aux_ll[par][c.rank];
+      for (int j = 0; j < n_aux; ++j) st_ll(dst + j, aux_in[j], e);
+      st_ll(dst + n_aux, check_val, e);
+      const unsigned long long* mine = me->aux_ll[par][threadIdx.x];
+      const unsigned long long t0 = comm_gtimer();
+      for (int j = 0; j < nw; ++j) {
+        while ((unsigned)(ld_ll(mine + j) >> 32) != e) {
+          if (comm_gtimer() - t0 > 20000000000ull) {
+            printf("recnn_b200 scalar exchange: rank %d timed out waiting for rank %d (epoch %u)\n", c.rank, (int)threadIdx.x, e);
+            __trap();
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      bool bad = false;
+      for (int p = 0; p < W; ++p) bad = bad || __uint_as_float((unsigned)ld_ll(&me->aux_ll[par][p][n_aux])) != check_val;
+      if (bad && err_flag) *err_flag = 1;
+      for (int j = 0; j < n_aux; ++j) {
+        float t = 0.f;
+        for (int p = 0; p < W; ++p) t += __uint_as_float((unsigned)ld_ll(&me->aux_ll[par][p][j]));
+        aux_out[j] = t;
+      }
+      *((volatile unsigned*)&me->epoch) = e;
+    }
+    return;
+  }
   // ---- A: push slice s of my gradient to owner s (remote stores), aux floats to everyone
   for (long long i = tid; i < units; i += nth) {
     const int s = (int)(i / slice);
@@ -170,10 +212,9 @@ allreduce_kernel(CommPeers c, float* __restrict__ buf, long long n, float max_no
   __syncthreads();
   if (threadIdx.x == 0) s_sig = atomicInc(&me->arrive_a, gridDim.x - 1) == gridDim.x - 1;
   __syncthreads();
-  if (s_sig) raise_flags(nullptr, c, false, e);       // every CTA's stores are visible system-wide
+  if (s_sig) raise_flags(c, false, e);       // every CTA's stores are visible system-wide
   // ---- B: owner: wait for all contributions, reduce my slice in rank order, push it to everyone
   wait_flags(me->flag_a, e, W, c.rank, "the contribution");
-  if (n > 0) {       // a scalar-only exchange (n == 0: the aux floats went to every peer in phase A) needs one hop only
   {
     const long long lo = (long long)c.rank * slice;
     const long long cnt = units - lo < slice ? (units - lo > 0 ? units - lo : 0) : slice;
@@ -200,10 +241,9 @@ allreduce_kernel(CommPeers c, float* __restrict__ buf, long long n, float max_no
   __syncthreads();
   if (threadIdx.x == 0) s_sig = atomicInc(&me->arrive_b, gridDim.x - 1) == gridDim.x - 1;
   __syncthreads();
-  if (s_sig) raise_flags(nullptr, c, true, e);
+  if (s_sig) raise_flags(c, true, e);
   // ---- C: everyone: the reduced gradient is complete here
   wait_flags(me->flag_b, e, W, c.rank, "the reduced slice");
-  }   // n > 0
   if (threadIdx.x < 32) {
     float coef = 1.0f;
     if (coef_out) {
