@@ -4,32 +4,31 @@
 // GPUs of one box with an all-reduce of the Actor/Critic gradients over NVLink.  Calling NCCL between
 // the phases of the step costs three host-launched collectives and cuts the step's CUDA graph in three;
 // instead every rank maps its peers' staging buffers (cudaIpc, NVLink/NVSwitch peer access) and ONE
-// kernel per gradient arena does a TWO-SHOT all-reduce with remote STORES only (posted writes: nothing
-// ever waits on an NVLink read round trip), fused with everything that used to sit around it:
+// kernel per gradient arena does a TWO-SHOT all-reduce made of remote STORES only, in the style of NCCL's
+// low-latency protocol: every payload float travels as an 8-byte word {value, epoch}, so the receiver polls
+// the payload itself -- there are no flags, no system-scope fences and no arrival counters on the path
+// (r2m8 / r2m2b measured what those cost: a flag-and-fence version of this kernel took 31-47 us for a 16-byte
+// payload and 46-63 us for a 1.7 MB arena at 4-8 ranks; NCCL's own all_reduce 18 / 23-33 us).
 //
-//   A  reduce-scatter, push side: rank r owns slice r of the arena.  Every rank stores slice s of its local
-//      gradient into rank s's contribution buffer [my rank] (+ its few "aux" floats: loss partial sums and
-//      the global row count it assumed), fences, and raises flag A on every peer.
-//   B  owner side: wait for all W flags A, sum the W contributions of my slice IN RANK ORDER (the same
-//      bits on every rank), store the reduced slice into every peer's result buffer (+ this CTA's partial
-//      L1 norm of the slice), fence, raise flag B on every peer.
-//   C  wait for all W flags B.  Every rank now holds the whole reduced gradient: sum the aux floats in rank
-//      order (-> global loss means), form the reference's clip_grad_norm_(params, -1, 1) coefficient from the
-//      L1 partials (fixed order), write the gradient back to the caller's arena (scaled by the coefficient when
-//      there is one) and -- when the caller passes a built-in optimizer -- apply SGD/Adam in the same pass.
+//   A  reduce-scatter, push side: rank r owns slice r of the arena.  Every rank sums its split-K partials on the
+//      fly (GradSource) and stores slice s of its gradient into rank s's contribution buffer [my rank], plus its few
+//      "aux" words (loss partial sums, the global row count it assumed) into every peer.
+//   B  owner side: for every element of my slice wait for the W contributions, sum them IN RANK ORDER (the same bits
+//      on every rank), store the reduced element into every peer's result buffer (+ this CTA's partial L1 norm).
+//   C  every rank waits for the elements of the whole reduced gradient as it consumes them: clip coefficient from
+//      the L1 partials in a fixed order (actor), global loss means from the aux words, gradient written back
+//      (scaled by the coefficient when there is one) and the built-in optimizer applied in the same pass.
 //
-// Bytes on NVLink per rank and arena: 2 (W-1)/W x 1.72 MB (3.0 MB at W = 8) instead of the (W-1) x 1.72 MB of
-// remote READS (12 MB at W = 8) of the one-shot version of round 1; two flag hops instead of one.
-// It is an ordinary kernel on the step's stream, so the whole data-parallel step is captured in one
-// CUDA graph exactly like the single-GPU step.  All sums are taken in rank order 0..W-1 on every rank,
-// so all replicas hold bit-identical gradients (and therefore weights) after every step.
+// Bytes on NVLink per rank and arena: 2 x 2 (W-1)/W x 1.72 MB (the epoch tags double the payload; 6 MB at W = 8).
+// It is an ordinary kernel on the step's stream, so the whole data-parallel step is captured in one CUDA graph
+// exactly like the single-GPU step.  All sums are taken in rank order on every rank, so all replicas hold
+// bit-identical gradients (and therefore weights) after every step.
 //
 // Protocol (epoch e = number of collectives issued so far on this communicator + 1; all on one stream):
-//   * contribution / result / aux buffers are double buffered by e & 1.  A rank can only be one epoch ahead
-//     of any peer (it needs every peer's flags of epoch e to finish e), so when it writes buffers (e+2) & 1
-//     = e & 1 during epoch e+2 every peer has completed its epoch-e kernel and no longer reads them.
-//   * flags hold epochs and are compared as signed distances (a 32-bit wrap is harmless).
-//   * waits are bounded (~20 s of %globaltimer): a lost peer makes the kernel trap instead of hanging the GPU.
+//   * all buffers are double buffered by e & 1.  A rank can only be one epoch ahead of any peer (it needs every
+//     peer's words of epoch e to finish e), so when it writes buffers (e+2) & 1 = e & 1 during epoch e+2 every peer
+//     has completed its epoch-e kernel and no longer reads them.
+//   * polls are bounded (~20 s of %globaltimer): a lost peer makes the kernel trap instead of hanging the GPU.
 //   * ranks that disagree on n_rows_global (uneven shards without batch["n_rows_global"]) raise *err_flag.
 #include <string.h>
 
@@ -43,22 +42,20 @@ namespace recnn {
 constexpr int kMaxRanks = 8;
 constexpr int kCommThreads = 512;
 constexpr int kMaxAux = 8;
+typedef unsigned long long ll_word;     // {epoch (high 32 bits), fp32 value (low 32 bits)}
 
 struct CommDev {                       // lives at the head of every rank's shared allocation
-  unsigned flag_a[kMaxRanks];          // flag_a[src] = last epoch whose contributions src has published here
-  unsigned flag_b[kMaxRanks];          // flag_b[src] = last epoch whose reduced slice src has published here
   unsigned epoch;                      // collectives completed by this rank           (local)
-  unsigned arrive_a, arrive_b, done;   // CTA counters (wrap to 0)                     (local)
-  unsigned pad[12];
-  float aux[2][kMaxRanks][kMaxAux + 1];           // [e & 1][src]: aux floats, then the row count src assumed
-  unsigned long long aux_ll[2][kMaxRanks][kMaxAux + 1];   // the same for scalar-only exchanges: {value, epoch} words
-  float l1[2][kMaxRanks][kNumSMs];                // [e & 1][src][cta]: partial L1 norms of src's reduced slice
+  unsigned done;                       // CTAs that finished (wraps to 0)              (local)
+  unsigned pad[30];
+  ll_word aux[2][kMaxRanks][kMaxAux + 1];          // [e & 1][src]: aux floats, then the row count src assumed
+  ll_word l1[2][kMaxRanks][kNumSMs];               // [e & 1][src][cta]: partial L1 norms of src's reduced slice
 };
 
 struct CommPeers {                     // kernel parameter
   CommDev* ctrl[kMaxRanks];
-  float* contrib[kMaxRanks];           // [2][W][slice_cap] floats: contributions to THAT rank's slice
-  float* result[kMaxRanks];            // [2][capacity] floats: the reduced gradient, assembled by the owners
+  ll_word* contrib[kMaxRanks];         // [2][W][slice_cap] words: contributions to THAT rank's slice
+  ll_word* result[kMaxRanks];          // [2][capacity] words: the reduced gradient, assembled by the owners
   long long capacity, slice_cap;
   int rank, world;
 };
@@ -89,53 +86,53 @@ __device__ __forceinline__ unsigned long long comm_gtimer() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
+__device__ __forceinline__ ll_word ll_pack(float v, unsigned e) {
+  return ((ll_word)e << 32) | (ll_word)__float_as_uint(v);
 }
-__device__ __forceinline__ void st_relaxed_sys(unsigned* p, unsigned v) {
-  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_ll(ll_word* p, float v, unsigned e) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(ll_pack(v, e)) : "memory");
 }
-// Raise flags[rank] = e on every peer.  Called by the whole CTA that arrived last (all CTAs' payload stores are fenced
-// and counted by then): ONE system-scope fence, then W relaxed flag stores issued by W different threads in parallel.
-// (r2m8 measured what W sequential st.release.sys from one thread cost: each release drains the thread's outstanding
-// remote stores again -- 31 us per collective at W = 4 and 47 us at W = 8 for a 16-byte payload.)
-__device__ __forceinline__ void raise_flags(CommPeers& c, bool phase_b, unsigned e) {
-  if ((int)threadIdx.x < c.world) {
-    __threadfence_system();
-    CommDev* peer = c.ctrl[threadIdx.x];
-    st_relaxed_sys(phase_b ? &peer->flag_b[c.rank] : &peer->flag_a[c.rank], e);
-  }
+__device__ __forceinline__ void st_ll2(ll_word* p, float v0, float v1, unsigned e) {      // p 16-byte aligned
+  asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(ll_pack(v0, e)), "l"(ll_pack(v1, e)) : "memory");
 }
-// "LL" words of the scalar-only exchange: {value, epoch} travel in ONE 8-byte store, so the receiver polls the
-// payload itself and no fence or flag is needed (NCCL's low-latency protocol, for 36 bytes per peer)
-__device__ __forceinline__ void st_ll(unsigned long long* p, float v, unsigned e) {
-  const unsigned long long w = ((unsigned long long)e << 32) | (unsigned long long)__float_as_uint(v);
-  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_ll(const unsigned long long* p) {
-  unsigned long long w;
+__device__ __forceinline__ ll_word ld_ll(const ll_word* p) {
+  ll_word w;
   asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
   return w;
 }
-// threads [0, world) poll one peer's flag each; bounded
-__device__ __forceinline__ void wait_flags(const unsigned* flags, unsigned e, int world, int rank, const char* what) {
-  if ((int)threadIdx.x < world) {
-    const unsigned long long t0 = comm_gtimer();
-    while ((int)(ld_acquire_sys(&flags[threadIdx.x]) - e) < 0) {
-      if (comm_gtimer() - t0 > 20000000000ull) {
-        printf("recnn_b200 allreduce: rank %d timed out waiting for %s of rank %d (epoch %u)\n", rank, what,
-               (int)threadIdx.x, e);
-        __trap();
-      }
-    }
+__device__ __forceinline__ void comm_timeout(int rank, unsigned e, const char* what) {
+  printf("recnn_b200 allreduce: rank %d timed out waiting for %s (epoch %u)\n", rank, what, e);
+  __trap();
+}
+// spin until the word carries epoch e; returns its value
+__device__ __forceinline__ float wait_ll(const ll_word* p, unsigned e, int rank, const char* what) {
+  ll_word w = ld_ll(p);
+  if ((unsigned)(w >> 32) == e) return __uint_as_float((unsigned)w);
+  const unsigned long long t0 = comm_gtimer();
+  unsigned spins = 0;
+  for (;;) {
+    w = ld_ll(p);
+    if ((unsigned)(w >> 32) == e) return __uint_as_float((unsigned)w);
+    if ((++spins & 1023u) == 0 && comm_gtimer() - t0 > 20000000000ull) comm_timeout(rank, e, what);
   }
-  __syncthreads();
+}
+__device__ __forceinline__ void wait_ll2(const ll_word* p, unsigned e, int rank, const char* what, float& v0, float& v1) {
+  const unsigned long long t0 = comm_gtimer();
+  unsigned spins = 0;
+  for (;;) {
+    ll_word w0, w1;
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
+    if ((unsigned)(w0 >> 32) == e && (unsigned)(w1 >> 32) == e) {
+      v0 = __uint_as_float((unsigned)w0);
+      v1 = __uint_as_float((unsigned)w1);
+      return;
+    }
+    if ((++spins & 1023u) == 0 && comm_gtimer() - t0 > 20000000000ull) comm_timeout(rank, e, what);
+  }
 }
 
-// grid <= number of SMs (all CTAs must be co-resident: they wait for each other's peers).
-// VEC = 4: n % 4 == 0 and buf 16-byte aligned (the arenas); VEC = 1: anything.
+// grid <= number of SMs (all CTAs must be co-resident: they wait for words other CTAs -- of other ranks -- produce).
+// VEC = 2: n even and buf 8-byte aligned (the arenas): two elements = one 16-byte store of two words; VEC = 1: anything.
 template <int VEC>
 __global__ void __launch_bounds__(kCommThreads, 1)
 allreduce_kernel(CommPeers c, float* __restrict__ buf, long long n, float max_norm, float* coef_out, float* l1_out,
@@ -143,7 +140,7 @@ allreduce_kernel(CommPeers c, float* __restrict__ buf, long long n, float max_no
                  GradSource src) {
   __shared__ float red[32];
   __shared__ unsigned s_epoch;
-  __shared__ bool s_last, s_sig;
+  __shared__ bool s_last;
   __shared__ float s_coef;
   __shared__ OptStep s_st;
   CommDev* me = c.ctrl[c.rank];
@@ -153,97 +150,66 @@ allreduce_kernel(CommPeers c, float* __restrict__ buf, long long n, float max_no
   const int par = (int)(e & 1u);
   const int W = c.world;
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
-  using V = typename std::conditional<VEC == 4, float4, float>::type;
-  const long long units = n / VEC;                               // VEC == 4 => n % 4 == 0
-  const long long slice = (units + W - 1) / W;                   // units per owner (the last slice may be short)
+  const long long units = n / VEC;                               // VEC == 2 => n % 2 == 0
+  const long long slice = units > 0 ? (units + W - 1) / W : 1;   // units per owner (the last slice may be short)
 
-  if (n == 0) {
-    // ---- scalar-only exchange (one CTA): LL words to every peer, poll my own copies, sum in rank order.  One NVLink
-    // write latency end to end; no fences, no flags.
-    const int nw = n_aux + 1;
-    if ((int)threadIdx.x < W) {
-      unsigned long long* dst = c.ctrl[threadIdx.x]->aux_ll[par][c.rank];
-      for (int j = 0; j < n_aux; ++j) st_ll(dst + j, aux_in[j], e);
-      st_ll(dst + n_aux, check_val, e);
-      const unsigned long long* mine = me->aux_ll[par][threadIdx.x];
-      const unsigned long long t0 = comm_gtimer();
-      for (int j = 0; j < nw; ++j) {
-        while ((unsigned)(ld_ll(mine + j) >> 32) != e) {
-          if (comm_gtimer() - t0 > 20000000000ull) {
-            printf("recnn_b200 scalar exchange: rank %d timed out waiting for rank %d (epoch %u)\n", c.rank, (int)threadIdx.x, e);
-            __trap();
-          }
-        }
-      }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      bool bad = false;
-      for (int p = 0; p < W; ++p) bad = bad || __uint_as_float((unsigned)ld_ll(&me->aux_ll[par][p][n_aux])) != check_val;
-      if (bad && err_flag) *err_flag = 1;
-      for (int j = 0; j < n_aux; ++j) {
-        float t = 0.f;
-        for (int p = 0; p < W; ++p) t += __uint_as_float((unsigned)ld_ll(&me->aux_ll[par][p][j]));
-        aux_out[j] = t;
-      }
-      *((volatile unsigned*)&me->epoch) = e;
-    }
-    return;
-  }
-  // ---- A: push slice s of my gradient to owner s (remote stores), aux floats to everyone
+  // ---- A: push slice s of my gradient to owner s, aux words to everyone (remote stores, nothing to wait for)
   for (long long i = tid; i < units; i += nth) {
     const int s = (int)(i / slice);
-    V* dst = reinterpret_cast<V*>(c.contrib[s] + ((long long)par * W + c.rank) * c.slice_cap);
-    V g;
-    if (src.n_layers) {              // the local gradient is still in split-K partials: reduce them on the way out
-      if constexpr (VEC == 4) g = grad4_at(src, buf, (unsigned)(4 * i));
-      else g = grad_at(src, buf, i);
+    ll_word* dst = c.contrib[s] + ((long long)par * W + c.rank) * c.slice_cap + (i - (long long)s * slice) * VEC;
+    if constexpr (VEC == 2) {
+      float g0, g1;
+      if (src.n_layers) {            // the local gradient is still in split-K partials: reduce them on the way out
+        const float4 q = grad4_at(src, buf, (unsigned)((2 * i) & ~3ll));
+        g0 = (i & 1) ? q.z : q.x;
+        g1 = (i & 1) ? q.w : q.y;
+      } else {
+        const float2 q = reinterpret_cast<const float2*>(buf)[i];
+        g0 = q.x; g1 = q.y;
+      }
+      st_ll2(dst, g0, g1, e);
     } else {
-      g = reinterpret_cast<const V*>(buf)[i];
+      st_ll(dst, src.n_layers ? grad_at(src, buf, i) : buf[i], e);
     }
-    dst[i - (long long)s * slice] = g;
   }
   if (blockIdx.x == 0 && (int)threadIdx.x < W) {
-    float* dst = c.ctrl[threadIdx.x]->aux[par][c.rank];
-    for (int j = 0; j < n_aux; ++j) dst[j] = aux_in[j];
-    dst[kMaxAux] = check_val;
+    ll_word* dst = c.ctrl[threadIdx.x]->aux[par][c.rank];
+    for (int j = 0; j < n_aux; ++j) st_ll(dst + j, aux_in[j], e);
+    st_ll(dst + kMaxAux, check_val, e);
   }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) s_sig = atomicInc(&me->arrive_a, gridDim.x - 1) == gridDim.x - 1;
-  __syncthreads();
-  if (s_sig) raise_flags(c, false, e);       // every CTA's stores are visible system-wide
-  // ---- B: owner: wait for all contributions, reduce my slice in rank order, push it to everyone
-  wait_flags(me->flag_a, e, W, c.rank, "the contribution");
-  {
+  // ---- B: owner: every element of my slice: wait for the W contributions, sum in rank order, push to everyone
+  if (units > 0) {
     const long long lo = (long long)c.rank * slice;
     const long long cnt = units - lo < slice ? (units - lo > 0 ? units - lo : 0) : slice;
-    const float* mine = c.contrib[c.rank] + (long long)par * W * c.slice_cap;
+    const ll_word* mine = c.contrib[c.rank] + (long long)par * W * c.slice_cap;
     float l1 = 0.f;
     for (long long i = tid; i < cnt; i += nth) {
-      V s = __ldcg(reinterpret_cast<const V*>(mine) + i);
-      for (int p = 1; p < W; ++p) {
-        const V v = __ldcg(reinterpret_cast<const V*>(mine + (long long)p * c.slice_cap) + i);
-        if constexpr (VEC == 4) { s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
-        else s += v;
+      float s0 = 0.f, s1 = 0.f;
+      for (int p = 0; p < W; ++p) {
+        const ll_word* w = mine + (long long)p * c.slice_cap + i * VEC;
+        if constexpr (VEC == 2) {
+          float v0, v1;
+          wait_ll2(w, e, c.rank, "a contribution", v0, v1);
+          s0 = p == 0 ? v0 : s0 + v0;
+          s1 = p == 0 ? v1 : s1 + v1;
+        } else {
+          const float v0 = wait_ll(w, e, c.rank, "a contribution");
+          s0 = p == 0 ? v0 : s0 + v0;
+        }
       }
-      if constexpr (VEC == 4) l1 += fabsf(s.x) + fabsf(s.y) + fabsf(s.z) + fabsf(s.w);
-      else l1 += fabsf(s);
-      for (int p = 0; p < W; ++p)
-        reinterpret_cast<V*>(c.result[p] + (long long)par * c.capacity)[lo + i] = s;
+      l1 += fabsf(s0) + (VEC == 2 ? fabsf(s1) : 0.f);
+      for (int p = 0; p < W; ++p) {
+        ll_word* dst = c.result[p] + (long long)par * c.capacity + (lo + i) * VEC;
+        if constexpr (VEC == 2) st_ll2(dst, s0, s1, e);
+        else st_ll(dst, s0, e);
+      }
     }
     if (coef_out) {
       l1 = block_sum(l1, red);
-      if ((int)threadIdx.x < W) c.ctrl[threadIdx.x]->l1[par][c.rank][blockIdx.x] = l1;
+      if ((int)threadIdx.x < W) st_ll(&c.ctrl[threadIdx.x]->l1[par][c.rank][blockIdx.x], l1, e);
     }
   }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) s_sig = atomicInc(&me->arrive_b, gridDim.x - 1) == gridDim.x - 1;
-  __syncthreads();
-  if (s_sig) raise_flags(c, true, e);
-  // ---- C: everyone: the reduced gradient is complete here
-  wait_flags(me->flag_b, e, W, c.rank, "the reduced slice");
+  // ---- C: everyone: scalars first (clip coefficient, loss sums, optimizer step constants)
   if (threadIdx.x < 32) {
     float coef = 1.0f;
     if (coef_out) {
@@ -251,7 +217,8 @@ allreduce_kernel(CommPeers c, float* __restrict__ buf, long long n, float max_no
       // list, then a shuffle tree -- the same order on every rank and CTA, so every replica gets the same bits
       const int total = W * (int)gridDim.x;
       float t = 0.f;
-      for (int k = (int)threadIdx.x; k < total; k += 32) t += __ldcg(&me->l1[par][k / (int)gridDim.x][k % (int)gridDim.x]);
+      for (int k = (int)threadIdx.x; k < total; k += 32)
+        t += wait_ll(&me->l1[par][k / (int)gridDim.x][k % (int)gridDim.x], e, c.rank, "an L1 partial");
       t = warp_sum(t);
       coef = fminf(max_norm / (t + 1e-6f), 1.0f);     // clip_grad_norm_: max_norm / (total_norm + 1e-6), <= 1
       if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -265,39 +232,37 @@ allreduce_kernel(CommPeers c, float* __restrict__ buf, long long n, float max_no
         s_st = opt_step_scalars(opt.kind, opt.beta1, opt.beta2, opt.lr, opt.wd, opt.n_sma_threshold, opt.k_look, *opt.t + 1);
       if (blockIdx.x == 0) {
         bool bad = false;
-        for (int p = 0; p < W; ++p) bad = bad || __ldcg(&me->aux[par][p][kMaxAux]) != check_val;
+        for (int p = 0; p < W; ++p) bad = bad || wait_ll(&me->aux[par][p][kMaxAux], e, c.rank, "a peer's row count") != check_val;
         if (bad && err_flag) *err_flag = 1;
         for (int j = 0; j < n_aux; ++j) {
           float t = 0.f;
-          for (int p = 0; p < W; ++p) t += __ldcg(&me->aux[par][p][j]);
+          for (int p = 0; p < W; ++p) t += wait_ll(&me->aux[par][p][j], e, c.rank, "a peer's loss sum");
           aux_out[j] = t;
         }
       }
     }
   }
   __syncthreads();
+  // ---- the reduced gradient, element by element as it arrives: write back (scaled) and apply the optimizer
   {
     const float coef = s_coef;
     const bool scale = coef_out != nullptr;
     const int t_next = opt.kind != RECNN_OPT_EXTERNAL ? *opt.t + 1 : 0;
     const OptStep ost = s_st;
-    const float* res = c.result[c.rank] + (long long)par * c.capacity;
+    const ll_word* res = c.result[c.rank] + (long long)par * c.capacity;
     for (long long i = tid; i < units; i += nth) {
-      V g = __ldcg(reinterpret_cast<const V*>(res) + i);
+      float g0, g1 = 0.f;
+      if constexpr (VEC == 2) wait_ll2(res + i * 2, e, c.rank, "a reduced element", g0, g1);
+      else g0 = wait_ll(res + i, e, c.rank, "a reduced element");
       if (scale) {
-        if constexpr (VEC == 4) { g.x = __fmul_rn(g.x, coef); g.y = __fmul_rn(g.y, coef); g.z = __fmul_rn(g.z, coef); g.w = __fmul_rn(g.w, coef); }
-        else g = __fmul_rn(g, coef);
+        g0 = __fmul_rn(g0, coef);
+        g1 = __fmul_rn(g1, coef);
       }
-      reinterpret_cast<V*>(buf)[i] = g;              // the caller-visible .grad (scaled, as the reference leaves it)
+      if constexpr (VEC == 2) reinterpret_cast<float2*>(buf)[i] = make_float2(g0, g1);   // the caller-visible .grad
+      else buf[i] = g0;
       if (opt.kind != RECNN_OPT_EXTERNAL) {
-        if constexpr (VEC == 4) {
-          opt_apply(opt.kind, opt.k, ost, t_next, opt.p, opt.m, opt.v, opt.slow, 4 * i + 0, g.x);
-          opt_apply(opt.kind, opt.k, ost, t_next, opt.p, opt.m, opt.v, opt.slow, 4 * i + 1, g.y);
-          opt_apply(opt.kind, opt.k, ost, t_next, opt.p, opt.m, opt.v, opt.slow, 4 * i + 2, g.z);
-          opt_apply(opt.kind, opt.k, ost, t_next, opt.p, opt.m, opt.v, opt.slow, 4 * i + 3, g.w);
-        } else {
-          opt_apply(opt.kind, opt.k, ost, t_next, opt.p, opt.m, opt.v, opt.slow, i, g);
-        }
+        opt_apply(opt.kind, opt.k, ost, t_next, opt.p, opt.m, opt.v, opt.slow, i * VEC, g0);
+        if constexpr (VEC == 2) opt_apply(opt.kind, opt.k, ost, t_next, opt.p, opt.m, opt.v, opt.slow, i * VEC + 1, g1);
       }
     }
   }
@@ -336,13 +301,15 @@ int launch_comm_allreduce(const recnn_comm* comm, float* buf, int64_t n, const C
   GradSource gsrc;
   memset(&gsrc, 0, sizeof(gsrc));
   if (r.src) gsrc = *r.src;
-  const int64_t per = (int64_t)kCommThreads * 4 * 2;              // two float4 per thread
+  const int64_t per = (int64_t)kCommThreads * 8;                   // eight floats per thread
   int64_t blocks = ceil_div(n, per);
   const int grid = (int)(blocks < 1 ? 1 : (blocks > kNumSMs ? kNumSMs : blocks));
-  const bool vec = (n & 3) == 0 && ((reinterpret_cast<uintptr_t>(buf) & 15) == 0) &&
-                   (opt.kind == RECNN_OPT_EXTERNAL || (reinterpret_cast<uintptr_t>(opt.p) & 15) == 0);
+  // partial-sourced gradients are read four at a time: the arena case (n % 4 == 0, 16-byte aligned)
+  const bool vec = (n & 1) == 0 && ((reinterpret_cast<uintptr_t>(buf) & 7) == 0) &&
+                   (!r.src || ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(buf) & 15) == 0));
+  RECNN_REQUIRE(vec || !r.src, "partial-sourced gradients need a 16-byte aligned arena");
   if (vec)
-    allreduce_kernel<4><<<grid, kCommThreads, 0, st>>>(comm->peers, buf, n, r.max_norm, r.coef, r.l1_out, r.aux_in,
+    allreduce_kernel<2><<<grid, kCommThreads, 0, st>>>(comm->peers, buf, n, r.max_norm, r.coef, r.l1_out, r.aux_in,
                                                         r.aux_out, r.n_aux, r.check_val, r.err_flag, opt, gsrc);
   else
     allreduce_kernel<1><<<grid, kCommThreads, 0, st>>>(comm->peers, buf, n, r.max_norm, r.coef, r.l1_out, r.aux_in,
@@ -355,12 +322,12 @@ int launch_comm_allreduce(const recnn_comm* comm, float* buf, int64_t n, const C
 
 using namespace recnn;
 
-// staging layout of one rank: CommDev | contrib [2][W][slice_cap] | result [2][capacity]   (floats)
+// staging layout of one rank: CommDev | contrib [2][W][slice_cap] | result [2][capacity]   (8-byte words)
 static size_t comm_ctrl_bytes() { return (size_t)round_up((int64_t)sizeof(CommDev), 256); }
 static void comm_carve(recnn_comm* c, int p, void* base) {
   char* b = static_cast<char*>(base);
   c->peers.ctrl[p] = reinterpret_cast<CommDev*>(b);
-  c->peers.contrib[p] = reinterpret_cast<float*>(b + comm_ctrl_bytes());
+  c->peers.contrib[p] = reinterpret_cast<ll_word*>(b + comm_ctrl_bytes());
   c->peers.result[p] = c->peers.contrib[p] + 2ll * c->peers.world * c->peers.slice_cap;
 }
 
@@ -375,11 +342,11 @@ extern "C" int recnn_comm_create(int32_t rank, int32_t world, int64_t capacity_f
     c->opened[i] = nullptr; c->peers.ctrl[i] = nullptr; c->peers.contrib[i] = nullptr; c->peers.result[i] = nullptr;
   }
   c->peers.capacity = capacity_floats;
-  c->peers.slice_cap = round_up(ceil_div(capacity_floats, world), 4);
+  c->peers.slice_cap = round_up(ceil_div(capacity_floats, world), 4) + 4;
   c->peers.rank = rank;
   c->peers.world = world;
   const size_t bytes = comm_ctrl_bytes() +
-                       sizeof(float) * (size_t)(2 * world * c->peers.slice_cap + 2 * capacity_floats);
+                       sizeof(ll_word) * (size_t)(2 * world * c->peers.slice_cap + 2 * capacity_floats);
   cudaError_t e = cudaMalloc(&c->local_base, bytes);
   if (e != cudaSuccess) {
     delete c;
