@@ -316,6 +316,42 @@ RECNN_API int recnn_retrieve_topk(const float* queries, int64_t n_queries, int32
                                   int64_t* ids_out, float* dist_out, void* workspace, int64_t workspace_bytes,
                                   void* stream);
 
+/* ---- REINFORCE with (Top-K) off-policy correction: the policy side ------------------
+ * DiscreteActor (recnn/nn/models.py:76-99): probs = softmax(W2 relu(W1 s + b1) + b2), one output per item.
+ * Parameter arena in nn.Module.parameters() order -- linear1.weight [H, S], linear1.bias, linear2.weight
+ * [num_items, H], linear2.bias -- matrix rows padded to 16-byte multiples (recnn_discrete_layout). */
+typedef struct recnn_discrete_dims {
+  int32_t state_dim, hidden, num_items, reserved;
+} recnn_discrete_dims;
+/* out[7]: offsets of w1, b1, w2, b2; row pitches of w1, w2; total float count */
+RECNN_API int recnn_discrete_layout(const recnn_discrete_dims* d, int64_t* out);
+/* floats of scratch for n_rows rows: forward only (backward = 0) or recnn_reinforce_policy_grad (backward = 1) */
+RECNN_API int64_t recnn_discrete_scratch_floats(const recnn_discrete_dims* d, int64_t n_rows, int32_t backward);
+/* DiscreteActor.forward (models.py:95-99): probs_out fp32 [n_rows, num_items] dense */
+RECNN_API int recnn_discrete_forward(const recnn_discrete_dims* d, const float* params, const float* state,
+                                     int64_t n_rows, float* probs_out, float* scratch, void* stream);
+/* Categorical(probs).sample() + .log_prob(sample) (models.py:107-110, 121-143): inverse CDF on `uniforms`
+ * [n_rows] in [0,1) when given (replayable), else on Philox(seed, draw, row).  probs fp32 [n_rows, ld >= num_items];
+ * rows are normalised by their sum and clamped to [eps, 1-eps] before the log, as torch does. */
+RECNN_API int recnn_categorical_sample(const float* probs, int64_t n_rows, int32_t num_items, int64_t ld,
+                                       const float* uniforms, uint64_t seed, int64_t draw, int64_t* action_out,
+                                       float* log_prob_out, void* stream);
+/* Categorical(probs).log_prob(action) for given actions; *oob_flag (may be NULL) is set when an id is out of range */
+RECNN_API int recnn_categorical_log_prob(const float* probs, int64_t n_rows, int32_t num_items, int64_t ld,
+                                         const int64_t* action, float* log_prob_out, int32_t* oob_flag, void* stream);
+/* ChooseREINFORCE (recnn/nn/update/reinforce.py:10-65): the three policy losses */
+enum { RECNN_REINFORCE_BASIC = 0, RECNN_REINFORCE_CORRECTED = 1, RECNN_REINFORCE_TOPK = 2 };
+/* Policy loss and its gradient over the n_rows rows saved since the last policy update (the reference's
+ * saved_log_probs / correction / lambda_k lists, concatenated): state [n_rows, state_dim], action int64 [n_rows]
+ * (the sampled item), beta_log_prob [n_rows] (NULL for BASIC), returns [n_rows] (the normalised discounted return of
+ * the env step the row was saved at, reinforce.py:44-52).  Recomputes the forward, writes the gradient of every
+ * parameter into `grads` (arena geometry; overwritten, i.e. zero_grad + backward), out[0] = loss (fp32),
+ * out[1] = int32 flag: an action id was outside [0, num_items) (that row contributed nothing). */
+RECNN_API int recnn_reinforce_policy_grad(const recnn_discrete_dims* d, const float* params, float* grads,
+                                          const float* state, const int64_t* action, const float* beta_log_prob,
+                                          const float* returns, int64_t n_rows, int32_t method, int32_t top_k,
+                                          float* out, float* scratch, void* stream);
+
 /* ---- data parallel: all-reduce over NVLink peer memory ------------------------------------------
  * BASELINE north_star: "partition the embedding gather + update across the 8 GPUs of one box with
  * an allreduce of the Actor/Critic gradients over NVLink".  The reference itself is single-process

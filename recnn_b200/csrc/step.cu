@@ -907,3 +907,6 @@ extern "C" int recnn_linear_forward(const float* x, int64_t n_rows, int in_dim, 
   }
   return linear_out(xs, weight, in_dim, bias, out_dim, n_rows, 0, nullptr, out, out_dim, st);
 }
+
+// ---------------------------------------------------------------- REINFORCE (policy side)
+#include "reinforce.cuh"

@@ -1,0 +1,64 @@
+"""The REINFORCE oracle (oracle/reinforce_oracle.py) against vectors produced by the unmodified reference
+(recnn/nn/models.py:76-184, recnn/nn/update/reinforce.py:10-65)."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from oracle import reinforce_oracle as RO
+from tests import _reinforce as RG
+
+
+@pytest.mark.parametrize("path", RG.FILES, ids=RG.IDS)
+def test_select_action_quantities(path):
+    c = RG.load(path)
+    g = c["g"]
+    for t in range(c["T"]):
+        probs, _ = RO.discrete_forward(c["params"], g["states"][t])
+        np.testing.assert_allclose(probs, g["probs"][t], rtol=2e-5, atol=1e-9)
+        lp = RO.categorical_log_prob(g["probs"][t], c["pi_action"][t])
+        np.testing.assert_allclose(lp, g["saved_log_probs"][t], rtol=1e-5, atol=1e-6)
+        if c["method"] != RO.BASIC:
+            blp = RO.categorical_log_prob(g["beta_probs"][t], c["beta_action"][t])
+            np.testing.assert_allclose(RO.correction(lp, blp), g["correction"][t], rtol=2e-5)
+        if c["method"] == RO.TOPK:
+            np.testing.assert_allclose(RO.lambda_k(lp, c["K"]), g["lambda_k"][t], rtol=2e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("path", RG.FILES, ids=RG.IDS)
+def test_returns(path):
+    c = RG.load(path)
+    np.testing.assert_allclose(RO.normalised_returns(c["g"]["rewards"]), c["g"]["returns"], rtol=2e-6, atol=2e-6)
+
+
+@pytest.mark.parametrize("path", RG.FILES, ids=RG.IDS)
+def test_loss_gradient_and_sgd_step(path):
+    c = RG.load(path)
+    g = c["g"]
+    ret = g["returns"][c["rows_step"]]
+    loss, grads, _ = RO.reinforce_policy_grad(c["params"], c["rows_state"], c["rows_action"], c["rows_beta_logp"], ret,
+                                              c["method"], c["K"])
+    assert loss == pytest.approx(float(g["loss"]), rel=2e-5, abs=1e-5)
+    names = {"w1": "linear1.weight", "b1": "linear1.bias", "w2": "linear2.weight", "b2": "linear2.bias"}
+    for k, n in names.items():
+        ref = g["grad." + n]
+        scale = np.abs(ref).max()
+        np.testing.assert_allclose(grads[k], ref, rtol=2e-4, atol=2e-6 * scale, err_msg=n)
+        after = c["params"][k].astype(np.float64) - float(g["lr"]) * grads[k]
+        np.testing.assert_allclose(after, g["after." + n], rtol=1e-5, atol=1e-6 * max(1.0, scale), err_msg=n)
+
+
+def test_inverse_cdf_sampling_is_a_categorical_draw():
+    rng = np.random.default_rng(5)
+    probs = rng.dirichlet(np.ones(7), size=1).astype(np.float32)
+    u = rng.random(20000).astype(np.float32)
+    act, lp, margin = RO.categorical_sample(np.repeat(probs, u.size, 0), u)
+    freq = np.bincount(act, minlength=7) / u.size
+    np.testing.assert_allclose(freq, probs[0], atol=0.012)
+    np.testing.assert_allclose(lp, np.log(probs[0].astype(np.float64) / probs[0].astype(np.float64).sum())[act], rtol=1e-6)
+    assert (margin >= 0).all()
+    # zero-probability outcomes are never drawn, u = 0 picks the first possible one
+    p = np.asarray([[0.0, 0.0, 0.5, 0.0, 0.5]], np.float32)
+    assert RO.categorical_sample(p, np.asarray([0.0], np.float32))[0][0] == 2
+    assert RO.categorical_sample(p, np.asarray([0.5], np.float32))[0][0] == 4
+    assert RO.categorical_sample(p, np.asarray([0.999], np.float32))[0][0] == 4
