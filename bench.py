@@ -607,6 +607,7 @@ def run_native(args):
             if not args.no_cpu_baseline:
                 other["cpu_baseline"] = cpu_sample(n_rows, oa, 8.0, min_steps=6, max_steps=30)
             del ob
+        reinforce = bench_reinforce(dev, not args.no_cpu_baseline) if (world == 1 and not args.no_other_algo) else None
         cpu = cpu_sample(n_rows, algo, 15.0) if (world == 1 and not args.no_cpu_baseline) else None
         cpu256 = cpu_sample(256, "ddpg", 4.0, min_steps=20, max_steps=400) if (world == 1 and not args.no_cpu_baseline) else None
         comm = getattr(agent.nets["policy_net"], "_recnn_dp", (0, 0, None))[2]
@@ -675,6 +676,8 @@ def run_native(args):
             line["cpu_baseline_n256"] = cpu256
         if other is not None:
             line["td3" if algo == "ddpg" else "ddpg"] = other
+        if reinforce is not None:
+            line["reinforce"] = reinforce
         if feed_info is not None:
             line["feed"] = feed_info
     if world > 1:
@@ -682,6 +685,80 @@ def run_native(args):
         dist.destroy_process_group()
     if line is not None:
         print(json.dumps(line))
+
+
+def bench_reinforce(dev, with_cpu):
+    """SURVEY 8f-2 at the shapes of the reference's Top-K notebook (DiscreteActor 1290 -> 2048 -> 5000 items,
+    Critic(1290, 5000, 2048), K = 10, policy_step = 10) with 128 rows per env step: recnn.nn.Reinforce.update() calls
+    per second, policy updates included (every 10th call back-propagates through the 10 saved batches)."""
+    import torch
+    import recnn_b200
+    from recnn_b200.nn import ChooseREINFORCE
+    S, H, I, N = FRAME * DIM + FRAME, 2048, 5000, 128
+    torch.manual_seed(7)
+    agent = recnn_b200.nn.Reinforce(recnn_b200.nn.DiscreteActor(S, I, H), recnn_b200.nn.Critic(S, I, H, 54e-2)).to(dev)
+    policy = agent.nets["policy_net"]
+    bw = torch.randn(I, S, device=dev) * 0.02
+
+    def select(state, action, K, writer, step, **kw):
+        beta = lambda s, action=None: torch.softmax(s @ bw.T, dim=1)       # noqa: E731  (the notebook's Beta net, frozen)
+        return policy._select_action_with_TopK_correction(state, beta, action, K=K, writer=writer, step=step)
+
+    policy.select_action = select
+    agent.params["reinforce"] = ChooseREINFORCE(ChooseREINFORCE.reinforce_with_TopK_correction)
+    agent.optimizers = {"policy_optimizer": recnn_b200.optim.Adam(policy.parameters(), lr=1e-5),
+                        "value_optimizer": recnn_b200.optim.Adam(agent.nets["value_net"].parameters(), lr=1e-5)}
+    g = torch.Generator(device="cpu").manual_seed(3)
+    batches = []
+    for _ in range(4):
+        a = torch.randint(0, I, (N,), generator=g)
+        batches.append({"state": torch.randn(N, S, generator=g).to(dev), "next_state": torch.randn(N, S, generator=g).to(dev),
+                        "action": torch.nn.functional.one_hot(a, I).float().to(dev),
+                        "reward": (torch.randint(1, 6, (N,), generator=g).float() - 3).to(dev),
+                        "done": torch.zeros(N).to(dev)})
+    lib = recnn_b200._lib.lib()
+
+    def run(k):
+        for i in range(k):
+            agent.update(batches[i % 4])
+            agent.step()
+        torch.cuda.synchronize(dev)
+
+    run(21)                                   # two policy updates: every shape seen
+    k = 100
+    k0 = lib.recnn_b200_launch_count()
+    t0 = time.perf_counter()
+    run(k)
+    dt = time.perf_counter() - t0
+    out = {"workload": "REINFORCE Top-K off-policy correction, DiscreteActor 1290-2048-%d, Critic(1290,%d,2048), %d rows/step, "
+                       "K=10, policy_step=10" % (I, I, N),
+           "updates_per_sec": k / dt, "ms_per_update": 1e3 * dt / k, "steps": k,
+           "gpu_launches": int(lib.recnn_b200_launch_count() - k0), "timing": "wall clock around %d Reinforce.update() calls "
+           "(host-driven: sampling, critic step, every 10th call the policy backward over 1280 saved rows), synchronised" % k,
+           "reference_incidental": "9.48 it/s at batch_size=10 users in the notebook's own log (unknown GPU, DataLoader included)"}
+    if with_cpu:
+        out["cpu_baseline"] = cpu_reinforce_sample(S, H, I, N)
+    return out
+
+
+def cpu_reinforce_sample(S, H, I, N):
+    """The float64 oracle of the POLICY update (forward + closed-form backward over 10 x N saved rows) on the host:
+    the part of a policy step that dominates; a bounded sample (3 updates)."""
+    from oracle import reinforce_oracle as RO
+    rng = np.random.default_rng(0)
+    p = RO.make_discrete_actor(rng, S, I, H)
+    rows = 10 * N
+    state = rng.normal(0, 1, (rows, S)).astype(np.float32)
+    act = rng.integers(0, I, rows)
+    blp = np.log(rng.uniform(1e-4, 5e-4, rows)).astype(np.float32)
+    ret = rng.normal(0, 1, rows).astype(np.float32)
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        RO.reinforce_policy_grad(p, state, act, blp, ret, RO.TOPK, 10)
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": 1.0 / dt, "unit": "policy updates/s (policy half only, 1280 saved rows)", "kind": "port",
+            "cores": int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1)), "sample": "%d policy updates, float64 numpy" % reps}
 
 
 FEED_BYTES_PER_ROW = (FRAME + 1) * 12 * 2 + 4          # read ids+ratings, write ids+ratings, write done

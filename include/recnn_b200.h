@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define RECNN_B200_ABI_VERSION 2
+#define RECNN_B200_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define RECNN_API __attribute__((visibility("default")))
@@ -272,6 +272,11 @@ typedef struct recnn_step_args {
   float* losses_host;      /* optional PINNED host buffer of 8 words: RECNN_PH_FINISH copies `losses` here (async) */
   float* next_action_out;  /* optional fp32[n_rows,A] (debug["next_action"]) */
   float* gen_action_out;   /* optional fp32[n_rows,A] (debug["gen_action"])  */
+  /* optional fp32[n_rows,A]: the target policy's action on next_state, computed by the caller.  When given the
+   * step does not run a target policy of its own (policy / target_policy may then be all-NULL for a call made only of
+   * the VALUE phases): this is how misc.py:28 is served when the policy is not an Actor -- the REINFORCE critic is
+   * updated against DiscreteActor probabilities (recnn/nn/update/reinforce.py:92-102). */
+  const float* next_action_in;
 
   void* workspace;
   int64_t workspace_bytes;

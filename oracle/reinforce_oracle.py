@@ -136,3 +136,24 @@ def correction(pi_logp, beta_logp):
 def lambda_k(pi_logp, K: int):
     """models.py:168."""
     return K * (1.0 - np.exp(np.asarray(pi_logp, np.float64))) ** (K - 1)
+
+
+def value_update(batch, params, nets, opts, masks, learn=True):
+    """The critic half of reinforce_update (reinforce.py:92-102 -> misc.py:10-55) with a DiscreteActor as the target
+    policy: next_action = target_policy_net(next_state) are PROBABILITIES [N, num_items], the batch action is the dense
+    one-hot.  Built from the DDPG oracle's primitives (oracle/recnn_oracle.py)."""
+    from oracle import recnn_oracle as O
+    s, a, s2 = batch["state"], batch["action"], batch["next_state"]
+    r, d = O._col(batch["reward"]), O._col(batch["done"])
+    a2 = discrete_forward(nets["target_policy_net"], s2, dtype=np.float32)[0].astype(F32)     # misc.py:28
+    q2, _ = O.critic_forward(nets["target_value_net"], s2, a2)                                 # :29
+    y = O.temporal_difference(r, d, params["gamma"], q2)                                       # :30-32
+    y = np.clip(y, F32(params["min_value"]), F32(params["max_value"]))                        # :33-35
+    q, cache = O.critic_forward(nets["value_net"], s, a, masks)                                # :37
+    diff = q - y
+    loss = F32(np.mean(diff * diff, dtype=F32))                                                # :39
+    if learn:
+        d_q = (F32(2.0) * diff / F32(diff.size)).astype(F32)
+        grads, _ = O._mlp_backward(nets["value_net"], cache, d_q, need_dx=False)
+        O.optimizer_step(opts["value_optimizer"], nets["value_net"], grads)                    # :42-44
+    return loss, {"next_action": a2, "expected_value": y, "value": q}

@@ -417,6 +417,10 @@ static int phase_value_grad(Ctx& c) {
   const bool fuse_head = fuse_env && value_head_fusable(H);
 
   // target policy on next_state, eval mode (misc.py:28 / td3.py:73) (+ clipped noise, td3.py:74-78)
+  if (a.next_action_in) {       // ... unless the caller ran its own (next_action_in: any policy class)
+    RECNN_CHECK_CUDA(cudaMemcpy2DAsync(a2 + c.lead, c.ldA * 4, a.next_action_in, (size_t)A * 4, (size_t)A * 4, c.n,
+                                       cudaMemcpyDeviceToDevice, c.st));
+  } else {
   RECNN_PROPAGATE(actor_hidden(c, a.target_policy.params, c.S2, false, 0, X0, X1, c.st));
   if (c.aux && c.p_deferred) {
     RECNN_CHECK_CUDA(cudaEventRecord(c.aux->ev[4], c.st));
@@ -429,6 +433,7 @@ static int phase_value_grad(Ctx& c) {
   const Seg x1s = {X1, H, H, 0};
   RECNN_PROPAGATE(linear_out(x1s, a.target_policy.params + c.la.w3, c.la.ld3, a.target_policy.params + c.la.b3, A,
                              c.n, 0, &nz, a2 + c.lead, c.ldA, c.st));
+  }
   if (a.next_action_out)
     RECNN_CHECK_CUDA(cudaMemcpy2DAsync(a.next_action_out, (size_t)A * 4, a2 + c.lead, c.ldA * 4, (size_t)A * 4, c.n,
                                        cudaMemcpyDeviceToDevice, c.st));
@@ -674,7 +679,10 @@ static int run_step(const recnn_step_args* a, int algo, void* stream) {
   }
   RECNN_REQUIRE(a->done != nullptr, "done");
   const int n_critics = algo == RECNN_ALGO_TD3 ? 2 : 1;
-  RECNN_REQUIRE(a->policy.params && a->target_policy.params, "policy nets");
+  const int policy_phases = RECNN_PH_POLICY_LOSS | RECNN_PH_POLICY_GRAD | RECNN_PH_POLICY_OPT | RECNN_PH_SOFT_UPDATE;
+  RECNN_REQUIRE((a->policy.params && a->target_policy.params) || (a->next_action_in && !(a->phases & policy_phases)),
+                "policy nets (or next_action_in for a call made of the value phases only)");
+  RECNN_REQUIRE(!a->next_action_in || algo == RECNN_ALGO_DDPG, "next_action_in is a DDPG-critic feature");
   for (int i = 0; i < n_critics; ++i)
     RECNN_REQUIRE(a->value[i].params && a->target_value[i].params, "value nets");
   if (a->dropout && !a->masks[0]) RECNN_REQUIRE(a->rng_step != nullptr, "perf-mode dropout needs rng_step");

@@ -59,6 +59,24 @@ def batch_tensor_embeddings(batch, item_embeddings_tensor, frame_size, *args, **
             "meta": {"users": users_t, "sizes": sizes_t}}
 
 
+def batch_contstate_discaction(batch, item_embeddings_tensor, frame_size, num_items, *args, **kwargs):
+    """Embed batch: continuous state, discrete action (utils.py:84-120), on the device.
+
+    Same gather kernel as ``batch_tensor_embeddings`` for state / next_state / reward / done; the action is the item id
+    of the last frame position -- returned as the reference's dense one-hot ``action`` [N, num_items] (what its
+    ``Critic(1290, num_items, ...)`` consumes) and as ``action_index`` int64 [N]."""
+    out = batch_tensor_embeddings(batch, item_embeddings_tensor, frame_size, *args, **kwargs)
+    dev = out["state"].device
+    index = batch["items"][:, -1].to(device=dev, dtype=torch.int64)
+    if int(index.max().item()) >= num_items or int(index.min().item()) < 0:
+        raise RuntimeError("index out of range for a one-hot action of %d items" % num_items)   # scatter_ raises too
+    one_hot = torch.zeros(index.shape[0], num_items, device=dev)
+    one_hot.scatter_(1, index.view(-1, 1), 1)
+    out["action"] = one_hot
+    out["action_index"] = index
+    return out
+
+
 def batch_frames(batch, item_embeddings_tensor, frame_size, *args, **kwargs):
     """embed_batch variant that does NOT materialise the state: returns the frame form
     (items, ratings, sizes, table) that ddpg_update / td3_update gather on the device

@@ -1,4 +1,4 @@
-"""Algo / DDPG / TD3 wrappers with the reference's wiring (recnn/nn/algo.py:15-179).
+"""Algo / DDPG / TD3 / Reinforce wrappers with the reference's wiring (recnn/nn/algo.py:15-233).
 
 These are the dispatchers the update functions plug into (``Algo.algorithm``);
 they only hold state.  The reference builds ``torch_optimizer.Ranger(lr=1e-5,
@@ -86,3 +86,21 @@ class TD3(Algo):
                        "policy_lr": 1e-5, "value_lr": 1e-5, "actor_weight_init": 25e-2, "critic_weight_init": 6e-1}
         self.loss_layout = {"test": {"value1": [], "value2": [], "policy": [], "step": []},
                             "train": {"value1": [], "value2": [], "policy": [], "step": []}}
+
+
+class Reinforce(Algo):
+    """recnn/nn/algo.py:182-233."""
+
+    def __init__(self, policy_net, value_net):
+        super().__init__()
+        self.algorithm = update.reinforce_update
+        self.nets = {"value_net": value_net, "target_value_net": _target_of(value_net),
+                     "policy_net": policy_net, "target_policy_net": _target_of(policy_net)}
+        self.optimizers = {
+            "policy_optimizer": optim.Ranger(policy_net.parameters(), lr=1e-5, weight_decay=1e-2),
+            "value_optimizer": optim.Ranger(value_net.parameters(), lr=1e-5, weight_decay=1e-2),
+        }
+        self.params = {"reinforce": update.ChooseREINFORCE(update.ChooseREINFORCE.basic_reinforce), "K": 10,
+                       "gamma": 0.99, "min_value": -10, "max_value": 10, "policy_step": 10, "soft_tau": 0.001}
+        self.loss_layout = {"test": {"value": [], "policy": [], "step": []},
+                            "train": {"value": [], "policy": [], "step": []}}

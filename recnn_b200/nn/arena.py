@@ -20,13 +20,30 @@ import torch
 from .. import _lib
 
 
+def _is_discrete(module):
+    """Two-layer DiscreteActor (recnn/nn/models.py:76-99): linear1, linear2 and nothing else."""
+    return not hasattr(module, "linear3")
+
+
 def _params(module):
-    return [module.linear1.weight, module.linear1.bias, module.linear2.weight, module.linear2.bias,
-            module.linear3.weight, module.linear3.bias]
+    ps = [module.linear1.weight, module.linear1.bias, module.linear2.weight, module.linear2.bias]
+    if not _is_discrete(module):
+        ps += [module.linear3.weight, module.linear3.bias]
+    return ps
+
+
+def discrete_dims(module):
+    return _lib.DiscreteDims(module.linear1.in_features, module.linear1.out_features, module.linear2.out_features, 0)
 
 
 def net_layout(module):
-    """(offsets[6], pitches[3], count) of this module's arena, from the C library."""
+    """(offsets[6], pitches[3], count) of this module's arena, from the C library (4 offsets / 2 pitches for the
+    two-layer DiscreteActor)."""
+    if _is_discrete(module):
+        buf = (ctypes.c_int64 * 7)()
+        _lib.check(_lib.lib().recnn_discrete_layout(discrete_dims(module), buf))
+        v = list(buf)
+        return v[0:4], v[4:6], v[6]
     s = module.linear1.in_features
     h = module.linear1.out_features
     out = module.linear3.out_features

@@ -44,8 +44,16 @@ class StepEngine:
                 raise KeyError(k)
         self.policy = nets["policy_net"]
         pol = self.policy            # any module with linear1/2/3 works (also the reference's own classes)
-        self.dims = _lib.Dims(pol.linear1.in_features, pol.linear3.out_features, pol.linear1.out_features, 0)
         crit = nets[self.names[0]]
+        # REINFORCE (recnn/nn/update/reinforce.py:92-102): the policy is a two-layer DiscreteActor whose probabilities
+        # are the critic's "action"; only the critic half of the step runs here, fed with the target policy's output
+        self.discrete = not hasattr(pol, "linear3")
+        if self.discrete:
+            if algo != _lib.ALGO_DDPG:
+                raise ValueError("a DiscreteActor policy only goes with the DDPG-style critic step (value_update)")
+            self.dims = _lib.Dims(pol.linear1.in_features, pol.linear2.out_features, crit.linear1.out_features, 0)
+        else:
+            self.dims = _lib.Dims(pol.linear1.in_features, pol.linear3.out_features, pol.linear1.out_features, 0)
         if (crit.linear1.in_features != self.dims.state_dim + self.dims.action_dim
                 or crit.linear1.out_features != self.dims.hidden or crit.linear3.out_features != 1):
             raise ValueError("critic shape does not match the actor (expects input state_dim+action_dim, same hidden, 1 output)")
@@ -206,8 +214,12 @@ class StepEngine:
         a.done = st["done"].data_ptr()
         td3 = self.algo == _lib.ALGO_TD3
         pol_opt = optimizer.get("policy_optimizer") if learn else None
-        a.policy = self._c_net(nets["policy_net"], pol_opt, learn)
-        a.target_policy = self._c_net(nets["target_policy_net"], None, False)
+        if self.discrete:
+            pol_opt = None           # the step never touches the DiscreteActor: next_action_in replaces its forward
+            a.next_action_in = st["next_action"].data_ptr()
+        else:
+            a.policy = self._c_net(nets["policy_net"], pol_opt, learn)
+            a.target_policy = self._c_net(nets["target_policy_net"], None, False)
         a.policy_optim = self._c_optim(pol_opt)
         val_opts = []
         for i in range(2 if td3 else 1):
@@ -231,11 +243,11 @@ class StepEngine:
             a.noise_std = float(params["noise_std"])
             a.noise_clip = float(params["noise_clip"])
         a.soft_tau = float(params["soft_tau"])
-        online = [nets[k] for k in self.names if not k.startswith("target")]
+        online = [nets[k] for k in self.names if not k.startswith("target") and not (self.discrete and k == "policy_net")]
         if len({bool(m.training) for m in online}) != 1:
             raise ValueError("the online nets must all be in the same mode (train() / eval()): dropout is applied "
                              "to every online net or to none; the target nets always run in eval mode")
-        a.dropout = int(bool(nets["policy_net"].training))
+        a.dropout = int(bool(online[-1].training))
         if st["masks"] is not None:
             for i, m in enumerate(st["masks"]):
                 a.masks[i] = m.data_ptr()
@@ -405,7 +417,7 @@ class StepEngine:
             m = nets[name]
             pr = probes.get(name)
             if pr is None or pr[0] is not m:
-                pr = probes[name] = (m, m.linear1.weight, m.linear3.bias)
+                pr = probes[name] = (m, m.linear1.weight, m.linear3.bias if hasattr(m, "linear3") else m.linear2.bias)
             w, b = pr[1], pr[2]
             g = w.grad
             tok.append((w.data_ptr(), b.data_ptr(), 0 if g is None else g.data_ptr(), m.training))
@@ -516,6 +528,9 @@ def _value_only(self, batch, params, nets, optimizer, learn, debug):
     """recnn/nn/update/misc.py:10-55 on its own: critic step without the policy half."""
     with torch.cuda.device(self.device):
         st = self._stage_batch(batch)
+        if self.discrete:
+            # next_action = target_policy_net(next_state)   (misc.py:28 with a DiscreteActor: probabilities)
+            st["next_action"] = self._stage("next_action", nets["target_policy_net"](st["next_state"]), torch.float32)
         a, _, val_opts = self._build_args(st, nets, optimizer, params, learn, False)
         want_debug = None
         if not learn:

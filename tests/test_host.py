@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(handle, name), name
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     L = _lib.lib()                       # also verifies struct size / offsets
-    assert L.recnn_b200_abi_version() == 2
+    assert L.recnn_b200_abi_version() == 3
     assert L.recnn_sizeof_step_args() == ctypes.sizeof(_lib.StepArgs)
 
 
