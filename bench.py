@@ -642,20 +642,20 @@ def run_native(args):
             "roofline": {"bound": "tensor", "kernel": "layer-1 forward GEMM [4096x1290]x[1290x256] (tc_gemm_kernel, tcgen05 kind::tf32, 3 MMA passes/product)",
                          "achieved": 3.0 * l1_tflops, "algorithmic_fp32": l1_tflops, "peak": tf32_peak, "unit": "TFLOP/s",
                          "frac": 3.0 * l1_tflops / tf32_peak,
-                         "traffic": 22518272, "traffic_source": "dram__bytes_read+write per launch, profiles/r2g/ncu_tc_gemm_tile64_raw.csv (ncu --set full)", "peak_source": "%s bf16 %.0f TF/s / 2 (TF32 kind)" % (peaks["source"], peaks["bf16"]),
+                         "traffic": 22518784, "traffic_source": "dram__bytes_read+write per launch, profiles/r2i/r2i_tc_gemm_raw.csv (ncu --set full)", "peak_source": "%s bf16 %.0f TF/s / 2 (TF32 kind)" % (peaks["source"], peaks["bf16"]),
                          "ms": l1_ms, "tile_n": best_tile, "per_tile": {str(k): v for k, v in l1.items()},
                          "timing": "8 launches on 8 distinct state images (8 x 21 MB > L2) captured in one CUDA graph, "
                                    "replayed 10x between CUDA events, L2 flushed between replays; median per launch",
                          "ms_single_launch_between_events": l1_single_ms},
             "roofline_gather": {"bound": "hbm", "kernel": "frame_gather_kernel", "achieved": gather_gbs,
                                 "peak": peaks["hbm"], "unit": "GB/s", "frac": gather_gbs / peaks["hbm"],
-                                "traffic": 11870208, "traffic_source": "dram__bytes_read+write per launch, profiles/r2g/ncu_gather_raw.csv: the 44 MB of "
+                                "traffic": 11989760, "traffic_source": "dram__bytes_read+write per launch, profiles/r2i/r2i_gather_raw.csv: the 44 MB of "
                                 "output is absorbed by the 126 MB L2 inside the kernel, so DRAM traffic << algorithmic bytes", "peak_source": peaks["source"], "ms": gather_ms, "ms_min": gather_ms_min, "ms_max": gather_ms_max,
                                 "ms_single_launch_between_events": gather_single_ms,
                                 "timing": "4 launches (own ids / outputs, 4 x 44 MB > L2) in one CUDA graph, replayed 10x between events; median per launch",
                                 "bytes_per_launch": n_rows * GATHER_BYTES_PER_ROW,
                                 "at_16x_rows": {"rows": big, "ms": gather_big_ms, "algorithmic_gbs": gather_big_gbs,
-                                                "traffic": 710113792, "traffic_source": "profiles/r2g/ncu_gather_65536rows_raw.csv (58.3 MB read + 651.8 MB written)",
+                                                "traffic": 710143488, "traffic_source": "profiles/r2i/r2i_gather_big_raw.csv (58.1 MB read + 652.1 MB written)",
                                                 "dram_gbs_est": (big * 10840 + N_ITEMS * DIM * 4) / (gather_big_ms * 1e-3) / 1e9,
                                                 "dram_frac_est": (big * 10840 + N_ITEMS * DIM * 4) / (gather_big_ms * 1e-3) / 1e9 / peaks["hbm"],
                                                 "note": "same kernel, 16x the rows: the 710 MB of output no longer fits in L2 and goes to HBM, "
@@ -663,8 +663,6 @@ def run_native(args):
             "clocks": clocks,
             "last_loss": r_dev["loss"],
         }
-        if args.opt:
-            line["config"]["options"] = {kv.partition("=")[0]: int(kv.partition("=")[2]) for kv in args.opt}
         if strong is not None:
             line["strong"] = strong
         if check is not None:
@@ -802,8 +800,6 @@ def main():
     ap.add_argument("--repeats", type=int, default=0, help="repeats of the K timed steps (default: 5 if K <= 100 else 3)")
     ap.add_argument("--algo", default="ddpg", choices=["ddpg", "td3"])
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
-                    help="library A/B switch (recnn_debug_set_option)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline legs (A/B runs)")
     ap.add_argument("--no-other-algo", action="store_true", help="skip the sub-object of the other algorithm")
     args = ap.parse_args()
@@ -813,11 +809,6 @@ def main():
         args.warmup = min(args.warmup, 3)
         run_reference(args)
     else:
-        if args.opt:
-            from recnn_b200 import _lib
-            for kv in args.opt:
-                name, _, val = kv.partition("=")
-                _lib.set_option(name, int(val))
         run_native(args)
 
 

@@ -164,18 +164,6 @@ def lib():
     return handle
 
 
-def set_option(name: str, value: int) -> int:
-    """Runtime A/B switch of the library (``recnn_debug_set_option``); returns the previous value.  Not part of the
-    product ABI.  Only the knobs of experiments still in flight exist (currently: "experiment")."""
-    h = lib()
-    fn = h.recnn_debug_set_option
-    fn.restype, fn.argtypes = C.c_int, [C.c_char_p, C.c_int]
-    prev = fn(name.encode(), int(value))
-    if prev < 0:
-        raise RecnnError("unknown option %r" % name)
-    return prev
-
-
 def check(status: int):
     if status != 0:
         msg = lib().recnn_b200_last_error()

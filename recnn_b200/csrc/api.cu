@@ -20,39 +20,7 @@ void set_error(const char* fmt, ...) {
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
-// Runtime switches for A/B experiments (recnn_debug_set_option / environment).  Round 2 measured and retired the
-// round-1 set (profiles/r2a): lean issue loop, programmatic dependent launch, one-wave split-K, side-stream column
-// sums, pad-column zeroing, 16-byte gather stores and 16 workers on 64-wide tiles are now simply how the kernels
-// work; pre-split weight planes, the LO2 accumulator rotation, 64-wide tiles everywhere and the unit-balanced
-// gather were measured as no better and deleted.  What is left are the knobs of experiments still in flight.
-static std::atomic<int> g_options[OPT_COUNT];
-static std::atomic<bool> g_options_init{false};
-static void init_options() {
-  if (g_options_init.load(std::memory_order_acquire)) return;
-  const struct { Option o; const char* env; int def; } table[] = {
-      {OPT_EXPERIMENT, "RECNN_B200_EXPERIMENT", 0},
-  };
-  for (const auto& t : table) {
-    const char* e = getenv(t.env);
-    g_options[t.o].store(e && *e ? atoi(e) : t.def, std::memory_order_relaxed);
-  }
-  g_options_init.store(true, std::memory_order_release);
-}
-int option(Option o) {
-  init_options();
-  return g_options[o].load(std::memory_order_relaxed);
-}
 }  // namespace recnn
-
-// returns the previous value, or -1 for an unknown name
-extern "C" RECNN_API int recnn_debug_set_option(const char* name, int value) {
-  recnn::init_options();
-  if (!name) return -1;
-  int idx = -1;
-  if (strcmp(name, "experiment") == 0) idx = recnn::OPT_EXPERIMENT;
-  if (idx < 0) return -1;
-  return recnn::g_options[idx].exchange(value);
-}
 
 extern "C" RECNN_API int64_t recnn_b200_launch_count(void) { return recnn::g_launches.load(); }
 extern "C" int recnn_b200_abi_version(void) { return RECNN_B200_ABI_VERSION; }

@@ -47,10 +47,6 @@ void count_launch();   // every kernel launch of this library bumps a process-wi
     if (_s != RECNN_OK) return _s;                                                    \
   } while (0)
 
-// ---- runtime switches (A/B experiments still in flight; recnn_debug_set_option) --------
-enum Option { OPT_EXPERIMENT = 0, OPT_COUNT = 1 };
-int option(Option o);
-
 constexpr int kNumSMs = 148;   // B200
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -508,8 +508,8 @@ static int phase_value_grad(Ctx& c) {
     const Seg sc1 = {c1, H, H, 0}, ss = {c.S, S, c.ldS, 0}, sa = {c.ACT, A + c.lead, c.ldA, c.lead};
     // When this call also runs the built-in optimizer, the split-K partials of layers 1-2 are not reduced by
     // kernels of their own: the optimizer (or the data-parallel all-reduce) pass sums them (GradSource).
-    const bool fuse_opt = (a.phases & RECNN_PH_VALUE_OPT) && a.value_optim.kind != RECNN_OPT_EXTERNAL &&
-                          !(option(OPT_EXPERIMENT) & 1);        // experiment bit 0: separate reduce kernels (A/B)
+    // (r2i A/B against separate reduce kernels: 2708 vs 2711 steps/s -- kept for the three launches it saves)
+    const bool fuse_opt = (a.phases & RECNN_PH_VALUE_OPT) && a.value_optim.kind != RECNN_OPT_EXTERNAL;
     GradSource gs;
     memset(&gs, 0, sizeof(gs));
     PartialLayer* d1 = fuse_opt ? &gs.l[0] : nullptr;

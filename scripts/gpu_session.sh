@@ -1,6 +1,6 @@
 #!/bin/bash
 # One single-GPU session: full GPU suite, bench, ncu launch list of a step, ncu --set full of the layer-1 GEMM and
-# the gather, and the experiment A/B (RECNN_B200_EXPERIMENT bits).  Outputs under gpurun_out/<tag>_*.
+# the gather.  Outputs under gpurun_out/<tag>_*.
 #   usage: bash scripts/gpu_session.sh <tag> [skip-ncu]
 cd "$(dirname "$0")/.." || exit 1
 tag=${1:-r2}
@@ -27,22 +27,6 @@ try:
 except Exception as e:
     print("bench failed:", e); print(open("$O/${tag}_bench.err").read()[-2000:])
 PY
-
-el "3. experiment A/B (bit 0: separate split-K reduce kernels instead of the fused optimizer pass)"
-for ex in 1; do
-  RECNN_B200_EXPERIMENT=$ex timeout 400 python -m pytest tests/test_gpu_tc.py tests/test_gpu_parity.py -m gpu -q --tb=line -p no:cacheprovider \
-    -k "not tight and not full_size" > $O/${tag}_tests_exp$ex.log 2>&1
-  echo "exp$ex tests: $(tail -1 $O/${tag}_tests_exp$ex.log)"
-  timeout 200 python bench.py --steps 100 --warmup 10 --no-cpu-baseline --no-other-algo --opt experiment=$ex > $O/${tag}_bench_exp$ex.json 2> $O/${tag}_bench_exp$ex.err
-  python - <<PY
-import json
-try:
-    d = json.load(open("$O/${tag}_bench_exp$ex.json"))
-    print("exp$ex: value %.1f  L1 %s" % (d["value"], {k: round(v["ms"] * 1e3, 2) for k, v in d["roofline"]["per_tile"].items()}))
-except Exception as e:
-    print("exp$ex bench failed:", e); print(open("$O/${tag}_bench_exp$ex.err").read()[-1500:])
-PY
-done
 
 if [ "$2" != "skip-ncu" ]; then
 el "4. ncu: launch list of the step"
