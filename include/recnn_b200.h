@@ -321,18 +321,6 @@ RECNN_API int recnn_retrieve_topk(const float* queries, int64_t n_queries, int32
                                   int64_t* ids_out, float* dist_out, void* workspace, int64_t workspace_bytes,
                                   void* stream);
 
-/* ---- CUDA-graph helpers -----------------------------------------------------------------------
- * One update step is a fixed launch sequence (no allocation, no synchronisation), so hosts replay it as a CUDA graph.
- * These wrap stream capture and instantiate the graph with cudaGraphInstantiateFlagUseNodePriority: the step marks the
- * GEMMs of its dependency-critical chain with a higher CTA dispatch priority than the side chains that run beside it,
- * and only graphs instantiated with that flag honour per-node priorities (a plain cudaGraphInstantiate -- what
- * torch.cuda.CUDAGraph does -- runs every node at the launch stream's priority).
- *   recnn_graph_begin(stream); recnn_ddpg_step(&args, stream); recnn_graph_end(stream, &g);  ...  recnn_graph_launch(g, stream) */
-RECNN_API int recnn_graph_begin(void* stream);
-RECNN_API int recnn_graph_end(void* stream, void** graph_out);
-RECNN_API int recnn_graph_launch(void* graph, void* stream);
-RECNN_API int recnn_graph_destroy(void* graph);
-
 /* ---- REINFORCE with (Top-K) off-policy correction: the policy side ------------------
  * DiscreteActor (recnn/nn/models.py:76-99): probs = softmax(W2 relu(W1 s + b1) + b2), one output per item.
  * Parameter arena in nn.Module.parameters() order -- linear1.weight [H, S], linear1.bias, linear2.weight

@@ -105,10 +105,6 @@ SIGNATURES = {
     "recnn_retrieve_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int64, C.c_int32]),
     "recnn_retrieve_topk": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
                                       C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
-    "recnn_graph_begin": (C.c_int, [C.c_void_p]),
-    "recnn_graph_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
-    "recnn_graph_launch": (C.c_int, [C.c_void_p, C.c_void_p]),
-    "recnn_graph_destroy": (C.c_int, [C.c_void_p]),
     "recnn_discrete_layout": (C.c_int, [C.POINTER(DiscreteDims), C.POINTER(C.c_int64)]),
     "recnn_discrete_scratch_floats": (C.c_int64, [C.POINTER(DiscreteDims), C.c_int64, C.c_int32]),
     "recnn_discrete_forward": (C.c_int, [C.POINTER(DiscreteDims), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,

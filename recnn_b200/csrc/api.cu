@@ -45,33 +45,3 @@ extern "C" RECNN_API int64_t recnn_offsetof_step_args(int field) {
     default: return -1;
   }
 }
-
-// ---- CUDA-graph helpers (include/recnn_b200.h) ------------------------------------------------------------------
-extern "C" int recnn_graph_begin(void* stream) {
-  RECNN_CHECK_CUDA(cudaStreamBeginCapture(static_cast<cudaStream_t>(stream), cudaStreamCaptureModeThreadLocal));
-  return RECNN_OK;
-}
-
-extern "C" int recnn_graph_end(void* stream, void** graph_out) {
-  RECNN_REQUIRE(graph_out != nullptr, "graph_out");
-  *graph_out = nullptr;
-  cudaGraph_t g = nullptr;
-  RECNN_CHECK_CUDA(cudaStreamEndCapture(static_cast<cudaStream_t>(stream), &g));
-  cudaGraphExec_t exec = nullptr;
-  const cudaError_t e = cudaGraphInstantiateWithFlags(&exec, g, cudaGraphInstantiateFlagUseNodePriority);
-  cudaGraphDestroy(g);
-  RECNN_CHECK_CUDA(e);
-  *graph_out = exec;
-  return RECNN_OK;
-}
-
-extern "C" int recnn_graph_launch(void* graph, void* stream) {
-  RECNN_REQUIRE(graph != nullptr, "graph");
-  RECNN_CHECK_CUDA(cudaGraphLaunch(static_cast<cudaGraphExec_t>(graph), static_cast<cudaStream_t>(stream)));
-  return RECNN_OK;
-}
-
-extern "C" int recnn_graph_destroy(void* graph) {
-  if (graph) RECNN_CHECK_CUDA(cudaGraphExecDestroy(static_cast<cudaGraphExec_t>(graph)));
-  return RECNN_OK;
-}

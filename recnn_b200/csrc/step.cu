@@ -195,28 +195,6 @@ struct AloneScope {
   ~AloneScope() { t_alone = prev; }
 };
 
-// Experiment (RECNN_B200_PRIO): 1 = GEMMs launched on the step's main stream (the dependency-critical chain: target
-// policy -> target critic -> value head -> dX -> dW1 -> optimizer -> policy-loss critic) get the device's highest CTA
-// dispatch priority, so the side chains (online critic / online policy forward, dW2) only take SMs the critical chain
-// does not want; 2 = additionally 64-wide tiles (128 CTAs) for the critical chain's [4096 x 256] layers.
-static int prio_mode() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("RECNN_B200_PRIO");
-    v = e ? atoi(e) : 0;
-  }
-  return v;
-}
-static thread_local cudaStream_t t_main_stream = nullptr;
-static void set_priority_for(cudaStream_t st) {
-  static int greatest = 1;
-  if (greatest == 1) {
-    int least = 0;
-    if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) greatest = 0;
-  }
-  tc::set_launch_priority((prio_mode() >= 1 && st == t_main_stream) ? greatest : 0);
-}
-
 static int pick_bn(int64_t M, int N) {
   // 128-wide tiles when they still yield >= 64 CTAs; otherwise 64-wide (more CTAs, less reuse)
   const int64_t mt = ceil_div(M, 128);
@@ -238,7 +216,6 @@ static int gemm_nt(const Seg& x0, const Seg& x1, const float* W, long long ldw, 
     tc::Problem p;
     memset(&p, 0, sizeof(p));
     p.M = (int)n; p.N = N; p.K0 = x0.cols; p.K1 = x1.cols; p.b_k1_offset = x0.cols - x1.lead;
-    set_priority_for(st);
     const int r = tc::launch<false, false, EPI>(a0, a1, b, p, 1, pick_bn(n, N), e, st);
     return r < 0 ? r : RECNN_OK;
   }
@@ -284,7 +261,6 @@ static int backprop_hidden(const float* dZ, int C, const float* W, long long ldw
     memset(&p, 0, sizeof(p));
     p.M = (int)n; p.N = K; p.K0 = C; p.b_k1_offset = C; p.b_n_offset = col0;
     const int bn = pick_bn(n, K);
-    set_priority_for(st);
     const int r = h ? tc::launch<false, true, EPI_GATE>(a0, a1, b, p, 1, bn, e, st)
                     : tc::launch<false, true, EPI_STORE>(a0, a1, b, p, 1, bn, e, st);
     return r < 0 ? r : RECNN_OK;
@@ -331,7 +307,6 @@ static int weight_grad(const float* dZ, int C, const Seg& x0, const Seg& x1, int
       memset(&p, 0, sizeof(p));
       p.M = C; p.N = s->cols; p.K0 = (int)n; p.n_out_offset = cols0[i]; p.n_skip = i == 0 ? x1.lead : 0;
       const int bn = s->cols > 64 ? 128 : 64;
-      set_priority_for((i == 0 && use_side) ? side->stream : st);
       const int r = tc::launch<true, true, EPI_PARTIAL>(a0, a1, b, p, req, bn, e, (i == 0 && use_side) ? side->stream : st);
       if (r < 0) return r;
       if (r != splits) {
@@ -446,10 +421,7 @@ static int phase_value_grad(Ctx& c) {
     RECNN_CHECK_CUDA(cudaMemcpy2DAsync(a2 + c.lead, c.ldA * 4, a.next_action_in, (size_t)A * 4, (size_t)A * 4, c.n,
                                        cudaMemcpyDeviceToDevice, c.st));
   } else {
-  {
-    AloneScope wide(prio_mode() >= 2);
-    RECNN_PROPAGATE(actor_hidden(c, a.target_policy.params, c.S2, false, 0, X0, X1, c.st));
-  }
+  RECNN_PROPAGATE(actor_hidden(c, a.target_policy.params, c.S2, false, 0, X0, X1, c.st));
   if (c.aux && c.p_deferred) {
     RECNN_CHECK_CUDA(cudaEventRecord(c.aux->ev[4], c.st));
     RECNN_CHECK_CUDA(cudaStreamWaitEvent(c.aux->sp, c.aux->ev[4], 0));
@@ -477,7 +449,7 @@ static int phase_value_grad(Ctx& c) {
     RECNN_CHECK_CUDA(cudaEventRecord(c.aux->ev[7], c.aux->sw));
   }
   for (int i = 0; i < n_critics; ++i) {
-    AloneScope alone((c.aux != nullptr && !c.p_prefetched && !tc1_side) || prio_mode() >= 2);   // alone unless another chain runs alongside
+    AloneScope alone(c.aux != nullptr && !c.p_prefetched && !tc1_side);   // alone unless another chain runs alongside
     float* th2 = X1;
     if (i == 1 && tc1_side) {
       RECNN_CHECK_CUDA(cudaStreamWaitEvent(c.st, c.aux->ev[7], 0));
@@ -723,7 +695,6 @@ static int run_step(const recnn_step_args* a, int algo, void* stream) {
   c.lc = critic_layout(c.d);
   c.n = a->n_rows;
   c.st = static_cast<cudaStream_t>(stream);
-  t_main_stream = c.st;
   c.ws = carve(c.d, c.n, a->workspace);
   if (c.ws.bytes > a->workspace_bytes) {
     set_error("workspace too small: need %lld bytes, got %lld", (long long)c.ws.bytes, (long long)a->workspace_bytes);

@@ -10,9 +10,6 @@
 namespace recnn {
 namespace tc {
 
-thread_local int t_priority = 0;
-void set_launch_priority(int p) { t_priority = p; }
-
 EncodeTiledFn get_encode_fn() {
   static EncodeTiledFn fn = nullptr;
   static std::once_flag once;
@@ -103,16 +100,11 @@ static int launch_cfg(const Operand& A0, const Operand& A1, const Operand& B, co
   cfg.blockDim = dim3(C::THREADS, 1, 1);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (t_priority != 0) {          // CTA dispatch priority of this launch (critical-path GEMMs of the step)
-    attr[1].id = cudaLaunchAttributePriority;
-    attr[1].val.priority = t_priority;
-    cfg.numAttrs = 2;
-  }
   RECNN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<C, EPI>, ma0, ma1, mb, p, epi));
   RECNN_CHECK_LAUNCH("tc_gemm_kernel");
   if (debug) {

@@ -714,8 +714,6 @@ struct Operand {
 
 // k-blocks (of bk) per split and the effective split count for a requested split count.
 int split_plan(int K_total_blocks, int splits_req, int* k_chunk, int bk = 16);
-// CTA dispatch priority of the following launches of this thread (0: default; negative = more urgent)
-void set_launch_priority(int p);
 
 // Launch one GEMM.  Returns the effective number of k-splits (> 0) or a negative RECNN_E_* code.
 template <bool A_MN, bool B_MN, int EPI>

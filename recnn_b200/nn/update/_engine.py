@@ -29,44 +29,6 @@ TD3_NETS = ("value_net1", "target_value_net1", "value_net2", "target_value_net2"
             "target_policy_net")
 
 
-class _StepGraph:
-    """One captured update step, instantiated by the library (recnn_graph_*: per-node launch priorities are honoured,
-    which torch.cuda.CUDAGraph's plain instantiation would ignore).  ``body`` must only launch work on the current
-    stream (the C step does); it runs once, under capture, on a side stream."""
-
-    def __init__(self, device, body):
-        import ctypes
-        self.device = device
-        self.handle = ctypes.c_void_p()
-        L = _lib.lib()
-        cur = torch.cuda.current_stream(device)
-        side = torch.cuda.Stream(device)
-        side.wait_stream(cur)
-        self.result = None
-        with torch.cuda.stream(side):
-            _lib.check(L.recnn_graph_begin(side.cuda_stream))
-            try:
-                self.result = body()
-            except BaseException:
-                tmp = ctypes.c_void_p()
-                L.recnn_graph_end(side.cuda_stream, ctypes.byref(tmp))      # leave capture mode before re-raising
-                L.recnn_graph_destroy(tmp)
-                raise
-            _lib.check(L.recnn_graph_end(side.cuda_stream, ctypes.byref(self.handle)))
-        cur.wait_stream(side)
-
-    def replay(self):
-        _lib.check(_lib.lib().recnn_graph_launch(self.handle, _lib.stream_ptr(self.device)))
-
-    def __del__(self):
-        try:
-            if self.handle:
-                _lib.lib().recnn_graph_destroy(self.handle)
-                self.handle = None
-        except Exception:
-            pass
-
-
 class StepEngine:
     def __init__(self, algo, nets, device):
         self.algo = algo
@@ -367,13 +329,9 @@ class StepEngine:
             self._invalidate()
         try:
             torch.cuda.synchronize(self.device)
-            if self.world == 1 or a.comm:
-                g = _StepGraph(self.device, lambda: self._body(a, nets, do_policy))
-                n_kernels = g.result
-            else:                          # NCCL calls inside the step: torch's capture keeps their buffers alive
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    n_kernels = self._body(a, nets, do_policy)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                n_kernels = self._body(a, nets, do_policy)
             self.graphs[key] = (g, n_kernels)
             g.replay()
             self.kernels += n_kernels
