@@ -33,9 +33,9 @@
 //                 tile next to it                                                      (split[s])
 //                 (2) drain: TMEM chunk -> registers, running sum += chunk             (acc_empty[buf])
 //                 (3) epilogue on the register-resident row (bias/relu/dropout/...), store.
-// Programmatic dependent launch: every kernel calls griddepcontrol.launch_dependents at entry and
-// griddepcontrol.wait after its prologue (barrier init, TMEM allocation, tensor-map prefetch), and is launched
-// with programmatic stream serialization, so the next GEMM's prologue overlaps this one's drain / epilogue.
+// Programmatic dependent launch: the TMA warp calls griddepcontrol.launch_dependents once its last load is issued, every
+// kernel parks at griddepcontrol.wait after its prologue (barrier init, TMEM allocation, tensor-map prefetch), and is
+// launched with programmatic stream serialization, so the next GEMM's prologue overlaps this one's drain / epilogue.
 // Operand tiles in smem are the canonical UMMA layouts written by TMA with hardware
 // swizzle, so the splitter is swizzle-agnostic (same offset in the `lo` buffer) and the
 // same smem descriptors serve hi and lo.
@@ -193,7 +193,7 @@ __device__ __forceinline__ void mma_tf32_ta(uint32_t d_tmem, uint32_t a_tmem, ui
       : "memory");
 }
 // Programmatic dependent launch: launch_dependents lets the next kernel of the stream
-// be scheduled onto idle SMs while this one still runs; its threads park at griddep_wait() -- after their prologue,
+// be scheduled onto idle SMs while this one finishes; its threads park at griddep_wait() -- after their prologue,
 // before any global-memory access -- until this grid has completed and its writes are visible.  Both are no-ops for
 // a launch without the programmatic-serialization attribute.
 __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -416,7 +416,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM, z = blockIdx.z;
-  griddep_launch_dependents();                                // the next kernel of the stream may start its prologue
   if (threadIdx.x == 0) RECNN_TRACE(0);                       // kernel entry
   // k-blocks: segment 0 then segment 1, each padded up to a multiple of BK (TMA zero-fills the tail)
   const int nkb0 = (p.K0 + BK - 1) / BK, nkb1 = (p.K1 + BK - 1) / BK;
@@ -489,6 +488,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       __syncwarp();
       if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1u; }
     }
+    // All loads issued, STAGES k-blocks before the last MMA: NOW the next kernel of the stream may be scheduled (one thread's
+    // trigger counts for its CTA).  Its CTAs run their prologue and park at griddepcontrol.wait holding an SM each, so
+    // releasing them at kernel entry (r1-r2i) let them squat on SMs that concurrent GEMMs of the step's other chains
+    // could have used for a whole kernel duration; released here they wait for an epilogue's length.  r2k, DDPG step:
+    // trigger at entry 2708 steps/s, never (dependents start at grid exit) 2750-2764, here 2823.
+    griddep_launch_dependents();
   } else if (warp == 1 || warp == 2) {
     // ===================================================== MMA issuer(s)
     // The whole warp walks the pipeline (so every value below is warp-uniform and lives in uniform
