@@ -642,20 +642,20 @@ def run_native(args):
             "roofline": {"bound": "tensor", "kernel": "layer-1 forward GEMM [4096x1290]x[1290x256] (tc_gemm_kernel, tcgen05 kind::tf32, 3 MMA passes/product)",
                          "achieved": 3.0 * l1_tflops, "algorithmic_fp32": l1_tflops, "peak": tf32_peak, "unit": "TFLOP/s",
                          "frac": 3.0 * l1_tflops / tf32_peak,
-                         "traffic": 22518784, "traffic_source": "dram__bytes_read+write per launch, profiles/r2i/r2i_tc_gemm_raw.csv (ncu --set full)", "peak_source": "%s bf16 %.0f TF/s / 2 (TF32 kind)" % (peaks["source"], peaks["bf16"]),
+                         "traffic": 22518784, "traffic_source": "dram__bytes_read+write per launch, profiles/r2k/r2k_tc_gemm_raw.csv (ncu --set full)", "peak_source": "%s bf16 %.0f TF/s / 2 (TF32 kind)" % (peaks["source"], peaks["bf16"]),
                          "ms": l1_ms, "tile_n": best_tile, "per_tile": {str(k): v for k, v in l1.items()},
                          "timing": "8 launches on 8 distinct state images (8 x 21 MB > L2) captured in one CUDA graph, "
                                    "replayed 10x between CUDA events, L2 flushed between replays; median per launch",
                          "ms_single_launch_between_events": l1_single_ms},
             "roofline_gather": {"bound": "hbm", "kernel": "frame_gather_kernel", "achieved": gather_gbs,
                                 "peak": peaks["hbm"], "unit": "GB/s", "frac": gather_gbs / peaks["hbm"],
-                                "traffic": 11989760, "traffic_source": "dram__bytes_read+write per launch, profiles/r2i/r2i_gather_raw.csv: the 44 MB of "
+                                "traffic": 12184064, "traffic_source": "dram__bytes_read+write per launch, profiles/r2k/r2k_gather_raw.csv: the 44 MB of "
                                 "output is absorbed by the 126 MB L2 inside the kernel, so DRAM traffic << algorithmic bytes", "peak_source": peaks["source"], "ms": gather_ms, "ms_min": gather_ms_min, "ms_max": gather_ms_max,
                                 "ms_single_launch_between_events": gather_single_ms,
                                 "timing": "4 launches (own ids / outputs, 4 x 44 MB > L2) in one CUDA graph, replayed 10x between events; median per launch",
                                 "bytes_per_launch": n_rows * GATHER_BYTES_PER_ROW,
                                 "at_16x_rows": {"rows": big, "ms": gather_big_ms, "algorithmic_gbs": gather_big_gbs,
-                                                "traffic": 710143488, "traffic_source": "profiles/r2i/r2i_gather_big_raw.csv (58.1 MB read + 652.1 MB written)",
+                                                "traffic": 710117376, "traffic_source": "profiles/r2k/r2k_gather_big_raw.csv (58.2 MB read + 651.9 MB written)",
                                                 "dram_gbs_est": (big * 10840 + N_ITEMS * DIM * 4) / (gather_big_ms * 1e-3) / 1e9,
                                                 "dram_frac_est": (big * 10840 + N_ITEMS * DIM * 4) / (gather_big_ms * 1e-3) / 1e9 / peaks["hbm"],
                                                 "note": "same kernel, 16x the rows: the 710 MB of output no longer fits in L2 and goes to HBM, "
