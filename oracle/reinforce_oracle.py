@@ -157,3 +157,59 @@ def value_update(batch, params, nets, opts, masks, learn=True):
         grads, _ = O._mlp_backward(nets["value_net"], cache, d_q, need_dx=False)
         O.optimizer_step(opts["value_optimizer"], nets["value_net"], grads)                    # :42-44
     return loss, {"next_action": a2, "expected_value": y, "value": q}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Vocabulary-parallel formulation (BASELINE configs[4]: 1M items over 8 GPUs) -- DESIGN STUDY, no CUDA counterpart yet.
+# The item dimension of linear2 (and of the softmax) is sharded over W ranks; linear1 is replicated.  The functions below
+# restate the policy gradient as W per-rank computations plus the three exchanges a device implementation needs, and
+# tests/test_reinforce_oracle.py checks them against the unsharded oracle:
+#   exchange 1 (all-gather, 3 floats per row and rank): local max m_r, local sum s_r = sum exp(z - m_r), and the logit of
+#               the drawn action (owner rank only, 0 elsewhere)
+#   exchange 2 (all-reduce, [rows, hidden]): dh = sum over ranks of dz_r @ W2_r
+# Everything else (dW2_r, db2_r of the shard; dW1, db1 replicated from the all-reduced dh) is rank-local.
+def shard_policy(p: dict, world: int):
+    """Split a DiscreteActor's linear2 rows into `world` contiguous shards (the last may be shorter)."""
+    items = p["w2"].shape[0]
+    per = -(-items // world)
+    shards = []
+    for r in range(world):
+        lo, hi = min(r * per, items), min((r + 1) * per, items)
+        shards.append({"w1": p["w1"], "b1": p["b1"], "w2": p["w2"][lo:hi], "b2": p["b2"][lo:hi], "offset": lo})
+    return shards
+
+
+def sharded_policy_grad(shards: list, state: np.ndarray, action: np.ndarray, beta_logp, ret: np.ndarray,
+                        method: int, K: int = 10):
+    """Loss and per-rank gradients of the vocabulary-sharded policy; see the exchanges above."""
+    n = state.shape[0]
+    x = state.astype(np.float64)
+    local = []
+    for sh in shards:                                                        # ---- rank-local forward
+        h = np.maximum(x @ sh["w1"].astype(np.float64).T + sh["b1"].astype(np.float64), 0)
+        z = h @ sh["w2"].astype(np.float64).T + sh["b2"].astype(np.float64)
+        cnt = z.shape[1]
+        m = z.max(axis=1) if cnt else np.full(n, -np.inf)
+        s = np.exp(z - m[:, None]).sum(axis=1) if cnt else np.zeros(n)
+        mine = (action >= sh["offset"]) & (action < sh["offset"] + cnt)
+        za = np.where(mine, z[np.arange(n), np.clip(action - sh["offset"], 0, max(cnt - 1, 0))] if cnt else 0.0, 0.0)
+        local.append({"h": h, "z": z, "m": m, "s": s, "za": za, "mine": mine})
+    # ---- exchange 1: every rank now holds (m_r, s_r, za_r) of all ranks
+    M = np.max([l["m"] for l in local], axis=0)
+    S = np.sum([l["s"] * np.exp(l["m"] - M) for l in local], axis=0)
+    za = np.sum([l["za"] for l in local], axis=0)
+    pa = np.exp(za - M) / S                                                  # pi[a], identical on every rank
+    L, g, _ = row_terms(pa, beta_logp, ret, method, K)
+    grads, dh = [], np.zeros_like(local[0]["h"])
+    for sh, l in zip(shards, local):                                         # ---- rank-local backward
+        probs = np.exp(l["z"] - M[:, None]) / S[:, None]
+        dz = -probs * g[:, None]
+        rows = np.nonzero(l["mine"])[0]
+        dz[rows, action[rows] - sh["offset"]] += g[rows]
+        grads.append({"w2": dz.T @ l["h"], "b2": dz.sum(0)})
+        dh += dz @ sh["w2"].astype(np.float64)                               # ---- exchange 2: all-reduce of dh
+    dh = dh * (local[0]["h"] > 0)
+    for gr in grads:                                                         # replicated layer 1
+        gr["w1"] = dh.T @ x
+        gr["b1"] = dh.sum(0)
+    return float(L.sum()), grads

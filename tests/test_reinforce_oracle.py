@@ -62,3 +62,29 @@ def test_inverse_cdf_sampling_is_a_categorical_draw():
     assert RO.categorical_sample(p, np.asarray([0.0], np.float32))[0][0] == 2
     assert RO.categorical_sample(p, np.asarray([0.5], np.float32))[0][0] == 4
     assert RO.categorical_sample(p, np.asarray([0.999], np.float32))[0][0] == 4
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("method", [RO.BASIC, RO.CORRECTED, RO.TOPK])
+def test_vocabulary_sharded_formulation_equals_unsharded(world, method):
+    """Design study for the 1M-item configuration: sharding linear2 / the softmax over ranks with an exchange of
+    (max, sum, drawn logit) per row and an all-reduce of dh reproduces the unsharded loss and gradients."""
+    rng = np.random.default_rng(world * 10 + method)
+    S, H, I, R = 20, 24, 101, 37                      # 101 items: uneven shards (and an empty one at world 8? no: 13 each)
+    p = RO.make_discrete_actor(rng, S, I, H)
+    state = rng.normal(0, 1, (R, S)).astype(np.float32)
+    action = rng.integers(0, I, R)
+    action[:3] = [0, I - 1, I // 2]
+    blp = np.log(rng.uniform(0.005, 0.02, R)).astype(np.float32)
+    ret = rng.normal(0, 1, R).astype(np.float32)
+    want_loss, want, _ = RO.reinforce_policy_grad(p, state, action, blp, ret, method, 7)
+    shards = RO.shard_policy(p, world)
+    got_loss, got = RO.sharded_policy_grad(shards, state, action, blp, ret, method, 7)
+    assert got_loss == pytest.approx(want_loss, rel=1e-12, abs=1e-12)
+    w2 = np.concatenate([g["w2"] for g in got], 0)
+    b2 = np.concatenate([g["b2"] for g in got], 0)
+    np.testing.assert_allclose(w2, want["w2"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(b2, want["b2"], rtol=1e-9, atol=1e-12)
+    for g in got:
+        np.testing.assert_allclose(g["w1"], want["w1"], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(g["b1"], want["b1"], rtol=1e-9, atol=1e-12)
