@@ -31,19 +31,11 @@ def write_losses(writer, loss_dict, kind="train"):
 
 
 class DummyWriter:
-    """No-op stand-in for torch.utils.tensorboard.SummaryWriter."""
+    """Stand-in for torch.utils.tensorboard.SummaryWriter that drops everything (utils/misc.py:15-35): every
+    ``add_*`` call and ``close`` is accepted and ignored."""
 
-    def add_figure(self, *args, **kwargs):
-        pass
+    @staticmethod
+    def _ignore(*args, **kwargs):
+        return None
 
-    def add_histogram(self, *args, **kwargs):
-        pass
-
-    def add_scalar(self, *args, **kwargs):
-        pass
-
-    def add_scalars(self, *args, **kwargs):
-        pass
-
-    def close(self, *args, **kwargs):
-        pass
+    add_figure = add_histogram = add_scalar = add_scalars = close = _ignore
