@@ -88,3 +88,39 @@ def test_vocabulary_sharded_formulation_equals_unsharded(world, method):
     for g in got:
         np.testing.assert_allclose(g["w1"], want["w1"], rtol=1e-9, atol=1e-12)
         np.testing.assert_allclose(g["b1"], want["b1"], rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("path", RG.FILES, ids=RG.IDS)
+def test_host_side_returns_of_the_mirror_match_the_reference(path, monkeypatch):
+    """recnn_b200.nn.ChooseREINFORCE.__call__ forms the normalised discounted returns on the host (reinforce.py:44-52)
+    before the one device call; with that call stubbed out the host arithmetic is checkable on a CPU box: the returns it
+    hands over are the reference's, the optimizer is stepped once and the policy's lists are cleared."""
+    import torch
+    import recnn_b200
+    from recnn_b200.nn.update import reinforce as mirror
+    c = RG.load(path)
+    seen = {}
+
+    def fake_policy_loss(policy, returns, method):
+        seen["returns"] = torch.as_tensor(returns).clone()
+        seen["method"] = method
+        return torch.tensor(1.5)
+
+    monkeypatch.setattr(mirror, "_policy_loss", fake_policy_loss)
+    policy = recnn_b200.nn.DiscreteActor(c["S"], c["I"], c["H"])
+    policy.rewards = [torch.tensor(float(r)) for r in c["g"]["rewards"]]
+    policy.saved_log_probs = [torch.zeros(1)] * c["T"]
+
+    class Opt:
+        steps = 0
+
+        def step(self):
+            Opt.steps += 1
+
+    chooser = recnn_b200.nn.ChooseREINFORCE(getattr(recnn_b200.nn.ChooseREINFORCE, c["method_name"]))
+    out = chooser(policy, Opt(), learn=True)
+    assert float(out) == 1.5 and Opt.steps == 1 and seen["method"] == c["method"]
+    np.testing.assert_allclose(seen["returns"].numpy(), c["g"]["returns"], rtol=1e-6, atol=1e-6)
+    assert policy.rewards == [] and policy.saved_log_probs == [] and policy._saved == []
+    with pytest.raises(TypeError):
+        recnn_b200.nn.ChooseREINFORCE(lambda p, r: 0)(policy, Opt())
